@@ -1,0 +1,240 @@
+/*
+ * svnet_b200.h -- C ABI of libsvnet_b200.so (sm_100a CUDA kernels for the SVNet inference hot path).
+ *
+ * The reference (hellozhuo/svnet) has no FFI layer: its only stable boundary is the Python
+ * nn.Module API.  This ABI sits directly underneath that API; every entry point
+ * cites the reference function whose arithmetic it replaces (paths relative to /root/reference).
+ * svnet_b200/*.py (the host-side mirror of models/sv_layers.py, models/utils/sv_util.py and the
+ * four SV model files) is the only caller; INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.  All pointers are DEVICE pointers on
+ *     the current CUDA device unless stated otherwise; buffers are caller-owned (the library is
+ *     stateless: no handles, no global mutable state, re-entrant across devices/threads).
+ *   - every launch goes to `stream` (a cudaStream_t passed as void*); nothing synchronises.
+ *   - return 0 on success; on failure a negative code, message via svnet_last_error()
+ *     (thread-local).  Shapes are validated before any launch.
+ *   - all floating point is fp32; indices are int32 inside the fused path, int64 at the
+ *     reference-facing boundary (torch.topk returns int64, sv_util.py:24).
+ *
+ * Point-feature views.  A point carries scalars s (Cs floats) and vectors v (3 x Cv floats, xyz
+ * outer / channel inner, sv_layers.py:88,113).  Kernels address them through strided views so that
+ * layer outputs can be written straight into the concatenated (svcat, sv_util.py:134-144) table:
+ *     s[r][c]    = s[r*lds + c]
+ *     v[r][x][c] = v[r*ldv + x*xs + c]
+ */
+#ifndef SVNET_B200_H
+#define SVNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVNET_ABI_VERSION 1
+
+/* error codes */
+#define SVNET_OK 0
+#define SVNET_ERR_ARG (-1)   /* bad shape / null pointer / unsupported size */
+#define SVNET_ERR_CUDA (-2)  /* CUDA runtime error on launch */
+
+/* activation codes */
+#define SVNET_ACT_NONE 0
+#define SVNET_ACT_LEAKY 1 /* LeakyReLU(0.2), sv_layers.py:167 */
+#define SVNET_ACT_RELU 2  /* sv_pointnet_cls.py:78-79 */
+
+typedef struct {
+    const float* s; /* may be NULL when Cs == 0 */
+    int lds;
+    int Cs;
+    const float* v; /* may be NULL when Cv == 0 */
+    int ldv;        /* row stride (floats) */
+    int xs;         /* xyz stride (floats) */
+    int Cv;
+} svnet_view;
+
+typedef struct {
+    float* s;
+    int lds;
+    int Cs;
+    float* v;
+    int ldv;
+    int xs;
+    int Cv;
+} svnet_mview;
+
+int svnet_version(void);
+const char* svnet_last_error(void);
+
+/* ---- one-time weight preparation ------------------------------------------------------------ */
+
+/* sign(W) bit-planes for a binarised Linear/Conv1d weight (sv_layers.py:43-45,70).
+ * W [rows][ldw] (first K columns used) -> bits_t [ceil(K/32)][rows] (word-major, bit b of word w
+ * = (W[row][32w+b] > 0)).  *zero_count (device int) receives the number of exactly-zero weights
+ * (sign(0)=0 is not representable in one plane; callers must reject > 0). */
+int svnet_pack_sign(const float* W, int rows, int K, int ldw, uint32_t* bits_t, int* zero_count, void* stream);
+
+/* eval-mode BatchNorm1d as y = x*a + c (torch.nn.BatchNorm1d with running stats; sv_layers.py:84,166):
+ * a = w/sqrt(var+eps), c = b - mean*a. */
+int svnet_fold_bn(const float* w, const float* b, const float* mean, const float* var, float eps, int C,
+                  float* a, float* c, void* stream);
+
+/* ---- graph construction --------------------------------------------------------------------- */
+
+/* knn(x,k), sv_util.py:19-25 -- feature of point r is [s | v(x=0) | v(x=1) | v(x=2)]
+ * (sv_util.py:100-101; layer 1: s = xyz, Cs = 3, Cv = 0).  score p_ij = ((-xx_j) - (-2 f_i.f_j)) - xx_i
+ * in fp32 with sequential fmaf chains over channels; k largest per row, nearest first, ties ->
+ * lowest index.  No BxNxN matrix is written.  idx32 and/or idx64 [B][N][k] (either may be NULL).
+ * 1 <= k <= min(N,128). */
+int svnet_knn(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, void* stream);
+
+/* get_graph_feature (nv=2, sv_util.py:28-62) / get_graph_feature_cross (nv=3, sv_util.py:64-88):
+ * xyz [B][N][3], idx int64 [B][N][k] -> out [B][N][k][3][nv].  Materialising parity path. */
+int svnet_graph_feature_xyz(const float* xyz, const int64_t* idx, int B, int N, int k, int nv, float* out,
+                            void* stream);
+
+/* get_graph_feature_sv, sv_util.py:106-114: s [B][N][Cs], v [B][N][3][Cv] ->
+ * sf [B][N][k][2Cs], vf [B][N][k][3][2Cv].  Materialising parity path. */
+int svnet_graph_feature_sv(const float* s, const float* v, const int64_t* idx, int B, int N, int k, int Cs,
+                           int Cv, float* sf, float* vf, void* stream);
+
+/* ---- SVBlock gate (sv_layers.py:156-161,179-183): g = sigmoid(G2 relu(G1 mean_rows(s))) -------- */
+
+/* rows variant: s [B][rows][lds] (Cs used); G1 [H][Cs], G2 [Co][H]; gate [B][Co] */
+int svnet_gate_rows(const float* s, int lds, int Cs, int B, int rows, const float* G1, const float* G2, int H,
+                    int Co, float* gate, void* stream);
+
+/* edge variant for get_graph_feature_sv edges: the block input is s_e = [s_j - s_i | s_i]
+ * (sv_util.py:114), whose mean over the N*k edges of a cloud is computed from the kNN in-degrees
+ * without touching an edge tensor.  G1 [H][2*Cs]. */
+int svnet_gate_edge(const svnet_view* in, const int32_t* idx, int B, int N, int k, const float* G1,
+                    const float* G2, int H, int Co, float* gate, void* stream);
+
+/* first-layer variant: s_e = init_scalar([x_j-x_i | x_i (| x_j x x_i)]) (sv_dgcnn_cls.py:49-50,
+ * sv_pointnet_cls.py:35-36).  Winit [3][nv]; G1 [H][3*nv]. */
+int svnet_gate_xyz(const float* xyz, const int32_t* idx, int B, int N, int k, int nv, const float* Winit,
+                   const float* G1, const float* G2, int H, int Co, float* gate, void* stream);
+
+/* ---- fused edge convolutions ---------------------------------------------------------------- */
+
+/* First edge layer: get_graph_feature[_cross] + init_scalar + SVBlock(FP) + svpool, fused
+ * (sv_dgcnn_cls.py:49-53, sv_pointnet_cls.py:35-39).  Everything is full precision in every model
+ * (sv_dgcnn_cls.py:29-30). */
+typedef struct {
+    const float* xyz;   /* [B][N][3] */
+    const int32_t* idx; /* [B][N][k] */
+    int B, N, k, nv;    /* nv = 2 (DGCNN) or 3 (PointNet, cross product channel) */
+    const float* Winit; /* init_scalar.linear.weight [3][nv] */
+    const float* Wz;    /* conv.v2s.linear.weight    [3][nv] */
+    const float* W1;    /* conv.linear1.weight       [Cout][6*nv] */
+    const float* bn1_a; /* folded bn1 [Cout] */
+    const float* bn1_c;
+    const float* W2;    /* conv.linear2.weight       [Cvo][nv] */
+    const float* bn2_a; /* folded bn2.bn [Cvo] */
+    const float* bn2_c;
+    const float* gate;  /* [B][Cvo] */
+    int Cout, Cvo;      /* Cout <= 64, Cvo <= 32 */
+    svnet_mview out;    /* pooled s (max over k) and v (mean over k) */
+} svnet_edge_xyz_params;
+int svnet_edge_xyz_fwd(const svnet_edge_xyz_params* p, void* stream);
+
+/* Edge layers 2..4: get_graph_feature_sv + SVBlock + svpool fused (sv_dgcnn_cls.py:55-65,
+ * sv_layers.py:172-196, sv_util.py:90-132).  Per edge (i, j = idx[i][e]):
+ *   s_e = [s_j - s_i | s_i], v_e = [v_j - v_i | v_i]                      (sv_util.py:109,114)
+ *   z = v_e Wz^T (* zscale), q[d][m] = sum_x v_e[x][d] z[x][m]             (sv_layers.py:116-125)
+ *   u = [s_e | q]   (K = 2Cs + 6Cv)
+ *   binary: t = sign(u + beta); y_o = scale1_o * sum_k t_k sign(W1)_ok     (sv_layers.py:36-49)
+ *           computed as XNOR/popcount on packed words with a zero-mask plane (sign(0) = 0)
+ *   fp:     y = W1 u, with the first 2Cs columns pre-reduced per point: y = (Ya_j - Ya_i) + Yb_i + W1q q
+ *   s' = act(y*bn1_a + bn1_c); pooled s = max_e s'                         (sv_layers.py:188-190)
+ *   w = v_e W2^T = (P_j - P_i) + Q_i  with per-point tables P = v W2a^T, Q = v W2b^T (scale2 folded in)
+ *   v' = w/n * (n*bn2_a + bn2_c) * gate, n = |w|_2 + 1e-6; pooled v = mean_e v'   (sv_layers.py:94-100,194)
+ */
+typedef struct {
+    svnet_view in;       /* per-point s (Cs) and v (3 x Cv) of the previous layer */
+    const int32_t* idx;  /* [B][N][k] */
+    int B, N, k;
+    int binary;
+    const float* Wz;     /* [3][2Cv]; already sign()ed when binary */
+    const float* zscale; /* [3] or NULL (fp) */
+    /* scalar branch, binary */
+    const float* beta;    /* [K] */
+    const uint32_t* W1b;  /* [Kw][Cout] sign bits, word-major (svnet_pack_sign) */
+    const float* scale1;  /* [Cout] */
+    /* scalar branch, fp */
+    const float* Yab;     /* [B*N][2*Cout]: Ya = s W1[:, :Cs]^T | Yb = s W1[:, Cs:2Cs]^T */
+    const float* W1q_t;   /* [6Cv][Cout] = W1[:, 2Cs:]^T (k-major) */
+    const float* bn1_a;   /* [Cout] */
+    const float* bn1_c;
+    int Cout;
+    /* vector branch */
+    const float* PQ;      /* [B*N][3][2*Cvo]: P | Q */
+    const float* bn2_a;   /* [Cvo] */
+    const float* bn2_c;
+    const float* gate;    /* [B][Cvo] */
+    int Cvo;
+    svnet_mview out;
+    /* optional parity taps (may be NULL): per edge sign words / nonzero-mask words [B*N*k][Kw] */
+    uint32_t* dbg_bits;
+    uint32_t* dbg_mask;
+} svnet_edge_params;
+int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream);
+
+/* ---- per-row building blocks (conv5, PointNet per-point blocks, heads, module-level API) ---- */
+
+/* u = [s | v2s(v)] for every row (sv_layers.py:185-186 / SVFuse :218-219), rows handled three at a
+ * time per warp.  Outputs (each optional):
+ *   u_out  [rows][ldu]      float u                       (fp linear1 input, SVFuse output)
+ *   z_out  [rows][9]        the 3x3 frames z              (trans_back, sv_layers.py:126-127)
+ *   bits/mask [rows][Kw]    sign(u + beta) > 0 / != 0     (binary linear1 input)
+ *   nvalid [rows]           number of non-zero signs per row (= popcount of the mask row)
+ * K = Cs + 3Cv.  With Cv == 0 this is a plain sign-pack of a float matrix (Linear ba, Conv1d). */
+int svnet_rows_prep(const svnet_view* in, long rows, const float* Wz, const float* zscale, const float* beta,
+                    float* u_out, int ldu, float* z_out, uint32_t* bits, uint32_t* mask, int32_t* nvalid,
+                    void* stream);
+
+/* y[r][o] = act(((nvalid_r - 2*popc((a_r ^ w_o) & m_r)) [+ cloud_dot[r / rows_per_cloud][o]]) * scale[o] * bn_a[o] + bn_c[o])
+ * (sv_layers.py:49 on packed words; bn/act optional).  bits/mask [rows][Kw]; W1b [Kw][Cout].
+ * If out_i32 != NULL the raw integer dot products are written instead (used to pre-reduce
+ * per-cloud-constant channels of the seg head, sv_dgcnn_partseg.py:117-121). */
+int svnet_binlinear_rows(const uint32_t* bits, const uint32_t* mask, const int32_t* nvalid, long rows, int K,
+                         const uint32_t* W1b, int Cout, const float* scale, const float* bias, const float* bn_a, const float* bn_c,
+                         int act, const int32_t* cloud_dot, long rows_per_cloud, float* out, int ldo,
+                         int32_t* out_i32, void* stream);
+
+/* Generic fp32 linear over (grouped) rows: C[m][n] = epi(sum_k A[m][k] * W[n][k]), sequential fmaf
+ * chain over k (== oracle order).  Row m lives at A + (m / G)*lda_g + (m % G)*lda_x; same for C.
+ *   sign_w: use sign(W) (binary weights, fp activations: sv_layers.py:43-49 with ba unset)
+ *   epilogue: *colscale[n], +bias[n], *bn_a[n]+bn_c[n], act -- each optional (NULL / 0)
+ *   vbn != 0 (requires G == 3): VectorBN + gate epilogue over the 3 rows of a group
+ *           (sv_layers.py:94-100,194): out = w/n*(n*bn_a+bn_c)*gate[group / groups_per_cloud][n] */
+typedef struct {
+    const float* A; long lda_g; int lda_x; int G;
+    const float* W; int ldw;
+    long M; int N, K;
+    int sign_w;
+    const float* colscale; const float* bias; const float* bn_a; const float* bn_c; int act;
+    int vbn; const float* gate; long groups_per_cloud;
+    float* C; long ldc_g; int ldc_x;
+} svnet_gemm_params;
+int svnet_linear_rows(const svnet_gemm_params* p, void* stream);
+
+/* VectorBN on materialised rows (module-level parity for sv_layers.VectorBN, :86-102):
+ * v [rows][3][C] contiguous -> out. */
+int svnet_vector_bn_rows(const float* v, long rows, int C, const float* bn_a, const float* bn_c, float* out,
+                         void* stream);
+
+/* Pool over the rows of each cloud: x [B][rows][ld] (C used).  max_out / mean_out [B][ldo] (C
+ * written), each optional (svpool dim=1, sv_util.py:125-131; adaptive_{max,avg}_pool1d,
+ * sv_dgcnn_cls.py:72-73).  v-shaped inputs are pooled as 3*Cv scalar columns. */
+int svnet_pool_rows(const float* x, int ld, int C, int B, long rows, float* max_out, float* mean_out, int ldo,
+                    void* stream);
+
+/* svpool over k on materialised edge tensors (module-level parity, sv_util.py:118-132) is
+ * svnet_pool_rows with B := B*N and rows := k. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVNET_B200_H */

@@ -1,0 +1,275 @@
+"""ctypes binding of libsvnet_b200.so (include/svnet_b200.h).
+
+The product path has no CPU fallback: if the shared object is missing or a call fails, a
+RuntimeError is raised.  torch is used only for device memory and the current stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvnet_b200.so")
+_lib = None
+
+ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
+BN_EPS = 1e-5
+
+c_int, c_long, c_float, c_void_p = ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_void_p
+
+EXPORTS = [
+    "svnet_version", "svnet_last_error", "svnet_pack_sign", "svnet_fold_bn", "svnet_knn",
+    "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
+    "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
+    "svnet_vector_bn_rows", "svnet_pool_rows",
+]
+
+
+class View(ctypes.Structure):
+    _fields_ = [("s", c_void_p), ("lds", c_int), ("Cs", c_int), ("v", c_void_p), ("ldv", c_int), ("xs", c_int),
+                ("Cv", c_int)]
+
+
+class EdgeXyzParams(ctypes.Structure):
+    _fields_ = [("xyz", c_void_p), ("idx", c_void_p), ("B", c_int), ("N", c_int), ("k", c_int), ("nv", c_int),
+                ("Winit", c_void_p), ("Wz", c_void_p), ("W1", c_void_p), ("bn1_a", c_void_p), ("bn1_c", c_void_p),
+                ("W2", c_void_p), ("bn2_a", c_void_p), ("bn2_c", c_void_p), ("gate", c_void_p), ("Cout", c_int),
+                ("Cvo", c_int), ("out", View)]
+
+
+class EdgeParams(ctypes.Structure):
+    _fields_ = [("inp", View), ("idx", c_void_p), ("B", c_int), ("N", c_int), ("k", c_int), ("binary", c_int),
+                ("Wz", c_void_p), ("zscale", c_void_p), ("beta", c_void_p), ("W1b", c_void_p), ("scale1", c_void_p),
+                ("Yab", c_void_p), ("W1q_t", c_void_p), ("bn1_a", c_void_p), ("bn1_c", c_void_p), ("Cout", c_int),
+                ("PQ", c_void_p), ("bn2_a", c_void_p), ("bn2_c", c_void_p), ("gate", c_void_p), ("Cvo", c_int),
+                ("out", View), ("dbg_bits", c_void_p), ("dbg_mask", c_void_p)]
+
+
+class GemmParams(ctypes.Structure):
+    _fields_ = [("A", c_void_p), ("lda_g", c_long), ("lda_x", c_int), ("G", c_int), ("W", c_void_p), ("ldw", c_int),
+                ("M", c_long), ("N", c_int), ("K", c_int), ("sign_w", c_int), ("colscale", c_void_p),
+                ("bias", c_void_p), ("bn_a", c_void_p), ("bn_c", c_void_p), ("act", c_int), ("vbn", c_int),
+                ("gate", c_void_p), ("groups_per_cloud", c_long), ("C", c_void_p), ("ldc_g", c_long),
+                ("ldc_x", c_int)]
+
+
+def lib():
+    """Load the CUDA library; fail loudly when it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "svnet_b200: %s not found -- build it with `python -m svnet_b200.build` "
+                "(there is no CPU/PyTorch fallback for the SV hot path)" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        l.svnet_last_error.restype = ctypes.c_char_p
+        for name in EXPORTS:
+            getattr(l, name)  # AttributeError if the symbol is missing
+        if l.svnet_version() != 1:
+            raise RuntimeError("svnet_b200: ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().svnet_last_error().decode()))
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _dev(t, dtype=torch.float32):
+    if not t.is_cuda:
+        raise RuntimeError("svnet_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+    if t.dtype != dtype:
+        raise TypeError("expected %s, got %s" % (dtype, t.dtype))
+    return t
+
+
+def view_of(s, v, Cs=None, Cv=None):
+    """View over contiguous-last-dim tensors: s (..., >=Cs) rows; v (..., 3, >=Cv)."""
+    vw = View()
+    if s is not None:
+        _dev(s)
+        assert s.stride(-1) == 1
+        vw.s, vw.lds, vw.Cs = s.data_ptr(), s.stride(-2) if s.dim() > 1 else s.shape[-1], (Cs if Cs is not None else s.shape[-1])
+    else:
+        vw.s, vw.lds, vw.Cs = 0, 0, 0
+    if v is not None:
+        _dev(v)
+        assert v.stride(-1) == 1
+        vw.v, vw.ldv, vw.xs, vw.Cv = v.data_ptr(), v.stride(-3) if v.dim() > 2 else 3 * v.stride(-2), v.stride(-2), (
+            Cv if Cv is not None else v.shape[-1])
+    else:
+        vw.v, vw.ldv, vw.xs, vw.Cv = 0, 0, 0, 0
+    return vw
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers (shapes validated again on the C side)
+# ------------------------------------------------------------------------------------------------
+def pack_sign(W2d):
+    """W (rows, K) float -> bits_t (Kw, rows) int32 (word-major); raises on exact-zero weights."""
+    W2d = _dev(W2d)
+    assert W2d.dim() == 2 and W2d.stride(1) == 1
+    rows, K = W2d.shape
+    bits = torch.empty(((K + 31) // 32, rows), dtype=torch.int32, device=W2d.device)
+    zc = torch.zeros(1, dtype=torch.int32, device=W2d.device)
+    _check(lib().svnet_pack_sign(_ptr(W2d), c_int(rows), c_int(K), c_int(W2d.stride(0)), _ptr(bits), _ptr(zc),
+                                 _stream()), "svnet_pack_sign")
+    if int(zc.item()) != 0:
+        raise NotImplementedError("binarised weight contains exact zeros (sign(0)=0 plane not supported)")
+    return bits
+
+
+def fold_bn(bn):
+    """nn.BatchNorm1d (eval) -> (a, c) with y = x*a + c."""
+    w, b, m, var = (_dev(t.detach()) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+    C = w.numel()
+    a = torch.empty(C, dtype=torch.float32, device=w.device)
+    c = torch.empty_like(a)
+    _check(lib().svnet_fold_bn(_ptr(w), _ptr(b), _ptr(m), _ptr(var), c_float(bn.eps), c_int(C), _ptr(a), _ptr(c),
+                               _stream()), "svnet_fold_bn")
+    return a, c
+
+
+def knn(view, B, N, k, want64=False, want32=True):
+    dev = torch.device("cuda", torch.cuda.current_device())
+    i32 = torch.empty((B, N, k), dtype=torch.int32, device=dev) if want32 else None
+    i64 = torch.empty((B, N, k), dtype=torch.int64, device=dev) if want64 else None
+    _check(lib().svnet_knn(ctypes.byref(view), c_int(B), c_int(N), c_int(k), _ptr(i32), _ptr(i64), _stream()),
+           "svnet_knn")
+    return i32, i64
+
+
+def graph_feature_xyz(xyz, idx64, nv):
+    B, N, k = idx64.shape
+    out = torch.empty((B, N, k, 3, nv), dtype=torch.float32, device=xyz.device)
+    _check(lib().svnet_graph_feature_xyz(_ptr(_dev(xyz)), _ptr(_dev(idx64, torch.int64)), c_int(B), c_int(N), c_int(k),
+                                         c_int(nv), _ptr(out), _stream()), "svnet_graph_feature_xyz")
+    return out
+
+
+def graph_feature_sv(s, v, idx64):
+    B, N, k = idx64.shape
+    Cs, Cv = s.shape[-1], v.shape[-1]
+    sf = torch.empty((B, N, k, 2 * Cs), dtype=torch.float32, device=s.device)
+    vf = torch.empty((B, N, k, 3, 2 * Cv), dtype=torch.float32, device=s.device)
+    _check(lib().svnet_graph_feature_sv(_ptr(_dev(s)), _ptr(_dev(v)), _ptr(_dev(idx64, torch.int64)), c_int(B), c_int(N),
+                                        c_int(k), c_int(Cs), c_int(Cv), _ptr(sf), _ptr(vf), _stream()),
+           "svnet_graph_feature_sv")
+    return sf, vf
+
+
+def gate_rows(s2d, lds, Cs, B, rows, G1, G2, out=None):
+    H, Co = G1.shape[0], G2.shape[0]
+    gate = out if out is not None else torch.empty((B, Co), dtype=torch.float32, device=s2d.device)
+    _check(lib().svnet_gate_rows(_ptr(_dev(s2d)), c_int(lds), c_int(Cs), c_int(B), c_int(rows), _ptr(_dev(G1)),
+                                 _ptr(_dev(G2)), c_int(H), c_int(Co), _ptr(gate), _stream()), "svnet_gate_rows")
+    return gate
+
+
+def gate_edge(view, idx32, B, N, k, G1, G2):
+    H, Co = G1.shape[0], G2.shape[0]
+    gate = torch.empty((B, Co), dtype=torch.float32, device=idx32.device)
+    _check(lib().svnet_gate_edge(ctypes.byref(view), _ptr(_dev(idx32, torch.int32)), c_int(B), c_int(N), c_int(k),
+                                 _ptr(_dev(G1)), _ptr(_dev(G2)), c_int(H), c_int(Co), _ptr(gate), _stream()),
+           "svnet_gate_edge")
+    return gate
+
+
+def gate_xyz(xyz, idx32, nv, Winit, G1, G2):
+    B, N, k = idx32.shape
+    H, Co = G1.shape[0], G2.shape[0]
+    gate = torch.empty((B, Co), dtype=torch.float32, device=xyz.device)
+    _check(lib().svnet_gate_xyz(_ptr(_dev(xyz)), _ptr(_dev(idx32, torch.int32)), c_int(B), c_int(N), c_int(k), c_int(nv),
+                                _ptr(_dev(Winit)), _ptr(_dev(G1)), _ptr(_dev(G2)), c_int(H), c_int(Co), _ptr(gate),
+                                _stream()), "svnet_gate_xyz")
+    return gate
+
+
+def edge_xyz_fwd(params):
+    _check(lib().svnet_edge_xyz_fwd(ctypes.byref(params), _stream()), "svnet_edge_xyz_fwd")
+
+
+def svblock_edge_fwd(params):
+    _check(lib().svnet_svblock_edge_fwd(ctypes.byref(params), _stream()), "svnet_svblock_edge_fwd")
+
+
+def rows_prep(view, rows, Wz=None, zscale=None, beta=None, u_out=None, ldu=0, z_out=None, want_bits=False):
+    K = view.Cs + 3 * view.Cv
+    dev = torch.device("cuda", torch.cuda.current_device())
+    bits = mask = nvalid = None
+    if want_bits:
+        Kw = (K + 31) // 32
+        bits = torch.empty((rows, Kw), dtype=torch.int32, device=dev)
+        mask = torch.empty((rows, Kw), dtype=torch.int32, device=dev)
+        nvalid = torch.empty((rows,), dtype=torch.int32, device=dev)
+    _check(lib().svnet_rows_prep(ctypes.byref(view), c_long(rows), _ptr(Wz), _ptr(zscale), _ptr(beta), _ptr(u_out),
+                                 c_int(ldu), _ptr(z_out), _ptr(bits), _ptr(mask), _ptr(nvalid), _stream()),
+           "svnet_rows_prep")
+    return bits, mask, nvalid
+
+
+def binlinear_rows(bits, mask, nvalid, K, W1b, Cout, scale=None, bias=None, bn=None, act=ACT_NONE, cloud_dot=None,
+                   rows_per_cloud=1, out=None, ldo=None, out_i32=False):
+    rows = bits.shape[0]
+    res_i32 = None
+    if out_i32:
+        res_i32 = torch.empty((rows, Cout), dtype=torch.int32, device=bits.device)
+    elif out is None:
+        out = torch.empty((rows, Cout), dtype=torch.float32, device=bits.device)
+        ldo = Cout
+    bn_a, bn_c = bn if bn is not None else (None, None)
+    _check(lib().svnet_binlinear_rows(_ptr(bits), _ptr(mask), _ptr(nvalid), c_long(rows), c_int(K), _ptr(W1b),
+                                      c_int(Cout), _ptr(scale), _ptr(bias), _ptr(bn_a), _ptr(bn_c), c_int(act),
+                                      _ptr(cloud_dot), c_long(rows_per_cloud), _ptr(out), c_int(ldo or 0),
+                                      _ptr(res_i32), _stream()), "svnet_binlinear_rows")
+    return res_i32 if out_i32 else out
+
+
+def linear_rows(A, lda_g, lda_x, G, M, K, W, N, C, ldc_g, ldc_x, sign_w=False, colscale=None, bias=None, bn=None,
+                act=ACT_NONE, vbn=False, gate=None, groups_per_cloud=1):
+    """Raw generic linear; A and C are tensors whose data_ptr() is the first element addressed."""
+    p = GemmParams()
+    p.A, p.lda_g, p.lda_x, p.G = A.data_ptr(), lda_g, lda_x, G
+    p.W, p.ldw = _dev(W).data_ptr(), W.stride(0)
+    p.M, p.N, p.K = M, N, K
+    p.sign_w = 1 if sign_w else 0
+    p.colscale = colscale.data_ptr() if colscale is not None else 0
+    p.bias = bias.data_ptr() if bias is not None else 0
+    p.bn_a, p.bn_c = (bn[0].data_ptr(), bn[1].data_ptr()) if bn is not None else (0, 0)
+    p.act = act
+    p.vbn = 1 if vbn else 0
+    p.gate = gate.data_ptr() if gate is not None else 0
+    p.groups_per_cloud = groups_per_cloud
+    p.C, p.ldc_g, p.ldc_x = C.data_ptr(), ldc_g, ldc_x
+    _check(lib().svnet_linear_rows(ctypes.byref(p), _stream()), "svnet_linear_rows")
+
+
+def vector_bn_rows(v, bn_a, bn_c):
+    C = v.shape[-1]
+    rows = v.numel() // (3 * C)
+    out = torch.empty_like(v)
+    _check(lib().svnet_vector_bn_rows(_ptr(_dev(v)), c_long(rows), c_int(C), _ptr(bn_a), _ptr(bn_c), _ptr(out),
+                                      _stream()), "svnet_vector_bn_rows")
+    return out
+
+
+def pool_rows(x, ld, C, B, rows, want_max=True, want_mean=False, max_out=None, mean_out=None, ldo=None):
+    dev = x.device
+    if want_max and max_out is None:
+        max_out = torch.empty((B, C), dtype=torch.float32, device=dev)
+    if want_mean and mean_out is None:
+        mean_out = torch.empty((B, C), dtype=torch.float32, device=dev)
+    if ldo is None:
+        ldo = C
+    _check(lib().svnet_pool_rows(_ptr(_dev(x)), c_int(ld), c_int(C), c_int(B), c_long(rows), _ptr(max_out),
+                                 _ptr(mean_out), c_int(ldo), _stream()), "svnet_pool_rows")
+    return max_out, mean_out

@@ -1,0 +1,154 @@
+// First edge layer, fully fused: get_graph_feature[_cross] + init_scalar + SVBlock(FP) + svpool.
+// Reference: models/sv_dgcnn_cls.py:49-53, models/sv_pointnet_cls.py:35-39,
+// models/utils/sv_util.py:28-88,118-132, models/sv_layers.py:111-129,172-196.
+//
+// One warp per centre point, one lane per edge (k > 32 takes several rounds).  Every edge quantity
+// lives in registers; the scalar branch reproduces the oracle's sequential fmaf chains so the
+// pooled scalars are bit-identical; the vector mean over k is a shuffle tree (tolerance-level).
+#include "common.cuh"
+
+namespace {
+
+constexpr int WARPS = 8;
+
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(SV_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SV_FULL, v, o);
+    return v;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(WARPS * 32) edge_xyz_kernel(svnet_edge_xyz_params p)
+{
+    constexpr int KU = 6 * NV;
+    extern __shared__ float sm[];
+    float* W1 = sm;                      // [Cout][KU]
+    float* a1 = W1 + p.Cout * KU;        // [Cout]
+    float* c1 = a1 + p.Cout;
+    float* W2 = c1 + p.Cout;             // [Cvo][NV]
+    float* a2 = W2 + p.Cvo * NV;
+    float* c2 = a2 + p.Cvo;
+    float* Wi = c2 + p.Cvo;              // [3][NV]
+    float* Wz = Wi + 3 * NV;             // [3][NV]
+    for (int i = threadIdx.x; i < p.Cout * KU; i += blockDim.x) W1[i] = p.W1[i];
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) { a1[i] = p.bn1_a[i]; c1[i] = p.bn1_c[i]; }
+    for (int i = threadIdx.x; i < p.Cvo * NV; i += blockDim.x) W2[i] = p.W2[i];
+    for (int i = threadIdx.x; i < p.Cvo; i += blockDim.x) { a2[i] = p.bn2_a[i]; c2[i] = p.bn2_c[i]; }
+    for (int i = threadIdx.x; i < 3 * NV; i += blockDim.x) { Wi[i] = p.Winit[i]; Wz[i] = p.Wz[i]; }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const long r = (long)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= (long)p.B * p.N) return;
+    const int b = (int)(r / p.N);
+    const float xi[3] = {p.xyz[r * 3], p.xyz[r * 3 + 1], p.xyz[r * 3 + 2]};
+
+    float smax[2] = {-INFINITY, -INFINITY};  // out o = lane, lane+32
+    float vsum[3] = {0.0f, 0.0f, 0.0f};      // out c = lane
+
+    for (int e0 = 0; e0 < p.k; e0 += 32) {
+        const int e = e0 + lane;
+        const bool valid = e < p.k;
+        const long j = (long)b * p.N + (valid ? p.idx[r * p.k + e] : 0);
+        const float xj[3] = {p.xyz[j * 3], p.xyz[j * 3 + 1], p.xyz[j * 3 + 2]};
+        float ve[3][NV];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { ve[a][0] = __fsub_rn(xj[a], xi[a]); ve[a][1] = xi[a]; }
+        if (NV == 3) {
+            ve[0][NV - 1] = __fsub_rn(__fmul_rn(xj[1], xi[2]), __fmul_rn(xj[2], xi[1]));
+            ve[1][NV - 1] = __fsub_rn(__fmul_rn(xj[2], xi[0]), __fmul_rn(xj[0], xi[2]));
+            ve[2][NV - 1] = __fsub_rn(__fmul_rn(xj[0], xi[1]), __fmul_rn(xj[1], xi[0]));
+        }
+        float u[KU];
+        // init_scalar and the block's own v2s: same form, different weights
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const float* W = pass == 0 ? Wi : Wz;
+            float z[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    float zz = 0.0f;
+#pragma unroll
+                    for (int d = 0; d < NV; ++d) zz = __fmaf_rn(ve[a][d], W[m * NV + d], zz);
+                    z[a][m] = zz;
+                }
+#pragma unroll
+            for (int d = 0; d < NV; ++d)
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    float q = __fmul_rn(ve[0][d], z[0][m]);
+                    q = __fmaf_rn(ve[1][d], z[1][m], q);
+                    q = __fmaf_rn(ve[2][d], z[2][m], q);
+                    u[pass * 3 * NV + d * 3 + m] = q;
+                }
+        }
+        // scalar branch: linear1 (fp) -> bn1 -> leaky -> max over edges
+        for (int o = 0; o < p.Cout; ++o) {
+            float y = 0.0f;
+#pragma unroll
+            for (int t = 0; t < KU; ++t) y = __fmaf_rn(u[t], W1[o * KU + t], y);
+            y = __fadd_rn(__fmul_rn(y, a1[o]), c1[o]);
+            y = y > 0.0f ? y : __fmul_rn(0.2f, y);
+            y = warp_max(valid ? y : -INFINITY);
+            if ((o & 31) == lane) smax[o >> 5] = fmaxf(smax[o >> 5], y);
+        }
+        // vector branch: linear2 (fp) -> VectorBN -> sum over edges
+        for (int c = 0; c < p.Cvo; ++c) {
+            float w[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float t = 0.0f;
+#pragma unroll
+                for (int d = 0; d < NV; ++d) t = __fmaf_rn(ve[a][d], W2[c * NV + d], t);
+                w[a] = t;
+            }
+            const float n = __fadd_rn(
+                __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(w[0], w[0]), __fmul_rn(w[1], w[1])), __fmul_rn(w[2], w[2]))),
+                1e-6f);
+            const float nb = __fadd_rn(__fmul_rn(n, a2[c]), c2[c]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float t = valid ? __fmul_rn(__fdiv_rn(w[a], n), nb) : 0.0f;
+                t = warp_sum(t);
+                if (c == lane) vsum[a] += t;
+            }
+        }
+    }
+    for (int o = lane; o < p.Cout; o += 32) p.out.s[r * p.out.lds + o] = smax[o >> 5];
+    if (lane < p.Cvo) {
+        const float g = p.gate[(long)b * p.Cvo + lane];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p.out.v[r * p.out.ldv + a * p.out.xs + lane] = (vsum[a] / (float)p.k) * g;
+    }
+}
+
+}  // namespace
+
+extern "C" int svnet_edge_xyz_fwd(const svnet_edge_xyz_params* p, void* stream)
+{
+    SV_REQUIRE(p, "svnet_edge_xyz_fwd: null params");
+    SV_REQUIRE(p->xyz && p->idx && p->Winit && p->Wz && p->W1 && p->bn1_a && p->bn1_c && p->W2 && p->bn2_a &&
+                   p->bn2_c && p->gate && p->out.s && p->out.v,
+               "svnet_edge_xyz_fwd: null pointer");
+    SV_REQUIRE(p->nv == 2 || p->nv == 3, "svnet_edge_xyz_fwd: nv=%d", p->nv);
+    SV_REQUIRE(p->B >= 0 && p->N >= 1 && p->k >= 1, "svnet_edge_xyz_fwd: bad shape");
+    SV_REQUIRE(p->Cout >= 1 && p->Cout <= 64 && p->Cvo >= 1 && p->Cvo <= 32,
+               "svnet_edge_xyz_fwd: Cout=%d (<=64) Cvo=%d (<=32) unsupported", p->Cout, p->Cvo);
+    const long P = (long)p->B * p->N;
+    if (P == 0) return SVNET_OK;
+    const size_t smem = sizeof(float) * ((size_t)p->Cout * 6 * p->nv + 2 * p->Cout + (size_t)p->Cvo * p->nv + 2 * p->Cvo + 6 * p->nv);
+    const int grid = sv_cdiv(P, WARPS);
+    if (p->nv == 2) edge_xyz_kernel<2><<<grid, WARPS * 32, smem, sv_stream(stream)>>>(*p);
+    else edge_xyz_kernel<3><<<grid, WARPS * 32, smem, sv_stream(stream)>>>(*p);
+    SV_CHECK_LAUNCH("svnet_edge_xyz_fwd");
+    return SVNET_OK;
+}

@@ -1,0 +1,227 @@
+// SVBlock gate: g = sigmoid(G2 relu(G1 mean(s)))  (reference models/sv_layers.py:156-161,179-183).
+// One CTA per cloud; the mean over the block's input rows is reduced in a fixed order (no float
+// atomics), then the two tiny linears run warp-per-output.
+//
+//   rows variant : mean over materialised rows
+//   edge variant : the rows are the N*k edges [s_j - s_i | s_i] of get_graph_feature_sv
+//                  (sv_util.py:114); sum_e s_j = sum_j indeg(j) s_j, so only the per-point table and
+//                  the kNN indices are read
+//   xyz variant  : the rows are init_scalar([x_j - x_i | x_i (| x_j x x_i)]) of the first layer
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SV_FULL, v, o);
+    return v;
+}
+
+// mean[Cin] in smem -> gate[Co] in global.  h is smem scratch [H].
+__device__ void gate_mlp(const float* mean, int Cin, const float* __restrict__ G1, const float* __restrict__ G2, int H,
+                         int Co, float* h, float* __restrict__ gate)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < H; j += NT / 32) {
+        float acc = 0.0f;
+        for (int c = lane; c < Cin; c += 32) acc = fmaf(mean[c], __ldg(G1 + (long)j * Cin + c), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) h[j] = acc > 0.0f ? acc : 0.0f;
+    }
+    __syncthreads();
+    for (int o = warp; o < Co; o += NT / 32) {
+        float acc = 0.0f;
+        for (int j = lane; j < H; j += 32) acc = fmaf(h[j], __ldg(G2 + (long)o * H + j), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) gate[o] = sv_sigmoid(acc);
+    }
+}
+
+// smem: mean[Cs] | h[H] | part[8][32]
+__global__ void __launch_bounds__(NT) gate_rows_kernel(const float* __restrict__ s, int lds, int Cs, long rows,
+                                                       const float* __restrict__ G1, const float* __restrict__ G2,
+                                                       int H, int Co, float* __restrict__ gate)
+{
+    extern __shared__ float sm[];
+    float* mean = sm;
+    float* h = mean + Cs;
+    float* part = h + H;
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const float* p = s + (long)b * rows * lds;
+    for (int c0 = 0; c0 < Cs; c0 += 32) {
+        const int c = c0 + lane;
+        float acc = 0.0f;
+        if (c < Cs)
+            for (long r = rg; r < rows; r += 8) acc += p[r * lds + c];
+        part[rg * 32 + lane] = acc;
+        __syncthreads();
+        if (rg == 0 && c < Cs) {
+            float t = part[lane];
+            for (int g = 1; g < 8; ++g) t += part[g * 32 + lane];
+            mean[c] = t / (float)rows;
+        }
+        __syncthreads();
+    }
+    gate_mlp(mean, Cs, G1, G2, H, Co, h, gate + (long)b * Co);
+}
+
+// smem: mean[2Cs] | h[H] | part[2][8][32] | indeg[N]
+__global__ void __launch_bounds__(NT) gate_edge_kernel(svnet_view in, const int32_t* __restrict__ idx, int N, int k,
+                                                       const float* __restrict__ G1, const float* __restrict__ G2,
+                                                       int H, int Co, float* __restrict__ gate)
+{
+    extern __shared__ float sm[];
+    const int Cs = in.Cs;
+    float* mean = sm;
+    float* h = mean + 2 * Cs;
+    float* part = h + H;
+    int* indeg = reinterpret_cast<int*>(part + 2 * 8 * 32);
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < N; i += NT) indeg[i] = 0;
+    __syncthreads();
+    const int32_t* ib = idx + (long)b * N * k;
+    for (long t = threadIdx.x; t < (long)N * k; t += NT) atomicAdd(&indeg[ib[t]], 1);
+    __syncthreads();
+    const float* p = in.s + (long)b * N * in.lds;
+    for (int c0 = 0; c0 < Cs; c0 += 32) {
+        const int c = c0 + lane;
+        float accd = 0.0f, accp = 0.0f;
+        if (c < Cs)
+            for (int r = rg; r < N; r += 8) {
+                float t = p[(long)r * in.lds + c];
+                accd = fmaf((float)indeg[r], t, accd);
+                accp += t;
+            }
+        part[rg * 32 + lane] = accd;
+        part[256 + rg * 32 + lane] = accp;
+        __syncthreads();
+        if (rg == 0 && c < Cs) {
+            float td = part[lane], tp = part[256 + lane];
+            for (int g = 1; g < 8; ++g) { td += part[g * 32 + lane]; tp += part[256 + g * 32 + lane]; }
+            const float mp = tp / (float)N;
+            mean[c] = td / ((float)N * (float)k) - mp;   // mean_e (s_j - s_i)
+            mean[Cs + c] = mp;                           // mean_e s_i
+        }
+        __syncthreads();
+    }
+    gate_mlp(mean, 2 * Cs, G1, G2, H, Co, h, gate + (long)b * Co);
+}
+
+// smem: mean[3nv] | h[H] | part[NT][9]
+template <int NV>
+__global__ void __launch_bounds__(NT) gate_xyz_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
+                                                      int N, int k, const float* __restrict__ Winit,
+                                                      const float* __restrict__ G1, const float* __restrict__ G2,
+                                                      int H, int Co, float* __restrict__ gate)
+{
+    extern __shared__ float sm[];
+    float* mean = sm;
+    float* h = mean + 3 * NV;
+    float* part = h + H;
+    const int b = blockIdx.x;
+    float W[3][NV];
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int d = 0; d < NV; ++d) W[m][d] = Winit[m * NV + d];
+    float acc[3 * NV];
+#pragma unroll
+    for (int q = 0; q < 3 * NV; ++q) acc[q] = 0.0f;
+    const float* xb = xyz + (long)b * N * 3;
+    const int32_t* ib = idx + (long)b * N * k;
+    for (long t = threadIdx.x; t < (long)N * k; t += NT) {
+        const int i = (int)(t / k);
+        const int j = ib[t];
+        float xi[3] = {xb[i * 3], xb[i * 3 + 1], xb[i * 3 + 2]};
+        float xj[3] = {xb[j * 3], xb[j * 3 + 1], xb[j * 3 + 2]};
+        float ve[3][NV];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { ve[a][0] = __fsub_rn(xj[a], xi[a]); ve[a][1] = xi[a]; }
+        if (NV == 3) {
+            ve[0][NV - 1] = __fsub_rn(__fmul_rn(xj[1], xi[2]), __fmul_rn(xj[2], xi[1]));
+            ve[1][NV - 1] = __fsub_rn(__fmul_rn(xj[2], xi[0]), __fmul_rn(xj[0], xi[2]));
+            ve[2][NV - 1] = __fsub_rn(__fmul_rn(xj[0], xi[1]), __fmul_rn(xj[1], xi[0]));
+        }
+        float z[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                float zz = 0.0f;
+#pragma unroll
+                for (int d = 0; d < NV; ++d) zz = __fmaf_rn(ve[a][d], W[m][d], zz);
+                z[a][m] = zz;
+            }
+#pragma unroll
+        for (int d = 0; d < NV; ++d)
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                float q = __fmul_rn(ve[0][d], z[0][m]);
+                q = __fmaf_rn(ve[1][d], z[1][m], q);
+                q = __fmaf_rn(ve[2][d], z[2][m], q);
+                acc[d * 3 + m] += q;
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < 3 * NV; ++q) part[threadIdx.x * 9 + q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < 3 * NV) {
+        float t = 0.0f;
+        for (int i = 0; i < NT; ++i) t += part[i * 9 + threadIdx.x];
+        mean[threadIdx.x] = t / ((float)N * (float)k);
+    }
+    __syncthreads();
+    gate_mlp(mean, 3 * NV, G1, G2, H, Co, h, gate + (long)b * Co);
+}
+
+}  // namespace
+
+extern "C" int svnet_gate_rows(const float* s, int lds, int Cs, int B, int rows, const float* G1, const float* G2,
+                               int H, int Co, float* gate, void* stream)
+{
+    SV_REQUIRE(s && G1 && G2 && gate, "svnet_gate_rows: null pointer");
+    SV_REQUIRE(Cs >= 1 && lds >= Cs && rows >= 1 && H >= 1 && Co >= 1 && B >= 0, "svnet_gate_rows: bad shape");
+    if (B == 0) return SVNET_OK;
+    const size_t smem = sizeof(float) * ((size_t)Cs + H + 256);
+    SV_REQUIRE(smem <= 200 * 1024, "svnet_gate_rows: Cs=%d too large", Cs);
+    if (smem > 48 * 1024)
+        SV_CUDA(cudaFuncSetAttribute(gate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gate_rows_kernel<<<B, NT, smem, sv_stream(stream)>>>(s, lds, Cs, rows, G1, G2, H, Co, gate);
+    SV_CHECK_LAUNCH("svnet_gate_rows");
+    return SVNET_OK;
+}
+
+extern "C" int svnet_gate_edge(const svnet_view* in, const int32_t* idx, int B, int N, int k, const float* G1,
+                               const float* G2, int H, int Co, float* gate, void* stream)
+{
+    SV_REQUIRE(in && in->s && idx && G1 && G2 && gate, "svnet_gate_edge: null pointer");
+    SV_REQUIRE(in->Cs >= 1 && N >= 1 && k >= 1 && H >= 1 && Co >= 1 && B >= 0, "svnet_gate_edge: bad shape");
+    if (B == 0) return SVNET_OK;
+    const size_t smem = sizeof(float) * ((size_t)2 * in->Cs + H + 512 + N);
+    SV_REQUIRE(smem <= 200 * 1024, "svnet_gate_edge: N=%d / Cs=%d too large", N, in->Cs);
+    if (smem > 48 * 1024)
+        SV_CUDA(cudaFuncSetAttribute(gate_edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gate_edge_kernel<<<B, NT, smem, sv_stream(stream)>>>(*in, idx, N, k, G1, G2, H, Co, gate);
+    SV_CHECK_LAUNCH("svnet_gate_edge");
+    return SVNET_OK;
+}
+
+extern "C" int svnet_gate_xyz(const float* xyz, const int32_t* idx, int B, int N, int k, int nv, const float* Winit,
+                              const float* G1, const float* G2, int H, int Co, float* gate, void* stream)
+{
+    SV_REQUIRE(xyz && idx && Winit && G1 && G2 && gate, "svnet_gate_xyz: null pointer");
+    SV_REQUIRE((nv == 2 || nv == 3) && N >= 1 && k >= 1 && H >= 1 && Co >= 1 && B >= 0, "svnet_gate_xyz: bad shape");
+    if (B == 0) return SVNET_OK;
+    const size_t smem = sizeof(float) * ((size_t)3 * nv + H + NT * 9);
+    if (nv == 2)
+        gate_xyz_kernel<2><<<B, NT, smem, sv_stream(stream)>>>(xyz, idx, N, k, Winit, G1, G2, H, Co, gate);
+    else
+        gate_xyz_kernel<3><<<B, NT, smem, sv_stream(stream)>>>(xyz, idx, N, k, Winit, G1, G2, H, Co, gate);
+    SV_CHECK_LAUNCH("svnet_gate_xyz");
+    return SVNET_OK;
+}

@@ -1,0 +1,99 @@
+"""Fused layer drivers shared by the SV model classes: they wire module parameters (packed once)
+into the C-ABI parameter blocks of the fused kernels.  No arithmetic happens here.
+"""
+import torch
+
+from . import _native as nv
+
+
+def _mview(s_out, v_out):
+    return nv.view_of(s_out, v_out)
+
+
+def first_edge_layer(xyz, B, N, k, nvec, init_scalar, blk, s_out, v_out, idx32=None):
+    """get_graph_feature[_cross] + init_scalar + SVBlock(FP) + svpool (sv_dgcnn_cls.py:49-53,
+    sv_pointnet_cls.py:35-39).  xyz (B*N, 3) contiguous.  Writes pooled (s, v) into the given
+    slices and returns the int32 kNN indices (B, N, k)."""
+    if blk.binary:
+        raise NotImplementedError("the first SVBlock is full precision in every SV model")
+    if idx32 is None:
+        idx32, _ = nv.knn(nv.view_of(xyz, None), B, N, k)
+    Winit, _ = init_scalar.wz()
+    Wz, _ = blk.v2s.wz()
+    G1, G2 = blk.gate_weights()
+    gate = nv.gate_xyz(xyz, idx32, nvec, Winit, G1, G2)
+    a1, c1 = blk.bn1_folded()
+    a2, c2 = blk.bn2.folded()
+    p = nv.EdgeXyzParams()
+    p.xyz, p.idx = xyz.data_ptr(), idx32.data_ptr()
+    p.B, p.N, p.k, p.nv = B, N, k, nvec
+    p.Winit, p.Wz = Winit.data_ptr(), Wz.data_ptr()
+    W1 = blk.linear1.weight.detach()
+    W2 = blk.linear2.weight.detach()
+    p.W1, p.bn1_a, p.bn1_c = W1.data_ptr(), a1.data_ptr(), c1.data_ptr()
+    p.W2, p.bn2_a, p.bn2_c = W2.data_ptr(), a2.data_ptr(), c2.data_ptr()
+    p.gate = gate.data_ptr()
+    p.Cout, p.Cvo = blk.out_dims
+    p.out = _mview(s_out, v_out)
+    nv.edge_xyz_fwd(p)
+    return idx32
+
+
+def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None):
+    """get_graph_feature_sv + SVBlock + svpool for edge layers 2..4 (sv_dgcnn_cls.py:55-65).
+    s_in (B*N, Cs) / v_in (B*N, 3, Cv) are (possibly strided) slices of the svcat table.
+    ``taps`` (dict) requests the per-edge sign/mask words for parity tests."""
+    R = B * N
+    Cs, Cv = s_in.shape[1], v_in.shape[2]
+    Cout, Cvo = blk.out_dims
+    assert blk.in_dims == (2 * Cs, 2 * Cv), (blk.in_dims, Cs, Cv)
+    dev = s_in.device
+    view = nv.view_of(s_in, v_in)
+    if idx32 is None:
+        idx32, _ = nv.knn(view, B, N, k)
+    G1, G2 = blk.gate_weights()
+    gate = nv.gate_edge(view, idx32, B, N, k, G1, G2)
+    # per-point tables for the vector branch: P | Q
+    Wpq, spq = blk.pq_weight()
+    PQ = torch.empty((R, 3, 2 * Cvo), dtype=torch.float32, device=dev)
+    nv.linear_rows(v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wpq, 2 * Cvo, PQ, 6 * Cvo, 2 * Cvo,
+                   sign_w=blk.linear2.bw, colscale=spq)
+    Wz, zs = blk.v2s.wz()
+    a1, c1 = blk.bn1_folded()
+    a2, c2 = blk.bn2.folded()
+    p = nv.EdgeParams()
+    p.inp = view
+    p.idx = idx32.data_ptr()
+    p.B, p.N, p.k = B, N, k
+    p.binary = 1 if blk.binary else 0
+    p.Wz = Wz.data_ptr()
+    p.zscale = zs.data_ptr() if zs is not None else 0
+    keep = [gate, PQ, Wz, zs, a1, c1, a2, c2]
+    if blk.binary:
+        lin = blk.linear1
+        beta, W1b, sc = lin.beta_vec(), lin.sign_bits(), lin.scale_vec()
+        p.beta, p.W1b, p.scale1 = beta.data_ptr(), W1b.data_ptr(), sc.data_ptr()
+        keep += [beta, W1b, sc]
+    else:
+        Wab, Wq_t = blk.yab_weight()
+        Yab = torch.empty((R, 2 * Cout), dtype=torch.float32, device=dev)
+        nv.linear_rows(s_in, s_in.stride(0), 0, 1, R, Cs, Wab, 2 * Cout, Yab, 2 * Cout, 0)
+        p.Yab, p.W1q_t = Yab.data_ptr(), Wq_t.data_ptr()
+        keep += [Yab, Wq_t]
+    p.bn1_a, p.bn1_c, p.Cout = a1.data_ptr(), c1.data_ptr(), Cout
+    p.PQ, p.bn2_a, p.bn2_c, p.gate, p.Cvo = PQ.data_ptr(), a2.data_ptr(), c2.data_ptr(), gate.data_ptr(), Cvo
+    p.out = _mview(s_out, v_out)
+    if taps is not None and blk.binary:
+        Kw = (2 * Cs + 6 * Cv + 31) // 32
+        taps["bits"] = torch.zeros((R * k, Kw), dtype=torch.int32, device=dev)
+        taps["mask"] = torch.zeros((R * k, Kw), dtype=torch.int32, device=dev)
+        p.dbg_bits, p.dbg_mask = taps["bits"].data_ptr(), taps["mask"].data_ptr()
+    nv.svblock_edge_fwd(p)
+    if taps is not None:
+        taps["gate"] = gate
+    return idx32
+
+
+def point_block(blk, s_in, v_in, B, rows_per_cloud, s_out=None, lds_out=None, v_out=None):
+    """Per-row SVBlock (conv5, PointNet blocks): thin alias of SVBlock.forward_rows."""
+    return blk.forward_rows(s_in, v_in, B, rows_per_cloud, s_out=s_out, lds_out=lds_out, v_out=v_out)

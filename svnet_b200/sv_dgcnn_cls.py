@@ -1,0 +1,96 @@
+"""SV-DGCNN classifier -- drop-in for the reference's models/sv_dgcnn_cls.py:22-82 (same
+constructor, same state_dict keys), with the forward re-planned around fused sm_100a kernels:
+
+    layer 1      knn -> gate_xyz -> edge_xyz_fwd             (sv_dgcnn_cls.py:48-53)
+    layers 2..4  knn -> gate_edge -> P|Q table -> svblock_edge_fwd   (:55-65)
+    conv5        gate_rows -> rows_prep (sign words) -> binlinear -> vector linear+VectorBN  (:67-68)
+    svfuse+pool  rows_prep (v2s floats) -> pool_rows (max | mean)   (:69-74)
+    head         2 x (sign-pack + popcount linear + BN + leaky) -> fp linear   (:76-80)
+
+Pooled layer outputs are written straight into the svcat table (s_cat, v_cat); no (B,N,k,C) edge
+tensor and no BxNxN distance matrix exist in HBM.
+"""
+import torch
+import torch.nn as nn
+
+from . import _native as nv
+from .fused import first_edge_layer, sv_edge_layer
+from .sv_layers import Linear, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, folded_bn
+
+
+class SV_DGCNN_CLS(nn.Module, _Cached):
+    def __init__(self, args, num_class=40):
+        super(SV_DGCNN_CLS, self).__init__()
+        self.k = args.k
+        self.binary = args.binary
+        p = 0 if self.binary else 0.5
+
+        self.init_scalar = Vector2Scalar(2, 3)
+        self.conv1 = SVBlock((6, 2), (64//2, 64//6))
+        self.conv2 = SVBlock((64//2*2, 64//6*2), (64//2, 64//6), self.binary)
+        self.conv3 = SVBlock((64//2*2, 64//6*2), (128//2, 128//6), self.binary)
+        self.conv4 = SVBlock((128//2*2, 128//6*2), (256//2, 256//6), self.binary)
+
+        self.conv5 = SVBlock((64//2*2+128//2+256//2, 64//6*2+128//6+256//6), (1024//2, 1024//6), self.binary)
+        self.svfuse = SVFuse(1024//6, 3, self.binary)
+
+        self.linear1 = Linear((1024//2+1024//6*3)*2, 512, bias=False, bw=self.binary, ba=self.binary)
+        self.bn1 = nn.BatchNorm1d(512)
+        self.dp1 = nn.Dropout(p=p)
+        self.linear2 = Linear(512, 256, bias=False, bw=self.binary, ba=self.binary)
+        self.bn2 = nn.BatchNorm1d(256)
+        self.dp2 = nn.Dropout(p=p)
+        self.linear3 = nn.Linear(256, num_class)
+
+    def forward(self, x, forced_idx=None, record=None):
+        """x (B, 3, N) float32 on CUDA -> logits (B, num_class).  ``forced_idx`` (list of 4 int32
+        (B,N,k) tensors) and ``record`` (dict) are test hooks (teacher forcing / intermediates)."""
+        _inference_only(self)
+        B, _, N = x.shape
+        k = self.k
+        dev = x.device
+        xyz = x.transpose(1, 2).contiguous().view(B * N, 3)
+        blocks = [self.conv1, self.conv2, self.conv3, self.conv4]
+        cs = [b.out_dims[0] for b in blocks]
+        cv = [b.out_dims[1] for b in blocks]
+        s_cat = torch.empty((B * N, sum(cs)), dtype=torch.float32, device=dev)
+        v_cat = torch.empty((B * N, 3, sum(cv)), dtype=torch.float32, device=dev)
+        so, vo = 0, 0
+        fi = forced_idx or [None] * 4
+        idxs = []
+        s_prev = v_prev = None
+        for li, blk in enumerate(blocks):
+            s_out = s_cat[:, so:so + cs[li]]
+            v_out = v_cat[:, :, vo:vo + cv[li]]
+            if li == 0:
+                idx = first_edge_layer(xyz, B, N, k, 2, self.init_scalar, blk, s_out, v_out, idx32=fi[0])
+            else:
+                taps = record.setdefault("taps%d" % li, {}) if record is not None and record.get("want_taps") else None
+                if record is not None and "teacher" in record:
+                    s_prev, v_prev = record["teacher"][li - 1]
+                idx = sv_edge_layer(s_prev, v_prev, B, N, k, blk, s_out, v_out, idx32=fi[li], taps=taps)
+            idxs.append(idx)
+            s_prev, v_prev = s_out, v_out
+            so += cs[li]
+            vo += cv[li]
+        if record is not None:
+            record["idx"] = idxs
+            record["s_cat"], record["v_cat"] = s_cat, v_cat
+        # conv5 (per point) -> svfuse -> max|mean over points
+        C5s, C5v = self.conv5.out_dims
+        fused = torch.empty((B * N, C5s + 3 * C5v), dtype=torch.float32, device=dev)
+        v5 = torch.empty((B * N, 3, C5v), dtype=torch.float32, device=dev)
+        self.conv5.forward_rows(s_cat, v_cat, B, N, s_out=fused, lds_out=fused.stride(0), v_out=v5)
+        self.svfuse.forward_rows(None, v5, out=fused)
+        Cf = fused.shape[1]
+        g = torch.empty((B, 2 * Cf), dtype=torch.float32, device=dev)
+        nv.pool_rows(fused, Cf, Cf, B, N, want_max=True, want_mean=True, max_out=g, mean_out=g[:, Cf:], ldo=2 * Cf)
+        # head
+        h = self.linear1.forward_rows(g, bn=folded_bn(self, "bn1"), act=nv.ACT_LEAKY)
+        h2 = self.linear2.forward_rows(h, bn=folded_bn(self, "bn2"), act=nv.ACT_LEAKY)
+        out = torch.empty((B, self.linear3.out_features), dtype=torch.float32, device=dev)
+        nv.linear_rows(h2, h2.stride(0), 0, 1, B, h2.shape[1], self.linear3.weight.detach(), out.shape[1], out,
+                       out.shape[1], 0, bias=self.linear3.bias.detach())
+        if record is not None:
+            record.update(fused=fused, glob=g, h1=h, h2=h2)
+        return out

@@ -1,0 +1,390 @@
+"""Host-side mirror of the reference's SV layer library (models/sv_layers.py), inference only.
+
+Same class names, constructor signatures, parameter names and ``state_dict`` layout as the
+reference, so ``load_state_dict(checkpoint['state_dict'])`` works unchanged; every ``forward`` runs
+hand-written sm_100a kernels through the C ABI (include/svnet_b200.h) -- there is no PyTorch or CPU
+fallback.  Training-mode paths (STE clamp, sv_layers.py:40-42,46-48) are not on the inference hot
+path: ``forward`` raises if ``self.training``.
+
+Packed weights (sign bit-planes, folded BatchNorm affines, re-laid-out weight slices) are built
+once per parameter version and cached on the module.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _native as nv
+from .sv_util import svpool
+
+EPS = 1e-6
+
+
+def _inference_only(m):
+    if m.training:
+        raise RuntimeError("%s: svnet_b200 implements the inference path only; call model.eval()"
+                           % type(m).__name__)
+
+
+def _sig(tensors):
+    return tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+
+
+class _Cached:
+    """Mixin: cache of derived (packed) tensors keyed on the parameters' versions."""
+
+    def _packed(self, key, deps, builder):
+        cache = self.__dict__.setdefault("_sv_cache", {})
+        sig = _sig(deps)
+        hit = cache.get(key)
+        if hit is None or hit[0] != sig:
+            with torch.no_grad():
+                hit = (sig, builder())
+            cache[key] = hit
+        return hit[1]
+
+
+def _rows2d(x):
+    """(..., C) contiguous -> (rows, C)"""
+    x = x.contiguous()
+    return x.view(-1, x.shape[-1])
+
+
+class Linear(nn.Linear, _Cached):
+    """sv_layers.py:20-53.  bw: binarise weights, ba: binarise activations (sign(x + beta))."""
+
+    def __init__(self, in_channels, out_channels, bias, bw=False, ba=False):
+        super(Linear, self).__init__(in_channels, out_channels, bias)
+        self.bw, self.ba = bw, ba
+        if ba:
+            self.beta = nn.Parameter(torch.zeros(1, in_channels))
+        if bw:
+            self.scale = nn.Parameter(torch.ones(1, out_channels) / math.sqrt(in_channels))
+
+    # -- packed forms ---------------------------------------------------------------------------
+    def sign_bits(self):
+        return self._packed("bits", (self.weight,), lambda: nv.pack_sign(self.weight.detach()))
+
+    def scale_vec(self):
+        return self._packed("scale", (self.scale,), lambda: self.scale.detach().reshape(-1).contiguous())
+
+    def beta_vec(self):
+        return self._packed("beta", (self.beta,), lambda: self.beta.detach().reshape(-1).contiguous())
+
+    def sign_weight(self):
+        return self._packed("signw", (self.weight,), lambda: torch.sign(self.weight.detach()).contiguous())
+
+    # -- forward --------------------------------------------------------------------------------
+    def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE, out=None, ldo=None):
+        """x2d (rows, K) -> (rows, Cout); optional fused BatchNorm affine + activation."""
+        rows, K = x2d.shape
+        Cout = self.out_features
+        bias = self.bias.detach() if self.bias is not None else None
+        if self.ba:
+            if not self.bw:
+                raise NotImplementedError("Linear(ba=True, bw=False) has no scale in the reference either")
+            bits, mask, nvalid = nv.rows_prep(nv.view_of(x2d, None), rows, beta=self.beta_vec(), want_bits=True)
+            return nv.binlinear_rows(bits, mask, nvalid, K, self.sign_bits(), Cout, scale=self.scale_vec(), bias=bias,
+                                     bn=bn, act=act, out=out, ldo=ldo)
+        if out is None:
+            out = torch.empty((rows, Cout), dtype=torch.float32, device=x2d.device)
+            ldo = Cout
+        nv.linear_rows(x2d, x2d.stride(0), 0, 1, rows, K, self.weight.detach(), Cout, out, ldo, 0,
+                       sign_w=self.bw, colscale=self.scale_vec() if self.bw else None, bias=bias, bn=bn, act=act)
+        return out
+
+    def forward(self, x):
+        _inference_only(self)
+        shape_x = x.shape
+        y = self.forward_rows(_rows2d(x))
+        return y.view(shape_x[:-1] + (y.shape[-1],))
+
+
+class Conv1d(nn.Conv1d, _Cached):
+    """sv_layers.py:55-78: kernel-1 convolution on (B, C, N), always bw & ba when ``binary``."""
+
+    def __init__(self, in_channels, out_channels, binary=False):
+        super(Conv1d, self).__init__(in_channels, out_channels, 1, bias=False)
+        print('Conv1d: ', in_channels, out_channels)
+        self.binary = binary
+        if binary:
+            self.beta = nn.Parameter(torch.zeros(1, in_channels, 1))
+            self.scale = nn.Parameter(torch.ones(1, out_channels, 1) / math.sqrt(in_channels))
+
+    def weight2d(self):
+        return self._packed("w2d", (self.weight,), lambda: self.weight.detach()[:, :, 0].contiguous())
+
+    def sign_bits(self, lo=0, hi=None):
+        return self._packed(("bits", lo, hi), (self.weight,),
+                            lambda: nv.pack_sign(self.weight.detach()[:, lo:hi, 0].contiguous()))
+
+    def scale_vec(self):
+        return self._packed("scale", (self.scale,), lambda: self.scale.detach().reshape(-1).contiguous())
+
+    def beta_vec(self):
+        return self._packed("beta", (self.beta,), lambda: self.beta.detach().reshape(-1).contiguous())
+
+    def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE):
+        rows, K = x2d.shape
+        Cout = self.out_channels
+        if self.binary:
+            bits, mask, nvalid = nv.rows_prep(nv.view_of(x2d, None), rows, beta=self.beta_vec(), want_bits=True)
+            return nv.binlinear_rows(bits, mask, nvalid, K, self.sign_bits(), Cout, scale=self.scale_vec(), bn=bn,
+                                     act=act)
+        out = torch.empty((rows, Cout), dtype=torch.float32, device=x2d.device)
+        nv.linear_rows(x2d, x2d.stride(0), 0, 1, rows, K, self.weight2d(), Cout, out, Cout, 0, bn=bn, act=act)
+        return out
+
+    def forward(self, x):
+        _inference_only(self)
+        B, C, N = x.shape
+        y = self.forward_rows(x.transpose(1, 2).contiguous().view(B * N, C))
+        return y.view(B, N, -1).transpose(1, 2).contiguous()
+
+
+class VectorBN(nn.Module, _Cached):
+    """sv_layers.py:81-102: rescale each 3-vector by BatchNorm1d(|v|)/|v|."""
+
+    def __init__(self, dim):
+        super(VectorBN, self).__init__()
+        self.bn = nn.BatchNorm1d(dim)
+
+    def folded(self):
+        bn = self.bn
+        return self._packed("fold", (bn.weight, bn.bias, bn.running_mean, bn.running_var), lambda: nv.fold_bn(bn))
+
+    def forward(self, v):
+        _inference_only(self)
+        a, c = self.folded()
+        return nv.vector_bn_rows(v.contiguous(), a, c)
+
+
+def folded_bn(owner, name):
+    """Folded eval affine of ``owner.<name>`` (an nn.BatchNorm1d), cached on ``owner``."""
+    bn = getattr(owner, name)
+    return owner._packed("fold_" + name, (bn.weight, bn.bias, bn.running_mean, bn.running_var),
+                         lambda: nv.fold_bn(bn))
+
+
+class Vector2Scalar(nn.Module, _Cached):
+    """sv_layers.py:104-129: invariant scalars s[d*m+j] = sum_i v[i,d] * (v W^T)[i,j]."""
+
+    def __init__(self, v_dim, multi, binary=False, trans_back=False):
+        super(Vector2Scalar, self).__init__()
+        if multi != 3:
+            raise NotImplementedError("svnet_b200 implements multi == 3 (the only value the SV models use)")
+        self.trans_back = trans_back
+        self.linear = Linear(v_dim, multi, bias=False, bw=binary)
+
+    def wz(self):
+        """(Wz (3, C) -- already sign()ed when binary --, zscale (3,) or None)"""
+        lin = self.linear
+        if lin.bw:
+            return lin.sign_weight(), lin.scale_vec()
+        return self._packed("wz", (lin.weight,), lambda: lin.weight.detach().contiguous()), None
+
+    def forward_rows(self, v3, u_out=None, ldu=None, want_z=False):
+        """v3 (rows, 3, C) strided view -> u (rows, 3C) written to u_out (row stride ldu)."""
+        rows, _, C = v3.shape
+        Wz, zs = self.wz()
+        if u_out is None:
+            u_out = torch.empty((rows, 3 * C), dtype=torch.float32, device=v3.device)
+            ldu = 3 * C
+        z = torch.empty((rows, 3, 3), dtype=torch.float32, device=v3.device) if want_z else None
+        nv.rows_prep(nv.view_of(None, v3), rows, Wz=Wz, zscale=zs, u_out=u_out, ldu=ldu, z_out=z)
+        return u_out, z
+
+    def forward(self, v):
+        '''
+        shape of v: B, N_points, [k,] 3, dim
+        '''
+        _inference_only(self)
+        assert v.ndim in [3, 4, 5], 'dim of v should be in [4, 5], got {}'.format(v.ndim)
+        v = v.contiguous()
+        lead = v.shape[:-2]
+        s, z = self.forward_rows(v.view(-1, 3, v.shape[-1]), want_z=self.trans_back)
+        s = s.view(lead + (-1,))
+        if self.trans_back:
+            return s, z.view(lead + (3, 3))
+        return s
+
+
+class VectorReLU(nn.Module):
+    """sv_layers.py:131-149 -- never instantiated by any SV model; kept for name parity only."""
+
+    def __init__(self):
+        super(VectorReLU, self).__init__()
+        self.div = 10
+
+    def forward(self, x):
+        raise NotImplementedError("VectorReLU is unused by the SV models (reference sv_layers.py:131-149)")
+
+
+class SVBlock(nn.Module, _Cached):
+    """sv_layers.py:151-196.  ``forward`` is the materialised (module-level) path over rows; the
+    DGCNN models call the fused edge kernels instead (sv_dgcnn_cls.py in this package)."""
+
+    def __init__(self, in_dims, out_dims, binary=False):
+        super(SVBlock, self).__init__()
+        print('SVBlock: ', in_dims, out_dims)
+        self.in_dims, self.out_dims, self.binary = tuple(in_dims), tuple(out_dims), binary
+
+        self.gate = nn.Sequential(
+                nn.Linear(in_dims[0], out_dims[1]//2, bias=False),
+                nn.ReLU(inplace=True),
+                nn.Linear(out_dims[1]//2, out_dims[1], bias=False),
+                nn.Sigmoid()
+                )
+
+        self.v2s = Vector2Scalar(in_dims[1], 3, binary=binary)
+
+        self.linear1 = Linear(in_dims[0] + in_dims[1] * 3, out_dims[0], bias=False, bw=binary, ba=binary)
+        self.bn1 = nn.BatchNorm1d(out_dims[0])
+        self.relu = nn.LeakyReLU(negative_slope=0.2)
+
+        self.linear2 = Linear(in_dims[1], out_dims[1], bias=False, bw=binary)
+        self.bn2 = VectorBN(out_dims[1])
+
+    # -- packed forms used by the fused kernels ---------------------------------------------------
+    def gate_weights(self):
+        return self.gate[0].weight.detach(), self.gate[2].weight.detach()
+
+    def bn1_folded(self):
+        return folded_bn(self, "bn1")
+
+    def pq_weight(self):
+        """[W2a; W2b] (2*Cvo, Cv_pt) and the matching column scale for the per-point P|Q table."""
+        lin = self.linear2
+
+        def build():
+            W = lin.weight.detach()
+            half = W.shape[1] // 2
+            Wc = torch.cat([W[:, :half], W[:, half:]], dim=0).contiguous()
+            sc = torch.cat([lin.scale.detach().reshape(-1)] * 2).contiguous() if lin.bw else None
+            return Wc, sc
+        deps = (lin.weight, lin.scale) if lin.bw else (lin.weight,)
+        return self._packed("pq", deps, build)
+
+    def yab_weight(self):
+        """fp linear1 split: ([W1a; W1b] (2*Cout, Cs_pt), W1q^T (6Cv_pt... = 3*Cv_e, Cout))."""
+        lin = self.linear1
+
+        def build():
+            W = lin.weight.detach()
+            cs = self.in_dims[0] // 2
+            Wab = torch.cat([W[:, :cs], W[:, cs:2 * cs]], dim=0).contiguous()
+            Wq_t = W[:, 2 * cs:].t().contiguous()
+            return Wab, Wq_t
+        return self._packed("yab", (lin.weight,), build)
+
+    # -- module-level forward over materialised rows --------------------------------------------
+    def forward_rows(self, s2d, v3, B, rows_per_cloud, s_out=None, lds_out=None, v_out=None):
+        """s2d (R, Cs) [row stride may exceed Cs], v3 (R, 3, Cv) strided.  Returns (s', v')."""
+        R = s2d.shape[0]
+        Cs, Cv = self.in_dims
+        Cso, Cvo = self.out_dims
+        dev = s2d.device
+        G1, G2 = self.gate_weights()
+        gate = nv.gate_rows(s2d, s2d.stride(0), Cs, B, rows_per_cloud, G1, G2)
+        Wz, zs = self.v2s.wz()
+        view = nv.view_of(s2d, v3, Cs=Cs, Cv=Cv)
+        bn1 = self.bn1_folded()
+        if s_out is None:
+            s_out = torch.empty((R, Cso), dtype=torch.float32, device=dev)
+            lds_out = Cso
+        K = Cs + 3 * Cv
+        if self.binary:
+            bits, mask, nvalid = nv.rows_prep(view, R, Wz=Wz, zscale=zs, beta=self.linear1.beta_vec(), want_bits=True)
+            nv.binlinear_rows(bits, mask, nvalid, K, self.linear1.sign_bits(), Cso, scale=self.linear1.scale_vec(),
+                              bn=bn1, act=nv.ACT_LEAKY, out=s_out, ldo=lds_out)
+        else:
+            u = torch.empty((R, K), dtype=torch.float32, device=dev)
+            nv.rows_prep(view, R, Wz=Wz, zscale=zs, u_out=u, ldu=K)
+            nv.linear_rows(u, K, 0, 1, R, K, self.linear1.weight.detach(), Cso, s_out, lds_out, 0, bn=bn1,
+                           act=nv.ACT_LEAKY)
+        if v_out is None:
+            v_out = torch.empty((R, 3, Cvo), dtype=torch.float32, device=dev)
+        lin2 = self.linear2
+        nv.linear_rows(v3, v3.stride(0), v3.stride(1), 3, 3 * R, Cv, lin2.weight.detach(), Cvo, v_out,
+                       v_out.stride(0), v_out.stride(1), sign_w=lin2.bw,
+                       colscale=lin2.scale_vec() if lin2.bw else None, bn=self.bn2.folded(), vbn=True, gate=gate,
+                       groups_per_cloud=rows_per_cloud)
+        return s_out, v_out
+
+    def forward(self, x):
+        '''
+        shape of s: B, N_points, [k,] s_dim
+        shape of v: B, N_points, [k,] 3, v_dim
+        '''
+        _inference_only(self)
+        s, v = x
+        s, v = s.contiguous(), v.contiguous()
+        B = s.shape[0]
+        lead = s.shape[:-1]
+        R = s.numel() // s.shape[-1]
+        so, vo = self.forward_rows(s.view(R, s.shape[-1]), v.view(R, 3, v.shape[-1]), B, R // B)
+        return so.view(lead + (-1,)), vo.view(lead + (3, -1))
+
+
+class SVFuse(nn.Module):
+    """sv_layers.py:198-220: cat[s, v2s(v)]."""
+
+    def __init__(self, v_dim, multi, binary, trans_back=False):
+        super(SVFuse, self).__init__()
+        print('SVFuse: ', v_dim)
+        self.trans_back = trans_back
+
+        self.v2s = Vector2Scalar(v_dim, multi, binary=binary, trans_back=trans_back)
+
+    def forward_rows(self, s2d, v3, out=None, want_z=False):
+        """-> (R, Cs + 3Cv) [, z (R,3,3)]; s2d may be None when ``out`` already holds the scalars."""
+        R, _, Cv = v3.shape
+        if out is None:
+            Cs = s2d.shape[1]
+            out = torch.empty((R, Cs + 3 * Cv), dtype=torch.float32, device=v3.device)
+            out[:, :Cs].copy_(s2d)
+        Cs = out.shape[1] - 3 * Cv
+        _, z = self.v2s.forward_rows(v3, u_out=out[:, Cs:], ldu=out.stride(0), want_z=want_z)
+        return out, z
+
+    def forward(self, x):
+        '''
+        shape of s: B, N_points, [k,] s_dim
+        shape of v: B, N_points, [k,] 3, v_dim
+        '''
+        s, v = x
+        s, v = s.contiguous(), v.contiguous()
+        lead = s.shape[:-1]
+        R = s.numel() // s.shape[-1]
+        out, z = self.forward_rows(s.view(R, -1), v.view(R, 3, v.shape[-1]), want_z=self.trans_back)
+        out = out.view(lead + (-1,))
+        if self.trans_back:
+            return out, z.view(lead + (3, 3))
+        return out
+
+
+class SV_STNkd(nn.Module):
+    """sv_layers.py:222-244."""
+
+    def __init__(self, dim, binary):
+        super(SV_STNkd, self).__init__()
+
+        self.conv1 = SVBlock(dim, (64//2, 64//6), binary=binary)
+        self.conv2 = SVBlock((64//2, 64//6), (128//2, 128//6), binary=binary)
+        self.conv3 = SVBlock((128//2, 128//6), (1024//2, 1024//6), binary=binary)
+
+        self.fc1 = SVBlock((1024//2, 1024//6), (512//2, 512//6), binary=binary)
+        self.fc2 = SVBlock((512//2, 512//6), (256//2, 256//6), binary=binary)
+        self.fc3 = SVBlock((256//2, 256//6), dim, binary=binary)
+
+    def forward(self, x):
+        x = self.conv1(x)
+        x = self.conv2(x)
+        x = self.conv3(x) # B, N_points, [3,] 1024//(2,6)
+        x = svpool(x, dim=1)
+
+        x = self.fc1(x)
+        x = self.fc2(x)
+        x = self.fc3(x) # B, [3,] dim
+
+        return x

