@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: SV-DGCNN clouds/sec (binary, ModelNet40 head, N=1024, k=20).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one forward of the hot path over one batch of B=32 synthetic clouds per GPU
+(BASELINE.json configs[1]).  Multi-GPU (launched by torchrun, one rank per GPU) shards by cloud
+batch -- weak scaling, B=32 per GPU -- with a single NCCL all-gather of the logits per step.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the
+same metric through the public nn.Module call with pinned HOST buffers (H2D of the clouds and D2H
+of the logits inside the timed region).  `roofline` is for the dominant kernel, timed live with
+CUDA events on its launch stream; `cpu_baseline` is the oracle port (C + OpenMP) on the host cores.
+`--impl reference` times that CPU port alone (the reference is pure Python/PyTorch and
+/root/reference does not exist on the GPU box).
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, N_POINTS, K_NN, N_CLASS, SEED = 32, 1024, 20, 40, 1002
+METRIC = "SV-DGCNN clouds/sec (1024 pts, k=20)"
+WORKLOAD = "SV-DGCNN binary ModelNet40 cls forward, B=32/GPU, N=1024, k=20, synthetic clouds + synthetic checkpoint"
+
+# algorithmic bytes per cloud for the cls path (fp32 features, int32 indices)
+F_L = [3, 62, 62, 127]
+O_L = [62, 62, 127, 254]
+
+
+def algorithmic_bytes_per_cloud(N=N_POINTS, k=K_NN):
+    total = 0
+    for f, o in zip(F_L, O_L):
+        total += 2 * 4 * N * f + 2 * 4 * N * k + 4 * N * o
+    total += 4 * N * sum(O_L) + 4 * (2 * 1022 + N_CLASS)
+    return total
+
+
+def edge_kernel_bytes_per_cloud(layer, N=N_POINTS, k=K_NN):
+    """K2 of SURVEY 8(d): read point table + idx, write pooled output (+ the P|Q table it gathers)."""
+    f, o = F_L[layer], O_L[layer]
+    return 4 * N * f + 4 * N * k + 4 * N * o
+
+
+def knn_kernel_bytes_per_cloud(layer, N=N_POINTS, k=K_NN):
+    return 4 * N * F_L[layer] + 4 * N * k
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_throughput(n_clouds, reps=1):
+    """Time the oracle port (C + OpenMP, all host threads) on a bounded sample of the workload."""
+    import numpy as np
+    import torch
+    from oracle import svnet_oracle as orc
+    import svnet_b200 as sv
+    from svnet_b200.synthetic import make_args, synthetic_clouds, synthetic_state_dict
+    orc.build()
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = sv.SV_DGCNN_CLS(make_args(k=K_NN, binary=True), N_CLASS)
+    sd = synthetic_state_dict(net.state_dict(), seed=SEED)
+    x = synthetic_clouds(n_clouds, N_POINTS, SEED).numpy()
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        y = orc.sv_dgcnn_cls(sd, x, K_NN)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert np.isfinite(y).all()
+    return n_clouds / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    n = 4
+    per_step = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_port_throughput(n)
+        if i >= args.warmup:
+            per_step.append(dt)
+        if sum(per_step) > 150:  # keep the whole run within a few minutes
+            break
+    ms = 1e3 * sum(per_step) / len(per_step)
+    value = n / (ms / 1e3)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": args.gpus,
+        "steps": len(per_step), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "%d clouds per step" % n},
+        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": cores, "kind": "port",
+                         "sample": "%d clouds of the same workload per step, oracle C port with OpenMP" % n},
+        "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import svnet_b200 as sv
+    from svnet_b200 import _native as nv
+    from svnet_b200.synthetic import make_args, synthetic_clouds, synthetic_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nv.lib()  # fail loudly if the CUDA library is missing
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = sv.SV_DGCNN_CLS(make_args(k=K_NN, binary=True), N_CLASS)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=SEED))
+    net = net.to(dev).eval()
+    B = B_PER_GPU
+    # each rank gets its own shard of the global batch (weak scaling: 32 clouds per GPU)
+    x_host = synthetic_clouds(B * world, N_POINTS, SEED)[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    x_dev = x_host.to(dev)
+    y_host = torch.empty((B, N_CLASS), dtype=torch.float32).pin_memory()
+    gathered = torch.empty((world * B, N_CLASS), dtype=torch.float32, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(xin):
+        y = net(xin)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y)
+        return y
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for e0, e1 in ev:
+            flush.zero_()          # flush L2 between steps (untimed)
+            e0.record()
+            fn()
+            e1.record()
+        barrier()
+        total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step(x_dev)
+        barrier()
+        # ---- device-resident throughput; the dominant kernels are bracketed with events live ----
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        nv.PROFILE[0] = {"svnet_knn", "svnet_svblock_edge_fwd"}
+        nv.TIMED.clear()
+        nv.ORDER.clear()
+        l0 = nv.LAUNCHES[0]
+        ms = timed(lambda: step(x_dev), args.steps)
+        launches = (nv.LAUNCHES[0] - l0) // args.steps
+        nv.PROFILE[0] = None
+        clocks = sampler.stop() if rank == 0 else None
+        per_call = {}
+        for name, e0, e1 in nv.ORDER:
+            per_call.setdefault(name, []).append(e0.elapsed_time(e1))
+
+        # ---- end to end through the public API with host buffers ----
+        def e2e_step():
+            xd = x_host.to(dev, non_blocking=True)
+            y = step(xd)
+            y_host.copy_(y, non_blocking=True)
+        for _ in range(3):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    # dominant kernel = the C-ABI call with the largest share of the step; per launch, 4 knn + 3 edge per step
+    def per_layer(name, n_per_step):
+        v = per_call.get(name, [])
+        return [sum(v[i::n_per_step]) / max(1, len(v[i::n_per_step])) for i in range(n_per_step)]
+    knn_ms = per_layer("svnet_knn", 4)
+    edge_ms = per_layer("svnet_svblock_edge_fwd", 3)
+    cand = [("svnet_knn[layer%d]" % (i + 1), knn_ms[i], knn_kernel_bytes_per_cloud(i) * B) for i in range(4)]
+    cand += [("svnet_svblock_edge_fwd[layer%d]" % (i + 2), edge_ms[i], edge_kernel_bytes_per_cloud(i + 1) * B) for i in range(3)]
+    dom = max(cand, key=lambda c: c[1])
+    achieved = dom[2] / (dom[1] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": dom[1], "algorithmic_bytes_per_launch": dom[2],
+                "step_share": {c[0]: c[1] / ms for c in cand},
+                "whole_step": {"algorithmic_bytes": algorithmic_bytes_per_cloud() * B,
+                               "achieved": algorithmic_bytes_per_cloud() * B / (ms * 1e-3) / 1e9,
+                               "frac": algorithmic_bytes_per_cloud() * B / (ms * 1e-3) / 1e9 / hbm_peak}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, dt = cpu_port_throughput(4)
+        cpu = {"value": v, "unit": "clouds/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "4 clouds of the same workload (N=1024, k=20), oracle C port with OpenMP, %.1f s" % dt}
+
+    out = {
+        "metric": METRIC, "value": world * B / (ms * 1e-3), "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (+u32 XNOR/popcount for the binarised linears)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": world * B, "n_points": N_POINTS, "k": K_NN,
+                   "parallelism": "batch-sharded x%d, all-gather of logits" % world,
+                   "l2": "flushed between steps (256 MiB memset, untimed)"},
+        "clocks": clocks,
+        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -71,9 +71,28 @@ def lib():
     return _lib
 
 
-def _check(rc, what):
+LAUNCHES = [0]        # C-ABI calls that enqueue kernels (bench.py reports it as gpu_launches)
+TIMED = {}            # name -> list of (start_event, end_event), filled when PROFILE[0] is set
+PROFILE = [None]      # None or a set of C-ABI names to bracket with CUDA events
+ORDER = []            # (name, start_event, end_event) in call order while profiling
+
+
+def _call(name, *args):
+    """Invoke one C-ABI entry point; optionally bracket it with CUDA events on the launch stream."""
+    fn = getattr(lib(), name)
+    prof = PROFILE[0]
+    if prof is not None and name in prof:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        TIMED.setdefault(name, []).append((e0, e1))
+        ORDER.append((name, e0, e1))
+    else:
+        rc = fn(*args)
+    LAUNCHES[0] += 1
     if rc != 0:
-        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().svnet_last_error().decode()))
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, lib().svnet_last_error().decode()))
 
 
 def _stream():
@@ -121,8 +140,8 @@ def pack_sign(W2d):
     rows, K = W2d.shape
     bits = torch.empty(((K + 31) // 32, rows), dtype=torch.int32, device=W2d.device)
     zc = torch.zeros(1, dtype=torch.int32, device=W2d.device)
-    _check(lib().svnet_pack_sign(_ptr(W2d), c_int(rows), c_int(K), c_int(W2d.stride(0)), _ptr(bits), _ptr(zc),
-                                 _stream()), "svnet_pack_sign")
+    _call("svnet_pack_sign", _ptr(W2d), c_int(rows), c_int(K), c_int(W2d.stride(0)), _ptr(bits), _ptr(zc),
+                                 _stream())
     if int(zc.item()) != 0:
         raise NotImplementedError("binarised weight contains exact zeros (sign(0)=0 plane not supported)")
     return bits
@@ -134,8 +153,8 @@ def fold_bn(bn):
     C = w.numel()
     a = torch.empty(C, dtype=torch.float32, device=w.device)
     c = torch.empty_like(a)
-    _check(lib().svnet_fold_bn(_ptr(w), _ptr(b), _ptr(m), _ptr(var), c_float(bn.eps), c_int(C), _ptr(a), _ptr(c),
-                               _stream()), "svnet_fold_bn")
+    _call("svnet_fold_bn", _ptr(w), _ptr(b), _ptr(m), _ptr(var), c_float(bn.eps), c_int(C), _ptr(a), _ptr(c),
+                               _stream())
     return a, c
 
 
@@ -143,16 +162,15 @@ def knn(view, B, N, k, want64=False, want32=True):
     dev = torch.device("cuda", torch.cuda.current_device())
     i32 = torch.empty((B, N, k), dtype=torch.int32, device=dev) if want32 else None
     i64 = torch.empty((B, N, k), dtype=torch.int64, device=dev) if want64 else None
-    _check(lib().svnet_knn(ctypes.byref(view), c_int(B), c_int(N), c_int(k), _ptr(i32), _ptr(i64), _stream()),
-           "svnet_knn")
+    _call("svnet_knn", ctypes.byref(view), c_int(B), c_int(N), c_int(k), _ptr(i32), _ptr(i64), _stream())
     return i32, i64
 
 
 def graph_feature_xyz(xyz, idx64, nv):
     B, N, k = idx64.shape
     out = torch.empty((B, N, k, 3, nv), dtype=torch.float32, device=xyz.device)
-    _check(lib().svnet_graph_feature_xyz(_ptr(_dev(xyz)), _ptr(_dev(idx64, torch.int64)), c_int(B), c_int(N), c_int(k),
-                                         c_int(nv), _ptr(out), _stream()), "svnet_graph_feature_xyz")
+    _call("svnet_graph_feature_xyz", _ptr(_dev(xyz)), _ptr(_dev(idx64, torch.int64)), c_int(B), c_int(N), c_int(k),
+                                         c_int(nv), _ptr(out), _stream())
     return out
 
 
@@ -161,26 +179,24 @@ def graph_feature_sv(s, v, idx64):
     Cs, Cv = s.shape[-1], v.shape[-1]
     sf = torch.empty((B, N, k, 2 * Cs), dtype=torch.float32, device=s.device)
     vf = torch.empty((B, N, k, 3, 2 * Cv), dtype=torch.float32, device=s.device)
-    _check(lib().svnet_graph_feature_sv(_ptr(_dev(s)), _ptr(_dev(v)), _ptr(_dev(idx64, torch.int64)), c_int(B), c_int(N),
-                                        c_int(k), c_int(Cs), c_int(Cv), _ptr(sf), _ptr(vf), _stream()),
-           "svnet_graph_feature_sv")
+    _call("svnet_graph_feature_sv", _ptr(_dev(s)), _ptr(_dev(v)), _ptr(_dev(idx64, torch.int64)), c_int(B), c_int(N),
+                                        c_int(k), c_int(Cs), c_int(Cv), _ptr(sf), _ptr(vf), _stream())
     return sf, vf
 
 
 def gate_rows(s2d, lds, Cs, B, rows, G1, G2, out=None):
     H, Co = G1.shape[0], G2.shape[0]
     gate = out if out is not None else torch.empty((B, Co), dtype=torch.float32, device=s2d.device)
-    _check(lib().svnet_gate_rows(_ptr(_dev(s2d)), c_int(lds), c_int(Cs), c_int(B), c_int(rows), _ptr(_dev(G1)),
-                                 _ptr(_dev(G2)), c_int(H), c_int(Co), _ptr(gate), _stream()), "svnet_gate_rows")
+    _call("svnet_gate_rows", _ptr(_dev(s2d)), c_int(lds), c_int(Cs), c_int(B), c_int(rows), _ptr(_dev(G1)),
+                                 _ptr(_dev(G2)), c_int(H), c_int(Co), _ptr(gate), _stream())
     return gate
 
 
 def gate_edge(view, idx32, B, N, k, G1, G2):
     H, Co = G1.shape[0], G2.shape[0]
     gate = torch.empty((B, Co), dtype=torch.float32, device=idx32.device)
-    _check(lib().svnet_gate_edge(ctypes.byref(view), _ptr(_dev(idx32, torch.int32)), c_int(B), c_int(N), c_int(k),
-                                 _ptr(_dev(G1)), _ptr(_dev(G2)), c_int(H), c_int(Co), _ptr(gate), _stream()),
-           "svnet_gate_edge")
+    _call("svnet_gate_edge", ctypes.byref(view), _ptr(_dev(idx32, torch.int32)), c_int(B), c_int(N), c_int(k),
+                                 _ptr(_dev(G1)), _ptr(_dev(G2)), c_int(H), c_int(Co), _ptr(gate), _stream())
     return gate
 
 
@@ -188,18 +204,18 @@ def gate_xyz(xyz, idx32, nv, Winit, G1, G2):
     B, N, k = idx32.shape
     H, Co = G1.shape[0], G2.shape[0]
     gate = torch.empty((B, Co), dtype=torch.float32, device=xyz.device)
-    _check(lib().svnet_gate_xyz(_ptr(_dev(xyz)), _ptr(_dev(idx32, torch.int32)), c_int(B), c_int(N), c_int(k), c_int(nv),
+    _call("svnet_gate_xyz", _ptr(_dev(xyz)), _ptr(_dev(idx32, torch.int32)), c_int(B), c_int(N), c_int(k), c_int(nv),
                                 _ptr(_dev(Winit)), _ptr(_dev(G1)), _ptr(_dev(G2)), c_int(H), c_int(Co), _ptr(gate),
-                                _stream()), "svnet_gate_xyz")
+                                _stream())
     return gate
 
 
 def edge_xyz_fwd(params):
-    _check(lib().svnet_edge_xyz_fwd(ctypes.byref(params), _stream()), "svnet_edge_xyz_fwd")
+    _call("svnet_edge_xyz_fwd", ctypes.byref(params), _stream())
 
 
 def svblock_edge_fwd(params):
-    _check(lib().svnet_svblock_edge_fwd(ctypes.byref(params), _stream()), "svnet_svblock_edge_fwd")
+    _call("svnet_svblock_edge_fwd", ctypes.byref(params), _stream())
 
 
 def rows_prep(view, rows, Wz=None, zscale=None, beta=None, u_out=None, ldu=0, z_out=None, want_bits=False):
@@ -211,9 +227,8 @@ def rows_prep(view, rows, Wz=None, zscale=None, beta=None, u_out=None, ldu=0, z_
         bits = torch.empty((rows, Kw), dtype=torch.int32, device=dev)
         mask = torch.empty((rows, Kw), dtype=torch.int32, device=dev)
         nvalid = torch.empty((rows,), dtype=torch.int32, device=dev)
-    _check(lib().svnet_rows_prep(ctypes.byref(view), c_long(rows), _ptr(Wz), _ptr(zscale), _ptr(beta), _ptr(u_out),
-                                 c_int(ldu), _ptr(z_out), _ptr(bits), _ptr(mask), _ptr(nvalid), _stream()),
-           "svnet_rows_prep")
+    _call("svnet_rows_prep", ctypes.byref(view), c_long(rows), _ptr(Wz), _ptr(zscale), _ptr(beta), _ptr(u_out),
+                                 c_int(ldu), _ptr(z_out), _ptr(bits), _ptr(mask), _ptr(nvalid), _stream())
     return bits, mask, nvalid
 
 
@@ -227,10 +242,10 @@ def binlinear_rows(bits, mask, nvalid, K, W1b, Cout, scale=None, bias=None, bn=N
         out = torch.empty((rows, Cout), dtype=torch.float32, device=bits.device)
         ldo = Cout
     bn_a, bn_c = bn if bn is not None else (None, None)
-    _check(lib().svnet_binlinear_rows(_ptr(bits), _ptr(mask), _ptr(nvalid), c_long(rows), c_int(K), _ptr(W1b),
+    _call("svnet_binlinear_rows", _ptr(bits), _ptr(mask), _ptr(nvalid), c_long(rows), c_int(K), _ptr(W1b),
                                       c_int(Cout), _ptr(scale), _ptr(bias), _ptr(bn_a), _ptr(bn_c), c_int(act),
                                       _ptr(cloud_dot), c_long(rows_per_cloud), _ptr(out), c_int(ldo or 0),
-                                      _ptr(res_i32), _stream()), "svnet_binlinear_rows")
+                                      _ptr(res_i32), _stream())
     return res_i32 if out_i32 else out
 
 
@@ -250,15 +265,15 @@ def linear_rows(A, lda_g, lda_x, G, M, K, W, N, C, ldc_g, ldc_x, sign_w=False, c
     p.gate = gate.data_ptr() if gate is not None else 0
     p.groups_per_cloud = groups_per_cloud
     p.C, p.ldc_g, p.ldc_x = C.data_ptr(), ldc_g, ldc_x
-    _check(lib().svnet_linear_rows(ctypes.byref(p), _stream()), "svnet_linear_rows")
+    _call("svnet_linear_rows", ctypes.byref(p), _stream())
 
 
 def vector_bn_rows(v, bn_a, bn_c):
     C = v.shape[-1]
     rows = v.numel() // (3 * C)
     out = torch.empty_like(v)
-    _check(lib().svnet_vector_bn_rows(_ptr(_dev(v)), c_long(rows), c_int(C), _ptr(bn_a), _ptr(bn_c), _ptr(out),
-                                      _stream()), "svnet_vector_bn_rows")
+    _call("svnet_vector_bn_rows", _ptr(_dev(v)), c_long(rows), c_int(C), _ptr(bn_a), _ptr(bn_c), _ptr(out),
+                                      _stream())
     return out
 
 
@@ -270,6 +285,6 @@ def pool_rows(x, ld, C, B, rows, want_max=True, want_mean=False, max_out=None, m
         mean_out = torch.empty((B, C), dtype=torch.float32, device=dev)
     if ldo is None:
         ldo = C
-    _check(lib().svnet_pool_rows(_ptr(_dev(x)), c_int(ld), c_int(C), c_int(B), c_long(rows), _ptr(max_out),
-                                 _ptr(mean_out), c_int(ldo), _stream()), "svnet_pool_rows")
+    _call("svnet_pool_rows", _ptr(_dev(x)), c_int(ld), c_int(C), c_int(B), c_long(rows), _ptr(max_out),
+                                 _ptr(mean_out), c_int(ldo), _stream())
     return max_out, mean_out

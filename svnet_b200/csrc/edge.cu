@@ -107,7 +107,9 @@ __device__ __forceinline__ void compute_z(const Smem& s, const Dims& d, int lane
         const float* cv = s.ctr + d.Cs + x * d.Cv;
         const float* wz = s.Wz + m * d.Cve;
         float acc = 0.0f;
+#pragma unroll 8
         for (int c = 0; c < d.Cv; ++c) acc = __fmaf_rn(__fsub_rn(nv[c], cv[c]), wz[c], acc);
+#pragma unroll 8
         for (int c = 0; c < d.Cv; ++c) acc = __fmaf_rn(cv[c], wz[d.Cv + c], acc);
         if (use_zscale) acc = __fmul_rn(acc, s.zscale[m]);
         s.zb[lane] = acc;
@@ -137,7 +139,7 @@ __device__ __forceinline__ float compute_q(const Smem& s, const Dims& d, int g, 
 }
 
 template <bool BIN, int OPT>
-__global__ void __launch_bounds__(WARPS * 32) svblock_edge_kernel(svnet_edge_params p)
+__global__ void __launch_bounds__(WARPS * 32, 3) svblock_edge_kernel(svnet_edge_params p)
 {
     extern __shared__ __align__(16) float smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(WARPS * 32) svblock_edge_kernel(svnet_edge_par
                 const int e = e0 + g;
                 const float* nrow = s.nb + (size_t)g * d.F;
                 int nval = 0;
+#pragma unroll 4
                 for (int wd = 0; wd < d.Kw; ++wd) {
                     const int kk = wd * 32 + lane;
                     float u = 0.0f;

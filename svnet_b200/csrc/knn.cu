@@ -51,7 +51,7 @@ __device__ __forceinline__ void topk_insert(TopK<R>& L, float cv, int cj, int la
 }
 
 template <int R>
-__global__ void __launch_bounds__(NT) knn_kernel(svnet_view in, int N, int k, int32_t* __restrict__ idx32,
+__global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k, int32_t* __restrict__ idx32,
                                                  int64_t* __restrict__ idx64)
 {
     extern __shared__ __align__(16) float smem[];

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--fp", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--profile", action="store_true")
     a = ap.parse_args()
     with contextlib.redirect_stdout(io.StringIO()):
         net = sv.SV_DGCNN_CLS(make_args(k=a.k, binary=not a.fp), 40)
@@ -53,6 +54,19 @@ def main():
     print("B=%d N=%d k=%d %s graph=%s: %.3f ms/forward  %.1f clouds/s  (%.2f us/cloud)" % (
         a.B, a.N, a.k, "fp" if a.fp else "bin", a.graph, ms, a.B / ms * 1e3, ms * 1e3 / a.B))
     print("logits[0,:4] =", y[0, :4].tolist())
+    if a.profile:
+        from svnet_b200 import _native as nv
+        nv.PROFILE[0] = set(nv.EXPORTS)
+        nv.ORDER.clear()
+        with torch.no_grad():
+            net(x)
+        torch.cuda.synchronize()
+        tot = 0.0
+        for name, s0, s1 in nv.ORDER:
+            t = s0.elapsed_time(s1)
+            tot += t
+            print("  %-28s %8.3f ms" % (name, t))
+        print("  sum %.3f ms" % tot)
 
 
 if __name__ == "__main__":
