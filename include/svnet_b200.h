@@ -189,9 +189,11 @@ int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream);
  *   z_out  [rows][9]        the 3x3 frames z              (trans_back, sv_layers.py:126-127)
  *   bits/mask [rows][Kw]    sign(u + beta) > 0 / != 0     (binary linear1 input)
  *   nvalid [rows]           number of non-zero signs per row (= popcount of the mask row)
+ * z_in [rows][9] (optional) supplies the frames instead of computing them from Wz: this is the
+ * einsum('bimj,bijk->bimk') projection of sv_pointnet_partseg.py:93.
  * K = Cs + 3Cv.  With Cv == 0 this is a plain sign-pack of a float matrix (Linear ba, Conv1d). */
-int svnet_rows_prep(const svnet_view* in, long rows, const float* Wz, const float* zscale, const float* beta,
-                    float* u_out, int ldu, float* z_out, uint32_t* bits, uint32_t* mask, int32_t* nvalid,
+int svnet_rows_prep(const svnet_view* in, long rows, const float* Wz, const float* zscale, const float* z_in,
+                    const float* beta, float* u_out, int ldu, float* z_out, uint32_t* bits, uint32_t* mask, int32_t* nvalid,
                     void* stream);
 
 /* y[r][o] = act(((nvalid_r - 2*popc((a_r ^ w_o) & m_r)) [+ cloud_dot[r / rows_per_cloud][o]]) * scale[o] * bn_a[o] + bn_c[o])

@@ -218,7 +218,8 @@ def svblock_edge_fwd(params):
     _call("svnet_svblock_edge_fwd", ctypes.byref(params), _stream())
 
 
-def rows_prep(view, rows, Wz=None, zscale=None, beta=None, u_out=None, ldu=0, z_out=None, want_bits=False):
+def rows_prep(view, rows, Wz=None, zscale=None, beta=None, u_out=None, ldu=0, z_out=None, want_bits=False,
+              z_in=None):
     K = view.Cs + 3 * view.Cv
     dev = torch.device("cuda", torch.cuda.current_device())
     bits = mask = nvalid = None
@@ -227,7 +228,7 @@ def rows_prep(view, rows, Wz=None, zscale=None, beta=None, u_out=None, ldu=0, z_
         bits = torch.empty((rows, Kw), dtype=torch.int32, device=dev)
         mask = torch.empty((rows, Kw), dtype=torch.int32, device=dev)
         nvalid = torch.empty((rows,), dtype=torch.int32, device=dev)
-    _call("svnet_rows_prep", ctypes.byref(view), c_long(rows), _ptr(Wz), _ptr(zscale), _ptr(beta), _ptr(u_out),
+    _call("svnet_rows_prep", ctypes.byref(view), c_long(rows), _ptr(Wz), _ptr(zscale), _ptr(z_in), _ptr(beta), _ptr(u_out),
                                  c_int(ldu), _ptr(z_out), _ptr(bits), _ptr(mask), _ptr(nvalid), _stream())
     return bits, mask, nvalid
 

@@ -13,6 +13,7 @@ constexpr int PW = 4;  // warps per CTA in rows_prep
 // chain over channels == oracle order), then all lanes build u lane-per-channel.
 __global__ void __launch_bounds__(PW * 32) rows_prep_kernel(svnet_view in, long rows, const float* __restrict__ Wz,
                                                             const float* __restrict__ zscale,
+                                                            const float* __restrict__ z_in,
                                                             const float* __restrict__ beta, float* __restrict__ u_out,
                                                             int ldu, float* __restrict__ z_out,
                                                             uint32_t* __restrict__ bits, uint32_t* __restrict__ mask,
@@ -30,11 +31,16 @@ __global__ void __launch_bounds__(PW * 32) rows_prep_kernel(svnet_view in, long 
         if (Cv > 0) {
             if (lane < ng * 9) {
                 const int g = lane / 9, xm = lane - g * 9, x = xm / 3, m = xm - x * 3;
-                const float* vp = in.v + (r0 + g) * in.ldv + x * in.xs;
-                const float* wz = Wz + m * Cv;
                 float acc = 0.0f;
-                for (int c = 0; c < Cv; ++c) acc = __fmaf_rn(__ldg(vp + c), __ldg(wz + c), acc);
-                if (zscale) acc = __fmul_rn(acc, __ldg(zscale + m));
+                if (z_in) {
+                    acc = __ldg(z_in + (r0 + g) * 9 + xm);
+                } else {
+                    const float* vp = in.v + (r0 + g) * in.ldv + x * in.xs;
+                    const float* wz = Wz + m * Cv;
+#pragma unroll 4
+                    for (int c = 0; c < Cv; ++c) acc = __fmaf_rn(__ldg(vp + c), __ldg(wz + c), acc);
+                    if (zscale) acc = __fmul_rn(acc, __ldg(zscale + m));
+                }
                 zb[lane] = acc;
                 if (z_out) z_out[(r0 + g) * 9 + xm] = acc;
             }
@@ -144,21 +150,21 @@ __global__ void __launch_bounds__(256) binlinear_rows_kernel(
 
 }  // namespace
 
-extern "C" int svnet_rows_prep(const svnet_view* in, long rows, const float* Wz, const float* zscale, const float* beta,
-                               float* u_out, int ldu, float* z_out, uint32_t* bits, uint32_t* mask, int32_t* nvalid,
+extern "C" int svnet_rows_prep(const svnet_view* in, long rows, const float* Wz, const float* zscale, const float* z_in,
+                               const float* beta, float* u_out, int ldu, float* z_out, uint32_t* bits, uint32_t* mask, int32_t* nvalid,
                                void* stream)
 {
     SV_REQUIRE(in, "svnet_rows_prep: null view");
     SV_REQUIRE(in->Cs + in->Cv >= 1 && rows >= 0, "svnet_rows_prep: bad shape");
     SV_REQUIRE(in->Cs == 0 || in->s, "svnet_rows_prep: null s");
-    SV_REQUIRE(in->Cv == 0 || (in->v && Wz), "svnet_rows_prep: null v / Wz");
+    SV_REQUIRE(in->Cv == 0 || (in->v && (Wz || z_in)), "svnet_rows_prep: null v / Wz");
     SV_REQUIRE(!bits || (mask && nvalid && beta), "svnet_rows_prep: bits output needs mask, nvalid and beta");
     SV_REQUIRE(u_out || bits || z_out, "svnet_rows_prep: no output requested");
     SV_REQUIRE(!u_out || ldu >= in->Cs + 3 * in->Cv, "svnet_rows_prep: ldu too small");
     if (rows == 0) return SVNET_OK;
     const long ngroups = (rows + 2) / 3;
     const int grid = (int)min((long)sv_cdiv(ngroups, PW), 148L * 64);
-    rows_prep_kernel<<<grid, PW * 32, 0, sv_stream(stream)>>>(*in, rows, Wz, zscale, beta, u_out, ldu, z_out, bits, mask,
+    rows_prep_kernel<<<grid, PW * 32, 0, sv_stream(stream)>>>(*in, rows, Wz, zscale, z_in, beta, u_out, ldu, z_out, bits, mask,
                                                                nvalid);
     SV_CHECK_LAUNCH("svnet_rows_prep");
     return SVNET_OK;

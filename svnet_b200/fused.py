@@ -97,3 +97,40 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
 def point_block(blk, s_in, v_in, B, rows_per_cloud, s_out=None, lds_out=None, v_out=None):
     """Per-row SVBlock (conv5, PointNet blocks): thin alias of SVBlock.forward_rows."""
     return blk.forward_rows(s_in, v_in, B, rows_per_cloud, s_out=s_out, lds_out=lds_out, v_out=v_out)
+
+
+def dgcnn_trunk(model, x, forced_idx=None, record=None):
+    """Edge layers 1..4 shared by SV_DGCNN_CLS / SV_DGCNN_PSEG (sv_dgcnn_cls.py:47-67,
+    sv_dgcnn_partseg.py:81-103).  Returns the svcat table (s_cat (B*N, sum Cs), v_cat (B*N, 3, sum Cv));
+    every layer writes its pooled output straight into its column slice."""
+    B, _, N = x.shape
+    k = model.k
+    dev = x.device
+    xyz = x.transpose(1, 2).contiguous().view(B * N, 3)
+    blocks = [model.conv1, model.conv2, model.conv3, model.conv4]
+    cs = [b.out_dims[0] for b in blocks]
+    cv = [b.out_dims[1] for b in blocks]
+    s_cat = torch.empty((B * N, sum(cs)), dtype=torch.float32, device=dev)
+    v_cat = torch.empty((B * N, 3, sum(cv)), dtype=torch.float32, device=dev)
+    so, vo = 0, 0
+    fi = forced_idx or [None] * 4
+    idxs = []
+    s_prev = v_prev = None
+    for li, blk in enumerate(blocks):
+        s_out = s_cat[:, so:so + cs[li]]
+        v_out = v_cat[:, :, vo:vo + cv[li]]
+        if li == 0:
+            idx = first_edge_layer(xyz, B, N, k, 2, model.init_scalar, blk, s_out, v_out, idx32=fi[0])
+        else:
+            taps = record.setdefault("taps%d" % li, {}) if record is not None and record.get("want_taps") else None
+            if record is not None and "teacher" in record:
+                s_prev, v_prev = record["teacher"][li - 1]
+            idx = sv_edge_layer(s_prev, v_prev, B, N, k, blk, s_out, v_out, idx32=fi[li], taps=taps)
+        idxs.append(idx)
+        s_prev, v_prev = s_out, v_out
+        so += cs[li]
+        vo += cv[li]
+    if record is not None:
+        record["idx"] = idxs
+        record["s_cat"], record["v_cat"] = s_cat, v_cat
+    return s_cat, v_cat

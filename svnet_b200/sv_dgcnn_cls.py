@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nv
-from .fused import first_edge_layer, sv_edge_layer
+from .fused import dgcnn_trunk
 from .sv_layers import Linear, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, folded_bn
 
 
@@ -47,35 +47,8 @@ class SV_DGCNN_CLS(nn.Module, _Cached):
         (B,N,k) tensors) and ``record`` (dict) are test hooks (teacher forcing / intermediates)."""
         _inference_only(self)
         B, _, N = x.shape
-        k = self.k
         dev = x.device
-        xyz = x.transpose(1, 2).contiguous().view(B * N, 3)
-        blocks = [self.conv1, self.conv2, self.conv3, self.conv4]
-        cs = [b.out_dims[0] for b in blocks]
-        cv = [b.out_dims[1] for b in blocks]
-        s_cat = torch.empty((B * N, sum(cs)), dtype=torch.float32, device=dev)
-        v_cat = torch.empty((B * N, 3, sum(cv)), dtype=torch.float32, device=dev)
-        so, vo = 0, 0
-        fi = forced_idx or [None] * 4
-        idxs = []
-        s_prev = v_prev = None
-        for li, blk in enumerate(blocks):
-            s_out = s_cat[:, so:so + cs[li]]
-            v_out = v_cat[:, :, vo:vo + cv[li]]
-            if li == 0:
-                idx = first_edge_layer(xyz, B, N, k, 2, self.init_scalar, blk, s_out, v_out, idx32=fi[0])
-            else:
-                taps = record.setdefault("taps%d" % li, {}) if record is not None and record.get("want_taps") else None
-                if record is not None and "teacher" in record:
-                    s_prev, v_prev = record["teacher"][li - 1]
-                idx = sv_edge_layer(s_prev, v_prev, B, N, k, blk, s_out, v_out, idx32=fi[li], taps=taps)
-            idxs.append(idx)
-            s_prev, v_prev = s_out, v_out
-            so += cs[li]
-            vo += cv[li]
-        if record is not None:
-            record["idx"] = idxs
-            record["s_cat"], record["v_cat"] = s_cat, v_cat
+        s_cat, v_cat = dgcnn_trunk(self, x, forced_idx, record)
         # conv5 (per point) -> svfuse -> max|mean over points
         C5s, C5v = self.conv5.out_dims
         fused = torch.empty((B * N, C5s + 3 * C5v), dtype=torch.float32, device=dev)

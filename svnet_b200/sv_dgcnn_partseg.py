@@ -1,0 +1,118 @@
+"""SV-DGCNN part segmentation -- drop-in for models/sv_dgcnn_partseg.py:40-128 (same constructor
+and state_dict keys).  Edge layers 1..4 are the fused kernels of the classifier; the tail runs on
+row-major (B*N, C) tables:
+
+    x_fine  = svfuse1(svcat)                      rows_prep (float u)                 (:104)
+    conv5   per-point SVBlock                     gate_rows, rows_prep, binlinear, vector linear (:106)
+    conv6/svfuse2 on the per-cloud pooled row     same kernels with rows = B           (:107-109)
+    svfuse3 + max over points                     rows_prep + pool_rows                (:111-112)
+    conv8   binary conv over 2144 channels, 1600 of which are per-cloud constants (the
+            ``repeat(1, 1, num_points)`` of :118): their sign words and popcounts are reduced once per
+            cloud and enter the per-point popcount linear as an integer offset      (:117-121)
+    conv9/10 binary conv + BN + leaky, conv11 fp                                       (:123-126)
+"""
+import torch
+import torch.nn as nn
+
+from . import _native as nv
+from .fused import dgcnn_trunk
+from .sv_layers import Conv1d, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, dense_rows, folded_bn
+
+
+def _get_visible_value(divisor=8):
+    def make_divisible(v):
+        """Round channel counts to a multiple of ``divisor`` without losing more than 10 %
+        (sv_dgcnn_partseg.py:18-32)."""
+        new_v = max(divisor, int(v + divisor / 2) // divisor * divisor)
+        if new_v < 0.9 * v:
+            new_v += divisor
+        return new_v
+    return make_divisible
+
+
+_V = _get_visible_value(8)
+
+
+class _Seq(nn.Sequential, _Cached):
+    """nn.Sequential(conv, BatchNorm1d, act) with a cached folded BN (keys '0', '1' as in the reference)."""
+
+    def bn_folded(self):
+        bn = self[1]
+        return self._packed("fold", (bn.weight, bn.bias, bn.running_mean, bn.running_var), lambda: nv.fold_bn(bn))
+
+
+class SV_DGCNN_PSEG(nn.Module):
+    def __init__(self, args, num_part):
+        super(SV_DGCNN_PSEG, self).__init__()
+        self.args = args
+        self.k = args.k
+        self.binary = args.binary
+        self.dropout = 0 if self.binary else args.dropout
+        self.emb = 1024
+
+        self.init_scalar = Vector2Scalar(2, 3)
+        self.conv1 = SVBlock((6, 2), (_V(64//2), _V(64//6)))
+        self.conv2 = SVBlock((_V(64//2)*2, _V(64//6)*2), (_V(64//2), _V(64//6)), self.binary)
+        self.conv3 = SVBlock((_V(64//2)*2, _V(64//6)*2), (_V(128//2), _V(128//6)), self.binary)
+        self.conv4 = SVBlock((_V(128//2)*2, _V(128//6)*2), (_V(256//2), _V(256//6)), self.binary)
+
+        cs_cat = _V(64//2)*2+_V(128//2)+_V(256//2)
+        cv_cat = _V(64//6)*2+_V(128//6)+_V(256//6)
+        self.svfuse1 = SVFuse(cv_cat, 3, self.binary)
+        self.conv5 = SVBlock((cs_cat, cv_cat), (_V(self.emb//2), _V(self.emb//6)), self.binary)
+        self.conv6 = SVBlock((_V(self.emb//2), _V(self.emb//6)), (_V(self.emb//4), _V(self.emb//12)), self.binary)
+        self.svfuse2 = SVFuse(_V(self.emb//12), 3, self.binary)
+        self.svfuse3 = SVFuse(_V(self.emb//6), 3, self.binary)
+        self.conv7 = _Seq(
+                nn.Conv1d(16, 64, kernel_size=1, bias=False),
+                nn.BatchNorm1d(64),
+                nn.LeakyReLU(negative_slope=0.2))
+        self.conv8 = _Seq(
+                Conv1d(_V(self.emb//2)+_V(self.emb//4)+(_V(self.emb//6)+_V(self.emb//12))*3+64+cs_cat+cv_cat*3, 256, self.binary),
+                nn.BatchNorm1d(256),
+                nn.LeakyReLU(negative_slope=0.2))
+        self.dp1 = nn.Dropout(p=self.dropout)
+        self.conv9 = _Seq(
+                Conv1d(256, 256, self.binary),
+                nn.BatchNorm1d(256),
+                nn.LeakyReLU(negative_slope=0.2))
+        self.dp2 = nn.Dropout(p=self.dropout)
+        self.conv10 = _Seq(
+                Conv1d(256, 128, self.binary),
+                nn.BatchNorm1d(128),
+                nn.LeakyReLU(negative_slope=0.2))
+        self.conv11 = nn.Conv1d(128, num_part, kernel_size=1, bias=False)
+
+    def forward(self, x, l, forced_idx=None, record=None):
+        """x (B,3,N), l (B,16) one-hot -> per-point part logits (B, num_part, N)."""
+        _inference_only(self)
+        B, _, N = x.shape
+        R = B * N
+        dev = x.device
+        s_cat, v_cat = dgcnn_trunk(self, x, forced_idx, record)
+        x_fine, _ = self.svfuse1.forward_rows(s_cat, v_cat)                       # (R, 544)
+        s5, v5 = self.conv5.forward_rows(s_cat, v_cat, B, N)                      # (R,512), (R,3,168)
+        # global branch: svpool over points -> conv6 -> svfuse2
+        C5s, C5v = self.conv5.out_dims
+        sp = torch.empty((B, C5s), dtype=torch.float32, device=dev)
+        vp = torch.empty((B, 3, C5v), dtype=torch.float32, device=dev)
+        nv.pool_rows(s5, C5s, C5s, B, N, want_max=True, want_mean=False, max_out=sp)
+        nv.pool_rows(v5, 3 * C5v, 3 * C5v, B, N, want_max=False, want_mean=True, mean_out=vp)
+        s6, v6 = self.conv6.forward_rows(sp, vp, B, 1)
+        x_pool, _ = self.svfuse2.forward_rows(s6, v6)                             # (B, 520)
+        f3, _ = self.svfuse3.forward_rows(s5, v5)                                 # (R, 1016)
+        C3 = f3.shape[1]
+        glob = torch.empty((B, C3 + x_pool.shape[1] + 64), dtype=torch.float32, device=dev)
+        nv.pool_rows(f3, C3, C3, B, N, want_max=True, max_out=glob, ldo=glob.shape[1])
+        glob[:, C3:C3 + x_pool.shape[1]].copy_(x_pool)
+        lab = dense_rows(self.conv7[0].weight, l.reshape(B, -1).contiguous().float(), bn=self.conv7.bn_folded(),
+                         act=nv.ACT_LEAKY)
+        glob[:, C3 + x_pool.shape[1]:].copy_(lab)
+        # segmentation head on rows; glob is constant per cloud
+        h = self.conv8[0].forward_rows(x_fine, bn=self.conv8.bn_folded(), act=nv.ACT_LEAKY, cloud=glob, rows_per_cloud=N)
+        h = self.conv9[0].forward_rows(h, bn=self.conv9.bn_folded(), act=nv.ACT_LEAKY)
+        h = self.conv10[0].forward_rows(h, bn=self.conv10.bn_folded(), act=nv.ACT_LEAKY)
+        out = dense_rows(self.conv11.weight, h)                                   # (R, num_part)
+        if record is not None:
+            record.update(glob=glob, x_fine=x_fine)
+        return out.view(B, N, -1).transpose(1, 2).contiguous()

@@ -124,15 +124,30 @@ class Conv1d(nn.Conv1d, _Cached):
     def beta_vec(self):
         return self._packed("beta", (self.beta,), lambda: self.beta.detach().reshape(-1).contiguous())
 
-    def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE):
-        rows, K = x2d.shape
+    def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE, cloud=None, rows_per_cloud=1):
+        """x2d (rows, Kp) -> (rows, Cout).  ``cloud`` (B, Kc), if given, holds per-cloud-constant
+        leading input channels (the ``repeat(1, 1, num_points)`` block of sv_dgcnn_partseg.py:118):
+        the layer input is [cloud[row // rows_per_cloud] | x2d[row]] and the constant part of every
+        dot product is reduced once per cloud instead of once per point."""
+        rows, Kp = x2d.shape
         Cout = self.out_channels
+        Kc = cloud.shape[1] if cloud is not None else 0
+        assert Kc + Kp == self.in_channels, (Kc, Kp, self.in_channels)
         if self.binary:
-            bits, mask, nvalid = nv.rows_prep(nv.view_of(x2d, None), rows, beta=self.beta_vec(), want_bits=True)
-            return nv.binlinear_rows(bits, mask, nvalid, K, self.sign_bits(), Cout, scale=self.scale_vec(), bn=bn,
-                                     act=act)
+            beta = self.beta_vec()
+            cdot = None
+            if cloud is not None:
+                cb, cm, cn = nv.rows_prep(nv.view_of(cloud, None), cloud.shape[0], beta=beta[:Kc], want_bits=True)
+                cdot = nv.binlinear_rows(cb, cm, cn, Kc, self.sign_bits(0, Kc), Cout, out_i32=True)
+            bits, mask, nvalid = nv.rows_prep(nv.view_of(x2d, None), rows, beta=beta[Kc:], want_bits=True)
+            return nv.binlinear_rows(bits, mask, nvalid, Kp, self.sign_bits(Kc, Kc + Kp), Cout, scale=self.scale_vec(),
+                                     bn=bn, act=act, cloud_dot=cdot, rows_per_cloud=rows_per_cloud)
+        if cloud is not None:
+            B = cloud.shape[0]
+            x2d = torch.cat([cloud.unsqueeze(1).expand(B, rows_per_cloud, Kc).reshape(rows, Kc), x2d], dim=1)
         out = torch.empty((rows, Cout), dtype=torch.float32, device=x2d.device)
-        nv.linear_rows(x2d, x2d.stride(0), 0, 1, rows, K, self.weight2d(), Cout, out, Cout, 0, bn=bn, act=act)
+        nv.linear_rows(x2d, x2d.stride(0), 0, 1, rows, Kc + Kp, self.weight2d(), Cout, out, Cout, 0,
+                       bias=self.bias.detach() if self.bias is not None else None, bn=bn, act=act)
         return out
 
     def forward(self, x):
@@ -388,3 +403,17 @@ class SV_STNkd(nn.Module):
         x = self.fc3(x) # B, [3,] dim
 
         return x
+
+
+def dense_rows(weight, x2d, bias=None, bn=None, act=nv.ACT_NONE):
+    """Plain fp nn.Linear / kernel-1 nn.Conv1d on rows: x2d (rows, K) -> (rows, Cout)."""
+    W = weight.detach()
+    if W.dim() == 3:
+        W = W[:, :, 0]
+    if W.stride(-1) != 1:
+        W = W.contiguous()
+    rows, K = x2d.shape
+    out = torch.empty((rows, W.shape[0]), dtype=torch.float32, device=x2d.device)
+    nv.linear_rows(x2d, x2d.stride(0), 0, 1, rows, K, W, W.shape[0], out, W.shape[0], 0,
+                   bias=bias.detach() if bias is not None else None, bn=bn, act=act)
+    return out

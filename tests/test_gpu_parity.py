@@ -307,3 +307,64 @@ def test_dgcnn_cls_batch_independence_and_full_size():
     with torch.no_grad():
         yf = net(x[:1].contiguous(), forced_idx=[cu(i, torch.int32) for i in rec["idx"]])
     assert torch.isfinite(yf).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# the other three model families
+# ------------------------------------------------------------------------------------------------
+OTHER_MODELS = [
+    ("dgcnn_pseg_bin", "SV_DGCNN_PSEG", "sv_dgcnn_pseg", True, 4),
+    ("dgcnn_pseg_fp", "SV_DGCNN_PSEG", "sv_dgcnn_pseg", True, 4),
+    ("pointnet_cls_fp", "SV_PointNet_CLS", "sv_pointnet_cls", False, 1),
+    ("pointnet_cls_bin", "SV_PointNet_CLS", "sv_pointnet_cls", False, 1),
+    ("pointnet_pseg_bin", "SV_PointNet_PSEG", "sv_pointnet_pseg", True, 1),
+    ("pointnet_pseg_fp", "SV_PointNet_PSEG", "sv_pointnet_pseg", True, 1),
+]
+
+
+@pytest.mark.parametrize("name,cls,ofn,with_label,nidx", OTHER_MODELS)
+def test_other_models_vs_reference_and_oracle(name, cls, ofn, with_label, nidx):
+    import svnet_b200 as sv
+    g = golden(name)
+    sd = golden_state_dict(g)
+    k, binary = int(g["k"]), bool(g["binary"])
+    net = quiet(getattr(sv, cls), make_args(k=k, binary=binary), int(g["ncls"]))
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    x = cu(g["x"])
+    gidx = [cu(g["idx%d" % i], torch.int32) for i in range(nidx)]
+    args = (x, cu(g["label"])) if with_label else (x,)
+    with torch.no_grad():
+        y = t2n(net(*args, forced_idx=gidx))
+        rec = {}
+        y_free = t2n(net(*args, record=rec))
+    assert y.shape == g["logits"].shape
+    assert_close(y, g["logits"], what=name + " logits (forced kNN) vs reference")
+    assert (y.argmax(1) == g["logits"].argmax(1)).all()
+    oargs = (sd, g["x"], g["label"], k) if with_label else (sd, g["x"], k)
+    yo = getattr(orc, ofn)(*oargs, forced_idx=[g["idx%d" % i] for i in range(nidx)])
+    assert_close(y, yo, what=name + " logits vs oracle")
+    agree = [float((t2n(rec["idx"][i]) == g["idx%d" % i]).all(-1).mean()) for i in range(nidx)]
+    assert min(agree) >= 0.98, agree
+    if min(agree) == 1.0:
+        assert_close(y_free, g["logits"], what=name + " logits (free-running)")
+
+
+def test_checkpoint_container_roundtrip(tmp_path):
+    """The reference saves {'epoch','state_dict' (module.-prefixed),...} (main_cls_dgcnn.py:208-214);
+    the drop-in must load it the way main_cls_dgcnn.py:125,142-144 does (through DataParallel)."""
+    import svnet_b200 as sv
+    from svnet_b200.synthetic import wrap_checkpoint
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=8, binary=True), 40)
+    sd = synthetic_state_dict(net.state_dict(), seed=5)
+    path = str(tmp_path / "sv_dgcnn_binary_modelnet40.pth")
+    torch.save(wrap_checkpoint(sd), path)
+    ckpt = torch.load(path, map_location="cpu")
+    model = torch.nn.DataParallel(net.to(DEV), device_ids=[0])
+    model.load_state_dict(ckpt["state_dict"])
+    model.eval()
+    x = synthetic_clouds(2, 64, 5).to(DEV)
+    with torch.no_grad():
+        y = model(x)
+    ref = orc.sv_dgcnn_cls(sd, t2n(x), 8)
+    assert_close(t2n(y), ref, what="DataParallel-wrapped forward vs oracle")
