@@ -1,0 +1,126 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol the header declares, the
+nn.Module mirror has the reference's state_dict layout, host-side logic (sharding, synthetic
+checkpoints, error behaviour without a GPU)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import golden, quiet
+from svnet_b200.synthetic import (make_args, state_dict_digest, strip_module_prefix, synthetic_clouds,
+                                  synthetic_state_dict, wrap_checkpoint)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_header_symbols():
+    from svnet_b200 import _native as nv
+    lib = nv.lib()
+    header = open(os.path.join(ROOT, "include", "svnet_b200.h")).read()
+    declared = set(re.findall(r"\b(svnet_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libsvnet_b200.so does not export %s" % name
+    assert set(nv.EXPORTS) == declared
+    assert lib.svnet_version() == 1
+
+
+def test_argument_errors_without_gpu():
+    """Shape validation happens before any launch, so it is testable without a device."""
+    import ctypes
+    from svnet_b200 import _native as nv
+    lib = nv.lib()
+    v = nv.View()
+    rc = lib.svnet_knn(ctypes.byref(v), 1, 8, 9, None, None, None)
+    assert rc == -1 and b"out of range" in lib.svnet_last_error()
+    rc = lib.svnet_pool_rows(None, 4, 4, 1, ctypes.c_long(4), None, None, 4, None)
+    assert rc == -1
+    with pytest.raises(RuntimeError):
+        import svnet_b200 as sv
+        sv.knn(torch.zeros(1, 3, 16), 4)  # CPU tensor: no fallback path exists
+
+
+MODEL_FIXTURES = [("dgcnn_cls_bin", "SV_DGCNN_CLS"), ("dgcnn_cls_fp", "SV_DGCNN_CLS"), ("dgcnn_pseg_bin", "SV_DGCNN_PSEG"),
+                  ("dgcnn_pseg_fp", "SV_DGCNN_PSEG"), ("pointnet_cls_bin", "SV_PointNet_CLS"),
+                  ("pointnet_cls_fp", "SV_PointNet_CLS"), ("pointnet_pseg_bin", "SV_PointNet_PSEG"),
+                  ("pointnet_pseg_fp", "SV_PointNet_PSEG")]
+
+
+@pytest.mark.parametrize("fixture,cls", MODEL_FIXTURES)
+def test_state_dict_layout_matches_reference(fixture, cls):
+    import svnet_b200 as sv
+    g = golden(fixture)
+    net = quiet(getattr(sv, cls), make_args(k=int(g["k"]), binary=bool(g["binary"])), int(g["ncls"]))
+    shapes = json.loads(str(g["sd_shapes"]))
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(shapes.keys())  # same keys in the same order as the reference
+    for key, (shape, dtype) in shapes.items():
+        assert list(sd[key].shape) == shape and str(sd[key].dtype) == dtype, key
+    # reference checkpoints are saved from DataParallel ('module.' prefix)
+    ck = wrap_checkpoint(synthetic_state_dict(sd, seed=3))
+    assert all(k.startswith("module.") for k in ck["state_dict"])
+    net.load_state_dict(strip_module_prefix(ck["state_dict"]))
+
+
+def test_synthetic_checkpoint_is_deterministic_and_representative():
+    import svnet_b200 as sv
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=20, binary=True), 40)
+    a = synthetic_state_dict(net.state_dict(), seed=11)
+    b = synthetic_state_dict(net.state_dict(), seed=11)
+    assert state_dict_digest(a) == state_dict_digest(b)
+    assert state_dict_digest(a) != state_dict_digest(synthetic_state_dict(net.state_dict(), seed=12))
+    assert (a["conv2.linear1.beta"] != 0).all() and (a["conv2.bn1.running_var"] > 0).all()
+    z = synthetic_state_dict(net.state_dict(), seed=11, beta_zero=True)
+    assert (z["conv2.linear1.beta"] == 0).all()
+    x = synthetic_clouds(3, 64, 1)
+    assert x.shape == (3, 3, 64) and abs(float(x.transpose(1, 2).norm(dim=2).max()) - 1.0) < 1e-5
+
+
+def test_training_mode_is_rejected():
+    import svnet_b200 as sv
+    blk = quiet(sv.SVBlock, (8, 2), (4, 2), True)
+    with pytest.raises(RuntimeError):
+        blk((torch.zeros(1, 4, 8), torch.zeros(1, 4, 3, 2)))
+
+
+def test_shard_bounds_cover_batch():
+    from svnet_b200.parallel import shard_bounds
+    for batch in (1, 7, 32, 33, 256):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(batch, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, batch, q):
+    import torch.distributed as dist
+    from svnet_b200.parallel import ShardedInference
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    torch.manual_seed(0)
+    x = torch.randn(batch, 3, 16)
+    lab = torch.randn(batch, 4)
+    f = lambda a, b: torch.cat([a.sum(dim=2) * 2.0, b], dim=1)  # per-cloud function, like an eval-mode forward
+    y = ShardedInference(f)(x, lab)
+    q.put((rank, torch.equal(y, f(x, lab))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [8, 5])
+def test_sharded_inference_gloo_world2(batch):
+    """N>1 path on CPU: batch sharding + all-gather reproduce the unsharded result on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + batch) % 500
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in res) == [0, 1] and all(ok for _, ok in res)
