@@ -15,6 +15,9 @@
 //   C. vector branch from the per-point tables P = v W2a^T, Q = v W2b^T:
 //      w = (P_j - P_i) + Q_i; VectorBN; gate; mean over edges.
 #include "common.cuh"
+#include <stdlib.h>
+
+int svnet_edge_fast_dispatch(const svnet_edge_params* p, cudaStream_t st);
 
 namespace {
 
@@ -384,6 +387,14 @@ extern "C" int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream)
     if ((long)p->B * p->N == 0) return SVNET_OK;
     if (p->binary) {
         SV_REQUIRE(p->beta && p->W1b && p->scale1, "svnet_svblock_edge_fwd: binary layer needs beta/W1b/scale1");
+        // shapes of the SV-DGCNN models have compile-time specialisations (edge_fast.cu);
+        // SVNET_EDGE_GENERIC=1 forces the generic kernel (tests cover both)
+        const char* force = getenv("SVNET_EDGE_GENERIC");
+        if (!(force && force[0] == '1')) {
+            const int h = svnet_edge_fast_dispatch(p, sv_stream(stream));
+            if (h < 0) return h;
+            if (h == 1) return SVNET_OK;
+        }
         return launch_edge<true>(p, sv_stream(stream));
     }
     SV_REQUIRE(p->Yab && p->W1q_t, "svnet_svblock_edge_fwd: fp layer needs Yab/W1q_t");

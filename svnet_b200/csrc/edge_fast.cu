@@ -1,0 +1,307 @@
+// K2 (specialised) -- fused binary SV edge convolution with compile-time layer shapes.
+// Same mathematics and bit-level contract as the generic kernel in edge.cu (see the header there and
+// include/svnet_b200.h: svnet_svblock_edge_fwd); the shapes of the SV-DGCNN classifier and
+// part-segmentation edge layers are template parameters so that every per-lane offset, the number of
+// sign words and all inner loops are resolved at compile time (the generic kernel spends 3-5x more
+// instructions on address arithmetic than on the arithmetic itself, profiles/r1_v1_*).
+//
+// One warp per centre point:
+//   P1  per edge: s_j - s_i + beta -> sign/mask words by __ballot_sync straight from registers;
+//       v_j - v_i -> shared memory (needed by the frame chains)
+//   P2  3x3 frames z for all k edges: 9k sequential fmaf chains spread over the lanes
+//   P3  q = v_e . z lane-per-channel -> sign/mask words
+//   P4  XNOR/popcount linear1 (lanes = output channels), BN, LeakyReLU, max over edges
+//   P5  vector branch from the per-point P|Q table, VectorBN, gate, mean over edges
+#include "common.cuh"
+
+namespace {
+
+
+template <int CS, int CV, int COUT, int CVO>
+struct Shape {
+    static constexpr int CVE = 2 * CV;
+    static constexpr int K = 2 * CS + 6 * CV;
+    static constexpr int KW = (K + 31) / 32;
+    static constexpr int TS = CS / 32;                 // s words per half
+    static constexpr int NVE = 3 * CV;                 // vector floats per point
+    static constexpr int TV = (NVE + 31) / 32;
+    static constexpr int QW = KW - 2 * TS;             // words of the q section
+    static constexpr int OPT = COUT / 32;
+    static constexpr int EB = (COUT / 32 >= 4) ? 12 : 20;  // edges accumulated per popcount pass (k padded to a multiple)
+    static constexpr int XS = (CV % 2 == 0) ? CV + 1 : CV;   // odd xyz stride in smem: conflict-free chains
+    static constexpr int ES = 3 * XS;                  // floats per staged edge
+    static_assert(CS % 32 == 0 && COUT % 32 == 0, "scalar widths must be multiples of 32");
+};
+
+template <int CS, int CV, int COUT, int CVO, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_bin_fast_kernel(svnet_edge_params p, int kp)
+{
+    using S = Shape<CS, CV, COUT, CVO>;
+    constexpr int EB = S::EB;
+    extern __shared__ __align__(16) float smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- CTA-shared: Wz [3][CVE], W1b [KW][COUT] ----
+    float* Wz = smem_raw;
+    uint32_t* W1b = reinterpret_cast<uint32_t*>(Wz + 3 * S::CVE + ((3 * S::CVE) & 1));
+    constexpr int SHARED = 3 * S::CVE + ((3 * S::CVE) & 1) + S::KW * COUT;
+    for (int i = threadIdx.x; i < 3 * S::CVE; i += blockDim.x) Wz[i] = p.Wz[i];
+    for (int i = threadIdx.x; i < S::KW * COUT; i += blockDim.x) W1b[i] = p.W1b[i];
+    // ---- per warp ----
+    const int per_warp = ((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3;
+    float* wbase = smem_raw + ((SHARED + 3) & ~3) + (size_t)warp * ((per_warp + 3) & ~3);
+    uint32_t* A = reinterpret_cast<uint32_t*>(wbase);            // [KW][kp]   (16B aligned rows: kp % 4 == 0)
+    uint32_t* M = A + S::KW * kp;                                 // [KW][kp]
+    int* nvalid = reinterpret_cast<int*>(M + S::KW * kp);         // [kp]
+    int* nidx = nvalid + kp;                                      // [kp]
+    float* vc = wbase + ((2 * S::KW * kp + 2 * kp + 3) & ~3);     // [3][XS] centre vectors
+    float* ves = vc + 3 * S::XS;                                  // [kp][3][XS] neighbour - centre
+    float* zb = ves + kp * S::ES;                                 // [kp][9]
+    __syncthreads();
+
+    const long r = (long)blockIdx.x * WARPS + warp;
+    if (r >= (long)p.B * p.N) return;
+    const int b = (int)(r / p.N);
+    const long cbase = (long)b * p.N;
+    const int k = p.k;
+
+    // ---- per-lane constants ----
+    float beta[S::KW];
+#pragma unroll
+    for (int w = 0; w < S::KW; ++w) beta[w] = (32 * w + lane < S::K) ? __ldg(p.beta + 32 * w + lane) : 0.0f;
+    int voff[S::TV], vso[S::TV];
+#pragma unroll
+    for (int t = 0; t < S::TV; ++t) {
+        const int f = 32 * t + lane, x = f / CV, d = f - x * CV;
+        voff[t] = (f < S::NVE) ? x * p.in.xs + d : -1;
+        vso[t] = x * S::XS + d;
+    }
+
+    // ---- P0: centre row ----
+    for (int e = lane; e < kp; e += 32) nidx[e] = e < k ? p.idx[r * k + e] : 0;
+    float si[S::TS], vi[S::TV];
+    const float* srow = p.in.s + r * p.in.lds;
+    const float* vrow = p.in.v + r * p.in.ldv;
+#pragma unroll
+    for (int t = 0; t < S::TS; ++t) si[t] = __ldg(srow + 32 * t + lane);
+#pragma unroll
+    for (int t = 0; t < S::TV; ++t) {
+        vi[t] = voff[t] >= 0 ? __ldg(vrow + voff[t]) : 0.0f;
+        if (voff[t] >= 0) vc[vso[t]] = vi[t];
+    }
+    unsigned cpos[S::TS], cnz[S::TS];
+    int ncen = 0;
+#pragma unroll
+    for (int t = 0; t < S::TS; ++t) {
+        const float u = __fadd_rn(si[t], beta[S::TS + t]);
+        cpos[t] = __ballot_sync(SV_FULL, u > 0.0f);
+        cnz[t] = __ballot_sync(SV_FULL, u != 0.0f);
+        ncen += __popc(cnz[t]);
+    }
+    // zero the padded edge slots (their mask stays 0 so they contribute nothing)
+    for (int i = lane; i < S::KW * kp; i += 32) { A[i] = 0u; M[i] = 0u; }
+    __syncwarp();
+
+    // ---- P1: neighbour rows -> S1 sign words (registers -> ballot) and v differences (smem) ----
+#pragma unroll 4
+    for (int e = 0; e < k; ++e) {
+        const long j = cbase + nidx[e];
+        const float* sj = p.in.s + j * p.in.lds;
+        const float* vj = p.in.v + j * p.in.ldv;
+        float sv[S::TS], vv[S::TV];
+#pragma unroll
+        for (int t = 0; t < S::TS; ++t) sv[t] = __ldg(sj + 32 * t + lane);
+#pragma unroll
+        for (int t = 0; t < S::TV; ++t) vv[t] = voff[t] >= 0 ? __ldg(vj + voff[t]) : 0.0f;
+        int nv = ncen;
+#pragma unroll
+        for (int t = 0; t < S::TS; ++t) {
+            const float u = __fadd_rn(__fsub_rn(sv[t], si[t]), beta[t]);
+            const unsigned pos = __ballot_sync(SV_FULL, u > 0.0f);
+            const unsigned nz = __ballot_sync(SV_FULL, u != 0.0f);
+            nv += __popc(nz);
+            if (lane == 0) {
+                A[t * kp + e] = pos; M[t * kp + e] = nz;
+                A[(S::TS + t) * kp + e] = cpos[t]; M[(S::TS + t) * kp + e] = cnz[t];
+            }
+        }
+        if (lane == 0) nvalid[e] = nv;
+#pragma unroll
+        for (int t = 0; t < S::TV; ++t)
+            if (voff[t] >= 0) ves[e * S::ES + vso[t]] = __fsub_rn(vv[t], vi[t]);
+    }
+    __syncwarp();
+
+    // ---- P2: frames z[e][x][m]: one sequential chain per (edge, x, m), 32 chains per round ----
+    const bool use_zscale = p.zscale != nullptr;
+    for (int task = lane; task < k * 9; task += 32) {
+        const int e = task / 9, xm = task - e * 9, x = xm / 3, m = xm - x * 3;
+        const float* dv = ves + e * S::ES + x * S::XS;
+        const float* cv = vc + x * S::XS;
+        const float* wz = Wz + m * S::CVE;
+        float acc = 0.0f;
+#pragma unroll
+        for (int d = 0; d < CV; ++d) acc = __fmaf_rn(dv[d], wz[d], acc);
+#pragma unroll
+        for (int d = 0; d < CV; ++d) acc = __fmaf_rn(cv[d], wz[CV + d], acc);
+        if (use_zscale) acc = __fmul_rn(acc, __ldg(p.zscale + m));
+        zb[task] = acc;
+    }
+    __syncwarp();
+
+    // ---- P3: q section sign words.  lane -> channel tq = 32t + lane = 3d + m ----
+    {
+        int qoff[S::QW], qstr[S::QW], zoff[S::QW];
+        bool qok[S::QW];
+#pragma unroll
+        for (int t = 0; t < S::QW; ++t) {
+            const int tq = 32 * t + lane, d = tq / 3, m = tq - d * 3;
+            qok[t] = tq < 6 * CV;
+            zoff[t] = m;
+            if (d < CV) { qoff[t] = (int)(ves - wbase) + d; qstr[t] = S::ES; }
+            else { qoff[t] = (int)(vc - wbase) + (qok[t] ? d - CV : 0); qstr[t] = 0; }
+        }
+#pragma unroll 2
+        for (int e = 0; e < k; ++e) {
+            const float* z = zb + e * 9;
+            int nv = 0;
+#pragma unroll
+            for (int t = 0; t < S::QW; ++t) {
+                const float* src = wbase + qoff[t] + e * qstr[t];
+                float q = __fmul_rn(src[0], z[zoff[t]]);
+                q = __fmaf_rn(src[S::XS], z[3 + zoff[t]], q);
+                q = __fmaf_rn(src[2 * S::XS], z[6 + zoff[t]], q);
+                const float u = qok[t] ? __fadd_rn(q, beta[2 * S::TS + t]) : 0.0f;
+                const unsigned pos = __ballot_sync(SV_FULL, u > 0.0f);
+                const unsigned nz = __ballot_sync(SV_FULL, u != 0.0f);
+                nv += __popc(nz);
+                if (lane == 0) { A[(2 * S::TS + t) * kp + e] = pos; M[(2 * S::TS + t) * kp + e] = nz; }
+            }
+            if (lane == 0) nvalid[e] += nv;
+        }
+    }
+    __syncwarp();
+    if (p.dbg_bits) {
+        for (int i = lane; i < k * S::KW; i += 32) {
+            const int e = i / S::KW, w = i - e * S::KW;
+            p.dbg_bits[(r * k + e) * S::KW + w] = A[w * kp + e];
+            if (p.dbg_mask) p.dbg_mask[(r * k + e) * S::KW + w] = M[w * kp + e];
+        }
+    }
+
+    // ---- P4: XNOR/popcount linear1, lanes = output channels ----
+    float smax[S::OPT];
+#pragma unroll
+    for (int oo = 0; oo < S::OPT; ++oo) smax[oo] = -INFINITY;
+    for (int eb = 0; eb < k; eb += EB) {
+        int acc[EB][S::OPT];
+#pragma unroll
+        for (int e = 0; e < EB; ++e)
+#pragma unroll
+            for (int oo = 0; oo < S::OPT; ++oo) acc[e][oo] = 0;
+#pragma unroll
+        for (int wd = 0; wd < S::KW; ++wd) {
+            uint32_t wv[S::OPT];
+#pragma unroll
+            for (int oo = 0; oo < S::OPT; ++oo) wv[oo] = W1b[wd * COUT + lane + 32 * oo];
+            const uint4* Ap = reinterpret_cast<const uint4*>(A + wd * kp + eb);
+            const uint4* Mp = reinterpret_cast<const uint4*>(M + wd * kp + eb);
+#pragma unroll
+            for (int e4 = 0; e4 < EB / 4; ++e4) {
+                const uint4 a4 = Ap[e4], m4 = Mp[e4];
+                const uint32_t av[4] = {a4.x, a4.y, a4.z, a4.w};
+                const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int oo = 0; oo < S::OPT; ++oo) acc[e4 * 4 + u][oo] += __popc((av[u] ^ wv[oo]) & mv[u]);
+            }
+        }
+#pragma unroll
+        for (int oo = 0; oo < S::OPT; ++oo) {
+            const int o = lane + 32 * oo;
+            const float sc = __ldg(p.scale1 + o), a1 = __ldg(p.bn1_a + o), c1 = __ldg(p.bn1_c + o);
+#pragma unroll
+            for (int e = 0; e < EB; ++e) {
+                if (eb + e < k) {
+                    const int dot = nvalid[eb + e] - 2 * acc[e][oo];
+                    float y = __fmul_rn((float)dot, sc);
+                    y = __fadd_rn(__fmul_rn(y, a1), c1);
+                    y = y > 0.0f ? y : __fmul_rn(0.2f, y);
+                    smax[oo] = fmaxf(smax[oo], y);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int oo = 0; oo < S::OPT; ++oo) p.out.s[r * p.out.lds + lane + 32 * oo] = smax[oo];
+
+    // ---- P5: vector branch, lanes = output vector channels ----
+    constexpr int LDP = 2 * CVO;
+    const float inv_k = 1.0f / (float)k;
+    for (int c = lane; c < CVO; c += 32) {
+        const float* pi = p.PQ + r * 3 * LDP + c;
+        const float p_i[3] = {__ldg(pi), __ldg(pi + LDP), __ldg(pi + 2 * LDP)};
+        const float q_i[3] = {__ldg(pi + CVO), __ldg(pi + LDP + CVO), __ldg(pi + 2 * LDP + CVO)};
+        const float a2 = __ldg(p.bn2_a + c), c2 = __ldg(p.bn2_c + c);
+        float sum[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+        for (int e = 0; e < k; ++e) {
+            const float* pj = p.PQ + (cbase + nidx[e]) * 3 * LDP + c;
+            float w[3];
+#pragma unroll
+            for (int x = 0; x < 3; ++x) w[x] = (__ldg(pj + x * LDP) - p_i[x]) + q_i[x];
+            const float n = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]) + 1e-6f;
+            const float t = (n * a2 + c2) / n;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) sum[x] += w[x] * t;
+        }
+        const float g = p.gate[(long)b * CVO + c] * inv_k;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + c] = sum[x] * g;
+    }
+}
+
+template <int CS, int CV, int COUT, int CVO>
+int launch_fast(const svnet_edge_params* p, cudaStream_t st)
+{
+    using S = Shape<CS, CV, COUT, CVO>;
+    constexpr int EB = S::EB;
+    const int kp = ((p->k + EB - 1) / EB) * EB;
+    constexpr int SHARED = 3 * S::CVE + ((3 * S::CVE) & 1) + S::KW * COUT;
+    const int per_warp = ((((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3) + 3) & ~3;
+    const long P = (long)p->B * p->N;
+    auto smem_for = [&](int warps) { return sizeof(float) * (size_t)(((SHARED + 3) & ~3) + warps * per_warp); };
+    if (smem_for(8) <= 72 * 1024) {
+        const size_t smem = smem_for(8);
+        SV_CUDA(cudaFuncSetAttribute(edge_bin_fast_kernel<CS, CV, COUT, CVO, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        edge_bin_fast_kernel<CS, CV, COUT, CVO, 8><<<sv_cdiv(P, 8), 256, smem, st>>>(*p, kp);
+    } else {
+        const size_t smem = smem_for(4);
+        SV_REQUIRE(smem <= 200 * 1024, "svnet_svblock_edge_fwd: k=%d too large for the fused kernel", p->k);
+        SV_CUDA(cudaFuncSetAttribute(edge_bin_fast_kernel<CS, CV, COUT, CVO, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        edge_bin_fast_kernel<CS, CV, COUT, CVO, 4><<<sv_cdiv(P, 4), 128, smem, st>>>(*p, kp);
+    }
+    SV_CHECK_LAUNCH("svnet_svblock_edge_fwd(fast)");
+    return SVNET_OK;
+}
+
+}  // namespace
+
+// Returns 1 if a specialised kernel handled the layer, 0 if the caller must use the generic kernel,
+// < 0 on error.
+int svnet_edge_fast_dispatch(const svnet_edge_params* p, cudaStream_t st)
+{
+    if (!p->binary) return 0;
+    const int cs = p->in.Cs, cv = p->in.Cv, co = p->Cout, cvo = p->Cvo;
+    int rc = 1;
+#define CASE(A, Bv, C, D) if (cs == A && cv == Bv && co == C && cvo == D) { rc = launch_fast<A, Bv, C, D>(p, st); return rc == SVNET_OK ? 1 : rc; }
+    CASE(32, 10, 32, 10)    // SV_DGCNN_CLS conv2
+    CASE(32, 10, 64, 21)    // SV_DGCNN_CLS conv3
+    CASE(64, 21, 128, 42)   // SV_DGCNN_CLS conv4
+    CASE(32, 16, 32, 16)    // SV_DGCNN_PSEG conv2
+    CASE(32, 16, 64, 24)    // SV_DGCNN_PSEG conv3
+    CASE(64, 24, 128, 40)   // SV_DGCNN_PSEG conv4
+#undef CASE
+    return 0;
+}

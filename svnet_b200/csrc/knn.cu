@@ -1,23 +1,32 @@
-// K1 -- kNN graph construction in one kernel: tiled pairwise scores in shared memory + per-row
-// top-k kept in registers of the owning warp.  Replaces sv_util.knn (reference
-// models/utils/sv_util.py:19-25), which materialises a BxNxN matrix and calls torch.topk.
+// K1 -- kNN graph construction in one kernel.  Replaces sv_util.knn (reference
+// models/utils/sv_util.py:19-25), which materialises a BxNxN matrix (bmm + 3 elementwise passes) and
+// calls torch.topk.  Here the score tile lives in registers, candidates that beat the row's current
+// k-th score are queued in shared memory, and the owning warp merges them into a sorted list held in
+// registers (one entry per lane).  Nothing but the (B,N,k) indices is written to HBM.
 //
 // Arithmetic contract (must match oracle/svnet_oracle.c:orc_knn bit for bit):
 //   dot_ij = chain fmaf over channels c ascending, starting from 0
 //   xx_i   = the same chain with both operands f_i
 //   p_ij   = ((-xx_j) - (-2*dot_ij)) - xx_i
 //   order  = larger p first; equal p -> smaller index first
+// (zero-padded channels add fmaf(0,0,acc) == acc, so padding a chunk does not change any bit.)
 #include "common.cuh"
 
 namespace {
 
 constexpr int TI = 64;    // query rows per CTA
-constexpr int TJ = 128;   // candidates per tile
-constexpr int KC = 32;    // channels per smem chunk
+constexpr int TJ = 128;   // candidates per tile (== queue capacity per row: a tile can never overflow it)
 constexpr int NT = 256;   // threads
-constexpr int ROWS_PER_WARP = TI / (NT / 32);  // 8
+constexpr int NW = NT / 32;
+constexpr int ROWS_PER_WARP = TI / NW;  // 8
+constexpr int MERGE_MIN = 7;            // >= this many survivors in a 32-chunk: sort-merge instead of inserting
 
 __device__ __forceinline__ int swz(int c, int r) { return r ^ ((c & 7) << 2); }
+
+__device__ __forceinline__ bool better(float av, int ai, float bv, int bi)
+{
+    return (av > bv) || (av == bv && ai < bi);
+}
 
 template <int R>
 struct TopK {
@@ -28,13 +37,9 @@ struct TopK {
 template <int R>
 __device__ __forceinline__ void topk_insert(TopK<R>& L, float cv, int cj, int lane)
 {
-    // position = number of entries that rank before the candidate
-    int P = 0;
+    int P = 0;  // number of entries that rank before the candidate
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        bool better = (L.v[r] > cv) || (L.v[r] == cv && L.i[r] < cj);
-        P += __popc(__ballot_sync(SV_FULL, better));
-    }
+    for (int r = 0; r < R; ++r) P += __popc(__ballot_sync(SV_FULL, better(L.v[r], L.i[r], cv, cj)));
 #pragma unroll
     for (int r = R - 1; r >= 0; --r) {
         float uv = __shfl_up_sync(SV_FULL, L.v[r], 1);
@@ -50,16 +55,50 @@ __device__ __forceinline__ void topk_insert(TopK<R>& L, float cv, int cj, int la
     }
 }
 
-template <int R>
+// compare-exchange with lane ^ j; keep the better element when `up`
+__device__ __forceinline__ void cex(float& v, int& i, int j, bool keep_better)
+{
+    const float ov = __shfl_xor_sync(SV_FULL, v, j);
+    const int oi = __shfl_xor_sync(SV_FULL, i, j);
+    const bool mine_better = better(v, i, ov, oi);
+    if (mine_better != keep_better) { v = ov; i = oi; }
+}
+
+// R == 1: merge 32 candidates (one per lane, any order) into the sorted list (best at lane 0)
+__device__ __forceinline__ void sort_merge32(TopK<1>& L, float cv, int cj, int lane, int k)
+{
+    // bitonic sort of the candidates, descending (best first)
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            const bool desc = (lane & size) == 0;       // this block is sorted best-first
+            const bool lower = (lane & j) == 0;
+            cex(cv, cj, j, desc == lower);
+        }
+    }
+    // top 32 of the union: list[i] vs candidates reversed -> bitonic sequence, then bitonic merge
+    const float rv = __shfl_sync(SV_FULL, cv, 31 - lane);
+    const int ri = __shfl_sync(SV_FULL, cj, 31 - lane);
+    if (better(rv, ri, L.v[0], L.i[0])) { L.v[0] = rv; L.i[0] = ri; }
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) cex(L.v[0], L.i[0], j, (lane & j) == 0);
+    if (lane >= k) { L.v[0] = -INFINITY; L.i[0] = 0x7fffffff; }
+}
+
+template <int R, int KC>
 __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k, int32_t* __restrict__ idx32,
-                                                 int64_t* __restrict__ idx64)
+                                                    int64_t* __restrict__ idx64)
 {
     extern __shared__ __align__(16) float smem[];
-    float* As = smem;                 // [KC][TI]   swizzled
-    float* Bs = As + KC * TI;         // [KC][TJ]   swizzled
-    float* D = Bs + KC * TJ;          // [TI][TJ]
-    float* xxi = D + TI * TJ;         // [TI]
-    float* xxj = xxi + TI;            // [TJ]
+    float* As = smem;                                   // [KC][TI]   swizzled
+    float* Bs = As + KC * TI;                           // [KC][TJ]   swizzled
+    float* xxi = Bs + KC * TJ;                          // [TI]
+    float* xxj = xxi + TI;                              // [TJ]
+    float* thr = xxj + TJ;                              // [TI] current k-th score per row
+    int* qcnt = reinterpret_cast<int*>(thr + TI);       // [TI]
+    float* qv = reinterpret_cast<float*>(qcnt + TI);    // [TI][TJ]
+    int* qj = reinterpret_cast<int*>(qv + TI * TJ);     // [TI][TJ]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
@@ -73,6 +112,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
     for (int rr = 0; rr < ROWS_PER_WARP; ++rr)
 #pragma unroll
         for (int r = 0; r < R; ++r) { L[rr].v[r] = -INFINITY; L[rr].i[r] = 0x7fffffff; }
+    if (tid < TI) { thr[tid] = -INFINITY; qcnt[tid] = 0; }
 
     const int ntiles = (N + TJ - 1) / TJ;
     for (int jt = 0; jt < ntiles; ++jt) {
@@ -85,31 +125,39 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
         float nrm = 0.0f;  // xx_j for tid < TJ; xx_i for TJ <= tid < TJ+TI (first tile only)
 
         for (int c0 = 0; c0 < C; c0 += KC) {
+            // ---- stage one channel chunk of the query rows and of the candidate rows (lane = channel) ----
+            const float* cptr = nullptr;
+            long cstride = 0;
+            if (lane < KC) {
+                const int c = c0 + lane;
+                if (c < in.Cs) { cptr = in.s + c; cstride = in.lds; }
+                else if (c < C) {
+                    const int cc = c - in.Cs, x = cc / in.Cv, d = cc - x * in.Cv;
+                    cptr = in.v + x * in.xs + d; cstride = in.ldv;
+                }
+            }
             __syncthreads();  // previous chunk fully consumed
-            // load chunk: warp loads one row's KC channels (lane = channel)
-            const int c = c0 + lane;
-            for (int r = warp; r < TI + TJ; r += NT / 32) {
-                float val = 0.0f;
-                if (r < TI) {
-                    int i = i0 + r;
-                    if (c < C && i < N) val = sv_feat(in, base + i, c);
-                    As[lane * TI + swz(lane, r)] = val;
-                } else {
-                    int j = j0 + (r - TI);
-                    if (c < C && j < N) val = sv_feat(in, base + j, c);
-                    Bs[lane * TJ + swz(lane, r - TI)] = val;
+            if (lane < KC) {
+                for (int r = warp; r < TI; r += NW) {
+                    const int i = i0 + r;
+                    As[lane * TI + swz(lane, r)] = (cptr && i < N) ? __ldg(cptr + (base + i) * cstride) : 0.0f;
+                }
+                for (int r = warp; r < TJ; r += NW) {
+                    const int j = j0 + r;
+                    Bs[lane * TJ + swz(lane, r)] = (cptr && j < N) ? __ldg(cptr + (base + j) * cstride) : 0.0f;
                 }
             }
             __syncthreads();
-            const int kc = min(KC, C - c0);
-            // squared norms, sequential chain over channels
+            // squared norms, sequential chain over channels (zero padding is exact)
             if (tid < TJ) {
-                for (int cc = 0; cc < kc; ++cc) { float t = Bs[cc * TJ + swz(cc, tid)]; nrm = __fmaf_rn(t, t, nrm); }
+#pragma unroll
+                for (int cc = 0; cc < KC; ++cc) { const float t = Bs[cc * TJ + swz(cc, tid)]; nrm = __fmaf_rn(t, t, nrm); }
             } else if (jt == 0 && tid < TJ + TI) {
-                for (int cc = 0; cc < kc; ++cc) { float t = As[cc * TI + swz(cc, tid - TJ)]; nrm = __fmaf_rn(t, t, nrm); }
+#pragma unroll
+                for (int cc = 0; cc < KC; ++cc) { const float t = As[cc * TI + swz(cc, tid - TJ)]; nrm = __fmaf_rn(t, t, nrm); }
             }
-#pragma unroll 8
-            for (int cc = 0; cc < kc; ++cc) {
+#pragma unroll
+            for (int cc = 0; cc < KC; ++cc) {
                 const float4 a4 = *reinterpret_cast<const float4*>(&As[cc * TI + swz(cc, ty * 4)]);
                 const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cc * TJ + swz(cc, tx * 4)]);
                 const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cc * TJ + swz(cc, 64 + tx * 4)]);
@@ -124,51 +172,64 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
         if (tid < TJ) xxj[tid] = nrm;
         else if (jt == 0 && tid < TJ + TI) xxi[tid - TJ] = nrm;
         __syncthreads();
-        // scores -> D
+        // ---- scores; candidates that reach the row's current k-th score go to the row's queue ----
+        {
+            float xj[8];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int r = ty * 4 + a;
-            const float xi = xxi[r];
-            float p[8];
+            for (int q = 0; q < 8; ++q) xj[q] = -xxj[(q < 4) ? (tx * 4 + q) : (64 + tx * 4 + (q - 4))];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int cidx = (q < 4) ? (tx * 4 + q) : (64 + tx * 4 + (q - 4));
-                const float inner = -2.0f * acc[a][q];
-                const float t = __fsub_rn(-xxj[cidx], inner);
-                p[q] = __fsub_rn(t, xi);
+            for (int a = 0; a < 4; ++a) {
+                const int r = ty * 4 + a;
+                const float xi = xxi[r];
+                const float tv = thr[r];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int col = (q < 4) ? (tx * 4 + q) : (64 + tx * 4 + (q - 4));
+                    const float inner = -2.0f * acc[a][q];
+                    const float p = __fsub_rn(__fsub_rn(xj[q], inner), xi);
+                    if (p >= tv && j0 + col < N) {
+                        const int slot = atomicAdd(&qcnt[r], 1);
+                        qv[r * TJ + slot] = p;
+                        qj[r * TJ + slot] = j0 + col;
+                    }
+                }
             }
-            *reinterpret_cast<float4*>(&D[r * TJ + tx * 4]) = make_float4(p[0], p[1], p[2], p[3]);
-            *reinterpret_cast<float4*>(&D[r * TJ + 64 + tx * 4]) = make_float4(p[4], p[5], p[6], p[7]);
         }
         __syncthreads();
-        // selection: warp owns rows warp*8 .. warp*8+7
+        // ---- drain: warp owns rows warp*8 .. warp*8+7 ----
 #pragma unroll
         for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
             const int r = warp * ROWS_PER_WARP + rr;
-            if (i0 + r >= N) continue;  // warp-uniform
-#pragma unroll
-            for (int q = 0; q < TJ / 32; ++q) {
-                const int j = j0 + q * 32 + lane;
-                const float p = D[r * TJ + q * 32 + lane];
+            const int cnt = qcnt[r];
+            if (cnt == 0) continue;  // warp-uniform
+            for (int q0 = 0; q0 < cnt; q0 += 32) {
+                const bool have = q0 + lane < cnt;
+                const float p = have ? qv[r * TJ + q0 + lane] : -INFINITY;
+                const int j = have ? qj[r * TJ + q0 + lane] : 0x7fffffff;
                 float wv = __shfl_sync(SV_FULL, L[rr].v[R - 1], (k - 1) & 31);
                 int wi = __shfl_sync(SV_FULL, L[rr].i[R - 1], (k - 1) & 31);
-                bool pass = (j < N) && ((p > wv) || (p == wv && j < wi));
-                unsigned m = __ballot_sync(SV_FULL, pass);
+                unsigned m = __ballot_sync(SV_FULL, have && better(p, j, wv, wi));
+                if (R == 1 && __popc(m) >= MERGE_MIN) {
+                    sort_merge32(reinterpret_cast<TopK<1>&>(L[rr]), p, j, lane, k);
+                    continue;
+                }
                 while (m) {
                     const int src = __ffs(m) - 1;
                     m &= m - 1;
                     const float cv = __shfl_sync(SV_FULL, p, src);
                     const int cj = __shfl_sync(SV_FULL, j, src);
-                    if ((cv > wv) || (cv == wv && cj < wi)) {  // warp-uniform
+                    if (better(cv, cj, wv, wi)) {  // warp-uniform
                         topk_insert<R>(L[rr], cv, cj, lane);
                         wv = __shfl_sync(SV_FULL, L[rr].v[R - 1], (k - 1) & 31);
                         wi = __shfl_sync(SV_FULL, L[rr].i[R - 1], (k - 1) & 31);
                     }
                 }
             }
+            const float wv = __shfl_sync(SV_FULL, L[rr].v[R - 1], (k - 1) & 31);
+            if (lane == 0) { qcnt[r] = 0; thr[r] = wv; }
         }
+        // (the next tile's first __syncthreads orders these writes before the next push phase)
     }
-    // write indices
 #pragma unroll
     for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
         const int i = i0 + warp * ROWS_PER_WARP + rr;
@@ -185,6 +246,17 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
     }
 }
 
+template <int R, int KC>
+int launch_knn(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, cudaStream_t st)
+{
+    const size_t smem = sizeof(float) * (KC * TI + KC * TJ + TI + TJ + TI + TI + 2 * TI * TJ);
+    dim3 grid(sv_cdiv(N, TI), B);
+    SV_CUDA(cudaFuncSetAttribute(knn_kernel<R, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_kernel<R, KC><<<grid, NT, smem, st>>>(*in, N, k, idx32, idx64);
+    SV_CHECK_LAUNCH("svnet_knn");
+    return SVNET_OK;
+}
+
 }  // namespace
 
 extern "C" int svnet_knn(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, void* stream)
@@ -198,20 +270,17 @@ extern "C" int svnet_knn(const svnet_view* in, int B, int N, int k, int32_t* idx
     SV_REQUIRE(in->Cv == 0 || in->v, "svnet_knn: null v");
     SV_REQUIRE(idx32 || idx64, "svnet_knn: no output buffer");
     if (B == 0) return SVNET_OK;
-    const size_t smem = sizeof(float) * (KC * TI + KC * TJ + TI * TJ + TI + TJ);
-    dim3 grid(sv_cdiv(N, TI), B);
     const int R = (k + 31) / 32;
+    const bool small = (in->Cs + 3 * in->Cv) <= 8;
     cudaStream_t st = sv_stream(stream);
-#define LAUNCH(RR)                                                                                          \
-    do {                                                                                                    \
-        SV_CUDA(cudaFuncSetAttribute(knn_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        knn_kernel<RR><<<grid, NT, smem, st>>>(*in, N, k, idx32, idx64);                                    \
-    } while (0)
-    if (R == 1) LAUNCH(1);
-    else if (R == 2) LAUNCH(2);
-    else if (R == 3) LAUNCH(3);
-    else LAUNCH(4);
-#undef LAUNCH
-    SV_CHECK_LAUNCH("svnet_knn");
-    return SVNET_OK;
+    if (small) {
+        if (R == 1) return launch_knn<1, 8>(in, B, N, k, idx32, idx64, st);
+        if (R == 2) return launch_knn<2, 8>(in, B, N, k, idx32, idx64, st);
+        if (R == 3) return launch_knn<3, 8>(in, B, N, k, idx32, idx64, st);
+        return launch_knn<4, 8>(in, B, N, k, idx32, idx64, st);
+    }
+    if (R == 1) return launch_knn<1, 32>(in, B, N, k, idx32, idx64, st);
+    if (R == 2) return launch_knn<2, 32>(in, B, N, k, idx32, idx64, st);
+    if (R == 3) return launch_knn<3, 32>(in, B, N, k, idx32, idx64, st);
+    return launch_knn<4, 32>(in, B, N, k, idx32, idx64, st);
 }
