@@ -222,6 +222,30 @@ typedef struct {
 } svnet_gemm_params;
 int svnet_linear_rows(const svnet_gemm_params* p, void* stream);
 
+/* Classification head, one CTA per cloud: up to three chained layers, each a binarised Linear
+ * (W1b + beta [+ scale]) or an fp Linear (W [Cout][K], sign_w for binary weights / fp activations),
+ * then optional bias, BatchNorm affine and activation (sv_dgcnn_cls.py:76-80, sv_pointnet_cls.py:76-81).
+ * x [B][ldx] (K0 used) -> out [B][ldo]. */
+typedef struct {
+    int Cout;
+    const uint32_t* W1b;  /* [Kw][Cout] sign bits or NULL */
+    const float* beta;    /* [K] (binary) */
+    const float* W;       /* [Cout][K] (fp) */
+    int sign_w;
+    const float* scale;   /* [Cout] or NULL */
+    const float* bias;    /* [Cout] or NULL */
+    const float* bn_a;    /* [Cout] or NULL */
+    const float* bn_c;
+    int act;
+} svnet_head_layer;
+typedef struct {
+    const float* x; int ldx; int K0; int B;
+    int nlayers;
+    svnet_head_layer layer[3];
+    float* out; int ldo;
+} svnet_head_params;
+int svnet_head_fwd(const svnet_head_params* p, void* stream);
+
 /* VectorBN on materialised rows (module-level parity for sv_layers.VectorBN, :86-102):
  * v [rows][3][C] contiguous -> out. */
 int svnet_vector_bn_rows(const float* v, long rows, int C, const float* bn_a, const float* bn_c, float* out,

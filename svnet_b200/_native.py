@@ -21,7 +21,7 @@ EXPORTS = [
     "svnet_version", "svnet_last_error", "svnet_pack_sign", "svnet_fold_bn", "svnet_knn",
     "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
-    "svnet_vector_bn_rows", "svnet_pool_rows",
+    "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd",
 ]
 
 
@@ -51,6 +51,16 @@ class GemmParams(ctypes.Structure):
                 ("bias", c_void_p), ("bn_a", c_void_p), ("bn_c", c_void_p), ("act", c_int), ("vbn", c_int),
                 ("gate", c_void_p), ("groups_per_cloud", c_long), ("C", c_void_p), ("ldc_g", c_long),
                 ("ldc_x", c_int)]
+
+
+class HeadLayer(ctypes.Structure):
+    _fields_ = [("Cout", c_int), ("W1b", c_void_p), ("beta", c_void_p), ("W", c_void_p), ("sign_w", c_int),
+                ("scale", c_void_p), ("bias", c_void_p), ("bn_a", c_void_p), ("bn_c", c_void_p), ("act", c_int)]
+
+
+class HeadParams(ctypes.Structure):
+    _fields_ = [("x", c_void_p), ("ldx", c_int), ("K0", c_int), ("B", c_int), ("nlayers", c_int),
+                ("layer", HeadLayer * 3), ("out", c_void_p), ("ldo", c_int)]
 
 
 def lib():
@@ -289,3 +299,26 @@ def pool_rows(x, ld, C, B, rows, want_max=True, want_mean=False, max_out=None, m
     _call("svnet_pool_rows", _ptr(_dev(x)), c_int(ld), c_int(C), c_int(B), c_long(rows), _ptr(max_out),
                                  _ptr(mean_out), c_int(ldo), _stream())
     return max_out, mean_out
+
+
+def head_fwd(x2d, layers):
+    """layers: list of dicts(Cout, W1b, beta, W, sign_w, scale, bias, bn=(a, c), act) -> (B, Cout_last)."""
+    B, K0 = x2d.shape
+    p = HeadParams()
+    p.x, p.ldx, p.K0, p.B, p.nlayers = _dev(x2d).data_ptr(), x2d.stride(0), K0, B, len(layers)
+    keep = []
+    for i, L in enumerate(layers):
+        hl = p.layer[i]
+        hl.Cout = L["Cout"]
+        for name in ("W1b", "beta", "W", "scale", "bias"):
+            t = L.get(name)
+            keep.append(t)
+            setattr(hl, name, t.data_ptr() if t is not None else 0)
+        bn = L.get("bn")
+        hl.bn_a, hl.bn_c = (bn[0].data_ptr(), bn[1].data_ptr()) if bn is not None else (0, 0)
+        hl.sign_w = 1 if L.get("sign_w") else 0
+        hl.act = L.get("act", ACT_NONE)
+    out = torch.empty((B, layers[-1]["Cout"]), dtype=torch.float32, device=x2d.device)
+    p.out, p.ldo = out.data_ptr(), out.shape[1]
+    _call("svnet_head_fwd", ctypes.byref(p), _stream())
+    return out

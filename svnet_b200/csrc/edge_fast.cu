@@ -16,6 +16,12 @@
 
 namespace {
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 template <int CS, int CV, int COUT, int CVO>
 struct Shape {
@@ -34,7 +40,7 @@ struct Shape {
 };
 
 template <int CS, int CV, int COUT, int CVO, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_bin_fast_kernel(svnet_edge_params p, int kp)
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 3 : 2) : ((COUT <= 64) ? 6 : 4)) edge_bin_fast_kernel(svnet_edge_params p, int kp)
 {
     using S = Shape<CS, CV, COUT, CVO>;
     constexpr int EB = S::EB;
@@ -48,7 +54,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_bin_fas
     for (int i = threadIdx.x; i < 3 * S::CVE; i += blockDim.x) Wz[i] = p.Wz[i];
     for (int i = threadIdx.x; i < S::KW * COUT; i += blockDim.x) W1b[i] = p.W1b[i];
     // ---- per warp ----
-    const int per_warp = ((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3;
+    const int per_warp = ((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3 + kp * CS;
     float* wbase = smem_raw + ((SHARED + 3) & ~3) + (size_t)warp * ((per_warp + 3) & ~3);
     uint32_t* A = reinterpret_cast<uint32_t*>(wbase);            // [KW][kp]   (16B aligned rows: kp % 4 == 0)
     uint32_t* M = A + S::KW * kp;                                 // [KW][kp]
@@ -57,6 +63,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_bin_fas
     float* vc = wbase + ((2 * S::KW * kp + 2 * kp + 3) & ~3);     // [3][XS] centre vectors
     float* ves = vc + 3 * S::XS;                                  // [kp][3][XS] neighbour - centre
     float* zb = ves + kp * S::ES;                                 // [kp][9]
+    float* raws = zb + kp * 9 + 3;                                // [kp][CS] staged neighbour scalars
     __syncthreads();
 
     const long r = (long)blockIdx.x * WARPS + warp;
@@ -102,33 +109,35 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_bin_fas
     for (int i = lane; i < S::KW * kp; i += 32) { A[i] = 0u; M[i] = 0u; }
     __syncwarp();
 
-    // ---- P1: neighbour rows -> S1 sign words (registers -> ballot) and v differences (smem) ----
-#pragma unroll 4
+    // ---- P1: gather all k neighbour rows with cp.async (one latency exposure), then S1 sign words
+    //      (ballot) and v differences in place ----
     for (int e = 0; e < k; ++e) {
         const long j = cbase + nidx[e];
-        const float* sj = p.in.s + j * p.in.lds;
+        const float* sj = p.in.s + j * p.in.lds + lane;
         const float* vj = p.in.v + j * p.in.ldv;
-        float sv[S::TS], vv[S::TV];
 #pragma unroll
-        for (int t = 0; t < S::TS; ++t) sv[t] = __ldg(sj + 32 * t + lane);
+        for (int t = 0; t < S::TS; ++t) cp_async4(raws + e * CS + 32 * t + lane, sj + 32 * t);
 #pragma unroll
-        for (int t = 0; t < S::TV; ++t) vv[t] = voff[t] >= 0 ? __ldg(vj + voff[t]) : 0.0f;
+        for (int t = 0; t < S::TV; ++t)
+            if (voff[t] >= 0) cp_async4(ves + e * S::ES + vso[t], vj + voff[t]);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+#pragma unroll 2
+    for (int e = 0; e < k; ++e) {
         int nv = ncen;
 #pragma unroll
         for (int t = 0; t < S::TS; ++t) {
-            const float u = __fadd_rn(__fsub_rn(sv[t], si[t]), beta[t]);
+            const float u = __fadd_rn(__fsub_rn(raws[e * CS + 32 * t + lane], si[t]), beta[t]);
             const unsigned pos = __ballot_sync(SV_FULL, u > 0.0f);
             const unsigned nz = __ballot_sync(SV_FULL, u != 0.0f);
             nv += __popc(nz);
-            if (lane == 0) {
-                A[t * kp + e] = pos; M[t * kp + e] = nz;
-                A[(S::TS + t) * kp + e] = cpos[t]; M[(S::TS + t) * kp + e] = cnz[t];
-            }
+            if (lane == 0) { A[t * kp + e] = pos; M[t * kp + e] = nz; }
         }
         if (lane == 0) nvalid[e] = nv;
 #pragma unroll
         for (int t = 0; t < S::TV; ++t)
-            if (voff[t] >= 0) ves[e * S::ES + vso[t]] = __fsub_rn(vv[t], vi[t]);
+            if (voff[t] >= 0) ves[e * S::ES + vso[t]] = __fsub_rn(ves[e * S::ES + vso[t]], vi[t]);
     }
     __syncwarp();
 
@@ -184,8 +193,12 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_bin_fas
     if (p.dbg_bits) {
         for (int i = lane; i < k * S::KW; i += 32) {
             const int e = i / S::KW, w = i - e * S::KW;
-            p.dbg_bits[(r * k + e) * S::KW + w] = A[w * kp + e];
-            if (p.dbg_mask) p.dbg_mask[(r * k + e) * S::KW + w] = M[w * kp + e];
+            unsigned aw = A[w * kp + e], mw = M[w * kp + e];
+#pragma unroll
+            for (int t = 0; t < S::TS; ++t)
+                if (w == S::TS + t) { aw = cpos[t]; mw = cnz[t]; }
+            p.dbg_bits[(r * k + e) * S::KW + w] = aw;
+            if (p.dbg_mask) p.dbg_mask[(r * k + e) * S::KW + w] = mw;
         }
     }
 
@@ -201,6 +214,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_bin_fas
             for (int oo = 0; oo < S::OPT; ++oo) acc[e][oo] = 0;
 #pragma unroll
         for (int wd = 0; wd < S::KW; ++wd) {
+            if (wd >= S::TS && wd < 2 * S::TS) continue;  // centre words: same for every edge, added below
             uint32_t wv[S::OPT];
 #pragma unroll
             for (int oo = 0; oo < S::OPT; ++oo) wv[oo] = W1b[wd * COUT + lane + 32 * oo];
@@ -221,10 +235,13 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_bin_fas
         for (int oo = 0; oo < S::OPT; ++oo) {
             const int o = lane + 32 * oo;
             const float sc = __ldg(p.scale1 + o), a1 = __ldg(p.bn1_a + o), c1 = __ldg(p.bn1_c + o);
+            int cmis = 0;  // mismatches of the centre words (identical for all edges of this point)
+#pragma unroll
+            for (int t = 0; t < S::TS; ++t) cmis += __popc((cpos[t] ^ W1b[(S::TS + t) * COUT + o]) & cnz[t]);
 #pragma unroll
             for (int e = 0; e < EB; ++e) {
                 if (eb + e < k) {
-                    const int dot = nvalid[eb + e] - 2 * acc[e][oo];
+                    const int dot = nvalid[eb + e] - 2 * (acc[e][oo] + cmis);
                     float y = __fmul_rn((float)dot, sc);
                     y = __fadd_rn(__fmul_rn(y, a1), c1);
                     y = y > 0.0f ? y : __fmul_rn(0.2f, y);
@@ -245,7 +262,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_bin_fas
         const float q_i[3] = {__ldg(pi + CVO), __ldg(pi + LDP + CVO), __ldg(pi + 2 * LDP + CVO)};
         const float a2 = __ldg(p.bn2_a + c), c2 = __ldg(p.bn2_c + c);
         float sum[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll 4
+#pragma unroll 10
         for (int e = 0; e < k; ++e) {
             const float* pj = p.PQ + (cbase + nidx[e]) * 3 * LDP + c;
             float w[3];
@@ -269,7 +286,7 @@ int launch_fast(const svnet_edge_params* p, cudaStream_t st)
     constexpr int EB = S::EB;
     const int kp = ((p->k + EB - 1) / EB) * EB;
     constexpr int SHARED = 3 * S::CVE + ((3 * S::CVE) & 1) + S::KW * COUT;
-    const int per_warp = ((((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3) + 3) & ~3;
+    const int per_warp = ((((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3 + kp * CS) + 3) & ~3;
     const long P = (long)p->B * p->N;
     auto smem_for = [&](int warps) { return sizeof(float) * (size_t)(((SHARED + 3) & ~3) + warps * per_warp); };
     if (smem_for(8) <= 72 * 1024) {

@@ -23,67 +23,94 @@ constexpr int MERGE_MIN = 7;            // >= this many survivors in a 32-chunk:
 
 __device__ __forceinline__ int swz(int c, int r) { return r ^ ((c & 7) << 2); }
 
-__device__ __forceinline__ bool better(float av, int ai, float bv, int bi)
+// Ordering keys: (score desc, index asc) as one unsigned 64-bit compare.
+//   hi = order-preserving map of the fp32 score (-0 is folded into +0 first, so that float equality
+//        and key equality agree), lo = ~index (smaller index -> larger key).  Empty slots are key 0,
+//        which ranks below every real candidate (even -inf).
+typedef unsigned long long key_t;
+
+__device__ __forceinline__ key_t make_key(float p, int j)
 {
-    return (av > bv) || (av == bv && ai < bi);
+    const unsigned f = __float_as_uint(p + 0.0f);
+    const unsigned hi = (f & 0x80000000u) ? ~f : (f | 0x80000000u);
+    return ((key_t)hi << 32) | (unsigned)(~j);
+}
+__device__ __forceinline__ float key_score(key_t k)
+{
+    const unsigned hi = (unsigned)(k >> 32);
+    if (hi == 0u) return -INFINITY;
+    return __uint_as_float((hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi);
+}
+__device__ __forceinline__ int key_index(key_t k) { return (int)(~(unsigned)k); }
+
+__device__ __forceinline__ key_t shfl_key(key_t k, int src)
+{
+    const unsigned lo = __shfl_sync(SV_FULL, (unsigned)k, src);
+    const unsigned hi = __shfl_sync(SV_FULL, (unsigned)(k >> 32), src);
+    return ((key_t)hi << 32) | lo;
+}
+__device__ __forceinline__ key_t shfl_up_key(key_t k)
+{
+    const unsigned lo = __shfl_up_sync(SV_FULL, (unsigned)k, 1);
+    const unsigned hi = __shfl_up_sync(SV_FULL, (unsigned)(k >> 32), 1);
+    return ((key_t)hi << 32) | lo;
+}
+__device__ __forceinline__ key_t shfl_xor_key(key_t k, int m)
+{
+    const unsigned lo = __shfl_xor_sync(SV_FULL, (unsigned)k, m);
+    const unsigned hi = __shfl_xor_sync(SV_FULL, (unsigned)(k >> 32), m);
+    return ((key_t)hi << 32) | lo;
 }
 
 template <int R>
 struct TopK {
-    float v[R];
-    int i[R];
+    key_t k[R];   // sorted, best (largest key) at position 0; position = r*32 + lane
 };
 
 template <int R>
-__device__ __forceinline__ void topk_insert(TopK<R>& L, float cv, int cj, int lane)
+__device__ __forceinline__ void topk_insert(TopK<R>& L, key_t c, int lane)
 {
     int P = 0;  // number of entries that rank before the candidate
 #pragma unroll
-    for (int r = 0; r < R; ++r) P += __popc(__ballot_sync(SV_FULL, better(L.v[r], L.i[r], cv, cj)));
+    for (int r = 0; r < R; ++r) P += __popc(__ballot_sync(SV_FULL, L.k[r] > c));
 #pragma unroll
     for (int r = R - 1; r >= 0; --r) {
-        float uv = __shfl_up_sync(SV_FULL, L.v[r], 1);
-        int ui = __shfl_up_sync(SV_FULL, L.i[r], 1);
+        key_t up = shfl_up_key(L.k[r]);
         if (r > 0) {
-            float pv = __shfl_sync(SV_FULL, L.v[r - 1], 31);
-            int pi = __shfl_sync(SV_FULL, L.i[r - 1], 31);
-            if (lane == 0) { uv = pv; ui = pi; }
+            const key_t prev = shfl_key(L.k[r - 1], 31);
+            if (lane == 0) up = prev;
         }
-        int pos = r * 32 + lane;
-        if (pos > P) { L.v[r] = uv; L.i[r] = ui; }
-        else if (pos == P) { L.v[r] = cv; L.i[r] = cj; }
+        const int pos = r * 32 + lane;
+        if (pos > P) L.k[r] = up;
+        else if (pos == P) L.k[r] = c;
     }
 }
 
-// compare-exchange with lane ^ j; keep the better element when `up`
-__device__ __forceinline__ void cex(float& v, int& i, int j, bool keep_better)
+// compare-exchange with lane ^ j
+__device__ __forceinline__ void cex(key_t& k, int j, bool keep_better)
 {
-    const float ov = __shfl_xor_sync(SV_FULL, v, j);
-    const int oi = __shfl_xor_sync(SV_FULL, i, j);
-    const bool mine_better = better(v, i, ov, oi);
-    if (mine_better != keep_better) { v = ov; i = oi; }
+    const key_t o = shfl_xor_key(k, j);
+    if ((k > o) != keep_better) k = o;
 }
 
 // R == 1: merge 32 candidates (one per lane, any order) into the sorted list (best at lane 0)
-__device__ __forceinline__ void sort_merge32(TopK<1>& L, float cv, int cj, int lane, int k)
+__device__ __forceinline__ void sort_merge32(TopK<1>& L, key_t c, int lane, int k)
 {
-    // bitonic sort of the candidates, descending (best first)
 #pragma unroll
     for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
         for (int j = size >> 1; j > 0; j >>= 1) {
             const bool desc = (lane & size) == 0;       // this block is sorted best-first
             const bool lower = (lane & j) == 0;
-            cex(cv, cj, j, desc == lower);
+            cex(c, j, desc == lower);
         }
     }
     // top 32 of the union: list[i] vs candidates reversed -> bitonic sequence, then bitonic merge
-    const float rv = __shfl_sync(SV_FULL, cv, 31 - lane);
-    const int ri = __shfl_sync(SV_FULL, cj, 31 - lane);
-    if (better(rv, ri, L.v[0], L.i[0])) { L.v[0] = rv; L.i[0] = ri; }
+    const key_t rv = shfl_key(c, 31 - lane);
+    if (rv > L.k[0]) L.k[0] = rv;
 #pragma unroll
-    for (int j = 16; j > 0; j >>= 1) cex(L.v[0], L.i[0], j, (lane & j) == 0);
-    if (lane >= k) { L.v[0] = -INFINITY; L.i[0] = 0x7fffffff; }
+    for (int j = 16; j > 0; j >>= 1) cex(L.k[0], j, (lane & j) == 0);
+    if (lane >= k) L.k[0] = 0ull;
 }
 
 template <int R, int KC>
@@ -111,7 +138,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
 #pragma unroll
     for (int rr = 0; rr < ROWS_PER_WARP; ++rr)
 #pragma unroll
-        for (int r = 0; r < R; ++r) { L[rr].v[r] = -INFINITY; L[rr].i[r] = 0x7fffffff; }
+        for (int r = 0; r < R; ++r) L[rr].k[r] = 0ull;
     if (tid < TI) { thr[tid] = -INFINITY; qcnt[tid] = 0; }
 
     const int ntiles = (N + TJ - 1) / TJ;
@@ -138,14 +165,15 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
             }
             __syncthreads();  // previous chunk fully consumed
             if (lane < KC) {
-                for (int r = warp; r < TI; r += NW) {
-                    const int i = i0 + r;
-                    As[lane * TI + swz(lane, r)] = (cptr && i < N) ? __ldg(cptr + (base + i) * cstride) : 0.0f;
-                }
-                for (int r = warp; r < TJ; r += NW) {
-                    const int j = j0 + r;
-                    Bs[lane * TJ + swz(lane, r)] = (cptr && j < N) ? __ldg(cptr + (base + j) * cstride) : 0.0f;
-                }
+                const long step = (long)NW * cstride;
+                const float* pa = cptr + (base + i0 + warp) * cstride;
+#pragma unroll 4
+                for (int r = warp; r < TI; r += NW, pa += step)
+                    As[lane * TI + swz(lane, r)] = (cptr && i0 + r < N) ? __ldg(pa) : 0.0f;
+                const float* pb = cptr + (base + j0 + warp) * cstride;
+#pragma unroll 4
+                for (int r = warp; r < TJ; r += NW, pb += step)
+                    Bs[lane * TJ + swz(lane, r)] = (cptr && j0 + r < N) ? __ldg(pb) : 0.0f;
             }
             __syncthreads();
             // squared norms, sequential chain over channels (zero padding is exact)
@@ -204,29 +232,25 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
             if (cnt == 0) continue;  // warp-uniform
             for (int q0 = 0; q0 < cnt; q0 += 32) {
                 const bool have = q0 + lane < cnt;
-                const float p = have ? qv[r * TJ + q0 + lane] : -INFINITY;
-                const int j = have ? qj[r * TJ + q0 + lane] : 0x7fffffff;
-                float wv = __shfl_sync(SV_FULL, L[rr].v[R - 1], (k - 1) & 31);
-                int wi = __shfl_sync(SV_FULL, L[rr].i[R - 1], (k - 1) & 31);
-                unsigned m = __ballot_sync(SV_FULL, have && better(p, j, wv, wi));
+                const key_t c = have ? make_key(qv[r * TJ + q0 + lane], qj[r * TJ + q0 + lane]) : 0ull;
+                key_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
+                unsigned m = __ballot_sync(SV_FULL, c > worst);
                 if (R == 1 && __popc(m) >= MERGE_MIN) {
-                    sort_merge32(reinterpret_cast<TopK<1>&>(L[rr]), p, j, lane, k);
+                    sort_merge32(reinterpret_cast<TopK<1>&>(L[rr]), c, lane, k);
                     continue;
                 }
                 while (m) {
                     const int src = __ffs(m) - 1;
                     m &= m - 1;
-                    const float cv = __shfl_sync(SV_FULL, p, src);
-                    const int cj = __shfl_sync(SV_FULL, j, src);
-                    if (better(cv, cj, wv, wi)) {  // warp-uniform
-                        topk_insert<R>(L[rr], cv, cj, lane);
-                        wv = __shfl_sync(SV_FULL, L[rr].v[R - 1], (k - 1) & 31);
-                        wi = __shfl_sync(SV_FULL, L[rr].i[R - 1], (k - 1) & 31);
+                    const key_t cc = shfl_key(c, src);
+                    if (cc > worst) {  // warp-uniform
+                        topk_insert<R>(L[rr], cc, lane);
+                        worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
                     }
                 }
             }
-            const float wv = __shfl_sync(SV_FULL, L[rr].v[R - 1], (k - 1) & 31);
-            if (lane == 0) { qcnt[r] = 0; thr[r] = wv; }
+            const key_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
+            if (lane == 0) { qcnt[r] = 0; thr[r] = key_score(worst); }
         }
         // (the next tile's first __syncthreads orders these writes before the next push phase)
     }
@@ -239,8 +263,8 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
             const int pos = r * 32 + lane;
             if (pos < k) {
                 const long o = (base + i) * k + pos;
-                if (idx32) idx32[o] = L[rr].i[r];
-                if (idx64) idx64[o] = (int64_t)L[rr].i[r];
+                if (idx32) idx32[o] = key_index(L[rr].k[r]);
+                if (idx64) idx64[o] = (int64_t)key_index(L[rr].k[r]);
             }
         }
     }

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from . import _native as nv
 from .fused import dgcnn_trunk
-from .sv_layers import Linear, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, folded_bn
+from .sv_layers import Linear, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, folded_bn, head_layer
 
 
 class SV_DGCNN_CLS(nn.Module, _Cached):
@@ -58,12 +58,10 @@ class SV_DGCNN_CLS(nn.Module, _Cached):
         Cf = fused.shape[1]
         g = torch.empty((B, 2 * Cf), dtype=torch.float32, device=dev)
         nv.pool_rows(fused, Cf, Cf, B, N, want_max=True, want_mean=True, max_out=g, mean_out=g[:, Cf:], ldo=2 * Cf)
-        # head
-        h = self.linear1.forward_rows(g, bn=folded_bn(self, "bn1"), act=nv.ACT_LEAKY)
-        h2 = self.linear2.forward_rows(h, bn=folded_bn(self, "bn2"), act=nv.ACT_LEAKY)
-        out = torch.empty((B, self.linear3.out_features), dtype=torch.float32, device=dev)
-        nv.linear_rows(h2, h2.stride(0), 0, 1, B, h2.shape[1], self.linear3.weight.detach(), out.shape[1], out,
-                       out.shape[1], 0, bias=self.linear3.bias.detach())
+        # head: three chained layers in one kernel, one CTA per cloud
+        out = nv.head_fwd(g, [head_layer(self.linear1, folded_bn(self, "bn1"), nv.ACT_LEAKY),
+                              head_layer(self.linear2, folded_bn(self, "bn2"), nv.ACT_LEAKY),
+                              head_layer(self.linear3)])
         if record is not None:
-            record.update(fused=fused, glob=g, h1=h, h2=h2)
+            record.update(fused=fused, glob=g)
         return out

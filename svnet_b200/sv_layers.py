@@ -417,3 +417,17 @@ def dense_rows(weight, x2d, bias=None, bn=None, act=nv.ACT_NONE):
     nv.linear_rows(x2d, x2d.stride(0), 0, 1, rows, K, W, W.shape[0], out, W.shape[0], 0,
                    bias=bias.detach() if bias is not None else None, bn=bn, act=act)
     return out
+
+
+def head_layer(lin, bn=None, act=nv.ACT_NONE):
+    """Descriptor of one layer of the fused classification head (svnet_head_fwd) from an
+    sv_layers.Linear (any bw/ba combination the reference uses) or a plain nn.Linear."""
+    d = {"Cout": lin.out_features, "bn": bn, "act": act,
+         "bias": lin.bias.detach() if lin.bias is not None else None}
+    if getattr(lin, "ba", False):
+        d.update(W1b=lin.sign_bits(), beta=lin.beta_vec(), scale=lin.scale_vec())
+    elif getattr(lin, "bw", False):
+        d.update(W=lin.weight.detach(), sign_w=True, scale=lin.scale_vec())
+    else:
+        d.update(W=lin.weight.detach())
+    return d

@@ -7,7 +7,8 @@ import torch.nn as nn
 
 from . import _native as nv
 from .fused import first_edge_layer
-from .sv_layers import Linear, SV_STNkd, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, dense_rows, folded_bn
+from .sv_layers import (Linear, SV_STNkd, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, dense_rows,
+                        folded_bn, head_layer)
 
 
 def _bcast_rows(dst, src, N):
@@ -115,6 +116,7 @@ class SV_PointNet_CLS(nn.Module, _Cached):
     def forward(self, x, forced_idx=None, record=None):
         _inference_only(self)
         f = self.feat(x, forced_idx=forced_idx, record=record)
-        h = self.fc1.forward_rows(f, bn=folded_bn(self, "bn1"), act=nv.ACT_RELU)
-        h = self.fc2.forward_rows(h, bn=folded_bn(self, "bn2"), act=nv.ACT_RELU)   # dropout = identity in eval
-        return dense_rows(self.fc3.weight, h, bias=self.fc3.bias)
+        # dropout is the identity in eval; ReLU (not LeakyReLU) in this head (:78-79)
+        return nv.head_fwd(f, [head_layer(self.fc1, folded_bn(self, "bn1"), nv.ACT_RELU),
+                               head_layer(self.fc2, folded_bn(self, "bn2"), nv.ACT_RELU),
+                               head_layer(self.fc3)])
