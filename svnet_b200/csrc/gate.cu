@@ -8,6 +8,8 @@
 //                  the kNN indices are read
 //   xyz variant  : the rows are init_scalar([x_j - x_i | x_i (| x_j x x_i)]) of the first layer
 #include "common.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -67,6 +69,53 @@ __global__ void __launch_bounds__(NT) gate_rows_kernel(const float* __restrict__
         __syncthreads();
     }
     gate_mlp(mean, Cs, G1, G2, H, Co, h, gate + (long)b * Co);
+}
+
+// Cluster variant for many rows per cloud (conv5: N rows x 256 channels): a thread-block cluster of
+// CL CTAs per cloud splits the rows, partial column sums meet in distributed shared memory and rank
+// 0 finishes (fixed summation order -> deterministic).  smem: psum[Cs] | mean[Cs] | h[H] | part[8][32]
+constexpr int CL = 8;
+__global__ void __launch_bounds__(NT) gate_rows_cluster_kernel(const float* __restrict__ s, int lds, int Cs, long rows,
+                                                               const float* __restrict__ G1,
+                                                               const float* __restrict__ G2, int H, int Co,
+                                                               float* __restrict__ gate)
+{
+    extern __shared__ float sm[];
+    float* psum = sm;
+    float* mean = psum + Cs;
+    float* h = mean + Cs;
+    float* part = h + H;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    const int b = blockIdx.x / CL;
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const long r_lo = rows * rank / CL, r_hi = rows * (rank + 1) / CL;
+    const float* p = s + (long)b * rows * lds;
+    for (int c0 = 0; c0 < Cs; c0 += 32) {
+        const int c = c0 + lane;
+        float acc = 0.0f;
+        if (c < Cs)
+            for (long r = r_lo + rg; r < r_hi; r += 8) acc += p[r * lds + c];
+        part[rg * 32 + lane] = acc;
+        __syncthreads();
+        if (rg == 0 && c < Cs) {
+            float t = part[lane];
+            for (int g = 1; g < 8; ++g) t += part[g * 32 + lane];
+            psum[c] = t;
+        }
+        __syncthreads();
+    }
+    cluster.sync();
+    if (rank == 0) {
+        for (int c = threadIdx.x; c < Cs; c += NT) {
+            float t = 0.0f;
+            for (unsigned q = 0; q < CL; ++q) t += cluster.map_shared_rank(psum, q)[c];
+            mean[c] = t / (float)rows;
+        }
+        __syncthreads();
+    }
+    cluster.sync();   // remote psum must stay alive until rank 0 has read it
+    if (rank == 0) gate_mlp(mean, Cs, G1, G2, H, Co, h, gate + (long)b * Co);
 }
 
 // smem: mean[2Cs] | h[H] | part[2][8][32] | indeg[N]
@@ -187,6 +236,24 @@ extern "C" int svnet_gate_rows(const float* s, int lds, int Cs, int B, int rows,
     SV_REQUIRE(s && G1 && G2 && gate, "svnet_gate_rows: null pointer");
     SV_REQUIRE(Cs >= 1 && lds >= Cs && rows >= 1 && H >= 1 && Co >= 1 && B >= 0, "svnet_gate_rows: bad shape");
     if (B == 0) return SVNET_OK;
+    if (rows >= 512) {
+        const size_t smem_c = sizeof(float) * ((size_t)2 * Cs + H + 256);
+        SV_REQUIRE(smem_c <= 200 * 1024, "svnet_gate_rows: Cs=%d too large", Cs);
+        if (smem_c > 48 * 1024)
+            SV_CUDA(cudaFuncSetAttribute(gate_rows_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(B * CL);
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = smem_c;
+        cfg.stream = sv_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        SV_CUDA(cudaLaunchKernelEx(&cfg, gate_rows_cluster_kernel, s, lds, Cs, (long)rows, G1, G2, H, Co, gate));
+        SV_CHECK_LAUNCH("svnet_gate_rows(cluster)");
+        return SVNET_OK;
+    }
     const size_t smem = sizeof(float) * ((size_t)Cs + H + 256);
     SV_REQUIRE(smem <= 200 * 1024, "svnet_gate_rows: Cs=%d too large", Cs);
     if (smem > 48 * 1024)

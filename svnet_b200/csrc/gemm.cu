@@ -35,7 +35,13 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(svnet_gemm_params p)
             const long m = m0 + mm;
             const int k = k0 + kk;
             float v = 0.0f;
-            if (m < p.M && k < p.K) v = __ldg(p.A + (m / p.G) * p.lda_g + (m % p.G) * (long)p.lda_x + k);
+            if (m < p.M && k < p.K) {
+                long off;
+                if (p.G == 1) off = m * p.lda_g;
+                else if (p.G == 3) { const unsigned g = (unsigned)m / 3u; off = (long)g * p.lda_g + (long)((unsigned)m - 3u * g) * p.lda_x; }
+                else off = (m / p.G) * p.lda_g + (m % p.G) * (long)p.lda_x;
+                v = __ldg(p.A + off + k);
+            }
             As[kk][swz(kk, mm)] = v;
         }
         for (int i = tid; i < BN_ * BK; i += 256) {
@@ -93,7 +99,11 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(svnet_gemm_params p)
     for (int a = 0; a < TM; ++a) {
         const long m = m0 + ty * TM + a;
         if (m >= p.M) continue;
-        float* crow = p.C + (m / p.G) * p.ldc_g + (m % p.G) * (long)p.ldc_x;
+        long coff;
+        if (p.G == 1) coff = m * p.ldc_g;
+        else if (p.G == 3) { const unsigned g = (unsigned)m / 3u; coff = (long)g * p.ldc_g + (long)((unsigned)m - 3u * g) * p.ldc_x; }
+        else coff = (m / p.G) * p.ldc_g + (m % p.G) * (long)p.ldc_x;
+        float* crow = p.C + coff;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int n = n0 + tx * 4 + c;
@@ -114,6 +124,7 @@ extern "C" int svnet_linear_rows(const svnet_gemm_params* p, void* stream)
     SV_REQUIRE(p, "svnet_linear_rows: null params");
     SV_REQUIRE(p->A && p->W && p->C, "svnet_linear_rows: null pointer");
     SV_REQUIRE(p->M >= 0 && p->N >= 1 && p->K >= 1 && p->G >= 1 && p->ldw >= p->K, "svnet_linear_rows: bad shape");
+    SV_REQUIRE(p->M < (1L << 31), "svnet_linear_rows: M too large");
     SV_REQUIRE((p->bn_a == nullptr) == (p->bn_c == nullptr), "svnet_linear_rows: bn_a/bn_c must come together");
     if (p->vbn) {
         SV_REQUIRE(p->G == 3 && p->M % 3 == 0 && p->bn_a, "svnet_linear_rows: vbn needs G == 3, M %% 3 == 0 and bn");
