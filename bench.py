@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -122,7 +122,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count()
-    n = 4
+    v0, _ = cpu_port_throughput(4)
+    n = int(min(64, max(4, round(2.0 * v0 / 4) * 4)))   # ~2 s of CPU work per step
     per_step = []
     for i in range(args.warmup + args.steps):
         v, dt = cpu_port_throughput(n)
@@ -148,7 +149,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -212,13 +213,20 @@ def main():
         return float(t.item()) / steps
 
     with torch.no_grad():
-        for _ in range(args.warmup):
-            step(x_dev)
-        barrier()
-        # ---- device-resident throughput; the dominant kernels are bracketed with events live ----
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for _ in range(args.warmup):
+            step(x_dev)
+        barrier()
+        if rank == 0:
+            t_wait = time.time()
+            while not sampler.rows and time.time() - t_wait < 3.0:   # nvidia-smi start-up (no collective here)
+                net(x_dev)
+            torch.cuda.synchronize()
+            sampler.rows.clear()
+        barrier()
+        # ---- device-resident throughput; the dominant kernels are bracketed with events live ----
         nv.PROFILE[0] = {"svnet_knn", "svnet_svblock_edge_fwd"}
         nv.TIMED.clear()
         nv.ORDER.clear()
@@ -263,8 +271,13 @@ def main():
     cand += [("svnet_svblock_edge_fwd[layer%d]" % (i + 2), edge_ms[i], edge_kernel_bytes_per_cloud(i + 1) * B) for i in range(3)]
     dom = max(cand, key=lambda c: c[1])
     achieved = dom[2] / (dom[1] * 1e-3) / 1e9
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dom[0])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": dom[1], "algorithmic_bytes_per_launch": dom[2],
                 "step_share": {c[0]: c[1] / ms for c in cand},
                 "whole_step": {"algorithmic_bytes": algorithmic_bytes_per_cloud() * B,
@@ -273,9 +286,11 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, dt = cpu_port_throughput(4)
+        v, dt = cpu_port_throughput(4)                      # probe, then a sample worth ~15 s of CPU work
+        n_cpu = int(min(256, max(4, round(15.0 * v / 4) * 4)))
+        v, dt = cpu_port_throughput(n_cpu)
         cpu = {"value": v, "unit": "clouds/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "4 clouds of the same workload (N=1024, k=20), oracle C port with OpenMP, %.1f s" % dt}
+               "sample": "%d clouds of the same workload (N=1024, k=20), oracle C port with OpenMP, %.1f s" % (n_cpu, dt)}
 
     out = {
         "metric": METRIC, "value": world * B / (ms * 1e-3), "unit": "clouds/s", "n_gpus": world, "steps": args.steps,

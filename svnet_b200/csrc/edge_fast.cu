@@ -33,14 +33,15 @@ struct Shape {
     static constexpr int TV = (NVE + 31) / 32;
     static constexpr int QW = KW - 2 * TS;             // words of the q section
     static constexpr int OPT = COUT / 32;
-    static constexpr int EB = (COUT / 32 >= 4) ? 12 : 20;  // edges accumulated per popcount pass (k padded to a multiple)
+    static constexpr int EB = 20;                       // edges accumulated per popcount pass (k padded to a multiple)
+    static constexpr int OPP = (COUT / 32 > 2) ? 2 : COUT / 32;   // output channels per lane per pass
     static constexpr int XS = (CV % 2 == 0) ? CV + 1 : CV;   // odd xyz stride in smem: conflict-free chains
     static constexpr int ES = 3 * XS;                  // floats per staged edge
     static_assert(CS % 32 == 0 && COUT % 32 == 0, "scalar widths must be multiples of 32");
 };
 
 template <int CS, int CV, int COUT, int CVO, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 3 : 2) : ((COUT <= 64) ? 6 : 4)) edge_bin_fast_kernel(svnet_edge_params p, int kp)
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 3 : 6) edge_bin_fast_kernel(svnet_edge_params p, int kp)
 {
     using S = Shape<CS, CV, COUT, CVO>;
     constexpr int EB = S::EB;
@@ -170,13 +171,17 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 3 :
             if (d < CV) { qoff[t] = (int)(ves - wbase) + d; qstr[t] = S::ES; }
             else { qoff[t] = (int)(vc - wbase) + (qok[t] ? d - CV : 0); qstr[t] = 0; }
         }
+        const float* qsrc[S::QW];
+#pragma unroll
+        for (int t = 0; t < S::QW; ++t) qsrc[t] = wbase + qoff[t];
+        const float* z = zb;
 #pragma unroll 2
-        for (int e = 0; e < k; ++e) {
-            const float* z = zb + e * 9;
+        for (int e = 0; e < k; ++e, z += 9) {
             int nv = 0;
 #pragma unroll
             for (int t = 0; t < S::QW; ++t) {
-                const float* src = wbase + qoff[t] + e * qstr[t];
+                const float* src = qsrc[t];
+                qsrc[t] += qstr[t];
                 float q = __fmul_rn(src[0], z[zoff[t]]);
                 q = __fmaf_rn(src[S::XS], z[3 + zoff[t]], q);
                 q = __fmaf_rn(src[2 * S::XS], z[6 + zoff[t]], q);
@@ -202,56 +207,63 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 3 :
         }
     }
 
-    // ---- P4: XNOR/popcount linear1, lanes = output channels ----
-    float smax[S::OPT];
+    // ---- P4: XNOR/popcount linear1, lanes = output channels (OPP per lane per pass) ----
+#pragma unroll 1
+    for (int ob = 0; ob < S::OPT; ob += S::OPP) {
+        float smax[S::OPP];
+        int cmis[S::OPP];   // mismatches of the centre words (identical for all edges of this point)
 #pragma unroll
-    for (int oo = 0; oo < S::OPT; ++oo) smax[oo] = -INFINITY;
-    for (int eb = 0; eb < k; eb += EB) {
-        int acc[EB][S::OPT];
+        for (int oo = 0; oo < S::OPP; ++oo) {
+            smax[oo] = -INFINITY;
+            cmis[oo] = 0;
 #pragma unroll
-        for (int e = 0; e < EB; ++e)
-#pragma unroll
-            for (int oo = 0; oo < S::OPT; ++oo) acc[e][oo] = 0;
-#pragma unroll
-        for (int wd = 0; wd < S::KW; ++wd) {
-            if (wd >= S::TS && wd < 2 * S::TS) continue;  // centre words: same for every edge, added below
-            uint32_t wv[S::OPT];
-#pragma unroll
-            for (int oo = 0; oo < S::OPT; ++oo) wv[oo] = W1b[wd * COUT + lane + 32 * oo];
-            const uint4* Ap = reinterpret_cast<const uint4*>(A + wd * kp + eb);
-            const uint4* Mp = reinterpret_cast<const uint4*>(M + wd * kp + eb);
-#pragma unroll
-            for (int e4 = 0; e4 < EB / 4; ++e4) {
-                const uint4 a4 = Ap[e4], m4 = Mp[e4];
-                const uint32_t av[4] = {a4.x, a4.y, a4.z, a4.w};
-                const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int oo = 0; oo < S::OPT; ++oo) acc[e4 * 4 + u][oo] += __popc((av[u] ^ wv[oo]) & mv[u]);
-            }
+            for (int t = 0; t < S::TS; ++t)
+                cmis[oo] += __popc((cpos[t] ^ W1b[(S::TS + t) * COUT + lane + 32 * (ob + oo)]) & cnz[t]);
         }
+        for (int eb = 0; eb < k; eb += EB) {
+            int acc[EB][S::OPP];
 #pragma unroll
-        for (int oo = 0; oo < S::OPT; ++oo) {
-            const int o = lane + 32 * oo;
-            const float sc = __ldg(p.scale1 + o), a1 = __ldg(p.bn1_a + o), c1 = __ldg(p.bn1_c + o);
-            int cmis = 0;  // mismatches of the centre words (identical for all edges of this point)
+            for (int e = 0; e < EB; ++e)
 #pragma unroll
-            for (int t = 0; t < S::TS; ++t) cmis += __popc((cpos[t] ^ W1b[(S::TS + t) * COUT + o]) & cnz[t]);
+                for (int oo = 0; oo < S::OPP; ++oo) acc[e][oo] = 0;
 #pragma unroll
-            for (int e = 0; e < EB; ++e) {
-                if (eb + e < k) {
-                    const int dot = nvalid[eb + e] - 2 * (acc[e][oo] + cmis);
-                    float y = __fmul_rn((float)dot, sc);
-                    y = __fadd_rn(__fmul_rn(y, a1), c1);
-                    y = y > 0.0f ? y : __fmul_rn(0.2f, y);
-                    smax[oo] = fmaxf(smax[oo], y);
+            for (int wd = 0; wd < S::KW; ++wd) {
+                if (wd >= S::TS && wd < 2 * S::TS) continue;  // centre words: cmis
+                uint32_t wv[S::OPP];
+#pragma unroll
+                for (int oo = 0; oo < S::OPP; ++oo) wv[oo] = W1b[wd * COUT + lane + 32 * (ob + oo)];
+                const uint4* Ap = reinterpret_cast<const uint4*>(A + wd * kp + eb);
+                const uint4* Mp = reinterpret_cast<const uint4*>(M + wd * kp + eb);
+#pragma unroll
+                for (int e4 = 0; e4 < EB / 4; ++e4) {
+                    const uint4 a4 = Ap[e4], m4 = Mp[e4];
+                    const uint32_t av[4] = {a4.x, a4.y, a4.z, a4.w};
+                    const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int oo = 0; oo < S::OPP; ++oo) acc[e4 * 4 + u][oo] += __popc((av[u] ^ wv[oo]) & mv[u]);
+                }
+            }
+#pragma unroll
+            for (int oo = 0; oo < S::OPP; ++oo) {
+                const int o = lane + 32 * (ob + oo);
+                const float sc = __ldg(p.scale1 + o), a1 = __ldg(p.bn1_a + o), c1 = __ldg(p.bn1_c + o);
+#pragma unroll
+                for (int e = 0; e < EB; ++e) {
+                    if (eb + e < k) {
+                        const int dot = nvalid[eb + e] - 2 * (acc[e][oo] + cmis[oo]);
+                        float y = __fmul_rn((float)dot, sc);
+                        y = __fadd_rn(__fmul_rn(y, a1), c1);
+                        y = y > 0.0f ? y : __fmul_rn(0.2f, y);
+                        smax[oo] = fmaxf(smax[oo], y);
+                    }
                 }
             }
         }
-    }
 #pragma unroll
-    for (int oo = 0; oo < S::OPT; ++oo) p.out.s[r * p.out.lds + lane + 32 * oo] = smax[oo];
+        for (int oo = 0; oo < S::OPP; ++oo) p.out.s[r * p.out.lds + lane + 32 * (ob + oo)] = smax[oo];
+    }
 
     // ---- P5: vector branch, lanes = output vector channels ----
     constexpr int LDP = 2 * CVO;

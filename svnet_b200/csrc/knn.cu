@@ -93,26 +93,6 @@ __device__ __forceinline__ void cex(key_t& k, int j, bool keep_better)
     if ((k > o) != keep_better) k = o;
 }
 
-// R == 1: merge 32 candidates (one per lane, any order) into the sorted list (best at lane 0)
-__device__ __forceinline__ void sort_merge32(TopK<1>& L, key_t c, int lane, int k)
-{
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-        for (int j = size >> 1; j > 0; j >>= 1) {
-            const bool desc = (lane & size) == 0;       // this block is sorted best-first
-            const bool lower = (lane & j) == 0;
-            cex(c, j, desc == lower);
-        }
-    }
-    // top 32 of the union: list[i] vs candidates reversed -> bitonic sequence, then bitonic merge
-    const key_t rv = shfl_key(c, 31 - lane);
-    if (rv > L.k[0]) L.k[0] = rv;
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) cex(L.k[0], j, (lane & j) == 0);
-    if (lane >= k) L.k[0] = 0ull;
-}
-
 template <int R, int KC>
 __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k, int32_t* __restrict__ idx32,
                                                     int64_t* __restrict__ idx64)
@@ -224,33 +204,71 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
             }
         }
         __syncthreads();
-        // ---- drain: warp owns rows warp*8 .. warp*8+7 ----
+        // ---- drain: warp owns rows warp*8 .. warp*8+7.  The eight rows are processed in lock-step,
+        //      branch-free, so that their (latency-bound, shuffle-heavy) updates overlap ----
+        {
+            const int r0 = warp * ROWS_PER_WARP;
+            int cnts[ROWS_PER_WARP];
+            int maxc = 0;
 #pragma unroll
-        for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-            const int r = warp * ROWS_PER_WARP + rr;
-            const int cnt = qcnt[r];
-            if (cnt == 0) continue;  // warp-uniform
-            for (int q0 = 0; q0 < cnt; q0 += 32) {
-                const bool have = q0 + lane < cnt;
-                const key_t c = have ? make_key(qv[r * TJ + q0 + lane], qj[r * TJ + q0 + lane]) : 0ull;
-                key_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
-                unsigned m = __ballot_sync(SV_FULL, c > worst);
-                if (R == 1 && __popc(m) >= MERGE_MIN) {
-                    sort_merge32(reinterpret_cast<TopK<1>&>(L[rr]), c, lane, k);
+            for (int rr = 0; rr < ROWS_PER_WARP; ++rr) { cnts[rr] = qcnt[r0 + rr]; maxc = max(maxc, cnts[rr]); }
+            for (int q0 = 0; q0 < maxc; q0 += 32) {
+                key_t c[ROWS_PER_WARP];
+                unsigned m[ROWS_PER_WARP];
+                bool any_merge = false;
+#pragma unroll
+                for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                    const bool have = q0 + lane < cnts[rr];
+                    const int qi = (r0 + rr) * TJ + q0 + lane;
+                    c[rr] = have ? make_key(qv[qi], qj[qi]) : 0ull;
+                    const key_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
+                    m[rr] = __ballot_sync(SV_FULL, c[rr] > worst);
+                    any_merge |= __popc(m[rr]) >= MERGE_MIN;
+                }
+                if (R == 1 && any_merge) {
+                    // batched bitonic sort of the 8 candidate vectors, then merge into the 8 lists
+#pragma unroll
+                    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+                        for (int j = size >> 1; j > 0; j >>= 1) {
+                            const bool keep = ((lane & size) == 0) == ((lane & j) == 0);
+#pragma unroll
+                            for (int rr = 0; rr < ROWS_PER_WARP; ++rr) cex(c[rr], j, keep);
+                        }
+#pragma unroll
+                    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                        const key_t rv = shfl_key(c[rr], 31 - lane);
+                        if (rv > L[rr].k[0]) L[rr].k[0] = rv;
+                    }
+#pragma unroll
+                    for (int j = 16; j > 0; j >>= 1)
+#pragma unroll
+                        for (int rr = 0; rr < ROWS_PER_WARP; ++rr) cex(L[rr].k[0], j, (lane & j) == 0);
                     continue;
                 }
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const key_t cc = shfl_key(c, src);
-                    if (cc > worst) {  // warp-uniform
+                // insertion rounds: one candidate per row per round.  A candidate that no longer beats
+                // the (meanwhile improved) k-th entry lands at a position >= k, which is never read.
+                for (;;) {
+                    unsigned anym = 0u;
+#pragma unroll
+                    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) anym |= m[rr];
+                    if (!anym) break;
+#pragma unroll
+                    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                        const bool had = m[rr] != 0u;
+                        const int src = had ? (__ffs(m[rr]) - 1) : 0;
+                        m[rr] &= m[rr] - 1;
+                        key_t cc = shfl_key(c[rr], src);
+                        if (!had) cc = 0ull;
                         topk_insert<R>(L[rr], cc, lane);
-                        worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
                     }
                 }
             }
-            const key_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
-            if (lane == 0) { qcnt[r] = 0; thr[r] = key_score(worst); }
+#pragma unroll
+            for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+                const key_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
+                if (lane == 0 && cnts[rr] > 0) { qcnt[r0 + rr] = 0; thr[r0 + rr] = key_score(worst); }
+            }
         }
         // (the next tile's first __syncthreads orders these writes before the next push phase)
     }
