@@ -41,7 +41,7 @@ struct Shape {
 };
 
 template <int CS, int CV, int COUT, int CVO, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 3 : 6) edge_bin_fast_kernel(svnet_edge_params p, int kp)
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 4 : 3) : 6) edge_bin_fast_kernel(svnet_edge_params p, int kp)
 {
     using S = Shape<CS, CV, COUT, CVO>;
     constexpr int EB = S::EB;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 3 : 6) edge_bin_fas
     for (int i = threadIdx.x; i < 3 * S::CVE; i += blockDim.x) Wz[i] = p.Wz[i];
     for (int i = threadIdx.x; i < S::KW * COUT; i += blockDim.x) W1b[i] = p.W1b[i];
     // ---- per warp ----
-    const int per_warp = ((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3 + kp * CS;
+    const int per_warp = ((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3;
     float* wbase = smem_raw + ((SHARED + 3) & ~3) + (size_t)warp * ((per_warp + 3) & ~3);
     uint32_t* A = reinterpret_cast<uint32_t*>(wbase);            // [KW][kp]   (16B aligned rows: kp % 4 == 0)
     uint32_t* M = A + S::KW * kp;                                 // [KW][kp]
@@ -64,7 +64,6 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 3 : 6) edge_bin_fas
     float* vc = wbase + ((2 * S::KW * kp + 2 * kp + 3) & ~3);     // [3][XS] centre vectors
     float* ves = vc + 3 * S::XS;                                  // [kp][3][XS] neighbour - centre
     float* zb = ves + kp * S::ES;                                 // [kp][9]
-    float* raws = zb + kp * 9 + 3;                                // [kp][CS] staged neighbour scalars
     __syncthreads();
 
     const long r = (long)blockIdx.x * WARPS + warp;
@@ -110,32 +109,42 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 3 : 6) edge_bin_fas
     for (int i = lane; i < S::KW * kp; i += 32) { A[i] = 0u; M[i] = 0u; }
     __syncwarp();
 
-    // ---- P1: gather all k neighbour rows with cp.async (one latency exposure), then S1 sign words
-    //      (ballot) and v differences in place ----
+    // ---- P1: gather all k neighbour rows: vectors by cp.async straight into shared memory, scalars
+    //      into registers (EB rows in flight); one latency exposure for both.  Then S1 sign words by
+    //      ballot and the vector differences in place ----
     for (int e = 0; e < k; ++e) {
-        const long j = cbase + nidx[e];
-        const float* sj = p.in.s + j * p.in.lds + lane;
-        const float* vj = p.in.v + j * p.in.ldv;
-#pragma unroll
-        for (int t = 0; t < S::TS; ++t) cp_async4(raws + e * CS + 32 * t + lane, sj + 32 * t);
+        const float* vj = p.in.v + (cbase + nidx[e]) * p.in.ldv;
 #pragma unroll
         for (int t = 0; t < S::TV; ++t)
             if (voff[t] >= 0) cp_async4(ves + e * S::ES + vso[t], vj + voff[t]);
     }
+    for (int eb = 0; eb < k; eb += EB) {
+        float sv[EB][S::TS];
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            const float* sj = p.in.s + (cbase + nidx[eb + e]) * p.in.lds + lane;   // padded slots read row 0
+#pragma unroll
+            for (int t = 0; t < S::TS; ++t) sv[e][t] = __ldg(sj + 32 * t);
+        }
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            if (eb + e < k) {
+                int nv = ncen;
+#pragma unroll
+                for (int t = 0; t < S::TS; ++t) {
+                    const float u = __fadd_rn(__fsub_rn(sv[e][t], si[t]), beta[t]);
+                    const unsigned pos = __ballot_sync(SV_FULL, u > 0.0f);
+                    const unsigned nz = __ballot_sync(SV_FULL, u != 0.0f);
+                    nv += __popc(nz);
+                    if (lane == 0) { A[t * kp + eb + e] = pos; M[t * kp + eb + e] = nz; }
+                }
+                if (lane == 0) nvalid[eb + e] = nv;
+            }
+        }
+    }
     cp_async_wait_all();
     __syncwarp();
-#pragma unroll 2
     for (int e = 0; e < k; ++e) {
-        int nv = ncen;
-#pragma unroll
-        for (int t = 0; t < S::TS; ++t) {
-            const float u = __fadd_rn(__fsub_rn(raws[e * CS + 32 * t + lane], si[t]), beta[t]);
-            const unsigned pos = __ballot_sync(SV_FULL, u > 0.0f);
-            const unsigned nz = __ballot_sync(SV_FULL, u != 0.0f);
-            nv += __popc(nz);
-            if (lane == 0) { A[t * kp + e] = pos; M[t * kp + e] = nz; }
-        }
-        if (lane == 0) nvalid[e] = nv;
 #pragma unroll
         for (int t = 0; t < S::TV; ++t)
             if (voff[t] >= 0) ves[e * S::ES + vso[t]] = __fsub_rn(ves[e * S::ES + vso[t]], vi[t]);
@@ -298,7 +307,7 @@ int launch_fast(const svnet_edge_params* p, cudaStream_t st)
     constexpr int EB = S::EB;
     const int kp = ((p->k + EB - 1) / EB) * EB;
     constexpr int SHARED = 3 * S::CVE + ((3 * S::CVE) & 1) + S::KW * COUT;
-    const int per_warp = ((((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3 + kp * CS) + 3) & ~3;
+    const int per_warp = ((((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3) + 3) & ~3;
     const long P = (long)p->B * p->N;
     auto smem_for = [&](int warps) { return sizeof(float) * (size_t)(((SHARED + 3) & ~3) + warps * per_warp); };
     if (smem_for(8) <= 72 * 1024) {
