@@ -1,9 +1,28 @@
 """Fused layer drivers shared by the SV model classes: they wire module parameters (packed once)
 into the C-ABI parameter blocks of the fused kernels.  No arithmetic happens here.
 """
+import os
+
 import torch
 
 from . import _native as nv
+
+
+MAX_POINTS_PER_PASS = int(os.environ.get("SVNET_MAX_POINTS", 1 << 19))
+
+
+def chunked(impl, x, extras=(), hooks=False):
+    """Run ``impl(x_chunk, *extras_chunk)`` over cloud sub-batches so that the per-pass tables stay
+    bounded (B*N <= MAX_POINTS_PER_PASS points; clouds are independent in eval mode).
+    Test hooks (forced indices / recording) disable chunking."""
+    B, N = x.shape[0], x.shape[-1]
+    per = max(1, MAX_POINTS_PER_PASS // max(N, 1))
+    if hooks or B <= per:
+        return impl(x, *extras)
+    outs = []
+    for lo in range(0, B, per):
+        outs.append(impl(x[lo:lo + per].contiguous(), *[e[lo:lo + per].contiguous() for e in extras]))
+    return torch.cat(outs, dim=0)
 
 
 def _mview(s_out, v_out):

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nv
-from .fused import dgcnn_trunk
+from .fused import chunked, dgcnn_trunk
 from .sv_layers import Linear, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, folded_bn, head_layer
 
 
@@ -43,6 +43,10 @@ class SV_DGCNN_CLS(nn.Module, _Cached):
         self.linear3 = nn.Linear(256, num_class)
 
     def forward(self, x, forced_idx=None, record=None):
+        hooks = forced_idx is not None or record is not None
+        return chunked(lambda xc: self._forward(xc, forced_idx, record), x, hooks=hooks)
+
+    def _forward(self, x, forced_idx=None, record=None):
         """x (B, 3, N) float32 on CUDA -> logits (B, num_class).  ``forced_idx`` (list of 4 int32
         (B,N,k) tensors) and ``record`` (dict) are test hooks (teacher forcing / intermediates)."""
         _inference_only(self)

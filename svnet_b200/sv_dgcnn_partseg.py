@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nv
-from .fused import dgcnn_trunk
+from .fused import chunked, dgcnn_trunk
 from .sv_layers import Conv1d, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, dense_rows, folded_bn
 
 
@@ -84,6 +84,10 @@ class SV_DGCNN_PSEG(nn.Module):
         self.conv11 = nn.Conv1d(128, num_part, kernel_size=1, bias=False)
 
     def forward(self, x, l, forced_idx=None, record=None):
+        hooks = forced_idx is not None or record is not None
+        return chunked(lambda xc, lc: self._forward(xc, lc, forced_idx, record), x, (l,), hooks=hooks)
+
+    def _forward(self, x, l, forced_idx=None, record=None):
         """x (B,3,N), l (B,16) one-hot -> per-point part logits (B, num_part, N)."""
         _inference_only(self)
         B, _, N = x.shape

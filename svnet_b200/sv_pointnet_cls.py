@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nv
-from .fused import first_edge_layer
+from .fused import chunked, first_edge_layer
 from .sv_layers import (Linear, SV_STNkd, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, dense_rows,
                         folded_bn, head_layer)
 
@@ -114,6 +114,10 @@ class SV_PointNet_CLS(nn.Module, _Cached):
         self.relu = nn.ReLU()
 
     def forward(self, x, forced_idx=None, record=None):
+        hooks = forced_idx is not None or record is not None
+        return chunked(lambda xc: self._forward(xc, forced_idx, record), x, hooks=hooks)
+
+    def _forward(self, x, forced_idx=None, record=None):
         _inference_only(self)
         f = self.feat(x, forced_idx=forced_idx, record=record)
         # dropout is the identity in eval; ReLU (not LeakyReLU) in this head (:78-79)

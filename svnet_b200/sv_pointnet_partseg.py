@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nv
-from .fused import first_edge_layer
+from .fused import chunked, first_edge_layer
 from .sv_dgcnn_partseg import _Seq
 from .sv_layers import Conv1d, SV_STNkd, SVBlock, SVFuse, Vector2Scalar, _inference_only, dense_rows
 from .sv_pointnet_cls import _bcast_rows, stn_rows
@@ -55,6 +55,10 @@ class SV_PointNet_PSEG(nn.Module):
         self.convs4 = nn.Conv1d(128, num_part, 1)
 
     def forward(self, x, l, forced_idx=None, record=None):
+        hooks = forced_idx is not None or record is not None
+        return chunked(lambda xc, lc: self._forward(xc, lc, forced_idx, record), x, (l,), hooks=hooks)
+
+    def _forward(self, x, l, forced_idx=None, record=None):
         """x (B,3,N), l (B,1,16) or (B,16) -> (B, num_part, N)   (sv_pointnet_partseg.py:55-97)"""
         _inference_only(self)
         B, D, N = x.size()

@@ -368,3 +368,35 @@ def test_checkpoint_container_roundtrip(tmp_path):
         y = model(x)
     ref = orc.sv_dgcnn_cls(sd, t2n(x), 8)
     assert_close(t2n(y), ref, what="DataParallel-wrapped forward vs oracle")
+
+
+def test_full_size_configs_run_and_are_batch_independent():
+    """BASELINE.json shapes beyond cfg2: part segmentation at N=2048, k=40 (cfg4, 8 of its 16 clouds
+    per GPU) and a large-batch classifier pass that exercises the sub-batch chunking; every cloud's
+    output must equal the output of that cloud run alone (bit for bit: clouds are independent)."""
+    import svnet_b200 as sv
+    from svnet_b200 import fused
+    from svnet_b200.synthetic import one_hot_labels
+    net = quiet(sv.SV_DGCNN_PSEG, make_args(k=40, binary=True), 50)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=1004))
+    net = net.to(DEV).eval()
+    x = synthetic_clouds(8, 2048, 1004).to(DEV)
+    l = one_hot_labels(8).to(DEV)
+    with torch.no_grad():
+        y = net(x, l)
+        y3 = net(x[3:4].contiguous(), l[3:4].contiguous())
+    assert tuple(y.shape) == (8, 50, 2048) and torch.isfinite(y).all()
+    assert torch.equal(y[3:4], y3)
+    cls = quiet(sv.SV_DGCNN_CLS, make_args(k=20, binary=True), 40)
+    cls.load_state_dict(synthetic_state_dict(cls.state_dict(), seed=1005))
+    cls = cls.to(DEV).eval()
+    xb = synthetic_clouds(24, 1024, 1005).to(DEV)
+    old = fused.MAX_POINTS_PER_PASS
+    try:
+        with torch.no_grad():
+            y_full = cls(xb)
+            fused.MAX_POINTS_PER_PASS = 5 * 1024      # force 5-cloud sub-batches (24 = 4*5 + 4)
+            y_chunk = cls(xb)
+    finally:
+        fused.MAX_POINTS_PER_PASS = old
+    assert torch.equal(y_full, y_chunk)
