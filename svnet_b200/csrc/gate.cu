@@ -161,6 +161,82 @@ __global__ void __launch_bounds__(NT) gate_edge_kernel(svnet_view in, const int3
     gate_mlp(mean, 2 * Cs, G1, G2, H, Co, h, gate + (long)b * Co);
 }
 
+// Cluster variant of gate_edge: CL CTAs per cloud.  Each CTA histograms its slice of the kNN indices,
+// the partial histograms are summed through distributed shared memory for the CTA's slice of rows,
+// partial column sums meet in rank 0 (fixed order -> deterministic).
+// smem: psum[2Cs] | mean[2Cs] | h[H] | part[2][8][32] | hist[N] | indeg[N/CL + 1]
+__global__ void __launch_bounds__(NT) gate_edge_cluster_kernel(svnet_view in, const int32_t* __restrict__ idx, int N, int k,
+                                                               const float* __restrict__ G1,
+                                                               const float* __restrict__ G2, int H, int Co,
+                                                               float* __restrict__ gate)
+{
+    extern __shared__ float sm[];
+    const int Cs = in.Cs;
+    float* psum = sm;
+    float* mean = psum + 2 * Cs;
+    float* h = mean + 2 * Cs;
+    float* part = h + H;
+    int* hist = reinterpret_cast<int*>(part + 2 * 8 * 32);
+    int* indeg = hist + N;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    const int b = blockIdx.x / CL;
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < N; i += NT) hist[i] = 0;
+    __syncthreads();
+    const long E = (long)N * k;
+    const long e_lo = E * rank / CL, e_hi = E * (rank + 1) / CL;
+    const int32_t* ib = idx + (long)b * E;
+    for (long t = e_lo + threadIdx.x; t < e_hi; t += NT) atomicAdd(&hist[ib[t]], 1);
+    cluster.sync();
+    // total in-degree of this CTA's rows, gathered from the CL partial histograms
+    const int r_lo = (int)((long)N * rank / CL), r_hi = (int)((long)N * (rank + 1) / CL);
+    for (int r = r_lo + threadIdx.x; r < r_hi; r += NT) {
+        int d = 0;
+        for (unsigned q = 0; q < CL; ++q) d += cluster.map_shared_rank(hist, q)[r];
+        indeg[r - r_lo] = d;
+    }
+    cluster.sync();   // every CTA is done reading remote histograms
+    const float* p = in.s + (long)b * N * in.lds;
+    for (int c0 = 0; c0 < Cs; c0 += 32) {
+        const int c = c0 + lane;
+        float accd = 0.0f, accp = 0.0f;
+        if (c < Cs)
+            for (int r = r_lo + rg; r < r_hi; r += 8) {
+                const float t = p[(long)r * in.lds + c];
+                accd = fmaf((float)indeg[r - r_lo], t, accd);
+                accp += t;
+            }
+        part[rg * 32 + lane] = accd;
+        part[256 + rg * 32 + lane] = accp;
+        __syncthreads();
+        if (rg == 0 && c < Cs) {
+            float td = part[lane], tp = part[256 + lane];
+            for (int g = 1; g < 8; ++g) { td += part[g * 32 + lane]; tp += part[256 + g * 32 + lane]; }
+            psum[c] = td;
+            psum[Cs + c] = tp;
+        }
+        __syncthreads();
+    }
+    cluster.sync();
+    if (rank == 0) {
+        for (int c = threadIdx.x; c < Cs; c += NT) {
+            float td = 0.0f, tp = 0.0f;
+            for (unsigned q = 0; q < CL; ++q) {
+                const float* rp = cluster.map_shared_rank(psum, q);
+                td += rp[c];
+                tp += rp[Cs + c];
+            }
+            const float mp = tp / (float)N;
+            mean[c] = td / ((float)N * (float)k) - mp;
+            mean[Cs + c] = mp;
+        }
+        __syncthreads();
+    }
+    cluster.sync();
+    if (rank == 0) gate_mlp(mean, 2 * Cs, G1, G2, H, Co, h, gate + (long)b * Co);
+}
+
 // smem: mean[3nv] | h[H] | part[NT][9]
 template <int NV>
 __global__ void __launch_bounds__(NT) gate_xyz_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
@@ -269,6 +345,26 @@ extern "C" int svnet_gate_edge(const svnet_view* in, const int32_t* idx, int B, 
     SV_REQUIRE(in && in->s && idx && G1 && G2 && gate, "svnet_gate_edge: null pointer");
     SV_REQUIRE(in->Cs >= 1 && N >= 1 && k >= 1 && H >= 1 && Co >= 1 && B >= 0, "svnet_gate_edge: bad shape");
     if (B == 0) return SVNET_OK;
+    if (N >= 512) {
+        {
+            const size_t smem_c = sizeof(float) * ((size_t)4 * in->Cs + H + 512 + N + N / CL + 2);
+            SV_REQUIRE(smem_c <= 200 * 1024, "svnet_gate_edge: N=%d / Cs=%d too large", N, in->Cs);
+            if (smem_c > 48 * 1024)
+                SV_CUDA(cudaFuncSetAttribute(gate_edge_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(B * CL);
+            cfg.blockDim = dim3(NT);
+            cfg.dynamicSmemBytes = smem_c;
+            cfg.stream = sv_stream(stream);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            SV_CUDA(cudaLaunchKernelEx(&cfg, gate_edge_cluster_kernel, *in, idx, N, k, G1, G2, H, Co, gate));
+            SV_CHECK_LAUNCH("svnet_gate_edge(cluster)");
+            return SVNET_OK;
+        }
+    }
     const size_t smem = sizeof(float) * ((size_t)2 * in->Cs + H + 512 + N);
     SV_REQUIRE(smem <= 200 * 1024, "svnet_gate_edge: N=%d / Cs=%d too large", N, in->Cs);
     if (smem > 48 * 1024)

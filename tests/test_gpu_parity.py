@@ -306,7 +306,9 @@ def test_dgcnn_cls_batch_independence_and_full_size():
     # teacher-forced with the oracle's graphs, logits must agree
     with torch.no_grad():
         yf = net(x[:1].contiguous(), forced_idx=[cu(i, torch.int32) for i in rec["idx"]])
-    assert torch.isfinite(yf).all()
+    # N=1024 runs the cluster/DSMEM gate kernels and the specialised edge kernels
+    assert_close(t2n(yf), yo, what="cfg2-shaped logits vs oracle (kNN graphs forced)")
+    assert (t2n(yf).argmax(1) == yo.argmax(1)).all()
 
 
 # ------------------------------------------------------------------------------------------------
