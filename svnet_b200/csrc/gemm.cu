@@ -6,6 +6,8 @@
 // Reference: models/sv_layers.py:29-53 (Linear), :86-102 (VectorBN), :192-194.
 #include "common.cuh"
 
+int svnet_signlinear_tc_dispatch(const svnet_gemm_params* p, cudaStream_t st);
+
 namespace {
 
 constexpr int BN_ = 64, BK = 16;
@@ -132,6 +134,11 @@ extern "C" int svnet_linear_rows(const svnet_gemm_params* p, void* stream)
     }
     if (p->M == 0) return SVNET_OK;
     cudaStream_t st = sv_stream(stream);
+    {   // binary-weight vector linears: exact-split bf16 tensor-core kernel (gemm_tc.cu)
+        const int h = svnet_signlinear_tc_dispatch(p, st);
+        if (h < 0) return h;
+        if (h == 1) return SVNET_OK;
+    }
     if (p->vbn) {
         dim3 grid(sv_cdiv(p->M, 48), sv_cdiv(p->N, BN_));
         linear_rows_kernel<3><<<grid, 256, 0, st>>>(*p);
