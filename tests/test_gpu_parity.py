@@ -402,3 +402,38 @@ def test_full_size_configs_run_and_are_batch_independent():
     finally:
         fused.MAX_POINTS_PER_PASS = old
     assert torch.equal(y_full, y_chunk)
+
+
+@pytest.mark.parametrize("cls_name,k,N", [("SV_DGCNN_PSEG", 40, 192), ("SV_DGCNN_CLS", 20, 320)])
+def test_fast_edge_kernels_teacher_forced_k_full(cls_name, k, N):
+    """The shape-specialised edge kernels at the BASELINE neighbourhood sizes (k=20 cls, k=40 pseg:
+    two popcount passes, 4-warp CTAs), teacher-forced with the oracle's per-layer inputs and graphs:
+    pooled scalars bit-identical, pooled vectors within tolerance."""
+    import svnet_b200 as sv
+    net = quiet(getattr(sv, cls_name), make_args(k=k, binary=True), 50 if "PSEG" in cls_name else 40)
+    sd = synthetic_state_dict(net.state_dict(), seed=2000 + k)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    x = synthetic_clouds(1, N, 77 + k, rotate=True)
+    rec_o = {}
+    P = orc.Params(sd)
+    outs = orc._dgcnn_trunk(P, x.numpy(), k, None, rec_o.setdefault("r", {"idx": [], "pools": []}))
+    ro = rec_o["r"]
+    teacher = [(cu(s).view(N, -1), cu(v).view(N, 3, -1)) for (s, v) in ro["pools"][:3]]
+    rec = {"teacher": teacher}
+    fi = [cu(i, torch.int32) for i in ro["idx"]]
+    with torch.no_grad():
+        if "PSEG" in cls_name:
+            from svnet_b200.synthetic import one_hot_labels
+            net(x.to(DEV), one_hot_labels(1).to(DEV), forced_idx=fi, record=rec)
+        else:
+            net(x.to(DEV), forced_idx=fi, record=rec)
+    so = vo = 0
+    for li, (o_s, o_v) in enumerate(ro["pools"]):
+        cs, cv = o_s.shape[-1], o_v.shape[-1]
+        got_s = t2n(rec["s_cat"][:, so:so + cs]).reshape(1, N, cs)
+        got_v = t2n(rec["v_cat"][:, :, vo:vo + cv]).reshape(1, N, 3, cv)
+        assert (got_s == o_s).all(), "layer %d pooled scalars differ from the oracle" % (li + 1)
+        assert_close(got_v, o_v, rtol=1e-4, atol=1e-5, what="layer %d v" % (li + 1))
+        so += cs
+        vo += cv
