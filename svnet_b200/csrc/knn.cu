@@ -23,6 +23,14 @@ constexpr int MERGE_MIN = 7;            // >= this many survivors in a 32-chunk:
 
 __device__ __forceinline__ int swz(int c, int r) { return r ^ ((c & 7) << 2); }
 
+// 4-byte async copy global -> shared; nbytes == 0 writes zeros (padding rows / channels)
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gsrc, int nbytes)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(nbytes));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // Ordering keys: (score desc, index asc) as one unsigned 64-bit compare.
 //   hi = order-preserving map of the fp32 score (-0 is folded into +0 first, so that float equality
 //        and key equality agree), lo = ~index (smaller index -> larger key).  Empty slots are key 0,
@@ -98,14 +106,14 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
                                                     int64_t* __restrict__ idx64)
 {
     extern __shared__ __align__(16) float smem[];
-    float* As = smem;                                   // [KC][TI]   swizzled
-    float* Bs = As + KC * TI;                           // [KC][TJ]   swizzled
-    float* xxi = Bs + KC * TJ;                          // [TI]
+    float* As = smem;                                   // [2][KC][TI]   swizzled, double buffered
+    float* Bs = As + 2 * KC * TI;                       // [2][KC][TJ]   swizzled, double buffered
+    float* xxi = Bs + 2 * KC * TJ;                      // [TI]
     float* xxj = xxi + TI;                              // [TJ]
     float* thr = xxj + TJ;                              // [TI] current k-th score per row
     int* qcnt = reinterpret_cast<int*>(thr + TI);       // [TI]
-    float* qv = reinterpret_cast<float*>(qcnt + TI);    // [TI][TJ]
-    int* qj = reinterpret_cast<int*>(qv + TI * TJ);     // [TI][TJ]
+    float* qv = reinterpret_cast<float*>(qcnt + TI);    // [TI][TJ] queued scores
+    unsigned char* qj = reinterpret_cast<unsigned char*>(qv + TI * TJ);   // [TI][TJ] queued column within the tile
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
@@ -122,61 +130,81 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
     if (tid < TI) { thr[tid] = -INFINITY; qcnt[tid] = 0; }
 
     const int ntiles = (N + TJ - 1) / TJ;
-    for (int jt = 0; jt < ntiles; ++jt) {
-        const int j0 = jt * TJ;
-        float acc[4][8];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[a][q] = 0.0f;
-        float nrm = 0.0f;  // xx_j for tid < TJ; xx_i for TJ <= tid < TJ+TI (first tile only)
+    const int nch = (C + KC - 1) / KC;
+    const int nstages = ntiles * nch;
 
-        for (int c0 = 0; c0 < C; c0 += KC) {
-            // ---- stage one channel chunk of the query rows and of the candidate rows (lane = channel) ----
-            const float* cptr = nullptr;
+    // stage s = (candidate tile jt, channel chunk ci): async copy of one chunk of the query rows and of
+    // the candidate rows into buffer `buf` (lane = channel, one row per warp iteration)
+    auto issue = [&](int s, int buf) {
+        if (lane < KC) {
+            const int jt = s / nch, c = (s - jt * nch) * KC + lane, j0 = jt * TJ;
+            const float* cptr = in.s ? in.s : in.v;   // any valid address for the zero-fill form
             long cstride = 0;
-            if (lane < KC) {
-                const int c = c0 + lane;
-                if (c < in.Cs) { cptr = in.s + c; cstride = in.lds; }
-                else if (c < C) {
-                    const int cc = c - in.Cs, x = cc / in.Cv, d = cc - x * in.Cv;
-                    cptr = in.v + x * in.xs + d; cstride = in.ldv;
-                }
+            bool cok = false;
+            if (c < in.Cs) { cptr = in.s + c; cstride = in.lds; cok = true; }
+            else if (c < C) {
+                const int cc = c - in.Cs, x = cc / in.Cv, d = cc - x * in.Cv;
+                cptr = in.v + x * in.xs + d; cstride = in.ldv; cok = true;
             }
-            __syncthreads();  // previous chunk fully consumed
-            if (lane < KC) {
-                const long step = (long)NW * cstride;
-                const float* pa = cptr + (base + i0 + warp) * cstride;
+            float* Ad = As + buf * KC * TI + lane * TI;
+            float* Bd = Bs + buf * KC * TJ + lane * TJ;
+            const long step = (long)NW * cstride;
+            const float* pa = cptr + (base + i0 + warp) * cstride;
 #pragma unroll 4
-                for (int r = warp; r < TI; r += NW, pa += step)
-                    As[lane * TI + swz(lane, r)] = (cptr && i0 + r < N) ? __ldg(pa) : 0.0f;
-                const float* pb = cptr + (base + j0 + warp) * cstride;
+            for (int r = warp; r < TI; r += NW, pa += step) {
+                const bool ok = cok && (i0 + r < N);
+                cp_async4_zfill(Ad + swz(lane, r), ok ? pa : cptr, ok ? 4 : 0);
+            }
+            const float* pb = cptr + (base + j0 + warp) * cstride;
 #pragma unroll 4
-                for (int r = warp; r < TJ; r += NW, pb += step)
-                    Bs[lane * TJ + swz(lane, r)] = (cptr && j0 + r < N) ? __ldg(pb) : 0.0f;
-            }
-            __syncthreads();
-            // squared norms, sequential chain over channels (zero padding is exact)
-            if (tid < TJ) {
-#pragma unroll
-                for (int cc = 0; cc < KC; ++cc) { const float t = Bs[cc * TJ + swz(cc, tid)]; nrm = __fmaf_rn(t, t, nrm); }
-            } else if (jt == 0 && tid < TJ + TI) {
-#pragma unroll
-                for (int cc = 0; cc < KC; ++cc) { const float t = As[cc * TI + swz(cc, tid - TJ)]; nrm = __fmaf_rn(t, t, nrm); }
-            }
-#pragma unroll
-            for (int cc = 0; cc < KC; ++cc) {
-                const float4 a4 = *reinterpret_cast<const float4*>(&As[cc * TI + swz(cc, ty * 4)]);
-                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cc * TJ + swz(cc, tx * 4)]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cc * TJ + swz(cc, 64 + tx * 4)]);
-                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) acc[a][q] = __fmaf_rn(av[a], bv[q], acc[a][q]);
+            for (int r = warp; r < TJ; r += NW, pb += step) {
+                const bool ok = cok && (j0 + r < N);
+                cp_async4_zfill(Bd + swz(lane, r), ok ? pb : cptr, ok ? 4 : 0);
             }
         }
+    };
+
+    float acc[4][8];
+    float nrm = 0.0f;  // xx_j for tid < TJ; xx_i for TJ <= tid < TJ+TI (first tile only)
+    issue(0, 0);
+    for (int s = 0; s < nstages; ++s) {
+        const int buf = s & 1;
+        const int jt = s / nch, ci = s - jt * nch;
+        const int j0 = jt * TJ;
+        cp_async_wait_all();
+        __syncthreads();                 // stage s has landed for everyone; buffer buf^1 is free again
+        if (s + 1 < nstages) issue(s + 1, buf ^ 1);
+        if (ci == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[a][q] = 0.0f;
+            nrm = 0.0f;
+        }
+        const float* Ab = As + buf * KC * TI;
+        const float* Bb = Bs + buf * KC * TJ;
+        // squared norms, sequential chain over channels (zero padding is exact)
+        if (tid < TJ) {
+#pragma unroll
+            for (int cc = 0; cc < KC; ++cc) { const float t = Bb[cc * TJ + swz(cc, tid)]; nrm = __fmaf_rn(t, t, nrm); }
+        } else if (jt == 0 && tid < TJ + TI) {
+#pragma unroll
+            for (int cc = 0; cc < KC; ++cc) { const float t = Ab[cc * TI + swz(cc, tid - TJ)]; nrm = __fmaf_rn(t, t, nrm); }
+        }
+#pragma unroll
+        for (int cc = 0; cc < KC; ++cc) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&Ab[cc * TI + swz(cc, ty * 4)]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bb[cc * TJ + swz(cc, tx * 4)]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bb[cc * TJ + swz(cc, 64 + tx * 4)]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[a][q] = __fmaf_rn(av[a], bv[q], acc[a][q]);
+        }
+        if (ci != nch - 1) continue;     // more channel chunks of this tile to come
+
         if (tid < TJ) xxj[tid] = nrm;
         else if (jt == 0 && tid < TJ + TI) xxi[tid - TJ] = nrm;
         __syncthreads();
@@ -198,7 +226,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
                     if (p >= tv && j0 + col < N) {
                         const int slot = atomicAdd(&qcnt[r], 1);
                         qv[r * TJ + slot] = p;
-                        qj[r * TJ + slot] = j0 + col;
+                        qj[r * TJ + slot] = (unsigned char)col;
                     }
                 }
             }
@@ -220,7 +248,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
                 for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
                     const bool have = q0 + lane < cnts[rr];
                     const int qi = (r0 + rr) * TJ + q0 + lane;
-                    c[rr] = have ? make_key(qv[qi], qj[qi]) : 0ull;
+                    c[rr] = have ? make_key(qv[qi], j0 + (int)qj[qi]) : 0ull;
                     const key_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
                     m[rr] = __ballot_sync(SV_FULL, c[rr] > worst);
                     any_merge |= __popc(m[rr]) >= MERGE_MIN;
@@ -270,7 +298,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
                 if (lane == 0 && cnts[rr] > 0) { qcnt[r0 + rr] = 0; thr[r0 + rr] = key_score(worst); }
             }
         }
-        // (the next tile's first __syncthreads orders these writes before the next push phase)
+        // (the next stage's __syncthreads orders these writes before the next push phase)
     }
 #pragma unroll
     for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
@@ -291,7 +319,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
 template <int R, int KC>
 int launch_knn(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, cudaStream_t st)
 {
-    const size_t smem = sizeof(float) * (KC * TI + KC * TJ + TI + TJ + TI + TI + 2 * TI * TJ);
+    const size_t smem = sizeof(float) * (2 * KC * TI + 2 * KC * TJ + TI + TJ + TI + TI + TI * TJ) + TI * TJ;
     dim3 grid(sv_cdiv(N, TI), B);
     SV_CUDA(cudaFuncSetAttribute(knn_kernel<R, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_kernel<R, KC><<<grid, NT, smem, st>>>(*in, N, k, idx32, idx64);
