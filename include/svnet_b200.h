@@ -257,6 +257,11 @@ int svnet_vector_bn_rows(const float* v, long rows, int C, const float* bn_a, co
 int svnet_pool_rows(const float* x, int ld, int C, int B, long rows, float* max_out, float* mean_out, int ldo,
                     void* stream);
 
+/* Input side of the eval loop: out[b][c][n] = sum_d pts[b][n][d] * R[b][d][c]
+ * (pytorch3d Rotate.transform_points, then permute(0,2,1): main_cls_dgcnn.py:229-235).
+ * pts [B][N][3], R [B][3][3] or NULL (permute only) -> out [B][3][N]. */
+int svnet_rotate_permute(const float* pts, const float* R, int B, int N, float* out, void* stream);
+
 /* svpool over k on materialised edge tensors (module-level parity, sv_util.py:118-132) is
  * svnet_pool_rows with B := B*N and rows := k. */
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "svnet_version", "svnet_last_error", "svnet_pack_sign", "svnet_fold_bn", "svnet_knn",
     "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
-    "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd",
+    "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
 ]
 
 
@@ -321,4 +321,13 @@ def head_fwd(x2d, layers):
     out = torch.empty((B, layers[-1]["Cout"]), dtype=torch.float32, device=x2d.device)
     p.out, p.ldo = out.data_ptr(), out.shape[1]
     _call("svnet_head_fwd", ctypes.byref(p), _stream())
+    return out
+
+
+def rotate_permute(pts, R=None):
+    """pts (B,N,3) [, R (B,3,3)] -> (B,3,N) = (pts @ R).permute(0,2,1)"""
+    B, N, _ = pts.shape
+    out = torch.empty((B, 3, N), dtype=torch.float32, device=pts.device)
+    _call("svnet_rotate_permute", _ptr(_dev(pts.contiguous())), _ptr(R.contiguous() if R is not None else None),
+          c_int(B), c_int(N), _ptr(out), _stream())
     return out

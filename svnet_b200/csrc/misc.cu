@@ -225,3 +225,40 @@ extern "C" int svnet_pool_rows(const float* x, int ld, int C, int B, long rows, 
     SV_CHECK_LAUNCH("svnet_pool_rows");
     return SVNET_OK;
 }
+
+// ---- input side of the eval loop: random-rotation transform + (B,N,3)->(B,3,N) ----
+namespace {
+// out[b][c][n] = sum_d p[b][n][d] * R[b][d][c]   (pytorch3d Rotate.transform_points = points @ R, then
+// data.permute(0, 2, 1): reference main_cls_dgcnn.py:229-235)
+__global__ void rotate_permute_kernel(const float* __restrict__ pts, const float* __restrict__ R, int B, int N,
+                                      float* __restrict__ out)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)B * N) return;
+    const int b = (int)(t / N), n = (int)(t - (long)b * N);
+    const float p0 = pts[t * 3], p1 = pts[t * 3 + 1], p2 = pts[t * 3 + 2];
+    float* o = out + (long)b * 3 * N + n;
+    if (R) {
+        const float* r = R + (long)b * 9;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a = __fmul_rn(p0, r[c]);
+            a = __fmaf_rn(p1, r[3 + c], a);
+            a = __fmaf_rn(p2, r[6 + c], a);
+            o[(long)c * N] = a;
+        }
+    } else {
+        o[0] = p0; o[N] = p1; o[2L * N] = p2;
+    }
+}
+}  // namespace
+
+extern "C" int svnet_rotate_permute(const float* pts, const float* R, int B, int N, float* out, void* stream)
+{
+    SV_REQUIRE(pts && out, "svnet_rotate_permute: null pointer");
+    SV_REQUIRE(B >= 0 && N >= 1, "svnet_rotate_permute: bad shape");
+    if (B == 0) return SVNET_OK;
+    rotate_permute_kernel<<<sv_cdiv((long)B * N, 256), 256, 0, sv_stream(stream)>>>(pts, R, B, N, out);
+    SV_CHECK_LAUNCH("svnet_rotate_permute");
+    return SVNET_OK;
+}

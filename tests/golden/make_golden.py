@@ -267,8 +267,33 @@ def golden_models():
                  2, 64, 109, with_label=True)
 
 
+def golden_metrics():
+    """utils.calculate_shape_IoU (utils.py:68-91) on random predictions."""
+    import utils as ref_utils
+    rng = np.random.RandomState(5)
+    label = rng.randint(0, 16, size=(6, 1))
+    seg = np.zeros((6, 50), dtype=np.int64)
+    pred = np.zeros((6, 50), dtype=np.int64)
+    for i in range(6):
+        lo, n = ref_utils_index_start[label[i, 0]], ref_utils_seg_num[label[i, 0]]
+        seg[i] = rng.randint(lo, lo + n, size=50)
+        pred[i] = np.where(rng.rand(50) < 0.6, seg[i], rng.randint(0, 50, size=50))
+    seg[0] = seg[0][0]          # a shape with a single part present: empty unions count as IoU 1
+    pred[0] = seg[0]
+    ious = np.array(ref_utils.calculate_shape_IoU(pred, seg, label))
+    save("metrics", pred=pred, seg=seg, label=label, ious=ious)
+
+
+ref_utils_seg_num = [4, 2, 2, 4, 4, 3, 3, 2, 4, 2, 6, 2, 3, 3, 3, 3]
+ref_utils_index_start = [0, 4, 6, 8, 12, 16, 19, 22, 24, 28, 30, 36, 38, 41, 44, 47]
+
+
 if __name__ == "__main__":
+    if "--metrics-only" in sys.argv:
+        golden_metrics()
+        sys.exit(0)
     golden_knn()
     golden_graph_features()
     golden_layers()
     golden_models()
+    golden_metrics()

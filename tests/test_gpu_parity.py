@@ -437,3 +437,24 @@ def test_fast_edge_kernels_teacher_forced_k_full(cls_name, k, N):
         assert_close(got_v, o_v, rtol=1e-4, atol=1e-5, what="layer %d v" % (li + 1))
         so += cs
         vo += cv
+
+
+def test_rotate_permute_input_transform():
+    """Input side of the eval loop (main_cls_dgcnn.py:229-235): (B,N,3) @ R then permute -> (B,3,N)."""
+    from svnet_b200.evalutil import random_rotations, rotate_points
+    pts = synthetic_clouds(3, 200, 4).transpose(1, 2).contiguous()          # (B,N,3)
+    R = random_rotations(3, generator=torch.Generator().manual_seed(2))
+    out = rotate_points(pts.to(DEV), R.to(DEV))
+    ref = torch.bmm(pts.double(), R.double()).permute(0, 2, 1)
+    assert tuple(out.shape) == (3, 3, 200)
+    assert_close(t2n(out), ref.numpy(), rtol=1e-6, atol=1e-6)
+    assert torch.equal(rotate_points(pts.to(DEV)).cpu(), pts.permute(0, 2, 1))
+    # SO(3) invariance of the fp classifier (SURVEY.md 4.3): rotated input, same logits
+    import svnet_b200 as sv
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=12, binary=False), 40)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=33))
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        y0 = net(rotate_points(pts.to(DEV)))
+        y1 = net(out)
+    assert_close(t2n(y1), t2n(y0), rtol=1e-3, atol=1e-4, what="SO(3) invariance of fp logits")

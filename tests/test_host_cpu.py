@@ -124,3 +124,28 @@ def test_sharded_inference_gloo_world2(batch):
     for p in procs:
         p.join(timeout=60)
     assert sorted(r for r, _ in res) == [0, 1] and all(ok for _, ok in res)
+
+
+def test_shape_iou_matches_reference():
+    from svnet_b200.evalutil import calculate_shape_IoU, classification_metrics
+    g = golden("metrics")
+    ious = calculate_shape_IoU(g["pred"], g["seg"], g["label"])
+    assert np.allclose(ious, g["ious"], rtol=0, atol=1e-12)
+    acc, bal = classification_metrics([0, 0, 1, 1, 2], [0, 1, 1, 1, 2])
+    assert abs(acc - 0.8) < 1e-12 and abs(bal - (0.5 + 1 + 1) / 3) < 1e-12
+
+
+def test_checkpoint_helpers(tmp_path):
+    import svnet_b200 as sv
+    from svnet_b200.evalutil import load_checkpoint, load_weights, random_rotations
+    net = quiet(sv.SV_PointNet_CLS, make_args(k=8, binary=True), 40)
+    sd = synthetic_state_dict(net.state_dict(), seed=9)
+    path = str(tmp_path / "sv_pointnet_binary_modelnet40.pth")
+    torch.save(wrap_checkpoint(sd), path)
+    state = load_checkpoint(path)
+    assert set(state) >= {"epoch", "state_dict"} and all(k.startswith("module.") for k in state["state_dict"])
+    load_weights(net, path)
+    assert state_dict_digest(net.state_dict()) == state_dict_digest(sd)
+    R = random_rotations(5, generator=torch.Generator().manual_seed(1))
+    eye = torch.eye(3).expand(5, 3, 3)
+    assert torch.allclose(R @ R.transpose(1, 2), eye, atol=1e-5) and torch.allclose(torch.linalg.det(R), torch.ones(5), atol=1e-5)
