@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 int svnet_signlinear_tc_dispatch(const svnet_gemm_params* p, cudaStream_t st);
+int svnet_vlinear_tcgen05_dispatch(const svnet_gemm_params* p, cudaStream_t st);
 
 namespace {
 
@@ -134,7 +135,12 @@ extern "C" int svnet_linear_rows(const svnet_gemm_params* p, void* stream)
     }
     if (p->M == 0) return SVNET_OK;
     cudaStream_t st = sv_stream(stream);
-    {   // binary-weight vector linears: exact-split bf16 tensor-core kernel (gemm_tc.cu)
+    {   // binary-weight vector linear + VectorBN: tcgen05 / TMEM kernel (gemm_tcgen05.cu)
+        const int h = svnet_vlinear_tcgen05_dispatch(p, st);
+        if (h < 0) return h;
+        if (h == 1) return SVNET_OK;
+    }
+    {   // binary-weight vector linears: exact-split bf16 mma.sync kernel (gemm_tc.cu)
         const int h = svnet_signlinear_tc_dispatch(p, st);
         if (h < 0) return h;
         if (h == 1) return SVNET_OK;

@@ -458,3 +458,38 @@ def test_rotate_permute_input_transform():
         y0 = net(rotate_points(pts.to(DEV)))
         y1 = net(out)
     assert_close(t2n(y1), t2n(y0), rtol=1e-3, atol=1e-4, what="SO(3) invariance of fp logits")
+
+
+def test_vector_linear_tensor_core_paths_agree(monkeypatch):
+    """The binary-weight vector linear + VectorBN + gate has three implementations: CUDA cores
+    (sequential fp32 chains), mma.sync bf16 and tcgen05/TMEM bf16, the latter two on an exact 3-way
+    bf16 split of the activations.  All must agree to fp32 rounding, and with the oracle."""
+    from svnet_b200 import _native as nv
+    R, K, N, rpc = 1000, 83, 170, 250
+    v, W = rnd((R, 3, K), 1), rnd((N, K), 2)
+    sc = np.abs(rnd((N,), 3)) + 0.5
+    bn = tuple(np.ascontiguousarray(t, dtype=np.float32) for t in (np.abs(rnd((N,), 4)) + 0.5, rnd((N,), 5, 0.1),
+                                                                   rnd((N,), 6, 0.1), np.abs(rnd((N,), 7)) + 0.5))
+    gate = 1.0 / (1.0 + np.exp(-rnd((R // rpc, N), 8)))
+    ref = orc.scale_v(orc.vector_bn(orc.linear(v, W, scale=sc, bw=True), bn).reshape(R // rpc, rpc, 3, N), gate)
+    inv = 1.0 / np.sqrt(bn[3] + np.float32(1e-5))
+    a_np = (bn[0] * inv).astype(np.float32)
+    c_np = (bn[1] - bn[2] * a_np).astype(np.float32)
+    outs = {}
+    for name, env in (("cuda_cores", {"SVNET_TCGEN05": "0", "SVNET_NO_TC": "1"}),
+                      ("mma_sync", {"SVNET_TCGEN05": "0", "SVNET_NO_TC": "0"}),
+                      ("tcgen05", {"SVNET_TCGEN05": "1", "SVNET_NO_TC": "0"})):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        out = torch.zeros(R, 3, N, device=DEV)
+        vt = cu(v)
+        nv.linear_rows(vt, vt.stride(0), vt.stride(1), 3, 3 * R, K, cu(W), N, out, out.stride(0), out.stride(1),
+                       sign_w=True, colscale=cu(sc), bn=(cu(a_np), cu(c_np)), vbn=True, gate=cu(gate.astype(np.float32)),
+                       groups_per_cloud=rpc)
+        outs[name] = t2n(out).reshape(R // rpc, rpc, 3, N)
+        assert_close(outs[name], ref, what=name + " vs oracle")          # north_star tolerance
+    # the tensor-core paths only reorder the fp32 summation: typical agreement is ~1e-6 relative
+    for name in ("mma_sync", "tcgen05"):
+        assert_close(outs[name], outs["cuda_cores"], what=name + " vs CUDA cores")
+        rel = np.abs(outs[name] - outs["cuda_cores"]).mean() / np.abs(outs["cuda_cores"]).mean()
+        assert rel < 1e-5, (name, rel)
