@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(NTH, 2) vlinear_tcgen05_kernel(svnet_gemm_para
             const int c = mt * 128 + (warp & 3) * 32 + lane;
             const bool cok = c < p.N;
             const float cs = (cok && p.colscale) ? p.colscale[c] : 1.0f;
-            const float a2 = cok ? p.bn_a[c] : 0.0f, c2 = cok ? p.bn_c[c] : 0.0f;
+            const float a2 = (cok && p.vbn) ? p.bn_a[c] : 0.0f, c2 = (cok && p.vbn) ? p.bn_c[c] : 0.0f;
             const uint32_t tbase = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(mt * NCOL);
             const unsigned gpc = (unsigned)p.groups_per_cloud;
             for (int q0 = 0; q0 < PTS; q0 += 16) {
@@ -206,6 +206,11 @@ __global__ void __launch_bounds__(NTH, 2) vlinear_tcgen05_kernel(svnet_gemm_para
                     const long pnt = p0 + q0 + e;
                     if (!cok || pnt >= npoints) continue;
                     const float w0 = __fmul_rn(vx[e], cs), w1 = __fmul_rn(vy[e], cs), w2 = __fmul_rn(vz[e], cs);
+                    if (!p.vbn) {   // plain table (P|Q of the fused edge kernel)
+                        float* cq = p.C + pnt * p.ldc_g + c;
+                        cq[0] = w0; cq[p.ldc_x] = w1; cq[2L * p.ldc_x] = w2;
+                        continue;
+                    }
                     const float nrm = __fadd_rn(
                         __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, w0), __fmul_rn(w1, w1)), __fmul_rn(w2, w2))), 1e-6f);
                     const float nb = __fadd_rn(__fmul_rn(nrm, a2), c2);
@@ -231,8 +236,8 @@ int svnet_vlinear_tcgen05_dispatch(const svnet_gemm_params* p, cudaStream_t st)
 {
     const char* on = getenv("SVNET_TCGEN05");
     if (on && on[0] == '0') return 0;                         // SVNET_TCGEN05=0 falls back to mma.sync / CUDA cores
-    if (!p->sign_w || !p->vbn || p->G != 3 || p->M % 3 != 0) return 0;
-    if (p->K < 32 || p->K > 96 || p->N > 256 || p->bias || p->act != SVNET_ACT_NONE) return 0;
+    if (!p->sign_w || p->G != 3 || p->M % 3 != 0) return 0;
+    if (p->K > 96 || p->N > 256 || p->bias || p->act != SVNET_ACT_NONE || (!p->vbn && p->bn_a)) return 0;
     const int Kpad = (p->K + 15) / 16 * 16;
     const int MT = (p->N + 127) / 128;
     const long npoints = p->M / 3;
