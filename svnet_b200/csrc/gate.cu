@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(NT) gate_edge_cluster_kernel(svnet_view in, co
     if (rank == 0) gate_mlp(mean, 2 * Cs, G1, G2, H, Co, h, gate + (long)b * Co);
 }
 
-// smem: mean[3nv] | h[H] | part[NT][9]
+// smem: mean[3nv] | h[H] | part[NT][9] | psum[9]   (launched as a thread-block cluster per cloud)
 template <int NV>
 __global__ void __launch_bounds__(NT) gate_xyz_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ idx,
                                                       int N, int k, const float* __restrict__ Winit,
@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(NT) gate_xyz_kernel(const float* __restrict__ 
     float* mean = sm;
     float* h = mean + 3 * NV;
     float* part = h + H;
-    const int b = blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
+    const int b = blockIdx.x / csize;
     float W[3][NV];
 #pragma unroll
     for (int m = 0; m < 3; ++m)
@@ -259,7 +261,9 @@ __global__ void __launch_bounds__(NT) gate_xyz_kernel(const float* __restrict__ 
     for (int q = 0; q < 3 * NV; ++q) acc[q] = 0.0f;
     const float* xb = xyz + (long)b * N * 3;
     const int32_t* ib = idx + (long)b * N * k;
-    for (long t = threadIdx.x; t < (long)N * k; t += NT) {
+    const long E = (long)N * k;
+    const long e_lo = E * crank / csize, e_hi = E * (crank + 1) / csize;
+    for (long t = e_lo + threadIdx.x; t < e_hi; t += NT) {
         const int i = (int)(t / k);
         const int j = ib[t];
         float xi[3] = {xb[i * 3], xb[i * 3 + 1], xb[i * 3 + 2]};
@@ -295,13 +299,23 @@ __global__ void __launch_bounds__(NT) gate_xyz_kernel(const float* __restrict__ 
 #pragma unroll
     for (int q = 0; q < 3 * NV; ++q) part[threadIdx.x * 9 + q] = acc[q];
     __syncthreads();
+    float* psum = part + NT * 9;   // [9] this CTA's partial sums (read by rank 0 through DSMEM)
     if (threadIdx.x < 3 * NV) {
         float t = 0.0f;
         for (int i = 0; i < NT; ++i) t += part[i * 9 + threadIdx.x];
-        mean[threadIdx.x] = t / ((float)N * (float)k);
+        psum[threadIdx.x] = t;
     }
-    __syncthreads();
-    gate_mlp(mean, 3 * NV, G1, G2, H, Co, h, gate + (long)b * Co);
+    cluster.sync();
+    if (crank == 0) {
+        if (threadIdx.x < 3 * NV) {
+            float t = 0.0f;
+            for (unsigned q = 0; q < csize; ++q) t += cluster.map_shared_rank(psum, q)[threadIdx.x];
+            mean[threadIdx.x] = t / ((float)N * (float)k);
+        }
+        __syncthreads();
+    }
+    cluster.sync();
+    if (crank == 0) gate_mlp(mean, 3 * NV, G1, G2, H, Co, h, gate + (long)b * Co);
 }
 
 }  // namespace
@@ -380,11 +394,21 @@ extern "C" int svnet_gate_xyz(const float* xyz, const int32_t* idx, int B, int N
     SV_REQUIRE(xyz && idx && Winit && G1 && G2 && gate, "svnet_gate_xyz: null pointer");
     SV_REQUIRE((nv == 2 || nv == 3) && N >= 1 && k >= 1 && H >= 1 && Co >= 1 && B >= 0, "svnet_gate_xyz: bad shape");
     if (B == 0) return SVNET_OK;
-    const size_t smem = sizeof(float) * ((size_t)3 * nv + H + NT * 9);
+    const size_t smem = sizeof(float) * ((size_t)3 * nv + H + NT * 9 + 12);
+    const int cl = ((long)N * k >= 4096) ? CL : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * cl);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = sv_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     if (nv == 2)
-        gate_xyz_kernel<2><<<B, NT, smem, sv_stream(stream)>>>(xyz, idx, N, k, Winit, G1, G2, H, Co, gate);
+        SV_CUDA(cudaLaunchKernelEx(&cfg, gate_xyz_kernel<2>, xyz, idx, N, k, Winit, G1, G2, H, Co, gate));
     else
-        gate_xyz_kernel<3><<<B, NT, smem, sv_stream(stream)>>>(xyz, idx, N, k, Winit, G1, G2, H, Co, gate);
+        SV_CUDA(cudaLaunchKernelEx(&cfg, gate_xyz_kernel<3>, xyz, idx, N, k, Winit, G1, G2, H, Co, gate));
     SV_CHECK_LAUNCH("svnet_gate_xyz");
     return SVNET_OK;
 }

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(NTH, 2) vlinear_tcgen05_kernel(svnet_gemm_para
                     : "=r"(done)
                     : "r"(smem_u32(mbar)), "r"(phase)
                     : "memory");
-                if (++spins > (1L << 24)) { if (err_flag) atomicExch(err_flag, 1); break; }
+                if (++spins > (1L << 26)) { if (err_flag) atomicExch(err_flag, 1); __trap(); }   // fail loudly, never hang
             }
             phase ^= 1;
         }
