@@ -131,6 +131,120 @@ __global__ void __launch_bounds__(WARPS * 32) edge_xyz_kernel(svnet_edge_xyz_par
     }
 }
 
+// Shape-specialised variant: 8 centre points per warp, 4 lanes per point, every lane walks its share of
+// the point's edges sequentially and keeps the running max / sum of all outputs in registers; only
+// two shuffle steps per output at the very end.  All 32 lanes stay busy (the generic kernel above
+// uses one lane per edge: 20 of 32 at k=20) and there is no per-edge cross-lane reduction.
+template <int NV, int COUT, int CVO>
+__global__ void __launch_bounds__(WARPS * 32, 2) edge_xyz_fast_kernel(svnet_edge_xyz_params p)
+{
+    constexpr int KU = 6 * NV;
+    __shared__ float W1[COUT * KU], a1[COUT], c1[COUT], W2[CVO * NV], a2[CVO], c2[CVO], Wi[3 * NV], Wz[3 * NV];
+    for (int i = threadIdx.x; i < COUT * KU; i += blockDim.x) W1[i] = p.W1[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) { a1[i] = p.bn1_a[i]; c1[i] = p.bn1_c[i]; }
+    for (int i = threadIdx.x; i < CVO * NV; i += blockDim.x) W2[i] = p.W2[i];
+    for (int i = threadIdx.x; i < CVO; i += blockDim.x) { a2[i] = p.bn2_a[i]; c2[i] = p.bn2_c[i]; }
+    for (int i = threadIdx.x; i < 3 * NV; i += blockDim.x) { Wi[i] = p.Winit[i]; Wz[i] = p.Wz[i]; }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, sub = lane & 3;
+    const long r = ((long)blockIdx.x * WARPS + (threadIdx.x >> 5)) * 8 + (lane >> 2);
+    const bool rok = r < (long)p.B * p.N;
+    const long rr = rok ? r : 0;
+    const int b = (int)(rr / p.N);
+    const float xi[3] = {p.xyz[rr * 3], p.xyz[rr * 3 + 1], p.xyz[rr * 3 + 2]};
+
+    float smax[COUT], vsum[3][CVO];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) smax[o] = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CVO; ++c) { vsum[0][c] = 0.0f; vsum[1][c] = 0.0f; vsum[2][c] = 0.0f; }
+
+    for (int e = sub; e < p.k; e += 4) {
+        asm volatile("" ::: "memory");   // keep the (loop-invariant) weight loads inside the loop: no register blow-up
+        const long j = (long)b * p.N + p.idx[rr * p.k + e];
+        const float xj[3] = {p.xyz[j * 3], p.xyz[j * 3 + 1], p.xyz[j * 3 + 2]};
+        float ve[3][NV];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { ve[a][0] = __fsub_rn(xj[a], xi[a]); ve[a][1] = xi[a]; }
+        if (NV == 3) {
+            ve[0][NV - 1] = __fsub_rn(__fmul_rn(xj[1], xi[2]), __fmul_rn(xj[2], xi[1]));
+            ve[1][NV - 1] = __fsub_rn(__fmul_rn(xj[2], xi[0]), __fmul_rn(xj[0], xi[2]));
+            ve[2][NV - 1] = __fsub_rn(__fmul_rn(xj[0], xi[1]), __fmul_rn(xj[1], xi[0]));
+        }
+        float u[KU];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const float* W = pass == 0 ? Wi : Wz;
+            float z[3][3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    float zz = 0.0f;
+#pragma unroll
+                    for (int d = 0; d < NV; ++d) zz = __fmaf_rn(ve[a][d], W[m * NV + d], zz);
+                    z[a][m] = zz;
+                }
+#pragma unroll
+            for (int d = 0; d < NV; ++d)
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    float q = __fmul_rn(ve[0][d], z[0][m]);
+                    q = __fmaf_rn(ve[1][d], z[1][m], q);
+                    q = __fmaf_rn(ve[2][d], z[2][m], q);
+                    u[pass * 3 * NV + d * 3 + m] = q;
+                }
+        }
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            float y = 0.0f;
+#pragma unroll
+            for (int t = 0; t < KU; ++t) y = __fmaf_rn(u[t], W1[o * KU + t], y);
+            y = __fadd_rn(__fmul_rn(y, a1[o]), c1[o]);
+            y = y > 0.0f ? y : __fmul_rn(0.2f, y);
+            smax[o] = fmaxf(smax[o], y);
+        }
+#pragma unroll
+        for (int c = 0; c < CVO; ++c) {
+            float w[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float t = 0.0f;
+#pragma unroll
+                for (int d = 0; d < NV; ++d) t = __fmaf_rn(ve[a][d], W2[c * NV + d], t);
+                w[a] = t;
+            }
+            const float n = __fadd_rn(
+                __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(w[0], w[0]), __fmul_rn(w[1], w[1])), __fmul_rn(w[2], w[2]))),
+                1e-6f);
+            const float nb = __fadd_rn(__fmul_rn(n, a2[c]), c2[c]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) vsum[a][c] += __fmul_rn(__fdiv_rn(w[a], n), nb);
+        }
+    }
+    // combine the four lanes of a point; lane `sub` stores outputs o = sub, sub+4, ...
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+        float m = smax[o];
+        m = fmaxf(m, __shfl_xor_sync(SV_FULL, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(SV_FULL, m, 2));
+        if (rok && (o & 3) == sub) p.out.s[r * p.out.lds + o] = m;
+    }
+    const float inv_k = 1.0f / (float)p.k;
+#pragma unroll
+    for (int c = 0; c < CVO; ++c) {
+        const float g = p.gate[(long)b * CVO + c];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float t = vsum[a][c];
+            t += __shfl_xor_sync(SV_FULL, t, 1);
+            t += __shfl_xor_sync(SV_FULL, t, 2);
+            if (rok && ((a * CVO + c) & 3) == sub) p.out.v[r * p.out.ldv + a * p.out.xs + c] = (t * inv_k) * g;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int svnet_edge_xyz_fwd(const svnet_edge_xyz_params* p, void* stream)
@@ -145,6 +259,18 @@ extern "C" int svnet_edge_xyz_fwd(const svnet_edge_xyz_params* p, void* stream)
                "svnet_edge_xyz_fwd: Cout=%d (<=64) Cvo=%d (<=32) unsupported", p->Cout, p->Cvo);
     const long P = (long)p->B * p->N;
     if (P == 0) return SVNET_OK;
+    if (P > 0) {
+        const int gridf = sv_cdiv(P, WARPS * 8);
+        bool done = true;
+        if (p->nv == 2 && p->Cout == 32 && p->Cvo == 10) edge_xyz_fast_kernel<2, 32, 10><<<gridf, WARPS * 32, 0, sv_stream(stream)>>>(*p);
+        else if (p->nv == 2 && p->Cout == 32 && p->Cvo == 16) edge_xyz_fast_kernel<2, 32, 16><<<gridf, WARPS * 32, 0, sv_stream(stream)>>>(*p);
+        else if (p->nv == 3 && p->Cout == 32 && p->Cvo == 10) edge_xyz_fast_kernel<3, 32, 10><<<gridf, WARPS * 32, 0, sv_stream(stream)>>>(*p);
+        else done = false;
+        if (done) {
+            SV_CHECK_LAUNCH("svnet_edge_xyz_fwd(fast)");
+            return SVNET_OK;
+        }
+    }
     const size_t smem = sizeof(float) * ((size_t)p->Cout * 6 * p->nv + 2 * p->Cout + (size_t)p->Cvo * p->nv + 2 * p->Cvo + 6 * p->nv);
     const int grid = sv_cdiv(P, WARPS);
     if (p->nv == 2) edge_xyz_kernel<2><<<grid, WARPS * 32, smem, sv_stream(stream)>>>(*p);
