@@ -493,3 +493,18 @@ def test_vector_linear_tensor_core_paths_agree(monkeypatch):
         assert_close(outs[name], outs["cuda_cores"], what=name + " vs CUDA cores")
         rel = np.abs(outs[name] - outs["cuda_cores"]).mean() / np.abs(outs["cuda_cores"]).mean()
         assert rel < 1e-5, (name, rel)
+
+
+def test_point_permutation_invariance_fp():
+    """SURVEY.md 4.3 property test: the fp classifier's logits do not depend on the order of the
+    points of a cloud (kNN, pooling and the gates are symmetric functions of the point set)."""
+    import svnet_b200 as sv
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=16, binary=False), 40)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=44))
+    net = net.to(DEV).eval()
+    x = synthetic_clouds(2, 300, 9).to(DEV)
+    perm = torch.randperm(300, generator=torch.Generator().manual_seed(3)).to(DEV)
+    with torch.no_grad():
+        y0 = net(x)
+        y1 = net(x[:, :, perm].contiguous())
+    assert_close(t2n(y1), t2n(y0), rtol=1e-3, atol=1e-4, what="permutation invariance")
