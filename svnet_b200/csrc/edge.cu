@@ -398,5 +398,13 @@ extern "C" int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream)
         return launch_edge<true>(p, sv_stream(stream));
     }
     SV_REQUIRE(p->Yab && p->W1q_t, "svnet_svblock_edge_fwd: fp layer needs Yab/W1q_t");
+    {
+        const char* force = getenv("SVNET_EDGE_GENERIC");
+        if (!(force && force[0] == '1')) {
+            const int h = svnet_edge_fast_dispatch(p, sv_stream(stream));
+            if (h < 0) return h;
+            if (h == 1) return SVNET_OK;
+        }
+    }
     return launch_edge<false>(p, sv_stream(stream));
 }

@@ -300,6 +300,219 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 4 :
     }
 }
 
+// ---- full-precision variant (SV-DGCNN fp models, cfg3): same gather / frame phases, the scalar
+// branch is a dense fp32 linear  y = (Ya_j - Ya_i) + Yb_i + W1q q  with q staged in shared memory
+// (edge index innermost so that 4 edges come with one 16-byte load) ----
+template <int CS, int CV, int COUT, int CVO, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_fp_fast_kernel(svnet_edge_params p, int kp)
+{
+    using S = Shape<CS, CV, COUT, CVO>;
+    constexpr int EB = S::EB;
+    constexpr int KQ = 6 * CV;
+    extern __shared__ __align__(16) float smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* Wz = smem_raw;                                   // [3][CVE], CTA-shared
+    constexpr int SHARED = (3 * S::CVE + 3) & ~3;
+    for (int i = threadIdx.x; i < 3 * S::CVE; i += blockDim.x) Wz[i] = p.Wz[i];
+    const int per_warp = (KQ * kp + 3 * S::XS + kp * S::ES + kp * 9 + 3 + kp + 3) & ~3;
+    float* wbase = smem_raw + SHARED + (size_t)warp * per_warp;
+    float* qs = wbase;                                      // [KQ][kp]  (16B aligned rows: kp % 4 == 0)
+    float* vc = qs + KQ * kp;                               // [3][XS]
+    float* ves = vc + 3 * S::XS;                            // [kp][3][XS]
+    float* zb = ves + kp * S::ES;                           // [kp][9]
+    int* nidx = reinterpret_cast<int*>(zb + kp * 9 + 3);    // [kp]
+    __syncthreads();
+
+    const long r = (long)blockIdx.x * WARPS + warp;
+    if (r >= (long)p.B * p.N) return;
+    const int b = (int)(r / p.N);
+    const long cbase = (long)b * p.N;
+    const int k = p.k;
+
+    int voff[S::TV], vso[S::TV];
+#pragma unroll
+    for (int t = 0; t < S::TV; ++t) {
+        const int f = 32 * t + lane, x = f / CV, d = f - x * CV;
+        voff[t] = (f < S::NVE) ? x * p.in.xs + d : -1;
+        vso[t] = x * S::XS + d;
+    }
+    for (int e = lane; e < kp; e += 32) nidx[e] = e < k ? p.idx[r * k + e] : 0;
+    float vi[S::TV];
+    const float* vrow = p.in.v + r * p.in.ldv;
+#pragma unroll
+    for (int t = 0; t < S::TV; ++t) {
+        vi[t] = voff[t] >= 0 ? __ldg(vrow + voff[t]) : 0.0f;
+        if (voff[t] >= 0) vc[vso[t]] = vi[t];
+    }
+    for (int i = lane; i < KQ * kp; i += 32) qs[i] = 0.0f;   // padded edge slots stay zero
+    __syncwarp();
+
+    // ---- P1: neighbour vectors by cp.async, differences in place ----
+    for (int e = 0; e < k; ++e) {
+        const float* vj = p.in.v + (cbase + nidx[e]) * p.in.ldv;
+#pragma unroll
+        for (int t = 0; t < S::TV; ++t)
+            if (voff[t] >= 0) cp_async4(ves + e * S::ES + vso[t], vj + voff[t]);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    for (int e = 0; e < k; ++e) {
+#pragma unroll
+        for (int t = 0; t < S::TV; ++t)
+            if (voff[t] >= 0) ves[e * S::ES + vso[t]] = __fsub_rn(ves[e * S::ES + vso[t]], vi[t]);
+    }
+    __syncwarp();
+
+    // ---- P2: frames (sequential chains, oracle order) ----
+    for (int task = lane; task < k * 9; task += 32) {
+        const int e = task / 9, xm = task - e * 9, x = xm / 3, m = xm - x * 3;
+        const float* dv = ves + e * S::ES + x * S::XS;
+        const float* cv = vc + x * S::XS;
+        const float* wz = Wz + m * S::CVE;
+        float acc = 0.0f;
+#pragma unroll
+        for (int d = 0; d < CV; ++d) acc = __fmaf_rn(dv[d], wz[d], acc);
+#pragma unroll
+        for (int d = 0; d < CV; ++d) acc = __fmaf_rn(cv[d], wz[CV + d], acc);
+        if (p.zscale) acc = __fmul_rn(acc, __ldg(p.zscale + m));
+        zb[task] = acc;
+    }
+    __syncwarp();
+
+    // ---- P3: q[e][3d+m] -> qs[t][e] ----
+    {
+        constexpr int QT = (KQ + 31) / 32;
+        const float* qsrc[QT];
+        int qstr[QT], zoff[QT];
+        bool qok[QT];
+#pragma unroll
+        for (int t = 0; t < QT; ++t) {
+            const int tq = 32 * t + lane, d = tq / 3, m = tq - d * 3;
+            qok[t] = tq < KQ;
+            zoff[t] = m;
+            if (d < CV) { qsrc[t] = ves + d; qstr[t] = S::ES; }
+            else { qsrc[t] = vc + (qok[t] ? d - CV : 0); qstr[t] = 0; }
+        }
+        const float* z = zb;
+#pragma unroll 2
+        for (int e = 0; e < k; ++e, z += 9) {
+#pragma unroll
+            for (int t = 0; t < QT; ++t) {
+                const float* src = qsrc[t];
+                qsrc[t] += qstr[t];
+                float q = __fmul_rn(src[0], z[zoff[t]]);
+                q = __fmaf_rn(src[S::XS], z[3 + zoff[t]], q);
+                q = __fmaf_rn(src[2 * S::XS], z[6 + zoff[t]], q);
+                if (qok[t]) qs[(32 * t + lane) * kp + e] = q;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- P4: dense fp32 linear1 + BN + LeakyReLU + max over edges; lanes = output channels ----
+#pragma unroll 1
+    for (int ob = 0; ob < S::OPT; ob += S::OPP) {
+        float smax[S::OPP];
+        float yi[S::OPP];
+#pragma unroll
+        for (int oo = 0; oo < S::OPP; ++oo) {
+            const int o = lane + 32 * (ob + oo);
+            smax[oo] = -INFINITY;
+            yi[oo] = __ldg(p.Yab + r * 2 * COUT + COUT + o) - __ldg(p.Yab + r * 2 * COUT + o);   // Yb_i - Ya_i
+        }
+        for (int eb = 0; eb < k; eb += EB) {
+            float acc[EB][S::OPP];
+#pragma unroll
+            for (int e = 0; e < EB; ++e) {
+                const float* yj = p.Yab + (cbase + nidx[eb + e]) * 2 * COUT + lane + 32 * ob;
+#pragma unroll
+                for (int oo = 0; oo < S::OPP; ++oo) acc[e][oo] = __ldg(yj + 32 * oo) + yi[oo];
+            }
+#pragma unroll 2
+            for (int t = 0; t < KQ; ++t) {
+                float wv[S::OPP];
+#pragma unroll
+                for (int oo = 0; oo < S::OPP; ++oo) wv[oo] = __ldg(p.W1q_t + (size_t)t * COUT + lane + 32 * (ob + oo));
+                const float4* qp = reinterpret_cast<const float4*>(qs + t * kp + eb);
+#pragma unroll
+                for (int e4 = 0; e4 < EB / 4; ++e4) {
+                    const float4 q4 = qp[e4];
+                    const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int oo = 0; oo < S::OPP; ++oo) acc[e4 * 4 + u][oo] = fmaf(qv[u], wv[oo], acc[e4 * 4 + u][oo]);
+                }
+            }
+#pragma unroll
+            for (int oo = 0; oo < S::OPP; ++oo) {
+                const int o = lane + 32 * (ob + oo);
+                const float a1 = __ldg(p.bn1_a + o), c1 = __ldg(p.bn1_c + o);
+#pragma unroll
+                for (int e = 0; e < EB; ++e) {
+                    if (eb + e < k) {
+                        float y = __fadd_rn(__fmul_rn(acc[e][oo], a1), c1);
+                        y = y > 0.0f ? y : __fmul_rn(0.2f, y);
+                        smax[oo] = fmaxf(smax[oo], y);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int oo = 0; oo < S::OPP; ++oo) p.out.s[r * p.out.lds + lane + 32 * (ob + oo)] = smax[oo];
+    }
+
+    // ---- P5: vector branch ----
+    constexpr int LDP = 2 * CVO;
+    const float inv_k = 1.0f / (float)k;
+    for (int c = lane; c < CVO; c += 32) {
+        const float* pi = p.PQ + r * 3 * LDP + c;
+        const float p_i[3] = {__ldg(pi), __ldg(pi + LDP), __ldg(pi + 2 * LDP)};
+        const float q_i[3] = {__ldg(pi + CVO), __ldg(pi + LDP + CVO), __ldg(pi + 2 * LDP + CVO)};
+        const float a2 = __ldg(p.bn2_a + c), c2 = __ldg(p.bn2_c + c);
+        float sum[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll 10
+        for (int e = 0; e < k; ++e) {
+            const float* pj = p.PQ + (cbase + nidx[e]) * 3 * LDP + c;
+            float w[3];
+#pragma unroll
+            for (int x = 0; x < 3; ++x) w[x] = (__ldg(pj + x * LDP) - p_i[x]) + q_i[x];
+            const float n = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]) + 1e-6f;
+            const float t = (n * a2 + c2) / n;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) sum[x] += w[x] * t;
+        }
+        const float g = p.gate[(long)b * CVO + c] * inv_k;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + c] = sum[x] * g;
+    }
+}
+
+template <int CS, int CV, int COUT, int CVO>
+int launch_fp_fast(const svnet_edge_params* p, cudaStream_t st)
+{
+    using S = Shape<CS, CV, COUT, CVO>;
+    constexpr int EB = S::EB;
+    constexpr int KQ = 6 * CV;
+    const int kp = ((p->k + EB - 1) / EB) * EB;
+    constexpr int SHARED = (3 * S::CVE + 3) & ~3;
+    const int per_warp = (KQ * kp + 3 * S::XS + kp * S::ES + kp * 9 + 3 + kp + 3) & ~3;
+    const long P = (long)p->B * p->N;
+    auto smem_for = [&](int warps) { return sizeof(float) * (size_t)(SHARED + warps * per_warp); };
+    if (smem_for(8) <= 100 * 1024) {
+        const size_t smem = smem_for(8);
+        SV_CUDA(cudaFuncSetAttribute(edge_fp_fast_kernel<CS, CV, COUT, CVO, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        edge_fp_fast_kernel<CS, CV, COUT, CVO, 8><<<sv_cdiv(P, 8), 256, smem, st>>>(*p, kp);
+    } else {
+        const size_t smem = smem_for(4);
+        SV_REQUIRE(smem <= 200 * 1024, "svnet_svblock_edge_fwd: k=%d too large for the fused fp kernel", p->k);
+        SV_CUDA(cudaFuncSetAttribute(edge_fp_fast_kernel<CS, CV, COUT, CVO, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        edge_fp_fast_kernel<CS, CV, COUT, CVO, 4><<<sv_cdiv(P, 4), 128, smem, st>>>(*p, kp);
+    }
+    SV_CHECK_LAUNCH("svnet_svblock_edge_fwd(fp fast)");
+    return SVNET_OK;
+}
+
 template <int CS, int CV, int COUT, int CVO>
 int launch_fast(const svnet_edge_params* p, cudaStream_t st)
 {
@@ -330,9 +543,19 @@ int launch_fast(const svnet_edge_params* p, cudaStream_t st)
 // < 0 on error.
 int svnet_edge_fast_dispatch(const svnet_edge_params* p, cudaStream_t st)
 {
-    if (!p->binary) return 0;
     const int cs = p->in.Cs, cv = p->in.Cv, co = p->Cout, cvo = p->Cvo;
     int rc = 1;
+    if (!p->binary) {
+#define FCASE(A, Bv, C, D) if (cs == A && cv == Bv && co == C && cvo == D) { rc = launch_fp_fast<A, Bv, C, D>(p, st); return rc == SVNET_OK ? 1 : rc; }
+        FCASE(32, 10, 32, 10)
+        FCASE(32, 10, 64, 21)
+        FCASE(64, 21, 128, 42)
+        FCASE(32, 16, 32, 16)
+        FCASE(32, 16, 64, 24)
+        FCASE(64, 24, 128, 40)
+#undef FCASE
+        return 0;
+    }
 #define CASE(A, Bv, C, D) if (cs == A && cv == Bv && co == C && cvo == D) { rc = launch_fast<A, Bv, C, D>(p, st); return rc == SVNET_OK ? 1 : rc; }
     CASE(32, 10, 32, 10)    // SV_DGCNN_CLS conv2
     CASE(32, 10, 64, 21)    // SV_DGCNN_CLS conv3
