@@ -26,6 +26,7 @@
 #ifndef SVNET_B200_H
 #define SVNET_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -88,6 +89,20 @@ int svnet_fold_bn(const float* w, const float* b, const float* mean, const float
  * lowest index.  No BxNxN matrix is written.  idx32 and/or idx64 [B][N][k] (either may be NULL).
  * 1 <= k <= min(N,128). */
 int svnet_knn(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, void* stream);
+
+/* Same result, bit for bit, with caller-owned scratch: when `workspace` holds at least
+ * svnet_knn_workspace_bytes() bytes (16-byte aligned) the pairwise scores run on the tcgen05 tensor
+ * cores as a FILTER (bf16 hi/mid/lo planes, fp32 accumulators in tensor memory) and every decision the
+ * filter cannot certify is re-taken with the exact fp32 chain above (csrc/knn_tc.cu).
+ * svnet_knn_workspace_bytes() returns 0 for shapes the tensor-core path does not cover (k > 24,
+ * N > 4096, N < 64, more than 160 channels); svnet_knn_ws then runs the CUDA-core kernel. */
+size_t svnet_knn_workspace_bytes(const svnet_view* in, int B, int N, int k);
+int svnet_knn_ws(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, void* workspace,
+                 size_t workspace_bytes, void* stream);
+/* Cumulative counters of the tensor-core path (profiling aid): rows, rows that needed exact
+ * re-scoring, rows that took the brute-force path, queued survivors, then CTAs and summed SM cycles of
+ * {pass A, threshold, pass B, finish}.  Host pointer to 12 values; reset != 0 clears. */
+int svnet_knn_tc_stats(unsigned long long* out12, int reset);
 
 /* get_graph_feature (nv=2, sv_util.py:28-62) / get_graph_feature_cross (nv=3, sv_util.py:64-88):
  * xyz [B][N][3], idx int64 [B][N][k] -> out [B][N][k][3][nv].  Materialising parity path. */

@@ -19,6 +19,7 @@ c_int, c_long, c_float, c_void_p = ctypes.c_int, ctypes.c_long, ctypes.c_float, 
 
 EXPORTS = [
     "svnet_version", "svnet_last_error", "svnet_pack_sign", "svnet_fold_bn", "svnet_knn",
+    "svnet_knn_ws", "svnet_knn_workspace_bytes", "svnet_knn_tc_stats",
     "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
@@ -73,6 +74,7 @@ def lib():
                 "(there is no CPU/PyTorch fallback for the SV hot path)" % LIB_PATH)
         l = ctypes.CDLL(LIB_PATH)
         l.svnet_last_error.restype = ctypes.c_char_p
+        l.svnet_knn_workspace_bytes.restype = ctypes.c_size_t
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
         if l.svnet_version() != 1:
@@ -172,7 +174,11 @@ def knn(view, B, N, k, want64=False, want32=True):
     dev = torch.device("cuda", torch.cuda.current_device())
     i32 = torch.empty((B, N, k), dtype=torch.int32, device=dev) if want32 else None
     i64 = torch.empty((B, N, k), dtype=torch.int64, device=dev) if want64 else None
-    _call("svnet_knn", ctypes.byref(view), c_int(B), c_int(N), c_int(k), _ptr(i32), _ptr(i64), _stream())
+    # scratch for the tensor-core filter (operand planes + norms); 0 bytes -> CUDA-core kernel
+    nbytes = int(lib().svnet_knn_workspace_bytes(ctypes.byref(view), c_int(B), c_int(N), c_int(k)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes > 0 else None
+    _call("svnet_knn_ws", ctypes.byref(view), c_int(B), c_int(N), c_int(k), _ptr(i32), _ptr(i64), _ptr(ws),
+          ctypes.c_size_t(nbytes), _stream())
     return i32, i64
 
 

@@ -11,8 +11,10 @@
 //   order  = larger p first; equal p -> smaller index first
 // (zero-padded channels add fmaf(0,0,acc) == acc, so padding a chunk does not change any bit.)
 #include "common.cuh"
+#include "knn_keys.cuh"
 
 namespace {
+using namespace svknn;
 
 constexpr int TI = 64;    // query rows per CTA
 constexpr int TJ = 128;   // candidates per tile (== queue capacity per row: a tile can never overflow it)
@@ -31,73 +33,10 @@ __device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gsrc
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// Ordering keys: (score desc, index asc) as one unsigned 64-bit compare.
-//   hi = order-preserving map of the fp32 score (-0 is folded into +0 first, so that float equality
-//        and key equality agree), lo = ~index (smaller index -> larger key).  Empty slots are key 0,
-//        which ranks below every real candidate (even -inf).
-typedef unsigned long long key_t;
-
-__device__ __forceinline__ key_t make_key(float p, int j)
-{
-    const unsigned f = __float_as_uint(p + 0.0f);
-    const unsigned hi = (f & 0x80000000u) ? ~f : (f | 0x80000000u);
-    return ((key_t)hi << 32) | (unsigned)(~j);
-}
-__device__ __forceinline__ float key_score(key_t k)
-{
-    const unsigned hi = (unsigned)(k >> 32);
-    if (hi == 0u) return -INFINITY;
-    return __uint_as_float((hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi);
-}
-__device__ __forceinline__ int key_index(key_t k) { return (int)(~(unsigned)k); }
-
-__device__ __forceinline__ key_t shfl_key(key_t k, int src)
-{
-    const unsigned lo = __shfl_sync(SV_FULL, (unsigned)k, src);
-    const unsigned hi = __shfl_sync(SV_FULL, (unsigned)(k >> 32), src);
-    return ((key_t)hi << 32) | lo;
-}
-__device__ __forceinline__ key_t shfl_up_key(key_t k)
-{
-    const unsigned lo = __shfl_up_sync(SV_FULL, (unsigned)k, 1);
-    const unsigned hi = __shfl_up_sync(SV_FULL, (unsigned)(k >> 32), 1);
-    return ((key_t)hi << 32) | lo;
-}
-__device__ __forceinline__ key_t shfl_xor_key(key_t k, int m)
-{
-    const unsigned lo = __shfl_xor_sync(SV_FULL, (unsigned)k, m);
-    const unsigned hi = __shfl_xor_sync(SV_FULL, (unsigned)(k >> 32), m);
-    return ((key_t)hi << 32) | lo;
-}
-
-template <int R>
-struct TopK {
-    key_t k[R];   // sorted, best (largest key) at position 0; position = r*32 + lane
-};
-
-template <int R>
-__device__ __forceinline__ void topk_insert(TopK<R>& L, key_t c, int lane)
-{
-    int P = 0;  // number of entries that rank before the candidate
-#pragma unroll
-    for (int r = 0; r < R; ++r) P += __popc(__ballot_sync(SV_FULL, L.k[r] > c));
-#pragma unroll
-    for (int r = R - 1; r >= 0; --r) {
-        key_t up = shfl_up_key(L.k[r]);
-        if (r > 0) {
-            const key_t prev = shfl_key(L.k[r - 1], 31);
-            if (lane == 0) up = prev;
-        }
-        const int pos = r * 32 + lane;
-        if (pos > P) L.k[r] = up;
-        else if (pos == P) L.k[r] = c;
-    }
-}
-
 // compare-exchange with lane ^ j
-__device__ __forceinline__ void cex(key_t& k, int j, bool keep_better)
+__device__ __forceinline__ void cex(kkey_t& k, int j, bool keep_better)
 {
-    const key_t o = shfl_xor_key(k, j);
+    const kkey_t o = shfl_xor_key(k, j);
     if ((k > o) != keep_better) k = o;
 }
 
@@ -241,7 +180,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
 #pragma unroll
             for (int rr = 0; rr < ROWS_PER_WARP; ++rr) { cnts[rr] = qcnt[r0 + rr]; maxc = max(maxc, cnts[rr]); }
             for (int q0 = 0; q0 < maxc; q0 += 32) {
-                key_t c[ROWS_PER_WARP];
+                kkey_t c[ROWS_PER_WARP];
                 unsigned m[ROWS_PER_WARP];
                 bool any_merge = false;
 #pragma unroll
@@ -249,7 +188,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
                     const bool have = q0 + lane < cnts[rr];
                     const int qi = (r0 + rr) * TJ + q0 + lane;
                     c[rr] = have ? make_key(qv[qi], j0 + (int)qj[qi]) : 0ull;
-                    const key_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
+                    const kkey_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
                     m[rr] = __ballot_sync(SV_FULL, c[rr] > worst);
                     any_merge |= __popc(m[rr]) >= MERGE_MIN;
                 }
@@ -265,7 +204,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
                         }
 #pragma unroll
                     for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-                        const key_t rv = shfl_key(c[rr], 31 - lane);
+                        const kkey_t rv = shfl_key(c[rr], 31 - lane);
                         if (rv > L[rr].k[0]) L[rr].k[0] = rv;
                     }
 #pragma unroll
@@ -286,7 +225,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
                         const bool had = m[rr] != 0u;
                         const int src = had ? (__ffs(m[rr]) - 1) : 0;
                         m[rr] &= m[rr] - 1;
-                        key_t cc = shfl_key(c[rr], src);
+                        kkey_t cc = shfl_key(c[rr], src);
                         if (!had) cc = 0ull;
                         topk_insert<R>(L[rr], cc, lane);
                     }
@@ -294,7 +233,7 @@ __global__ void __launch_bounds__(NT, 2) knn_kernel(svnet_view in, int N, int k,
             }
 #pragma unroll
             for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-                const key_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
+                const kkey_t worst = shfl_key(L[rr].k[R - 1], (k - 1) & 31);
                 if (lane == 0 && cnts[rr] > 0) { qcnt[r0 + rr] = 0; thr[r0 + rr] = key_score(worst); }
             }
         }
@@ -329,7 +268,23 @@ int launch_knn(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_
 
 }  // namespace
 
+size_t svnet_knn_tc_workspace(const svnet_view* in, int B, int N, int k);
+int svnet_knn_tc_dispatch(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, void* workspace,
+                          size_t workspace_bytes, cudaStream_t st);
+
+extern "C" size_t svnet_knn_workspace_bytes(const svnet_view* in, int B, int N, int k)
+{
+    if (!in || B < 1 || N < 1 || k < 1 || k > N) return 0;
+    return svnet_knn_tc_workspace(in, B, N, k);
+}
+
 extern "C" int svnet_knn(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, void* stream)
+{
+    return svnet_knn_ws(in, B, N, k, idx32, idx64, nullptr, 0, stream);
+}
+
+extern "C" int svnet_knn_ws(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, void* workspace,
+                            size_t workspace_bytes, void* stream)
 {
     SV_REQUIRE(in != nullptr, "svnet_knn: null view");
     SV_REQUIRE(B >= 0 && N >= 1, "svnet_knn: bad B=%d N=%d", B, N);
@@ -343,6 +298,10 @@ extern "C" int svnet_knn(const svnet_view* in, int B, int N, int k, int32_t* idx
     const int R = (k + 31) / 32;
     const bool small = (in->Cs + 3 * in->Cv) <= 8;
     cudaStream_t st = sv_stream(stream);
+    {   // tensor-core filter + exact re-scoring (knn_tc.cu) for the shapes it covers
+        const int handled = svnet_knn_tc_dispatch(in, B, N, k, idx32, idx64, workspace, workspace_bytes, st);
+        if (handled != 0) return handled < 0 ? handled : SVNET_OK;
+    }
     if (small) {
         if (R == 1) return launch_knn<1, 8>(in, B, N, k, idx32, idx64, st);
         if (R == 2) return launch_knn<2, 8>(in, B, N, k, idx32, idx64, st);
