@@ -23,7 +23,7 @@
 //                 exact path.
 // Error model: |p_ij - q_ij| <= EPS * (xx_i + xx_j), p = oracle chain score, q = tensor-core score.
 // Dropped plane products contribute < 2^-19, fp32 accumulation (tensor core and chain) < 2^-17 of
-// |f_i||f_j|; EPS = 2^-15 leaves a 4x margin.  Scores are handled in half scale:
+// |f_i||f_j|; see knn_tc_eps() for the bound that is used.  Scores are handled in half scale:
 //   q/2 = dot - (xx_i + xx_j)/2.
 #include "common.cuh"
 #include "knn_keys.cuh"
@@ -33,26 +33,28 @@ namespace {
 using namespace svknn;
 
 constexpr int TM = 128;                        // query rows per CTA == UMMA M
-constexpr int TN = 128;                        // candidates per block == UMMA N
+constexpr int TNB = 256;                       // candidates per block == UMMA N
 constexpr int KCH = 16;                        // channels per chunk == UMMA K for bf16
-constexpr int KB_BYTES = TM * 16;              // one 8-channel k-block of 128 rows (descriptor LBO)
-constexpr int PLANE_BYTES = 2 * KB_BYTES;      // one plane of a chunk
-constexpr int CHUNK_BYTES = 3 * PLANE_BYTES;   // hi | mid | lo
+constexpr int A_KB = TM * 16;                  // resident query operand: one 8-channel k-block (descriptor LBO)
+constexpr int A_PLANE = 2 * A_KB;
+constexpr int A_CHUNK = 3 * A_PLANE;           // hi | mid | lo, 12 KB
+constexpr int B_KB = TNB * 16;                 // streamed candidate operand, 256 rows
+constexpr int B_PLANE = 2 * B_KB;
+constexpr int B_CHUNK = 3 * B_PLANE;           // 24 KB
 constexpr int NSCAN = 256;                     // scanner threads: warps 0..7
 constexpr int NTHREADS = 320;                  // + warp 8 (MMA issue) + warp 9 (bulk-copy producer)
 constexpr int CAPH = 32;                       // survivor queue capacity per (row, column half)
-constexpr int QV_LD = CAPH + 1;                // padded strides (bank spread)
-constexpr int QJ_LD = CAPH + 2;
-constexpr int QUEUE_BYTES = 2 * TM * QV_LD * 4 + 2 * TM * QJ_LD * 2;
 constexpr int GROUPS = 64;
+constexpr int GM_BYTES = GROUPS * TM * 4;      // group maxima between the passes
+#ifndef FIN_MIN_BLOCKS
+#define FIN_MIN_BLOCKS 6
+#endif
+constexpr int FIN_WARPS = 8;                   // finish kernel: warps per CTA, one warp = one row
 constexpr int KMAX = 160;                      // padded channels
-constexpr int NU = KMAX / 32;                  // channel slots per lane in the exact re-scoring
-constexpr int MAX_STAGES = 8;
-constexpr float EPS = 1.0f / 32768.0f;         // 2^-15
+constexpr int MAX_STAGES = 5;
 constexpr int KNN_TC_MAX_K = 24;
-constexpr int UNION_BYTES = QUEUE_BYTES > GROUPS * TM * 4 ? QUEUE_BYTES : GROUPS * TM * 4;
 
-__device__ unsigned long long g_knn_tc_stats[12];   // rows, rows with exact re-scoring, brute-force rows, survivors
+__device__ unsigned long long g_knn_tc_stats[12];
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -128,52 +130,76 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
 __device__ __forceinline__ void scan_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(NSCAN) : "memory"); }
 
 // ---- pack: exact 3-way bf16 split into the canonical operand layout + exact norms --------------
-// pack[b][rb][kc][plane][kb][row 0..127][8 bf16]; xx[b][rb*128 + row] (+inf for rows >= N)
-__global__ void __launch_bounds__(128) knn_pack_kernel(svnet_view in, int N, int NRB, int NKC, unsigned char* __restrict__ pack,
+// pack[b][cb][kc][plane][kb][row 0..255][8 bf16]; xx[b][cb*256 + row] (+inf for rows >= N)
+// One CTA = 32 rows: coalesced row loads (lane = channel) into a shared tile, then thread (row, k-block)
+// splits 8 channels and writes one 16-byte piece per plane (32 consecutive rows = 512 contiguous bytes);
+// warp 0 also runs the sequential norm chains from the tile.
+constexpr int PACK_ROWS = 32;
+__global__ void __launch_bounds__(256) knn_pack_kernel(svnet_view in, int N, int NCB, int NKC, unsigned char* __restrict__ pack,
                                                        float* __restrict__ xx)
 {
-    const int rb = blockIdx.x, b = blockIdx.y, rr = threadIdx.x;
-    const int r = rb * TM + rr;
-    const bool valid = r < N;
-    const long row = (long)b * N + r;
+    extern __shared__ float tile[];                 // [32 rows][Kpad + 1]
+    const int b = blockIdx.y;
+    const int r0 = blockIdx.x * PACK_ROWS;          // first (padded) row of this CTA within the cloud
     const int C = in.Cs + 3 * in.Cv;
-    unsigned char* dst = pack + ((size_t)(b * NRB + rb) * NKC) * CHUNK_BYTES + rr * 16;
-    float nrm = 0.0f;
-    for (int kc = 0; kc < NKC; ++kc) {
+    const int Kpad = NKC * KCH, ld = Kpad + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // channel -> address pieces of this lane's channels
+    for (int c = lane; c < Kpad; c += 32) {
+        const float* src = nullptr;
+        long stride = 0;
+        if (c < in.Cs) { src = in.s + c; stride = in.lds; }
+        else if (c < C) {
+            const int cc = c - in.Cs;
+            const int x = (cc >= in.Cv ? 1 : 0) + (cc >= 2 * in.Cv ? 1 : 0);
+            src = in.v + (long)x * in.xs + (cc - x * in.Cv);
+            stride = in.ldv;
+        }
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-            float a[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int c = kc * KCH + kb * 8 + e;
-                a[e] = (valid && c < C) ? sv_feat(in, row, c) : 0.0f;
-                nrm = __fmaf_rn(a[e], a[e], nrm);   // zero padding: fmaf(0,0,x) == x
-            }
-            uint32_t hw[4], mw[4], lw[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                uint32_t hh = 0, mm = 0, ll = 0;
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float av = a[h * 2 + e];
-                    const uint32_t hb = __float_as_uint(av) & 0xFFFF0000u;
-                    const float r1 = av - __uint_as_float(hb);
-                    const uint32_t mb = __float_as_uint(r1) & 0xFFFF0000u;
-                    const float r2 = r1 - __uint_as_float(mb);
-                    const uint32_t lb = __float_as_uint(r2) & 0xFFFF0000u;
-                    hh |= (hb >> 16) << (16 * e);
-                    mm |= (mb >> 16) << (16 * e);
-                    ll |= (lb >> 16) << (16 * e);
-                }
-                hw[h] = hh; mw[h] = mm; lw[h] = ll;
-            }
-            unsigned char* d = dst + (size_t)kc * CHUNK_BYTES + kb * KB_BYTES;
-            *reinterpret_cast<uint4*>(d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(d + PLANE_BYTES) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-            *reinterpret_cast<uint4*>(d + 2 * PLANE_BYTES) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        for (int q = 0; q < PACK_ROWS / 8; ++q) {
+            const int rr = warp * (PACK_ROWS / 8) + q;
+            const int r = r0 + rr;
+            tile[rr * ld + c] = (src && r < N) ? __ldg(src + ((long)b * N + r) * stride) : 0.0f;
         }
     }
-    xx[(size_t)b * NRB * TM + r] = valid ? nrm : INFINITY;
+    __syncthreads();
+    if (warp == 0) {
+        const int r = r0 + lane;
+        float nrm = 0.0f;          // channel ascending chain, as oracle/svnet_oracle.c:orc_knn (zero padding is exact)
+        const float* tr = tile + lane * ld;
+#pragma unroll 8
+        for (int c = 0; c < C; ++c) nrm = __fmaf_rn(tr[c], tr[c], nrm);
+        xx[(size_t)b * NCB * TNB + r] = r < N ? nrm : INFINITY;
+    }
+    const int cb = r0 / TNB, rin = r0 % TNB;
+    unsigned char* dst0 = pack + ((size_t)(b * NCB + cb) * NKC) * B_CHUNK + (size_t)rin * 16;
+    for (int item = tid; item < PACK_ROWS * 2 * NKC; item += 256) {
+        const int rr = item & 31, kbg = item >> 5;              // consecutive threads: consecutive rows
+        const int kc = kbg >> 1, kb = kbg & 1;
+        const float* a = tile + rr * ld + kbg * 8;
+        uint32_t hw[4], mw[4], lw[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            uint32_t hh = 0, mm = 0, ll = 0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float av = a[h * 2 + e];
+                const uint32_t hb = __float_as_uint(av) & 0xFFFF0000u;
+                const float r1 = av - __uint_as_float(hb);
+                const uint32_t mb = __float_as_uint(r1) & 0xFFFF0000u;
+                const float r2 = r1 - __uint_as_float(mb);
+                const uint32_t lb = __float_as_uint(r2) & 0xFFFF0000u;
+                hh |= (hb >> 16) << (16 * e);
+                mm |= (mb >> 16) << (16 * e);
+                ll |= (lb >> 16) << (16 * e);
+            }
+            hw[h] = hh; mw[h] = mm; lw[h] = ll;
+        }
+        unsigned char* d = dst0 + (size_t)kc * B_CHUNK + kb * B_KB + rr * 16;
+        *reinterpret_cast<uint4*>(d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(d + B_PLANE) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        *reinterpret_cast<uint4*>(d + 2 * B_PLANE) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
 }
 
 // ---- exact oracle chain: dot over channels ascending [s | v x0 | v x1 | v x2] ------------------
@@ -204,9 +230,14 @@ __device__ __forceinline__ float exact_score(float dot, float xxi, float xxj)
 
 struct knn_tc_args {
     svnet_view in;
-    int N, k, NRB, NKC, stages;
+    int N, k, NCB, NKC, stages;
+    float eps;                   // |p_ij - q_ij| <= eps * (xx_i + xx_j)
     const unsigned char* pack;
-    const float* xx;
+    const float* xx;             // [B][NCB*256]
+    float2* gq;                  // survivor queues [B*N rows][2 halves][CAPH] of (half-scale score, index bits)
+    int* gqcnt;                  // [B*N][2]
+    int xcap;                    // finish kernel: candidate rows staged per chunk
+    int stats;                   // != 0: accumulate g_knn_tc_stats (same-address atomics: profiling runs only)
     int32_t* idx32;
     int64_t* idx64;
 };
@@ -241,257 +272,16 @@ __device__ void brute_force_row(const knn_tc_args& p, long base, int i, const fl
     out = L.k[0];
 }
 
-// bitonic sort, descending, of four rows in lock-step (ILP across the rows hides the shuffle latency);
-// row a holds W*32 keys, key[a][w] at position w*32 + lane
-template <int W>
-__device__ __forceinline__ void sort4_desc(kkey_t (&key)[4][W], int lane)
-{
-#pragma unroll
-    for (int size = 2; size <= 32 * W; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                const bool desc = (((w * 32 + lane) & size) == 0);
-                if (stride >= 32) {
-                    const int pw = w ^ (stride >> 5);
-                    if (pw > w) {
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            const kkey_t x = key[a][w], y = key[a][pw];
-                            const bool swap = desc ? (x < y) : (x > y);
-                            if (swap) { key[a][w] = y; key[a][pw] = x; }
-                        }
-                    }
-                } else {
-                    const bool keep_larger = (((lane & stride) == 0) == desc);
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        const kkey_t o = shfl_xor_key(key[a][w], stride);
-                        if ((key[a][w] > o) != keep_larger) key[a][w] = o;
-                    }
-                }
-            }
-        }
-    }
-}
-
-struct fin_ctx {
-    const knn_tc_args* p;
-    long base;
-    int i0, C, Cp, xcap, lane;
-    const float* xxs;
-    const float* qv;
-    const unsigned short* qj;
-    float* stage;          // this warp's staging area: 4 query rows, then xcap candidate rows, stride Cp
-    int coff[NU];          // channel lane+32u -> offset inside the s row / the v row
-    unsigned smask;        // bit u: channel lane+32u lives in the scalar part
-    float emax;            // largest observed |p - q| / (xx_i + xx_j)
-};
-
-__device__ __forceinline__ const float* fin_src(const fin_ctx& f, long row, int u)
-{
-    const svnet_view& in = f.p->in;
-    return ((f.smask >> u) & 1u) ? in.s + row * in.lds + f.coff[u] : in.v + row * in.ldv + f.coff[u];
-}
-
-// Finish four rows (r0 .. r0+3 of the CTA) in lock-step: sort the survivors by approximate score,
-// find the neighbours the error bound does not separate, re-score those with the exact chain
-// (candidate rows gathered with cp.async into shared memory), re-sort, write the first k indices.
-template <int W>
-__device__ __forceinline__ void finish_group(fin_ctx& f, int r0, const int (&c0)[4], const int (&cnt)[4], const bool (&ok)[4],
-                                             unsigned long long& st_exact)
-{
-    const int lane = f.lane, k = f.p->k;
-    kkey_t key[4][W];
-    float xxi[4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int r = r0 + a;
-        xxi[a] = ok[a] ? f.xxs[f.i0 + r] : 0.0f;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const int e = w * 32 + lane;
-            kkey_t kk = 0ull;
-            if (ok[a] && e < cnt[a]) {
-                const int h = e < c0[a] ? 0 : 1, sl = h ? e - c0[a] : e;
-                kk = make_key(f.qv[(r * 2 + h) * QV_LD + sl], (int)f.qj[(r * 2 + h) * QJ_LD + sl]);
-            }
-            key[a][w] = kk;
-        }
-    }
-    sort4_desc<W>(key, lane);
-
-    // ---- neighbours in this order that the error bound does not separate ----
-    unsigned long long rel[4];
-    bool any = false;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        unsigned long long amb = 0ull;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            kkey_t nx = shfl_key(key[a][w], (lane + 1) & 31);
-            if (w + 1 < W) {
-                const kkey_t nx2 = shfl_key(key[a][(w + 1 < W) ? w + 1 : w], 0);
-                if (lane == 31) nx = nx2;
-            }
-            const int e = w * 32 + lane;
-            bool am = false;
-            if (ok[a] && e + 1 < cnt[a]) {
-                const float tol = 0.5f * EPS * (2.0f * xxi[a] + f.xxs[key_index(key[a][w])] + f.xxs[key_index(nx)]);
-                am = (key_score(key[a][w]) - key_score(nx)) <= tol;
-            }
-            amb |= (unsigned long long)__ballot_sync(SV_FULL, am) << (32 * w);
-        }
-        // pairs that can change the first k positions: pairs e <= k-1 and the runs continuing from them
-        unsigned long long rl = amb & ((1ull << k) - 1ull);
-        for (;;) {
-            const unsigned long long nx = (rl << 1) & amb & ~rl;
-            if (!nx) break;
-            rl |= nx;
-        }
-        rel[a] = rl;
-        any |= rl != 0ull;
-    }
-
-    if (any) {
-        unsigned long long flagged[4];
-        int pre[4][W];       // ordinals of the flagged entries in (a, w, lane) order
-        int T = 0;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            flagged[a] = rel[a] | (rel[a] << 1);
-            if (rel[a]) st_exact++;
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                pre[a][w] = T;
-                T += __popc((unsigned)(flagged[a] >> (32 * w)));
-            }
-        }
-        unsigned sc[4][W];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int w = 0; w < W; ++w) sc[a][w] = 0u;
-        float* arow = f.stage;
-        float* exb = f.stage + 4 * f.Cp;
-        const unsigned lt = (1u << lane) - 1u;
-        for (int ch0 = 0; ch0 < T; ch0 += f.xcap) {
-            __syncwarp();
-            if (ch0 == 0) {
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-                    if (rel[a]) {
-#pragma unroll
-                        for (int u = 0; u < NU; ++u)
-                            if (lane + 32 * u < f.C) cp_async4(arow + a * f.Cp + lane + 32 * u, fin_src(f, f.base + f.i0 + r0 + a, u));
-                    }
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    const unsigned mfull = (unsigned)(flagged[a] >> (32 * w));
-                    unsigned m = mfull;
-                    const int jmine = key_index(key[a][w]);
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int o = pre[a][w] + __popc(mfull & ((1u << src) - 1u)) - ch0;
-                        if (o < 0 || o >= f.xcap) continue;
-                        const int j = __shfl_sync(SV_FULL, jmine, src);
-#pragma unroll
-                        for (int u = 0; u < NU; ++u)
-                            if (lane + 32 * u < f.C) cp_async4(exb + o * f.Cp + lane + 32 * u, fin_src(f, f.base + j, u));
-                    }
-                }
-            cp_async_wait_all();
-            __syncwarp();
-            // exact chains (channel ascending), the four rows interleaved
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                bool mine[4];
-                const float* bp[4];
-                float dot[4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const unsigned mfull = (unsigned)(flagged[a] >> (32 * w));
-                    const int o = pre[a][w] + __popc(mfull & lt) - ch0;
-                    mine[a] = ((mfull >> lane) & 1u) && o >= 0 && o < f.xcap;
-                    bp[a] = exb + (mine[a] ? o : 0) * f.Cp;
-                    dot[a] = 0.0f;
-                }
-                if (mine[0] || mine[1] || mine[2] || mine[3]) {
-                    for (int c = 0; c < f.C; ++c) {
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-                            if (mine[a]) dot[a] = __fmaf_rn(arow[a * f.Cp + c], bp[a][c], dot[a]);
-                    }
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-                        if (mine[a]) {
-                            const int j = key_index(key[a][w]);
-                            const float xj = f.xxs[j];
-                            const float pe = exact_score(dot[a], xxi[a], xj);
-                            sc[a][w] = (unsigned)(make_key(pe, 0) >> 32);
-                            const float qa = 2.0f * key_score(key[a][w]) - xxi[a];      // tensor-core score
-                            f.emax = fmaxf(f.emax, fabsf(pe - qa) / (xxi[a] + xj));
-                        }
-                }
-            }
-        }
-        // composite keys: (run start asc, exact score desc, index asc); unflagged entries are their own run.
-        // Rows without ambiguity keep (approximate score, index) keys: sorting them again changes nothing.
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            if (!rel[a]) continue;
-            const unsigned long long starts = ~(rel[a] << 1);      // e starts a run iff pair (e-1, e) is not ambiguous
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                const int e = w * 32 + lane;
-                if (e < cnt[a]) {
-                    const int j = key_index(key[a][w]);
-                    const int seg = 63 - __clzll((long long)(starts & ((2ull << e) - 1ull)));
-                    key[a][w] = ((kkey_t)(127 - seg) << 44) | ((kkey_t)sc[a][w] << 12) | (kkey_t)(4095 - j);
-                } else {
-                    key[a][w] = 0ull;
-                }
-            }
-        }
-        sort4_desc<W>(key, lane);
-    }
-
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        if (!ok[a]) continue;
-        const bool comp = any && rel[a] != 0ull;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const int pos = w * 32 + lane;
-            if (pos < k) {
-                const long o = (f.base + f.i0 + r0 + a) * k + pos;
-                const int j = comp ? 4095 - (int)(key[a][w] & 4095ull) : key_index(key[a][w]);
-                if (f.p->idx32) f.p->idx32[o] = j;
-                if (f.p->idx64) f.p->idx64[o] = (int64_t)j;
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
 {
     extern __shared__ __align__(1024) unsigned char smraw[];
-    const int NKC = p.NKC, S = p.stages, NB = p.NRB;
-    unsigned char* As = smraw;                                        // NKC chunks, resident
-    unsigned char* Ring = As + (size_t)NKC * CHUNK_BYTES;             // S chunks
-    float* xxs = reinterpret_cast<float*>(Ring + (size_t)S * CHUNK_BYTES);   // [NRB*128]
-    float* un = xxs + NB * TM;                                        // union: gm [64][128]  |  survivor queues
-    float* gm = un;
-    float* qv = un;                                                   // [128 rows][2 halves][QV_LD]
-    unsigned short* qj = reinterpret_cast<unsigned short*>(un + 2 * TM * QV_LD);   // [128][2][QJ_LD]
-    float* thr = un + UNION_BYTES / 4;                                // [128]
-    int* qcnt = reinterpret_cast<int*>(thr + TM);                     // [128][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + 2 * TM);      // barA | full[S] | empty[S] | tfull[2] | tempty[2]
+    const int NKC = p.NKC, S = p.stages, NB = p.NCB;
+    unsigned char* As = smraw;                                        // NKC query chunks (128 rows), resident
+    unsigned char* Ring = As + (size_t)NKC * A_CHUNK;                 // S candidate chunks (256 rows)
+    float* xxs = reinterpret_cast<float*>(Ring + (size_t)S * B_CHUNK);   // [NCB*256]
+    float* gm = xxs + NB * TNB;                                       // [64 groups][128 rows]
+    float* thr = gm + GROUPS * TM;                                    // [128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(thr + TM);           // barA | full[S] | empty[S] | tfull[2] | tempty[2]
     uint64_t* barA = bars;
     uint64_t* full = bars + 1;
     uint64_t* empty = full + MAX_STAGES;
@@ -512,31 +302,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(2 * TN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(2 * TNB));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const unsigned char* cloud_pack = p.pack + (size_t)b * NB * NKC * CHUNK_BYTES;
+    const unsigned char* cloud_pack = p.pack + (size_t)b * NB * NKC * B_CHUNK;
     const int nblk = 2 * NB;     // pass A then pass B over the candidate blocks
 
     if (warp == 9) {
         // ================= producer: bulk copies of operand chunks =================
         if (lane == 0) {
-            mbar_expect_tx(barA, (uint32_t)(NKC * CHUNK_BYTES));
-            const unsigned char* src = cloud_pack + (size_t)rb * NKC * CHUNK_BYTES;
-            for (int kc = 0; kc < NKC; ++kc) bulk_g2s(As + (size_t)kc * CHUNK_BYTES, src + (size_t)kc * CHUNK_BYTES, CHUNK_BYTES, barA);
+            // query rows = one half of a 256-row block of the same pack: 6 pieces of 2 KB per chunk
+            mbar_expect_tx(barA, (uint32_t)(NKC * A_CHUNK));
+            const unsigned char* src = cloud_pack + (size_t)(rb >> 1) * NKC * B_CHUNK + (size_t)(rb & 1) * A_KB;
+            for (int kc = 0; kc < NKC; ++kc)
+                for (int pl = 0; pl < 3; ++pl)
+                    for (int kb = 0; kb < 2; ++kb)
+                        bulk_g2s(As + (size_t)kc * A_CHUNK + pl * A_PLANE + kb * A_KB,
+                                 src + (size_t)kc * B_CHUNK + pl * B_PLANE + kb * B_KB, A_KB, barA);
             int t = 0, s = 0;
             uint32_t ph = 0;
             for (int it = 0; it < nblk; ++it) {
                 const int cb = it >= NB ? it - NB : it;
-                const unsigned char* bsrc = cloud_pack + (size_t)cb * NKC * CHUNK_BYTES;
+                const unsigned char* bsrc = cloud_pack + (size_t)cb * NKC * B_CHUNK;
                 for (int kc = 0; kc < NKC; ++kc, ++t) {
                     if (t >= S) mbar_wait(empty + s, ph ^ 1u);
-                    mbar_expect_tx(full + s, CHUNK_BYTES);
-                    bulk_g2s(Ring + (size_t)s * CHUNK_BYTES, bsrc + (size_t)kc * CHUNK_BYTES, CHUNK_BYTES, full + s);
+                    mbar_expect_tx(full + s, B_CHUNK);
+                    bulk_g2s(Ring + (size_t)s * B_CHUNK, bsrc + (size_t)kc * B_CHUNK, B_CHUNK, full + s);
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
             }
@@ -544,10 +339,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
     } else if (warp == 8) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // D fp32, A/B bf16, both K-major, N = 128, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            const uint64_t adesc0 = make_desc(smem_u32(As), KB_BYTES, 128);
-            const uint64_t bdesc0 = make_desc(smem_u32(Ring), KB_BYTES, 128);
+            // D fp32, A/B bf16, both K-major, N = 256, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TNB >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint64_t adesc0 = make_desc(smem_u32(As), A_KB, 128);
+            const uint64_t bdesc0 = make_desc(smem_u32(Ring), B_KB, 128);
             mbar_wait(barA, 0);
             int s = 0;
             uint32_t ph = 0;
@@ -555,19 +350,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
                 const int buf = it & 1;
                 if (it >= 2) mbar_wait(tempty + buf, (uint32_t)(((it >> 1) - 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t dcol = tmem_base + (uint32_t)(buf * TN);
+                const uint32_t dcol = tmem_base + (uint32_t)(buf * TNB);
                 for (int kc = 0; kc < NKC; ++kc) {
                     mbar_wait(full + s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const uint64_t ad = adesc0 + (uint64_t)((kc * CHUNK_BYTES) >> 4);
-                    const uint64_t bd = bdesc0 + (uint64_t)((s * CHUNK_BYTES) >> 4);
-                    constexpr uint64_t P1 = PLANE_BYTES >> 4, P2 = (2 * PLANE_BYTES) >> 4;
+                    const uint64_t ad = adesc0 + (uint64_t)((kc * A_CHUNK) >> 4);
+                    const uint64_t bd = bdesc0 + (uint64_t)((s * B_CHUNK) >> 4);
+                    constexpr uint64_t A1 = A_PLANE >> 4, A2 = (2 * A_PLANE) >> 4, B1 = B_PLANE >> 4, B2 = (2 * B_PLANE) >> 4;
                     // plane products, small terms first: h*l, l*h, m*m, h*m, m*h, h*h
-                    umma_bf16(dcol, ad, bd + P2, idesc, kc == 0 ? 0u : 1u);
-                    umma_bf16(dcol, ad + P2, bd, idesc, 1u);
-                    umma_bf16(dcol, ad + P1, bd + P1, idesc, 1u);
-                    umma_bf16(dcol, ad, bd + P1, idesc, 1u);
-                    umma_bf16(dcol, ad + P1, bd, idesc, 1u);
+                    umma_bf16(dcol, ad, bd + B2, idesc, kc == 0 ? 0u : 1u);
+                    umma_bf16(dcol, ad + A2, bd, idesc, 1u);
+                    umma_bf16(dcol, ad + A1, bd + B1, idesc, 1u);
+                    umma_bf16(dcol, ad, bd + B1, idesc, 1u);
+                    umma_bf16(dcol, ad + A1, bd, idesc, 1u);
                     umma_bf16(dcol, ad, bd, idesc, 1u);
                     umma_commit(empty + s);     // the stage may be refilled once these MMAs have read it
                     if (++s == S) { s = 0; ph ^= 1u; }
@@ -579,21 +374,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
         // ================= scanners: warps 0..7, lane quarter = warp & 3, column half = warp >> 2 =================
         const int q4 = warp & 3, half = warp >> 2;
         const int row = q4 * 32 + lane;
-        long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0, tc4 = 0;
-        for (int j = tid; j < NB * TM; j += NSCAN) xxs[j] = __ldg(p.xx + (size_t)b * NB * TM + j);
+        long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
+        for (int j = tid; j < NB * TNB; j += NSCAN) xxs[j] = __ldg(p.xx + (size_t)b * NB * TNB + j);
         scan_bar();
         const bool row_ok = (i0 + row) < p.N;
         const float xi = xxs[i0 + row];
-        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 64);
-        constexpr float CA = -0.5f * (1.0f + EPS), CB = -0.5f * (1.0f - EPS);
+        const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * (TNB / 2));
+        const float CA = -0.5f * (1.0f + p.eps), CB = -0.5f * (1.0f - p.eps);
 
         float m[32];
 #pragma unroll
         for (int g = 0; g < 32; ++g) m[g] = -INFINITY;
         float R = INFINITY;
+        const float hxi = row_ok ? 0.5f * xi : 0.0f;
         int qn = 0;                                   // this thread's queue fill (row, half)
-        float* myqv = qv + (row * 2 + half) * QV_LD;
-        unsigned short* myqj = qj + (row * 2 + half) * QJ_LD;
+        float2* myq = p.gq + ((base + i0 + (row_ok ? row : 0)) * 2 + half) * CAPH;
 
         for (int it = 0; it < nblk; ++it) {
             const int buf = it & 1;
@@ -627,196 +422,422 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
 #pragma unroll
                     for (int i = 1; i < GROUPS; ++i)
                         if (i == k - 1) Lp = v[i];
-                    // hi_ij >= lower bound of the k-th score  <=>  V_ij >= Lp - EPS*xx_i (minus fp32 slack)
-                    const float r = Lp - EPS * xi - 9.5367431640625e-7f * (fabsf(Lp) + xi);
+                    // hi_ij >= lower bound of the k-th score  <=>  V_ij >= Lp - eps*xx_i (minus fp32 slack)
+                    const float r = Lp - p.eps * xi - 9.5367431640625e-7f * (fabsf(Lp) + xi);
                     thr[row] = row_ok ? r : INFINITY;
                 }
-                scan_bar();      // thresholds visible; gm (aliased by the queues) no longer read
+                scan_bar();
                 R = thr[row];
                 tc2 = clock64();
             }
             mbar_wait(tfull + buf, (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            float d0[32], d1[32];
-            tmem_ld32(trow + (uint32_t)(buf * TN), d0);
-            tmem_ld32(trow + (uint32_t)(buf * TN + 32), d1);
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + buf);      // this warp has drained the accumulator buffer
-            const int j0 = cb * TN + half * 64;
-            if (!passB) {
+            const int j0 = cb * TNB + half * (TNB / 2);
 #pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    const float4 x0 = *reinterpret_cast<const float4*>(xxs + j0 + c);
-                    const float4 x1 = *reinterpret_cast<const float4*>(xxs + j0 + 32 + c);
-                    m[c + 0] = fmaxf(m[c + 0], fmaxf(fmaf(x0.x, CA, d0[c + 0]), fmaf(x1.x, CA, d1[c + 0])));
-                    m[c + 1] = fmaxf(m[c + 1], fmaxf(fmaf(x0.y, CA, d0[c + 1]), fmaf(x1.y, CA, d1[c + 1])));
-                    m[c + 2] = fmaxf(m[c + 2], fmaxf(fmaf(x0.z, CA, d0[c + 2]), fmaf(x1.z, CA, d1[c + 2])));
-                    m[c + 3] = fmaxf(m[c + 3], fmaxf(fmaf(x0.w, CA, d0[c + 3]), fmaf(x1.w, CA, d1[c + 3])));
+            for (int part = 0; part < 4; ++part) {
+                float d[32];
+                tmem_ld32(trow + (uint32_t)(buf * TNB + part * 32), d);
+                if (part == 3) {
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty + buf);      // this warp has drained the accumulator buffer
                 }
-            } else {
-                // thread-private queue (row, half): predicated stores, no atomics
+                const float* xp = xxs + j0 + part * 32;
+                if (!passB) {
 #pragma unroll
-                for (int c = 0; c < 64; c += 4) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(xxs + j0 + c);
-                    const float xs4[4] = {x4.x, x4.y, x4.z, x4.w};
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 x4 = *reinterpret_cast<const float4*>(xp + c);
+                        m[c + 0] = fmaxf(m[c + 0], fmaf(x4.x, CA, d[c + 0]));
+                        m[c + 1] = fmaxf(m[c + 1], fmaf(x4.y, CA, d[c + 1]));
+                        m[c + 2] = fmaxf(m[c + 2], fmaf(x4.z, CA, d[c + 2]));
+                        m[c + 3] = fmaxf(m[c + 3], fmaf(x4.w, CA, d[c + 3]));
+                    }
+                } else {
+                    // thread-private survivor queue (row, half) in global memory: no atomics
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float dv = (c + e) < 32 ? d0[(c + e) & 31] : d1[(c + e) & 31];
-                        if (fmaf(xs4[e], CB, dv) >= R) {
-                            if (qn < CAPH) {
-                                myqv[qn] = fmaf(xs4[e], -0.5f, dv);
-                                myqj[qn] = (unsigned short)(j0 + c + e);
-                            }
-                            ++qn;
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 x4 = *reinterpret_cast<const float4*>(xp + c);
+                        const float xs4[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const bool pass = fmaf(xs4[e], CB, d[c + e]) >= R;
+                            const float val = fmaf(xs4[e], -0.5f, d[c + e]) - hxi;      // q/2: small for near neighbours
+                            const unsigned st = (pass && qn < CAPH) ? 1u : 0u;
+                            // predicated 8-byte store, no branch (a vote + uniform branch around it measured 1.8x slower)
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v2.f32 [%1], {%2, %3};\n\t}\n" ::"r"(st),
+                                "l"(myq + qn), "f"(val), "f"(__int_as_float(j0 + part * 32 + c + e))
+                                : "memory");
+                            qn += pass ? 1 : 0;
                         }
                     }
                 }
             }
         }
-        qcnt[row * 2 + half] = qn;
-        scan_bar();     // all queues complete; operand buffers are free (every MMA has completed)
+        if (row_ok) p.gqcnt[(base + i0 + row) * 2 + half] = qn;
         tc3 = clock64();
-
-        // ================= finish: one warp = 16 rows, four at a time =================
-        fin_ctx f;
-        f.p = &p; f.base = base; f.i0 = i0; f.lane = lane;
-        f.C = p.in.Cs + 3 * p.in.Cv;
-        f.Cp = f.C | 1;
-        f.xxs = xxs; f.qv = qv; f.qj = qj;
-        const int stage_floats = (int)(((size_t)(NKC + S) * CHUNK_BYTES) / (8 * sizeof(float)));
-        f.stage = reinterpret_cast<float*>(As) + warp * stage_floats;
-        f.xcap = (stage_floats - 4 * f.Cp) / f.Cp;
-        f.emax = 0.0f;
-        f.smask = 0u;
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-            const int c = lane + 32 * u;
-            f.coff[u] = 0;
-            if (c < p.in.Cs) { f.smask |= 1u << u; f.coff[u] = c; }
-            else if (c < f.C) { const int cc = c - p.in.Cs, x = cc / p.in.Cv; f.coff[u] = x * p.in.xs + (cc - x * p.in.Cv); }
-        }
-        unsigned long long st_exact = 0, st_brute = 0, st_surv = 0, st_rows = 0;
-        for (int g = 0; g < 4; ++g) {
-            const int r0 = warp * 16 + g * 4;
-            if (i0 + r0 >= p.N) break;
-            int c0[4], cnt[4];
-            bool ok[4], brute[4];
-            bool wide = false;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const bool exists = (i0 + r0 + a) < p.N;
-                c0[a] = qcnt[(r0 + a) * 2];
-                const int c1 = qcnt[(r0 + a) * 2 + 1];
-                cnt[a] = c0[a] + c1;
-                const bool usable = c0[a] <= CAPH && c1 <= CAPH && cnt[a] >= k;
-                ok[a] = exists && usable;
-                brute[a] = exists && !usable;
-                wide |= ok[a] && cnt[a] > 32;
-                if (exists) { st_rows++; st_surv += (unsigned long long)cnt[a]; }
-            }
-            if (wide) finish_group<2>(f, r0, c0, cnt, ok, st_exact);
-            else finish_group<1>(f, r0, c0, cnt, ok, st_exact);
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                if (!brute[a]) continue;
-                const int i = i0 + r0 + a;
-                __syncwarp();
-                for (int c = lane; c < f.C; c += 32) f.stage[c] = sv_feat(p.in, base + i, c);
-                __syncwarp();
-                kkey_t out;
-                brute_force_row(p, base, i, f.stage, xxs, lane, out);
-                if (lane < k) {
-                    const long o = (base + i) * k + lane;
-                    if (p.idx32) p.idx32[o] = key_index(out);
-                    if (p.idx64) p.idx64[o] = (int64_t)key_index(out);
-                }
-                st_brute++;
-            }
-        }
-        tc4 = clock64();
-        if (tid == 0) {
+        if (tid == 0 && p.stats) {
             atomicAdd(&g_knn_tc_stats[4], 1ull);
             atomicAdd(&g_knn_tc_stats[5], (unsigned long long)(tc1 - tc0));
             atomicAdd(&g_knn_tc_stats[6], (unsigned long long)(tc2 - tc1));
             atomicAdd(&g_knn_tc_stats[7], (unsigned long long)(tc3 - tc2));
-            atomicAdd(&g_knn_tc_stats[8], (unsigned long long)(tc4 - tc3));
-        }
-        float em = f.emax;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) em = fmaxf(em, __shfl_xor_sync(SV_FULL, em, o));
-        if (lane == 0) {
-            atomicAdd(&g_knn_tc_stats[0], st_rows);
-            atomicAdd(&g_knn_tc_stats[1], st_exact);
-            atomicAdd(&g_knn_tc_stats[2], st_brute);
-            atomicAdd(&g_knn_tc_stats[3], st_surv);
-            atomicMax(&g_knn_tc_stats[9], (unsigned long long)__float_as_uint(em));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * TN));
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * TNB));
 }
 
-size_t knn_tc_smem(int NRB, int NKC, int stages)
+// staged rows of the exact re-scoring: stride = multiple of 4 floats with an odd number of float4s
+// (16-byte loads, lanes reading different rows fall into different bank groups)
+__host__ __device__ __forceinline__ int fin_stride(int C)
 {
-    return (size_t)(NKC + stages) * CHUNK_BYTES + (size_t)NRB * TM * 4 + UNION_BYTES + TM * 4 + 2 * TM * 4 +
+    const int q = (C + 3) >> 2;
+    return 4 * (q | 1);
+}
+constexpr int FIN_TAB_FLOATS = (KMAX * 8 + KMAX * 4) / 4;      // gather table: pointers + strides
+
+// bitonic sorts, descending, of 32 keys (one per lane)
+__device__ __forceinline__ void warp_sort32_desc(kkey_t& key, int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+        const bool desc = (lane & size) == 0;
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const kkey_t o = shfl_xor_key(key, stride);
+            const bool keep_larger = (((lane & stride) == 0) == desc);
+            if ((key > o) != keep_larger) key = o;
+        }
+    }
+}
+__device__ __forceinline__ void warp_sort32_desc_u32(unsigned& key, int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+        const bool desc = (lane & size) == 0;
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned o = __shfl_xor_sync(SV_FULL, key, stride);
+            const bool keep_larger = (((lane & stride) == 0) == desc);
+            key = keep_larger ? max(key, o) : min(key, o);
+        }
+    }
+}
+// approximate-order key: order-preserving map of the score with the low 5 bits replaced by the lane
+// that holds the entry (the lost bits are far below the error bound of the score); 0 = empty
+__device__ __forceinline__ unsigned approx_key(float s, int lane)
+{
+    const unsigned f = __float_as_uint(s + 0.0f);
+    const unsigned hi = (f & 0x80000000u) ? ~f : (f | 0x80000000u);
+    return ((hi & ~31u) | (unsigned)lane) | 32u * (hi < 64u);     // never below 32: empty slots are 0..31
+}
+
+// ---- finish kernel: one warp = one row.  High occupancy (small register / shared-memory footprint)
+//      hides the shuffle and gather latencies that a tensor-core CTA with 8 scanner warps cannot.
+//   1. survivors (<= 64) -> best 32 by approximate score (sorted, nearest first)
+//   2. neighbours in that order which the error bound does not separate form runs; runs that touch the
+//      first k positions are re-scored with the exact chain (rows gathered by cp.async, lane = entry)
+//   3. re-sort by (run, exact score desc, index asc), write the first k indices
+__global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_kernel(knn_tc_args p)
+{
+    extern __shared__ __align__(16) float fin_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * FIN_WARPS + warp;
+    const long base = (long)b * p.N;
+    const long rg = base + i;
+    const int k = p.k;
+    const int C = p.in.Cs + 3 * p.in.Cv, Cp = fin_stride(C);
+    const float* xxs = p.xx + (size_t)b * p.NCB * TNB;
+    // gather table shared by the CTA: channel c -> (address of that channel in row 0, row stride)
+    const float** gtab = reinterpret_cast<const float**>(fin_smem);
+    int* gstr = reinterpret_cast<int*>(gtab + KMAX);
+    for (int c = threadIdx.x; c < C; c += FIN_WARPS * 32) {
+        const int cc2 = c - p.in.Cs;
+        const int x = (cc2 >= p.in.Cv ? 1 : 0) + (cc2 >= 2 * p.in.Cv ? 1 : 0);
+        const bool in_s = c < p.in.Cs;
+        gtab[c] = in_s ? p.in.s + c : p.in.v + (long)x * p.in.xs + (cc2 - x * p.in.Cv);
+        gstr[c] = in_s ? p.in.lds : p.in.ldv;
+    }
+    __syncthreads();
+    if (i >= p.N) return;
+    float* arow = fin_smem + FIN_TAB_FLOATS + (size_t)warp * ((1 + p.xcap) * Cp);     // query row | xcap candidate rows
+    float* exb = arow + Cp;
+    const float2* q0 = p.gq + rg * 2 * CAPH;
+    const float2 h0 = __ldg(q0 + lane), h1 = __ldg(q0 + CAPH + lane);     // may hold stale data beyond the counts
+    const float xxi = __ldg(xxs + i);
+    const int2 cc = __ldg(reinterpret_cast<const int2*>(p.gqcnt) + rg);
+    const int c0 = cc.x, cnt = cc.x + cc.y;
+    bool brute = !(cc.x <= CAPH && cc.y <= CAPH && cnt >= k);
+    bool st_exact = false;
+    float emax = 0.0f;
+    kkey_t key = 0ull;
+    int jout = 0;
+    if (!brute) {
+        // both halves' queues are loaded without waiting for the counts; entry e of the row is
+        // half0[e] for e < c0, else half1[e - c0] (fetched by shuffle)
+        float2 ent;
+        {
+            const int sl = (lane - c0) & 31;
+            const float a1 = __shfl_sync(SV_FULL, h1.x, sl), b1 = __shfl_sync(SV_FULL, h1.y, sl);
+            ent = lane < c0 ? h0 : make_float2(a1, b1);
+        }
+        float xe = lane < cnt ? __ldg(xxs + __float_as_int(ent.y)) : 0.0f;      // norm of the entry's point
+        unsigned ak = lane < cnt ? approx_key(ent.x, lane) : (unsigned)lane;
+        warp_sort32_desc_u32(ak, lane);
+        float best_dropped = -INFINITY, xx_dropped = 0.0f;
+        float2 ent2 = make_float2(0.0f, 0.0f);
+        float xe2 = 0.0f;
+        bool from2 = false;
+        if (cnt > 32) {
+            // second half: keep the best 32 of the 64 (upper half of a bitonic merge), remember the best loser
+            const int e = 32 + lane;
+            {
+                const int sl = (e - c0) & 31;      // e >= 32 >= c0: always in half 1
+                ent2.x = __shfl_sync(SV_FULL, h1.x, sl);
+                ent2.y = __shfl_sync(SV_FULL, h1.y, sl);
+            }
+            xe2 = e < cnt ? __ldg(xxs + __float_as_int(ent2.y)) : 0.0f;
+            unsigned ak2 = e < cnt ? approx_key(ent2.x, lane) : (unsigned)lane;
+            warp_sort32_desc_u32(ak2, lane);
+            const unsigned rev = __shfl_sync(SV_FULL, ak2, 31 - lane);
+            const bool take2 = rev > ak;
+            const unsigned lose = take2 ? ak : rev;
+            const bool lose2 = !take2;                    // the loser came from the second half
+            ak = take2 ? rev : ak;
+            from2 = take2;
+            // best loser (score, largest norm), over the warp
+            const int ls = (int)(lose & 31u);
+            const float l1 = __shfl_sync(SV_FULL, ent.x, ls), l2 = __shfl_sync(SV_FULL, ent2.x, ls);
+            const float lx1 = __shfl_sync(SV_FULL, xe, ls), lx2 = __shfl_sync(SV_FULL, xe2, ls);
+            float lsc = lose >= 32u ? (lose2 ? l2 : l1) : -INFINITY;
+            float lxx = lose >= 32u ? (lose2 ? lx2 : lx1) : 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lsc = fmaxf(lsc, __shfl_xor_sync(SV_FULL, lsc, o));
+                lxx = fmaxf(lxx, __shfl_xor_sync(SV_FULL, lxx, o));
+            }
+            best_dropped = lsc; xx_dropped = lxx;
+            // two winners from different halves can share a lane field: sort (key, origin) as one 64-bit key
+            kkey_t wk = ((kkey_t)ak << 1) | (from2 ? 1ull : 0ull);
+            warp_sort32_desc(wk, lane);
+            ak = (unsigned)(wk >> 1);
+            from2 = (wk & 1ull) != 0ull;
+        }
+        // fetch the entry this position now holds
+        const int src = (int)(ak & 31u);
+        const int n = min(cnt, 32);
+        float sme = __shfl_sync(SV_FULL, ent.x, src);
+        int jme = __float_as_int(__shfl_sync(SV_FULL, ent.y, src));
+        float xj = __shfl_sync(SV_FULL, xe, src);
+        if (cnt > 32) {
+            const float s2 = __shfl_sync(SV_FULL, ent2.x, src);
+            const int j2 = __float_as_int(__shfl_sync(SV_FULL, ent2.y, src));
+            const float x2 = __shfl_sync(SV_FULL, xe2, src);
+            if (from2) { sme = s2; jme = j2; xj = x2; }
+        }
+        if (lane >= n) xj = 0.0f;
+        jout = jme;
+        // ---- neighbours in this order that the error bound does not separate ----
+        const float snx = __shfl_down_sync(SV_FULL, sme, 1);
+        const float xnx = __shfl_down_sync(SV_FULL, xj, 1);
+        bool am = false;
+        if (lane + 1 < n) am = (sme - snx) <= 0.5f * p.eps * (2.0f * xxi + xj + xnx);
+        const unsigned amb = __ballot_sync(SV_FULL, am);
+        unsigned rel = amb & ((1u << k) - 1u);       // pairs e <= k-1, then the runs continuing from them
+        for (;;) {
+            const unsigned nx = (rel << 1) & amb & ~rel;
+            if (!nx) break;
+            rel |= nx;
+        }
+        if (cnt > 32) {
+            // the dropped entries must be certainly worse than everything that can reach the first k positions
+            const int last = 32 - __clz(rel | (rel << 1) | ((1u << k) - 1u));   // one past the last position of interest
+            const float slast = __shfl_sync(SV_FULL, sme, last - 1);
+            float xkept = xj;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) xkept = fmaxf(xkept, __shfl_xor_sync(SV_FULL, xkept, o));
+            if (last >= 32 || (slast - best_dropped) <= 0.5f * p.eps * (2.0f * xxi + xkept + xx_dropped)) brute = true;
+        }
+        if (rel && !brute) {
+            st_exact = true;
+            const unsigned flagged = rel | (rel << 1);
+            const int T = __popc(flagged);
+            const unsigned lt = (1u << lane) - 1u;
+            const int myo = __popc(flagged & lt);
+            const bool mine = (flagged >> lane) & 1u;
+            unsigned sc = 0u;
+            const int nu = (C + 31) >> 5;
+            for (int ch0 = 0; ch0 < T; ch0 += p.xcap) {
+                __syncwarp();
+                if (ch0 == 0) {
+                    for (int u = 0; u < nu; ++u) {
+                        const int c = lane + 32 * u;
+                        if (c < C) cp_async4(arow + c, gtab[c] + rg * (long)gstr[c]);
+                    }
+                    if (lane < Cp - C) arow[C + lane] = 0.0f;            // zero padding of the float4 chains
+                }
+                unsigned m = flagged;
+                int o = -ch0;
+                while (m) {
+                    const int srcl = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (o >= 0 && o < p.xcap) {
+                        const long row = base + __shfl_sync(SV_FULL, jme, srcl);
+                        float* dstp = exb + o * Cp;
+                        for (int u = 0; u < nu; ++u) {
+                            const int c = lane + 32 * u;
+                            if (c < C) cp_async4(dstp + c, gtab[c] + row * (long)gstr[c]);
+                        }
+                        if (lane < Cp - C) dstp[C + lane] = 0.0f;
+                    }
+                    ++o;
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                const int ol = myo - ch0;
+                if (mine && ol >= 0 && ol < p.xcap) {
+                    const float4* bp = reinterpret_cast<const float4*>(exb + ol * Cp);
+                    const float4* ap = reinterpret_cast<const float4*>(arow);
+                    float dot = 0.0f;      // channel ascending; the zero padding adds fmaf(0,0,x) == x
+                    for (int c4 = 0; c4 < (C + 3) >> 2; ++c4) {
+                        const float4 av = ap[c4], bv = bp[c4];
+                        dot = __fmaf_rn(av.x, bv.x, dot);
+                        dot = __fmaf_rn(av.y, bv.y, dot);
+                        dot = __fmaf_rn(av.z, bv.z, dot);
+                        dot = __fmaf_rn(av.w, bv.w, dot);
+                    }
+                    const float pe = exact_score(dot, xxi, xj);
+                    sc = (unsigned)(make_key(pe, 0) >> 32);
+                    emax = fmaxf(emax, fabsf(pe - 2.0f * sme) / (xxi + xj));     // 2*sme = tensor-core score
+                }
+            }
+            // composite key: (run start asc, exact score desc, index asc); unflagged entries are their own run
+            const unsigned starts = ~(rel << 1);
+            if (lane < n) {
+                const int seg = 31 - __clz(starts & ((2u << lane) - 1u));
+                key = ((kkey_t)(127 - seg) << 44) | ((kkey_t)sc << 12) | (kkey_t)(4095 - jme);
+            } else {
+                key = 0ull;
+            }
+            warp_sort32_desc(key, lane);
+            jout = 4095 - (int)(key & 4095ull);
+        }
+    }
+    if (brute) {
+        __syncwarp();
+        for (int c = lane; c < C; c += 32) arow[c] = sv_feat(p.in, rg, c);
+        __syncwarp();
+        brute_force_row(p, base, i, arow, xxs, lane, key);
+        jout = key_index(key);
+    }
+    if (lane < k) {
+        const long o = rg * k + lane;
+        if (p.idx32) p.idx32[o] = jout;
+        if (p.idx64) p.idx64[o] = (int64_t)jout;
+    }
+    if (p.stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(SV_FULL, emax, o));
+        if (lane == 0) {
+            atomicAdd(&g_knn_tc_stats[0], 1ull);
+            if (st_exact) atomicAdd(&g_knn_tc_stats[1], 1ull);
+            if (brute) atomicAdd(&g_knn_tc_stats[2], 1ull);
+            atomicAdd(&g_knn_tc_stats[3], (unsigned long long)cnt);
+            if (emax > 0.0f) atomicMax(&g_knn_tc_stats[9], (unsigned long long)__float_as_uint(emax));
+        }
+    }
+}
+
+size_t knn_tc_smem(int NCB, int NKC, int stages)
+{
+    return (size_t)NKC * A_CHUNK + (size_t)stages * B_CHUNK + (size_t)NCB * TNB * 4 + GM_BYTES + TM * 4 +
            (1 + 2 * MAX_STAGES + 4) * 8 + 16;
+}
+
+// error model of the tensor-core score against the oracle chain, relative to (xx_i + xx_j):
+// truncating fp32 accumulation of 6 MMAs per 16 channels, chain rounding, dropped plane products,
+// final subtractions; x1.5 safety.  Observed maxima stay below 0.6x of the unscaled model.
+float knn_tc_eps(int C)
+{
+    const int NKC = (C + KCH - 1) / KCH;
+    return 1.5f * (NKC * 7.2e-7f + C * 3.0e-8f + 8.0e-7f);
 }
 
 }  // namespace
 
-static bool knn_tc_plan(const svnet_view* in, int B, int N, int k, int* NRB, int* NKC, int* stages, size_t* pack_bytes,
-                        size_t* xx_bytes)
+struct knn_tc_plan_t {
+    int NCB, NKC, stages, xcap;
+    size_t pack_bytes, xx_bytes, gq_bytes, cnt_bytes, fin_smem;
+};
+
+static bool knn_tc_plan(const svnet_view* in, int B, int N, int k, knn_tc_plan_t* pl)
 {
     const char* on = getenv("SVNET_KNN_TC");
     if (on && on[0] == '0') return false;
     const int C = in->Cs + 3 * in->Cv;
     if (B < 1 || k > KNN_TC_MAX_K || N > 4096 || C > KMAX || C < 1 || N < 64) return false;
-    *NRB = sv_cdiv(N, TM);
-    *NKC = sv_cdiv(C, KCH);
+    pl->NCB = sv_cdiv(N, TNB);
+    pl->NKC = sv_cdiv(C, KCH);
     int s = MAX_STAGES;
     const size_t limit = 227 * 1024;
-    while (s > 2 && knn_tc_smem(*NRB, *NKC, s) > limit) --s;
-    if (knn_tc_smem(*NRB, *NKC, s) > limit) return false;
-    *stages = s;
-    *pack_bytes = (size_t)B * *NRB * *NKC * CHUNK_BYTES;
-    *xx_bytes = (size_t)B * *NRB * TM * sizeof(float);
+    while (s > 2 && knn_tc_smem(pl->NCB, pl->NKC, s) > limit) --s;
+    if (knn_tc_smem(pl->NCB, pl->NKC, s) > limit) return false;
+    pl->stages = s;
+    const size_t a256 = 255;
+    pl->pack_bytes = ((size_t)B * pl->NCB * pl->NKC * B_CHUNK + a256) & ~a256;
+    pl->xx_bytes = ((size_t)B * pl->NCB * TNB * sizeof(float) + a256) & ~a256;
+    pl->gq_bytes = ((size_t)B * N * 2 * CAPH * sizeof(float2) + a256) & ~a256;
+    pl->cnt_bytes = ((size_t)B * N * 2 * sizeof(int) + a256) & ~a256;
+    const int Cp = fin_stride(C);
+    pl->xcap = Cp <= 68 ? 12 : 6;
+    pl->fin_smem = ((size_t)FIN_TAB_FLOATS + (size_t)FIN_WARPS * ((1 + pl->xcap) * Cp)) * sizeof(float);
     return true;
 }
 
 // Scratch bytes the tensor-core path needs for this shape; 0 when the shape is not covered.
 size_t svnet_knn_tc_workspace(const svnet_view* in, int B, int N, int k)
 {
-    int NRB, NKC, stages;
-    size_t pb, xb;
-    if (!knn_tc_plan(in, B, N, k, &NRB, &NKC, &stages, &pb, &xb)) return 0;
-    return pb + xb;
+    knn_tc_plan_t pl;
+    if (!knn_tc_plan(in, B, N, k, &pl)) return 0;
+    return pl.pack_bytes + pl.xx_bytes + pl.gq_bytes + pl.cnt_bytes;
 }
 
 // Returns 1 if handled, 0 if the caller should use the CUDA-core kernel, < 0 on error.
 int svnet_knn_tc_dispatch(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, void* workspace,
                           size_t workspace_bytes, cudaStream_t st)
 {
-    int NRB, NKC, stages;
-    size_t pack_bytes, xx_bytes;
-    if (!workspace || !knn_tc_plan(in, B, N, k, &NRB, &NKC, &stages, &pack_bytes, &xx_bytes)) return 0;
-    if (workspace_bytes < pack_bytes + xx_bytes || (reinterpret_cast<uintptr_t>(workspace) & 15)) return 0;
+    knn_tc_plan_t pl;
+    if (!workspace || !knn_tc_plan(in, B, N, k, &pl)) return 0;
+    if (workspace_bytes < pl.pack_bytes + pl.xx_bytes + pl.gq_bytes + pl.cnt_bytes || (reinterpret_cast<uintptr_t>(workspace) & 15))
+        return 0;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    float* xx = reinterpret_cast<float*>(ws + pack_bytes);
-    knn_pack_kernel<<<dim3(NRB, B), TM, 0, st>>>(*in, N, NRB, NKC, ws, xx);
-    SV_CHECK_LAUNCH("svnet_knn(pack)");
     knn_tc_args a;
-    a.in = *in; a.N = N; a.k = k; a.NRB = NRB; a.NKC = NKC; a.stages = stages;
-    a.pack = ws; a.xx = xx; a.idx32 = idx32; a.idx64 = idx64;
-    const size_t smem = knn_tc_smem(NRB, NKC, stages);
+    a.in = *in; a.N = N; a.k = k; a.NCB = pl.NCB; a.NKC = pl.NKC; a.stages = pl.stages; a.xcap = pl.xcap;
+    a.eps = knn_tc_eps(in->Cs + 3 * in->Cv);
+    {
+        const char* sv = getenv("SVNET_KNN_TC_STATS");
+        a.stats = (sv && sv[0] == '1') ? 1 : 0;
+    }
+    a.pack = ws;
+    a.xx = reinterpret_cast<float*>(ws + pl.pack_bytes);
+    a.gq = reinterpret_cast<float2*>(ws + pl.pack_bytes + pl.xx_bytes);
+    a.gqcnt = reinterpret_cast<int*>(ws + pl.pack_bytes + pl.xx_bytes + pl.gq_bytes);
+    a.idx32 = idx32; a.idx64 = idx64;
+    knn_pack_kernel<<<dim3(pl.NCB * (TNB / PACK_ROWS), B), 256, (size_t)PACK_ROWS * (pl.NKC * KCH + 1) * sizeof(float), st>>>(*in, N, pl.NCB, pl.NKC, ws, const_cast<float*>(a.xx));
+    SV_CHECK_LAUNCH("svnet_knn(pack)");
+    const size_t smem = knn_tc_smem(pl.NCB, pl.NKC, pl.stages);
     SV_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_tc_kernel<<<dim3(NRB, B), NTHREADS, smem, st>>>(a);
+    knn_tc_kernel<<<dim3(sv_cdiv(N, TM), B), NTHREADS, smem, st>>>(a);
     SV_CHECK_LAUNCH("svnet_knn(tcgen05)");
+    SV_CUDA(cudaFuncSetAttribute(knn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.fin_smem));
+    knn_finish_kernel<<<dim3(sv_cdiv(N, FIN_WARPS), B), FIN_WARPS * 32, pl.fin_smem, st>>>(a);
+    SV_CHECK_LAUNCH("svnet_knn(finish)");
     return 1;
 }
 
-// debug: rows, rows re-scored exactly, brute-force rows, survivors (cumulative since the last reset)
+// profiling counters (cumulative since the last reset), see include/svnet_b200.h
 extern "C" int svnet_knn_tc_stats(unsigned long long* out12, int reset)
 {
     SV_CUDA(cudaMemcpyFromSymbol(out12, g_knn_tc_stats, sizeof(unsigned long long) * 12));

@@ -41,6 +41,8 @@ def main():
               (32, 1024, 3, 20), (32, 1024, 62, 20), (32, 1024, 127, 20), (8, 4096, 62, 20)]
     if len(sys.argv) > 1 and sys.argv[1] == "quick":
         shapes = shapes[:5]
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        shapes = shapes[5:8]
     check_oracle = "--oracle" in sys.argv
     for (B, N, C, k) in shapes:
         g = torch.Generator().manual_seed(B * 131 + N + C)
@@ -49,8 +51,10 @@ def main():
             x = x * 0.3 + 1.0          # common offset: norms >> distances (the hard case for the filter)
         xd = x.cuda()
         stats()
+        os.environ["SVNET_KNN_TC_STATS"] = "1"
         a = run(xd, B, N, k, True)
         torch.cuda.synchronize()
+        os.environ["SVNET_KNN_TC_STATS"] = "0"
         st = stats()
         b = run(xd, B, N, k, False)
         torch.cuda.synchronize()

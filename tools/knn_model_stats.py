@@ -14,6 +14,9 @@ def stats():
 orig = nv.knn
 def knn(view, B, N, k, **kw):
     torch.cuda.synchronize(); stats()
+    os.environ["SVNET_KNN_TC_STATS"] = "1"
+    orig(view, B, N, k, **kw); torch.cuda.synchronize()
+    os.environ["SVNET_KNN_TC_STATS"] = "0"
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); r = orig(view, B, N, k, **kw); e1.record(); torch.cuda.synchronize()
     st = stats(); rows = max(st[0], 1)
