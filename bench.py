@@ -227,7 +227,7 @@ def main():
             sampler.rows.clear()
         barrier()
         # ---- device-resident throughput; the dominant kernels are bracketed with events live ----
-        nv.PROFILE[0] = {"svnet_knn", "svnet_svblock_edge_fwd"}
+        nv.PROFILE[0] = {"svnet_knn_ws", "svnet_svblock_edge_fwd"}
         nv.TIMED.clear()
         nv.ORDER.clear()
         l0 = nv.LAUNCHES[0]
@@ -265,7 +265,7 @@ def main():
     def per_layer(name, n_per_step):
         v = per_call.get(name, [])
         return [sum(v[i::n_per_step]) / max(1, len(v[i::n_per_step])) for i in range(n_per_step)]
-    knn_ms = per_layer("svnet_knn", 4)
+    knn_ms = per_layer("svnet_knn_ws", 4)
     edge_ms = per_layer("svnet_svblock_edge_fwd", 3)
     cand = [("svnet_knn[layer%d]" % (i + 1), knn_ms[i], knn_kernel_bytes_per_cloud(i) * B) for i in range(4)]
     cand += [("svnet_svblock_edge_fwd[layer%d]" % (i + 2), edge_ms[i], edge_kernel_bytes_per_cloud(i + 1) * B) for i in range(3)]
@@ -295,7 +295,7 @@ def main():
     out = {
         "metric": METRIC, "value": world * B / (ms * 1e-3), "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (+u32 XNOR/popcount for the binarised linears)", "data": "synthetic",
+        "dtype": "f32 (+u32 XNOR/popcount for the binarised linears; exact bf16x3 tcgen05 filter in front of the fp32 kNN)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B, "n_points": N_POINTS, "k": K_NN,
                    "parallelism": "batch-sharded x%d, all-gather of logits" % world,
                    "l2": "flushed between steps (256 MiB memset, untimed)"},

@@ -179,6 +179,8 @@ def knn(view, B, N, k, want64=False, want32=True):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes > 0 else None
     _call("svnet_knn_ws", ctypes.byref(view), c_int(B), c_int(N), c_int(k), _ptr(i32), _ptr(i64), _ptr(ws),
           ctypes.c_size_t(nbytes), _stream())
+    if nbytes > 0:
+        LAUNCHES[0] += 2     # tensor-core path = pack + tcgen05 + finish kernels
     return i32, i64
 
 

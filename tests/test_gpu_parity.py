@@ -102,6 +102,84 @@ def test_knn_full_size_properties():
         assert (rest.min(dim=2)[0] >= sel[:, :, -1] - 1e-5 * scale).all()
 
 
+def _tc_stats(reset=True):
+    import ctypes
+    from svnet_b200 import _native as nv
+    out = (ctypes.c_ulonglong * 12)()
+    assert nv.lib().svnet_knn_tc_stats(out, ctypes.c_int(1 if reset else 0)) == 0
+    return list(out)
+
+
+@pytest.mark.parametrize("case", ["duplicates", "lattice", "offset", "all_equal", "ragged", "two_clusters"])
+def test_knn_tensor_core_path_adversarial(case, monkeypatch):
+    """Shapes served by the tcgen05 filter (csrc/knn_tc.cu: N >= 64, k <= 24): exact ties (duplicated
+    points, lattice), norms much larger than neighbour gaps, everything equal (queue overflow ->
+    brute-force rows), N not a multiple of the 128/256 tiles.  Indices must equal the oracle's, and
+    the CUDA-core kernel's, bit for bit; the counters prove that the tensor-core path ran."""
+    import svnet_b200 as sv
+    from svnet_b200 import _native as nv
+    g = torch.Generator().manual_seed(17)
+    B, N, C, k = 2, 384, 62, 20
+    if case == "duplicates":
+        base = torch.randn((B, N // 4, C), generator=g)
+        feat = base.repeat(1, 4, 1)[:, torch.randperm(N, generator=g)]
+    elif case == "lattice":
+        B, N, C, k = 1, 343, 3, 20
+        ax = torch.arange(7, dtype=torch.float32)
+        feat = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, N, 3) * 0.25
+    elif case == "offset":
+        feat = torch.randn((B, N, C), generator=g) * 0.05 + 3.0
+    elif case == "all_equal":
+        B, N, C, k = 1, 200, 5, 8
+        feat = torch.ones((B, N, C)) * 0.5
+    elif case == "ragged":
+        B, N, C, k = 3, 333, 127, 24
+        feat = torch.randn((B, N, C), generator=g)
+    else:
+        B, N, C, k = 1, 1024, 30, 20
+        feat = torch.cat([torch.randn((B, 1000, C), generator=g) * 0.01, torch.randn((B, 24, C), generator=g) + 5.0], 1)
+    feat = feat.contiguous()
+    ref = orc.knn(feat.numpy(), k)
+    x = feat.to(DEV).view(B * N, C)
+    monkeypatch.setenv("SVNET_KNN_TC_STATS", "1")
+    _tc_stats()
+    monkeypatch.setenv("SVNET_KNN_TC", "1")
+    tc = t2n(nv.knn(nv.view_of(x, None), B, N, k)[0])
+    st = _tc_stats()
+    monkeypatch.setenv("SVNET_KNN_TC", "0")
+    cc = t2n(nv.knn(nv.view_of(x, None), B, N, k)[0])
+    assert st[0] == B * N, "tensor-core path did not run"
+    assert (cc == ref).all()
+    assert (tc == ref).all(), "%d rows differ" % int((tc != ref).any(-1).sum())
+    if case == "all_equal":
+        assert st[2] > 0      # every candidate reaches the threshold: the rows take the brute-force path
+
+
+def test_knn_tensor_core_error_model_on_model_features():
+    """The filter's error bound eps(C) (knn_tc_eps) must dominate the measured |tensor-core score -
+    oracle chain score| / (xx_i + xx_j) with margin on real layer features (binary SV-DGCNN)."""
+    import struct
+    import svnet_b200 as sv
+    import os
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=20, binary=True), 40)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=1002))
+    net = net.to(DEV).eval()
+    x = synthetic_clouds(8, 1024, 1002).to(DEV)
+    os.environ["SVNET_KNN_TC_STATS"] = "1"
+    try:
+        _tc_stats()
+        with torch.no_grad():
+            net(x)
+        torch.cuda.synchronize()
+        st = _tc_stats()
+    finally:
+        os.environ["SVNET_KNN_TC_STATS"] = "0"
+    assert st[0] == 4 * 8 * 1024 and st[2] == 0
+    err = struct.unpack("f", struct.pack("I", st[9] & 0xffffffff))[0]
+    eps_c127 = 1.5 * (8 * 7.2e-7 + 127 * 3.0e-8 + 8.0e-7)
+    assert 0.0 < err < eps_c127 / 1.5, err
+
+
 # ------------------------------------------------------------------------------------------------
 # module-level API vs golden (reference outputs) and oracle
 # ------------------------------------------------------------------------------------------------
