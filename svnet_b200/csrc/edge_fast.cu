@@ -13,6 +13,7 @@
 //   P4  XNOR/popcount linear1 (lanes = output channels), BN, LeakyReLU, max over edges
 //   P5  vector branch from the per-point P|Q table, VectorBN, gate, mean over edges
 #include "common.cuh"
+#include <limits.h>
 
 namespace {
 
@@ -39,6 +40,62 @@ struct Shape {
     static constexpr int ES = 3 * XS;                  // floats per staged edge
     static_assert(CS % 32 == 0 && COUT % 32 == 0, "scalar widths must be multiples of 32");
 };
+
+
+// ---- P5: vector branch from the per-point P|Q table: w_e = (P_j - P_i) + Q_i, VectorBN, gate, mean over
+// the edges.  Channels beyond a multiple of 32 are spread over lane groups (group g takes the edges
+// e = g, g+G, ...; partial sums meet by shuffle), so CVO = 10 keeps 30 lanes busy instead of 10.
+// Tolerance-level arithmetic (norms and mean pools are not bit-pinned): rsqrt /
+// fast division instead of the IEEE sequences.
+template <int CVO>
+__device__ __forceinline__ void vector_branch(const svnet_edge_params& p, long r, int b, long cbase, const int* nidx, int k, int lane)
+{
+    constexpr int LDP = 2 * CVO;
+    const float inv_k = 1.0f / (float)k;
+    constexpr int FULL = CVO / 32;                 // passes with 32 channels, one edge group
+    constexpr int R = CVO % 32;                    // remainder channels
+    constexpr int G = R > 0 ? 32 / R : 1;          // edge groups of the remainder pass
+#pragma unroll
+    for (int pass = 0; pass < FULL + (R > 0 ? 1 : 0); ++pass) {
+        const bool rem = pass == FULL;
+        const int g = rem ? lane / R : 0;
+        const int c = rem ? FULL * 32 + lane % (R > 0 ? R : 1) : pass * 32 + lane;
+        const int ng = rem ? G : 1;
+        const bool active = !rem || g < G;
+        float sum[3] = {0.0f, 0.0f, 0.0f};
+        if (active) {
+            const float* pi = p.PQ + r * 3 * LDP + c;
+            const float d_i[3] = {__ldg(pi + CVO) - __ldg(pi), __ldg(pi + LDP + CVO) - __ldg(pi + LDP),
+                                  __ldg(pi + 2 * LDP + CVO) - __ldg(pi + 2 * LDP)};      // Q_i - P_i
+            const float a2 = __ldg(p.bn2_a + c), c2 = __ldg(p.bn2_c + c);
+#pragma unroll 4
+            for (int e = g; e < k; e += ng) {
+                const float* pj = p.PQ + (cbase + nidx[e]) * 3 * LDP + c;
+                const float w0 = __ldg(pj) + d_i[0], w1 = __ldg(pj + LDP) + d_i[1], w2 = __ldg(pj + 2 * LDP) + d_i[2];
+                const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0 * w0));
+                const float n = (s2 > 0.0f ? s2 * rsqrtf(s2) : 0.0f) + 1e-6f;
+                const float t = a2 + __fdividef(c2, n);          // (n a2 + c2) / n
+                sum[0] = fmaf(w0, t, sum[0]);
+                sum[1] = fmaf(w1, t, sum[1]);
+                sum[2] = fmaf(w2, t, sum[2]);
+            }
+        }
+        if (rem && G > 1) {
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                float tot = sum[x];
+#pragma unroll
+                for (int gg = 1; gg < G; ++gg) tot += __shfl_sync(SV_FULL, sum[x], (lane % (R > 0 ? R : 1)) + gg * R);
+                sum[x] = tot;
+            }
+        }
+        if (active && g == 0) {
+            const float gt = p.gate[(long)b * CVO + c] * inv_k;
+#pragma unroll
+            for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + c] = sum[x] * gt;
+        }
+    }
+}
 
 template <int CS, int CV, int COUT, int CVO, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 4 : 3) : 6) edge_bin_fast_kernel(svnet_edge_params p, int kp)
@@ -219,11 +276,15 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 4 :
     // ---- P4: XNOR/popcount linear1, lanes = output channels (OPP per lane per pass) ----
 #pragma unroll 1
     for (int ob = 0; ob < S::OPT; ob += S::OPP) {
-        float smax[S::OPP];
+        // y = leaky(bn(scale * dot)) is a monotone function of the integer dot (every fp32 rounding is
+        // monotone), so max over the edges of y is y(max dot) or y(min dot): keep integer extremes and
+        // run the float epilogue once per output channel -- bit-identical to taking the max of all y.
+        int dmax[S::OPP], dmin[S::OPP];
         int cmis[S::OPP];   // mismatches of the centre words (identical for all edges of this point)
 #pragma unroll
         for (int oo = 0; oo < S::OPP; ++oo) {
-            smax[oo] = -INFINITY;
+            dmax[oo] = INT_MIN;
+            dmin[oo] = INT_MAX;
             cmis[oo] = 0;
 #pragma unroll
             for (int t = 0; t < S::TS; ++t)
@@ -255,49 +316,32 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 4 :
                 }
             }
 #pragma unroll
-            for (int oo = 0; oo < S::OPP; ++oo) {
-                const int o = lane + 32 * (ob + oo);
-                const float sc = __ldg(p.scale1 + o), a1 = __ldg(p.bn1_a + o), c1 = __ldg(p.bn1_c + o);
+            for (int e = 0; e < EB; ++e) {
+                if (eb + e < k) {
+                    const int nv = nvalid[eb + e];
 #pragma unroll
-                for (int e = 0; e < EB; ++e) {
-                    if (eb + e < k) {
-                        const int dot = nvalid[eb + e] - 2 * (acc[e][oo] + cmis[oo]);
-                        float y = __fmul_rn((float)dot, sc);
-                        y = __fadd_rn(__fmul_rn(y, a1), c1);
-                        y = y > 0.0f ? y : __fmul_rn(0.2f, y);
-                        smax[oo] = fmaxf(smax[oo], y);
+                    for (int oo = 0; oo < S::OPP; ++oo) {
+                        const int dot = nv - 2 * (acc[e][oo] + cmis[oo]);
+                        dmax[oo] = max(dmax[oo], dot);
+                        dmin[oo] = min(dmin[oo], dot);
                     }
                 }
             }
         }
 #pragma unroll
-        for (int oo = 0; oo < S::OPP; ++oo) p.out.s[r * p.out.lds + lane + 32 * (ob + oo)] = smax[oo];
+        for (int oo = 0; oo < S::OPP; ++oo) {
+            const int o = lane + 32 * (ob + oo);
+            const float sc = __ldg(p.scale1 + o), a1 = __ldg(p.bn1_a + o), c1 = __ldg(p.bn1_c + o);
+            float y0 = __fadd_rn(__fmul_rn(__fmul_rn((float)dmax[oo], sc), a1), c1);
+            float y1 = __fadd_rn(__fmul_rn(__fmul_rn((float)dmin[oo], sc), a1), c1);
+            y0 = y0 > 0.0f ? y0 : __fmul_rn(0.2f, y0);
+            y1 = y1 > 0.0f ? y1 : __fmul_rn(0.2f, y1);
+            p.out.s[r * p.out.lds + o] = fmaxf(y0, y1);
+        }
     }
 
-    // ---- P5: vector branch, lanes = output vector channels ----
-    constexpr int LDP = 2 * CVO;
-    const float inv_k = 1.0f / (float)k;
-    for (int c = lane; c < CVO; c += 32) {
-        const float* pi = p.PQ + r * 3 * LDP + c;
-        const float p_i[3] = {__ldg(pi), __ldg(pi + LDP), __ldg(pi + 2 * LDP)};
-        const float q_i[3] = {__ldg(pi + CVO), __ldg(pi + LDP + CVO), __ldg(pi + 2 * LDP + CVO)};
-        const float a2 = __ldg(p.bn2_a + c), c2 = __ldg(p.bn2_c + c);
-        float sum[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll 10
-        for (int e = 0; e < k; ++e) {
-            const float* pj = p.PQ + (cbase + nidx[e]) * 3 * LDP + c;
-            float w[3];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) w[x] = (__ldg(pj + x * LDP) - p_i[x]) + q_i[x];
-            const float n = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]) + 1e-6f;
-            const float t = (n * a2 + c2) / n;
-#pragma unroll
-            for (int x = 0; x < 3; ++x) sum[x] += w[x] * t;
-        }
-        const float g = p.gate[(long)b * CVO + c] * inv_k;
-#pragma unroll
-        for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + c] = sum[x] * g;
-    }
+    // ---- P5: vector branch ----
+    vector_branch<CVO>(p, r, b, cbase, nidx, k, lane);
 }
 
 // ---- full-precision variant (SV-DGCNN fp models, cfg3): same gather / frame phases, the scalar
@@ -463,29 +507,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_fp_fast
     }
 
     // ---- P5: vector branch ----
-    constexpr int LDP = 2 * CVO;
-    const float inv_k = 1.0f / (float)k;
-    for (int c = lane; c < CVO; c += 32) {
-        const float* pi = p.PQ + r * 3 * LDP + c;
-        const float p_i[3] = {__ldg(pi), __ldg(pi + LDP), __ldg(pi + 2 * LDP)};
-        const float q_i[3] = {__ldg(pi + CVO), __ldg(pi + LDP + CVO), __ldg(pi + 2 * LDP + CVO)};
-        const float a2 = __ldg(p.bn2_a + c), c2 = __ldg(p.bn2_c + c);
-        float sum[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll 10
-        for (int e = 0; e < k; ++e) {
-            const float* pj = p.PQ + (cbase + nidx[e]) * 3 * LDP + c;
-            float w[3];
-#pragma unroll
-            for (int x = 0; x < 3; ++x) w[x] = (__ldg(pj + x * LDP) - p_i[x]) + q_i[x];
-            const float n = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]) + 1e-6f;
-            const float t = (n * a2 + c2) / n;
-#pragma unroll
-            for (int x = 0; x < 3; ++x) sum[x] += w[x] * t;
-        }
-        const float g = p.gate[(long)b * CVO + c] * inv_k;
-#pragma unroll
-        for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + c] = sum[x] * g;
-    }
+    vector_branch<CVO>(p, r, b, cbase, nidx, k, lane);
 }
 
 template <int CS, int CV, int COUT, int CVO>

@@ -791,7 +791,11 @@ static bool knn_tc_plan(const svnet_view* in, int B, int N, int k, knn_tc_plan_t
     pl->gq_bytes = ((size_t)B * N * 2 * CAPH * sizeof(float2) + a256) & ~a256;
     pl->cnt_bytes = ((size_t)B * N * 2 * sizeof(int) + a256) & ~a256;
     const int Cp = fin_stride(C);
-    pl->xcap = Cp <= 68 ? 12 : 6;
+    pl->xcap = Cp <= 68 ? 12 : 8;
+    if (const char* xc = getenv("SVNET_KNN_XCAP")) {      // tuning aid
+        const int v = atoi(xc);
+        if (v >= 2 && v <= 32) pl->xcap = v;
+    }
     pl->fin_smem = ((size_t)FIN_TAB_FLOATS + (size_t)FIN_WARPS * ((1 + pl->xcap) * Cp)) * sizeof(float);
     return true;
 }
