@@ -29,16 +29,14 @@ COLS = [
 ]
 
 
-def main():
-    rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
+def summarise(rows):
+    """rows = parsed `ncu --page raw --csv` output -> markdown table (one row per captured launch)."""
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
-    print("| kernel | " + " | ".join(c[1] for c in COLS if c[0] in ix) + " |")
-    print("|---|" + "---|" * len([c for c in COLS if c[0] in ix]))
+    out = ["| kernel | " + " | ".join(c[1] for c in COLS if c[0] in ix) + " |",
+           "|---|" + "---|" * len([c for c in COLS if c[0] in ix])]
     for r in rows[2:]:
-        name = r[ix["Kernel Name"]].replace("void <unnamed>::", "").split("(")[0]
+        name = r[ix["Kernel Name"]].replace("void <unnamed>::", "").replace("<unnamed>::", "").split("(")[0]
         cells = []
         for k, _ in COLS:
             if k not in ix:
@@ -50,7 +48,17 @@ def main():
             except ValueError:
                 pass
             cells.append("%s %s" % (v, u) if u and u not in ("%", "") else v)
-        print("| %s | %s |" % (name, " | ".join(cells)))
+        out.append("| %s | %s |" % (name, " | ".join(cells)))
+    return "\n".join(out) + "\n"
+
+
+def main():
+    src = sys.argv[1]
+    if src.endswith(".csv"):
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    print(summarise(list(csv.reader(io.StringIO(raw)))), end="")
 
 
 if __name__ == "__main__":
