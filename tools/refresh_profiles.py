@@ -26,29 +26,35 @@ def main():
 
     def nbytes(r, key):
         return float(r[ix[key]].replace(",", "")) * mult[units[ix[key]]]
-    knn, edge = [], []
+    # A kNN call = pack + tcgen05 + finish kernels (or the CUDA-core knn_kernel); it belongs to the layer
+    # of the next edge kernel in launch order.  Edge layers are told apart by their template shapes, so a
+    # capture that starts mid-forward or covers more than one forward still maps correctly.
     body = rows[2:]
-    # the capture may start mid-forward: rotate so that it begins with layer 1's kNN (the pack kernel that
-    # precedes the first-layer gate / edge kernels)
-    names = [r[ix["Kernel Name"]] for r in body]
-    first_xyz = next((i for i, n in enumerate(names) if "gate_xyz" in n or "edge_xyz" in n), None)
-    if first_xyz is not None:
-        start = max(i for i in range(first_xyz) if "knn_pack_kernel" in names[i] or "knn_kernel" in names[i]) \
-            if any("knn_pack_kernel" in n or "knn_kernel" in n for n in names[:first_xyz]) else 0
-        body = body[start:] + body[:start]
+    d = {}
+    pending = None
+    edge_seen = []
     for r in body:
         t = nbytes(r, "dram__bytes_read.sum") + nbytes(r, "dram__bytes_write.sum")
         name = r[ix["Kernel Name"]]
-        if "knn_pack_kernel" in name:
-            knn.append(t)                      # a kNN call = pack + tcgen05 + finish kernels
-        elif "knn_tc_kernel" in name or "knn_finish_kernel" in name:
-            knn[-1] += t
-        elif "knn_kernel" in name:
-            knn.append(t)
-        if "edge_bin_fast" in name or "svblock_edge_kernel" in name:
-            edge.append(t)
-    d = {"svnet_knn[layer%d]" % (i + 1): t for i, t in enumerate(knn[:4])}
-    d.update({"svnet_svblock_edge_fwd[layer%d]" % (i + 2): t for i, t in enumerate(edge[:3])})
+        if "knn_pack_kernel" in name or ("knn_kernel" in name and "tc" not in name):
+            pending = t
+        elif ("knn_tc_kernel" in name or "knn_finish_kernel" in name) and pending is not None:
+            pending += t
+        elif "edge_xyz" in name:
+            if pending is not None:
+                d["svnet_knn[layer1]"] = pending
+            pending = None
+        elif "edge_bin_fast" in name or "svblock_edge_kernel" in name or "edge_fp_fast" in name:
+            shape = name.split("kernel<")[1].split(">")[0] if "kernel<" in name else "0, 0, 0, 0"
+            d["_edge_" + shape] = (t, pending)
+            pending = None
+    shapes = sorted([k[6:] for k in d if k.startswith("_edge_")], key=lambda sh: [int(v) for v in sh.split(",")[:4]])
+    for i, sh in enumerate(shapes):
+        t, kn = d.pop("_edge_" + sh)
+        d["svnet_svblock_edge_fwd[layer%d]" % (i + 2)] = t
+        if kn is not None:
+            d["svnet_knn[layer%d]" % (i + 2)] = kn
+    d = dict(sorted(d.items()))
     json.dump(d, open(os.path.join(ROOT, "profiles", "dram_traffic.json"), "w"), indent=1)
     for src, dst in (("launches_r1.csv", tag + "_launches.csv"), ("bench_r1.json", tag + "_bench.json")):
         p = os.path.join(ROOT, "gpurun_out", src)
