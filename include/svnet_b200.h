@@ -272,6 +272,15 @@ int svnet_vector_bn_rows(const float* v, long rows, int C, const float* bn_a, co
 int svnet_pool_rows(const float* x, int ld, int C, int B, long rows, float* max_out, float* mean_out, int ldo,
                     void* stream);
 
+/* SVFuse + global pooling of SV_DGCNN_CLS (sv_layers.py:206-220 with sv_dgcnn_cls.py:70-74), fused:
+ * q = v2s(v) [rows][3*Cv] is reduced on the fly to the per-cloud column max and mean; the fused table
+ * never reaches HBM.  in->v [B*rows_per_cloud][3][Cv] (in->Cs must be 0 / s ignored); Wz [3][Cv],
+ * zscale [3] or NULL; max_out / mean_out [B][ldo] (either may be NULL); 3*Cv <= 512.
+ * workspace: svnet_svfuse_pool_workspace() bytes (partials, combined in a fixed order). */
+size_t svnet_svfuse_pool_workspace(int B, int Cv, long rows_per_cloud);
+int svnet_svfuse_pool(const svnet_view* in, int B, long rows_per_cloud, const float* Wz, const float* zscale,
+                      float* max_out, float* mean_out, int ldo, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Input side of the eval loop: out[b][c][n] = sum_d pts[b][n][d] * R[b][d][c]
  * (pytorch3d Rotate.transform_points, then permute(0,2,1): main_cls_dgcnn.py:229-235).
  * pts [B][N][3], R [B][3][3] or NULL (permute only) -> out [B][3][N]. */

@@ -19,7 +19,7 @@ c_int, c_long, c_float, c_void_p = ctypes.c_int, ctypes.c_long, ctypes.c_float, 
 
 EXPORTS = [
     "svnet_version", "svnet_last_error", "svnet_pack_sign", "svnet_fold_bn", "svnet_knn",
-    "svnet_knn_ws", "svnet_knn_workspace_bytes", "svnet_knn_tc_stats",
+    "svnet_knn_ws", "svnet_knn_workspace_bytes", "svnet_knn_tc_stats", "svnet_svfuse_pool", "svnet_svfuse_pool_workspace",
     "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
@@ -75,6 +75,7 @@ def lib():
         l = ctypes.CDLL(LIB_PATH)
         l.svnet_last_error.restype = ctypes.c_char_p
         l.svnet_knn_workspace_bytes.restype = ctypes.c_size_t
+        l.svnet_svfuse_pool_workspace.restype = ctypes.c_size_t
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
         if l.svnet_version() != 1:
@@ -294,6 +295,17 @@ def vector_bn_rows(v, bn_a, bn_c):
     _call("svnet_vector_bn_rows", _ptr(_dev(v)), c_long(rows), c_int(C), _ptr(bn_a), _ptr(bn_c), _ptr(out),
                                       _stream())
     return out
+
+
+def svfuse_pool(v3, B, rows_per_cloud, Wz, zscale, max_out, mean_out, ldo):
+    """v2s(v) of SVFuse reduced straight to per-cloud max / mean (no fused table in HBM)."""
+    Cv = v3.shape[-1]
+    view = view_of(None, v3)
+    nbytes = int(lib().svnet_svfuse_pool_workspace(c_int(B), c_int(Cv), c_long(rows_per_cloud)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=v3.device)
+    _call("svnet_svfuse_pool", ctypes.byref(view), c_int(B), c_long(rows_per_cloud), _ptr(_dev(Wz)), _ptr(zscale),
+          _ptr(max_out), _ptr(mean_out), c_int(ldo), _ptr(ws), ctypes.c_size_t(nbytes), _stream())
+    LAUNCHES[0] += 1
 
 
 def pool_rows(x, ld, C, B, rows, want_max=True, want_mean=False, max_out=None, mean_out=None, ldo=None):

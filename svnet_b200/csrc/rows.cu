@@ -77,6 +77,110 @@ __global__ void __launch_bounds__(PW * 32) rows_prep_kernel(svnet_view in, long 
     }
 }
 
+// Staged variant: the three rows of a warp's group are first copied to shared memory with cp.async
+// (every load of the group in flight at once; the direct version above waits on ~Cv dependent L1/L2
+// round trips per row), Wz is CTA-shared; the arithmetic and its order are identical.
+__device__ __forceinline__ void rp_cp_async4(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+
+__global__ void __launch_bounds__(PW * 32) rows_prep_staged_kernel(svnet_view in, long rows, const float* __restrict__ Wz,
+                                                                   const float* __restrict__ zscale,
+                                                                   const float* __restrict__ beta, float* __restrict__ u_out,
+                                                                   int ldu, float* __restrict__ z_out,
+                                                                   uint32_t* __restrict__ bits, uint32_t* __restrict__ mask,
+                                                                   int32_t* __restrict__ nvalid)
+{
+    extern __shared__ float rp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Cs = in.Cs, Cv = in.Cv;
+    const int K = Cs + 3 * Cv, Kw = (K + 31) / 32;
+    const int V3 = 3 * Cv;                       // vector floats per row
+    float* wzs = rp_smem;                        // [3][Cv]
+    float* vsm = wzs + V3 + (size_t)warp * (3 * V3 + 28);     // [3 rows][3][Cv]
+    float* zb = vsm + 3 * V3;                    // [27]
+    for (int i = threadIdx.x; i < V3; i += PW * 32) wzs[i] = __ldg(Wz + i);
+    __syncthreads();
+    const long ngroups = (rows + 2) / 3;
+    for (long grp = (long)blockIdx.x * PW + warp; grp < ngroups; grp += (long)gridDim.x * PW) {
+        const long r0 = grp * 3;
+        const int ng = (int)min(3L, rows - r0);
+        // ---- stage the vectors of the group: [g][x][c], all copies in flight ----
+        for (int i = lane; i < V3; i += 32) {
+            const int x = i / Cv, c = i - x * Cv;
+            const float* src = in.v + r0 * in.ldv + (long)x * in.xs + c;
+            for (int g = 0; g < ng; ++g) rp_cp_async4(vsm + g * V3 + i, src + (long)g * in.ldv);
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        __syncwarp();
+        // ---- frames: sequential chain over channels == oracle order ----
+        if (lane < ng * 9) {
+            const int g = lane / 9, xm = lane - g * 9, x = xm / 3, m = xm - x * 3;
+            const float* vp = vsm + g * V3 + x * Cv;
+            const float* wz = wzs + m * Cv;
+            float acc = 0.0f;
+#pragma unroll 4
+            for (int c = 0; c < Cv; ++c) acc = __fmaf_rn(vp[c], wz[c], acc);
+            if (zscale) acc = __fmul_rn(acc, __ldg(zscale + m));
+            zb[lane] = acc;
+            if (z_out) z_out[(r0 + g) * 9 + xm] = acc;
+        }
+        __syncwarp();
+        for (int g = 0; g < ng; ++g) {
+            const long r = r0 + g;
+            const float* z = zb + g * 9;
+            const float* vr = vsm + g * V3;
+            int nval = 0;
+            // words that lie entirely in the scalar part: all loads issued before the first use
+            // (16 words cover Cs <= 512), compile-time indexing
+            const int ws_full = min(Cs >> 5, 16);
+            float spre[16];
+#pragma unroll
+            for (int w = 0; w < 16; ++w) spre[w] = (w < ws_full) ? __ldg(in.s + r * in.lds + w * 32 + lane) : 0.0f;
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+                if (w < ws_full) {
+                    const int kk = w * 32 + lane;
+                    const float u = spre[w];
+                    if (u_out) u_out[r * ldu + kk] = u;
+                    if (bits) {
+                        const float t = __fadd_rn(u, __ldg(beta + kk));
+                        const unsigned pos = __ballot_sync(SV_FULL, t > 0.0f);
+                        const unsigned nz = __ballot_sync(SV_FULL, t != 0.0f);
+                        nval += __popc(nz);
+                        if (lane == 0) { bits[r * Kw + w] = pos; mask[r * Kw + w] = nz; }
+                    }
+                }
+            }
+#pragma unroll 4
+            for (int wd = ws_full; wd < Kw; ++wd) {
+                const int kk = wd * 32 + lane;
+                float u = 0.0f;
+                if (kk < Cs) u = __ldg(in.s + r * in.lds + kk);
+                else if (kk < K) {
+                    const int t = kk - Cs, dd = t / 3, m = t - dd * 3;
+                    float q = __fmul_rn(vr[dd], z[m]);
+                    q = __fmaf_rn(vr[Cv + dd], z[3 + m], q);
+                    q = __fmaf_rn(vr[2 * Cv + dd], z[6 + m], q);
+                    u = q;
+                }
+                if (u_out && kk < K) u_out[r * ldu + kk] = u;
+                if (bits) {
+                    const float t = (kk < K) ? __fadd_rn(u, __ldg(beta + kk)) : 0.0f;
+                    const unsigned pos = __ballot_sync(SV_FULL, t > 0.0f);
+                    const unsigned nz = __ballot_sync(SV_FULL, t != 0.0f);
+                    nval += __popc(nz);
+                    if (lane == 0) { bits[r * Kw + wd] = pos; mask[r * Kw + wd] = nz; }
+                }
+            }
+            if (bits && lane == 0) nvalid[r] = nval;
+        }
+        __syncwarp();
+    }
+}
+
 // 64 rows x 64 outputs per CTA, 4x4 per thread, 16 words per smem chunk.
 constexpr int BR = 64, BO = 64, WC = 16;
 
@@ -150,6 +254,9 @@ __global__ void __launch_bounds__(256) binlinear_rows_kernel(
 
 }  // namespace
 
+int svnet_rows_prep_fast_dispatch(const svnet_view* in, long rows, const float* Wz, const float* zscale, const float* beta,
+                                  uint32_t* bits, uint32_t* mask, int32_t* nvalid, cudaStream_t st);
+
 extern "C" int svnet_rows_prep(const svnet_view* in, long rows, const float* Wz, const float* zscale, const float* z_in,
                                const float* beta, float* u_out, int ldu, float* z_out, uint32_t* bits, uint32_t* mask, int32_t* nvalid,
                                void* stream)
@@ -162,8 +269,21 @@ extern "C" int svnet_rows_prep(const svnet_view* in, long rows, const float* Wz,
     SV_REQUIRE(u_out || bits || z_out, "svnet_rows_prep: no output requested");
     SV_REQUIRE(!u_out || ldu >= in->Cs + 3 * in->Cv, "svnet_rows_prep: ldu too small");
     if (rows == 0) return SVNET_OK;
+    if (bits && !u_out && !z_in && !z_out) {      // sign words only: instruction-lean kernel (rows_fast.cu)
+        const int handled = svnet_rows_prep_fast_dispatch(in, rows, Wz, zscale, beta, bits, mask, nvalid, sv_stream(stream));
+        if (handled != 0) return handled < 0 ? handled : SVNET_OK;
+    }
     const long ngroups = (rows + 2) / 3;
     const int grid = (int)min((long)sv_cdiv(ngroups, PW), 148L * 64);
+    // staged variant when the group's vectors fit a modest shared-memory slice (conv5 / svfuse / PointNet blocks)
+    const size_t staged_smem = sizeof(float) * ((size_t)3 * in->Cv + (size_t)PW * (9 * in->Cv + 28));
+    if (in->Cv > 0 && !z_in && staged_smem <= 56 * 1024 && rows >= 1024) {
+        SV_CUDA(cudaFuncSetAttribute(rows_prep_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem));
+        rows_prep_staged_kernel<<<grid, PW * 32, staged_smem, sv_stream(stream)>>>(*in, rows, Wz, zscale, beta, u_out, ldu, z_out,
+                                                                                     bits, mask, nvalid);
+        SV_CHECK_LAUNCH("svnet_rows_prep(staged)");
+        return SVNET_OK;
+    }
     rows_prep_kernel<<<grid, PW * 32, 0, sv_stream(stream)>>>(*in, rows, Wz, zscale, z_in, beta, u_out, ldu, z_out, bits, mask,
                                                                nvalid);
     SV_CHECK_LAUNCH("svnet_rows_prep");

@@ -55,13 +55,23 @@ class SV_DGCNN_CLS(nn.Module, _Cached):
         s_cat, v_cat = dgcnn_trunk(self, x, forced_idx, record)
         # conv5 (per point) -> svfuse -> max|mean over points
         C5s, C5v = self.conv5.out_dims
-        fused = torch.empty((B * N, C5s + 3 * C5v), dtype=torch.float32, device=dev)
+        Cf = C5s + 3 * C5v
         v5 = torch.empty((B * N, 3, C5v), dtype=torch.float32, device=dev)
-        self.conv5.forward_rows(s_cat, v_cat, B, N, s_out=fused, lds_out=fused.stride(0), v_out=v5)
-        self.svfuse.forward_rows(None, v5, out=fused)
-        Cf = fused.shape[1]
         g = torch.empty((B, 2 * Cf), dtype=torch.float32, device=dev)
-        nv.pool_rows(fused, Cf, Cf, B, N, want_max=True, want_mean=True, max_out=g, mean_out=g[:, Cf:], ldo=2 * Cf)
+        fused = None
+        if record is None and 3 * C5v <= 512:
+            # svfuse + global pools without the (B*N, 1022) table: scalars are pooled from conv5's own output,
+            # v2s(v) is reduced on the fly (svnet_svfuse_pool)
+            s5 = torch.empty((B * N, C5s), dtype=torch.float32, device=dev)
+            self.conv5.forward_rows(s_cat, v_cat, B, N, s_out=s5, lds_out=C5s, v_out=v5)
+            nv.pool_rows(s5, C5s, C5s, B, N, want_max=True, want_mean=True, max_out=g, mean_out=g[:, Cf:], ldo=2 * Cf)
+            Wz, zs = self.svfuse.v2s.wz()
+            nv.svfuse_pool(v5, B, N, Wz, zs, g[:, C5s:], g[:, Cf + C5s:], 2 * Cf)
+        else:
+            fused = torch.empty((B * N, Cf), dtype=torch.float32, device=dev)
+            self.conv5.forward_rows(s_cat, v_cat, B, N, s_out=fused, lds_out=fused.stride(0), v_out=v5)
+            self.svfuse.forward_rows(None, v5, out=fused)
+            nv.pool_rows(fused, Cf, Cf, B, N, want_max=True, want_mean=True, max_out=g, mean_out=g[:, Cf:], ldo=2 * Cf)
         # head: three chained layers in one kernel, one CTA per cloud
         out = nv.head_fwd(g, [head_layer(self.linear1, folded_bn(self, "bn1"), nv.ACT_LEAKY),
                               head_layer(self.linear2, folded_bn(self, "bn2"), nv.ACT_LEAKY),

@@ -180,6 +180,50 @@ def test_knn_tensor_core_error_model_on_model_features():
     assert 0.0 < err < eps_c127 / 1.5, err
 
 
+def test_rows_prep_fast_bits_equal_generic_and_oracle():
+    """csrc/rows_fast.cu (sign words only, conv5 shape) against the generic kernel of csrc/rows.cu (forced by
+    also requesting u) and the oracle's v2s + sign planes: words must be bit-identical."""
+    from svnet_b200 import _native as nv
+    rows, Cs, Cv = 3001, 256, 83
+    s, v = rnd((rows, Cs), 5), rnd((rows, 3, Cv), 6)
+    Wz, beta = rnd((3, Cv), 7, 0.3), rnd((Cs + 3 * Cv,), 8, 0.05)
+    beta[::7] = 0.0
+    s[::5, ::3] = 0.0                                   # exact zeros: sign(0) = 0 -> mask plane
+    S, V = torch.zeros((rows, Cs + 9), device=DEV), torch.zeros((rows, 3, Cv + 4), device=DEV)
+    S[:, 4:4 + Cs], V[:, :, 2:2 + Cv] = cu(s), cu(v)
+    view = nv.view_of(S[:, 4:4 + Cs], V[:, :, 2:2 + Cv])
+    fast = nv.rows_prep(view, rows, Wz=cu(Wz), beta=cu(beta), want_bits=True)
+    u = torch.empty((rows, Cs + 3 * Cv), device=DEV)
+    slow = nv.rows_prep(view, rows, Wz=cu(Wz), beta=cu(beta), want_bits=True, u_out=u, ldu=u.stride(0))
+    for a, b in zip(fast, slow):
+        assert (a == b).all()
+    q = orc.v2s(v, Wz)
+    t = orc.sign_plane(np.concatenate([s, q], -1), beta)
+    pos, nz = t > 0, t != 0
+    K = Cs + 3 * Cv
+    bits = np.unpackbits(t2n(fast[0]).view(np.uint8).reshape(rows, -1), axis=1, bitorder="little")[:, :K]
+    msk = np.unpackbits(t2n(fast[1]).view(np.uint8).reshape(rows, -1), axis=1, bitorder="little")[:, :K]
+    assert (bits == pos.astype(np.uint8)).all() and (msk == nz.astype(np.uint8)).all()
+
+
+def test_svfuse_pool_equals_materialised_path():
+    """svnet_svfuse_pool (v2s reduced on the fly) against rows_prep(u_out) + pool_rows: the max is exact,
+    the mean differs only by the summation order."""
+    from svnet_b200 import _native as nv
+    B, N, Cv = 3, 1000, 170
+    v = cu(rnd((B * N, 3, Cv), 9))
+    Wz, zs = cu(rnd((3, Cv), 10, 0.2)), cu(np.abs(rnd((3,), 11)) + 0.5)
+    K = 3 * Cv
+    u = torch.empty((B * N, K), device=DEV)
+    nv.rows_prep(nv.view_of(None, v), B * N, Wz=Wz, zscale=zs, u_out=u, ldu=K)
+    mx, mean = nv.pool_rows(u, K, K, B, N, want_max=True, want_mean=True)
+    g = torch.zeros((B, 2 * K + 6), device=DEV)
+    nv.svfuse_pool(v, B, N, Wz, zs, g[:, 3:3 + K], g[:, 3 + K + 3:], g.stride(0))
+    assert (g[:, 3:3 + K] == mx).all()
+    assert_close(t2n(g[:, 6 + K:6 + 2 * K]), t2n(mean), rtol=1e-5, atol=1e-6, what="svfuse_pool mean")
+    assert float(g[:, :3].abs().max()) == 0.0 and float(g[:, 3 + K:6 + K].abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------------------------------------
 # module-level API vs golden (reference outputs) and oracle
 # ------------------------------------------------------------------------------------------------
