@@ -101,7 +101,10 @@ int svnet_knn_ws(const svnet_view* in, int B, int N, int k, int32_t* idx32, int6
                  size_t workspace_bytes, void* stream);
 /* Cumulative counters of the tensor-core path (profiling aid): rows, rows that needed exact
  * re-scoring, rows that took the brute-force path, queued survivors, then CTAs and summed SM cycles of
- * {pass A, threshold, pass B, finish}.  Host pointer to 12 values; reset != 0 clears. */
+ * {pass A, threshold, pass B}, [9] = float bits of the largest observed |tensor-core score - exact score| /
+ * (xx_i + xx_j), [10] = rows with more than 32 survivors (all re-scored exactly).  Counters are only
+ * accumulated when the environment variable SVNET_KNN_TC_STATS=1 (same-address atomics).
+ * Host pointer to 12 values; reset != 0 clears. */
 int svnet_knn_tc_stats(unsigned long long* out12, int reset);
 
 /* get_graph_feature (nv=2, sv_util.py:28-62) / get_graph_feature_cross (nv=3, sv_util.py:64-88):

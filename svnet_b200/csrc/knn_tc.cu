@@ -43,7 +43,7 @@ constexpr int B_PLANE = 2 * B_KB;
 constexpr int B_CHUNK = 3 * B_PLANE;           // 24 KB
 constexpr int NSCAN = 256;                     // scanner threads: warps 0..7
 constexpr int NTHREADS = 320;                  // + warp 8 (MMA issue) + warp 9 (bulk-copy producer)
-constexpr int CAPH = 32;                       // survivor queue capacity per (row, column half)
+constexpr int CAPH = 64;                       // survivor queue capacity per (row, column half)
 constexpr int GROUPS = 64;
 constexpr int GM_BYTES = GROUPS * TM * 4;      // group maxima between the passes
 #ifndef FIN_MIN_BLOCKS
@@ -533,12 +533,88 @@ __device__ __forceinline__ unsigned approx_key(float s, int lane)
     return ((hi & ~31u) | (unsigned)lane) | 32u * (hi < 64u);     // never below 32: empty slots are 0..31
 }
 
+// exact oracle-chain scores for the lanes in `flagged` (bit = lane, lane's candidate = jme, its norm = xj):
+// candidate rows are gathered with cp.async into shared memory in chunks of xcap rows, then every
+// flagged lane runs its own sequential chain (16-byte loads; zero padding is exact).  Returns the
+// order-preserving 32-bit image of the score (0 for lanes that are not flagged).
+struct fin_env {
+    const knn_tc_args* p;
+    const float** gtab;
+    const int* gstr;
+    float* arow;
+    float* exb;
+    long base, rg;
+    int C, Cp, lane;
+    float xxi;
+    bool arow_loaded;
+    float emax;
+};
+
+__device__ __forceinline__ unsigned exact_keys(fin_env& f, unsigned flagged, int jme, float xj, float sme)
+{
+    const int lane = f.lane, C = f.C, Cp = f.Cp, xcap = f.p->xcap;
+    const int T = __popc(flagged);
+    const int myo = __popc(flagged & ((1u << lane) - 1u));
+    const bool mine = (flagged >> lane) & 1u;
+    const int nu = (C + 31) >> 5;
+    unsigned sc = 0u;
+    for (int ch0 = 0; ch0 < T; ch0 += xcap) {
+        __syncwarp();
+        if (!f.arow_loaded) {
+            for (int u = 0; u < nu; ++u) {
+                const int c = lane + 32 * u;
+                if (c < C) cp_async4(f.arow + c, f.gtab[c] + f.rg * (long)f.gstr[c]);
+            }
+            if (lane < Cp - C) f.arow[C + lane] = 0.0f;            // zero padding of the float4 chains
+            f.arow_loaded = true;
+        }
+        unsigned m = flagged;
+        int o = -ch0;
+        while (m) {
+            const int srcl = __ffs(m) - 1;
+            m &= m - 1;
+            if (o >= 0 && o < xcap) {
+                const long row = f.base + __shfl_sync(SV_FULL, jme, srcl);
+                float* dstp = f.exb + o * Cp;
+                for (int u = 0; u < nu; ++u) {
+                    const int c = lane + 32 * u;
+                    if (c < C) cp_async4(dstp + c, f.gtab[c] + row * (long)f.gstr[c]);
+                }
+                if (lane < Cp - C) dstp[C + lane] = 0.0f;
+            }
+            ++o;
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        const int ol = myo - ch0;
+        if (mine && ol >= 0 && ol < xcap) {
+            const float4* bp = reinterpret_cast<const float4*>(f.exb + ol * Cp);
+            const float4* ap = reinterpret_cast<const float4*>(f.arow);
+            float dot = 0.0f;      // channel ascending; the zero padding adds fmaf(0,0,x) == x
+            for (int c4 = 0; c4 < (C + 3) >> 2; ++c4) {
+                const float4 av = ap[c4], bv = bp[c4];
+                dot = __fmaf_rn(av.x, bv.x, dot);
+                dot = __fmaf_rn(av.y, bv.y, dot);
+                dot = __fmaf_rn(av.z, bv.z, dot);
+                dot = __fmaf_rn(av.w, bv.w, dot);
+            }
+            const float pe = exact_score(dot, f.xxi, xj);
+            sc = (unsigned)(make_key(pe, 0) >> 32);
+            f.emax = fmaxf(f.emax, fabsf(pe - 2.0f * sme) / (f.xxi + xj));     // 2*sme = tensor-core score
+        }
+    }
+    return sc;
+}
+
 // ---- finish kernel: one warp = one row.  High occupancy (small register / shared-memory footprint)
 //      hides the shuffle and gather latencies that a tensor-core CTA with 8 scanner warps cannot.
-//   1. survivors (<= 64) -> best 32 by approximate score (sorted, nearest first)
-//   2. neighbours in that order which the error bound does not separate form runs; runs that touch the
-//      first k positions are re-scored with the exact chain (rows gathered by cp.async, lane = entry)
-//   3. re-sort by (run, exact score desc, index asc), write the first k indices
+//   <= 32 survivors (the normal case): sort by approximate score; neighbours in that order which the
+//      error bound does not separate form runs; runs that touch the first k positions are re-scored
+//      with the exact chain; re-sort by (run, exact score desc, index asc).
+//   33 .. 2*CAPH survivors (heavy ties, e.g. many identical binary features): every survivor is
+//      re-scored exactly, 32 at a time, and merged into the best 32 (always correct: the survivors
+//      contain the true top k).
+//   queue overflow: brute force over all candidates.
 __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_kernel(knn_tc_args p)
 {
     extern __shared__ __align__(16) float fin_smem[];
@@ -562,88 +638,50 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
     }
     __syncthreads();
     if (i >= p.N) return;
-    float* arow = fin_smem + FIN_TAB_FLOATS + (size_t)warp * ((1 + p.xcap) * Cp);     // query row | xcap candidate rows
-    float* exb = arow + Cp;
+    fin_env f;
+    f.p = &p; f.gtab = gtab; f.gstr = gstr;
+    f.arow = fin_smem + FIN_TAB_FLOATS + (size_t)warp * ((1 + p.xcap) * Cp);     // query row | xcap candidate rows
+    f.exb = f.arow + Cp;
+    f.base = base; f.rg = rg; f.C = C; f.Cp = Cp; f.lane = lane;
+    f.arow_loaded = false; f.emax = 0.0f;
     const float2* q0 = p.gq + rg * 2 * CAPH;
     const float2 h0 = __ldg(q0 + lane), h1 = __ldg(q0 + CAPH + lane);     // may hold stale data beyond the counts
     const float xxi = __ldg(xxs + i);
+    f.xxi = xxi;
     const int2 cc = __ldg(reinterpret_cast<const int2*>(p.gqcnt) + rg);
     const int c0 = cc.x, cnt = cc.x + cc.y;
-    bool brute = !(cc.x <= CAPH && cc.y <= CAPH && cnt >= k);
+    const bool brute = !(cc.x <= CAPH && cc.y <= CAPH && cnt >= k);
     bool st_exact = false;
-    float emax = 0.0f;
-    kkey_t key = 0ull;
     int jout = 0;
-    if (!brute) {
-        // both halves' queues are loaded without waiting for the counts; entry e of the row is
-        // half0[e] for e < c0, else half1[e - c0] (fetched by shuffle)
+    if (brute) {
+        for (int c = lane; c < C; c += 32) f.arow[c] = sv_feat(p.in, rg, c);
+        __syncwarp();
+        kkey_t key;
+        brute_force_row(p, base, i, f.arow, xxs, lane, key);
+        jout = key_index(key);
+    } else if (cnt <= 32) {
+        // entry e of the row is half0[e] for e < c0, else half1[e - c0] (fetched by shuffle)
         float2 ent;
         {
             const int sl = (lane - c0) & 31;
             const float a1 = __shfl_sync(SV_FULL, h1.x, sl), b1 = __shfl_sync(SV_FULL, h1.y, sl);
             ent = lane < c0 ? h0 : make_float2(a1, b1);
         }
-        float xe = lane < cnt ? __ldg(xxs + __float_as_int(ent.y)) : 0.0f;      // norm of the entry's point
+        const float xe = lane < cnt ? __ldg(xxs + __float_as_int(ent.y)) : 0.0f;      // norm of the entry's point
         unsigned ak = lane < cnt ? approx_key(ent.x, lane) : (unsigned)lane;
         warp_sort32_desc_u32(ak, lane);
-        float best_dropped = -INFINITY, xx_dropped = 0.0f;
-        float2 ent2 = make_float2(0.0f, 0.0f);
-        float xe2 = 0.0f;
-        bool from2 = false;
-        if (cnt > 32) {
-            // second half: keep the best 32 of the 64 (upper half of a bitonic merge), remember the best loser
-            const int e = 32 + lane;
-            {
-                const int sl = (e - c0) & 31;      // e >= 32 >= c0: always in half 1
-                ent2.x = __shfl_sync(SV_FULL, h1.x, sl);
-                ent2.y = __shfl_sync(SV_FULL, h1.y, sl);
-            }
-            xe2 = e < cnt ? __ldg(xxs + __float_as_int(ent2.y)) : 0.0f;
-            unsigned ak2 = e < cnt ? approx_key(ent2.x, lane) : (unsigned)lane;
-            warp_sort32_desc_u32(ak2, lane);
-            const unsigned rev = __shfl_sync(SV_FULL, ak2, 31 - lane);
-            const bool take2 = rev > ak;
-            const unsigned lose = take2 ? ak : rev;
-            const bool lose2 = !take2;                    // the loser came from the second half
-            ak = take2 ? rev : ak;
-            from2 = take2;
-            // best loser (score, largest norm), over the warp
-            const int ls = (int)(lose & 31u);
-            const float l1 = __shfl_sync(SV_FULL, ent.x, ls), l2 = __shfl_sync(SV_FULL, ent2.x, ls);
-            const float lx1 = __shfl_sync(SV_FULL, xe, ls), lx2 = __shfl_sync(SV_FULL, xe2, ls);
-            float lsc = lose >= 32u ? (lose2 ? l2 : l1) : -INFINITY;
-            float lxx = lose >= 32u ? (lose2 ? lx2 : lx1) : 0.0f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lsc = fmaxf(lsc, __shfl_xor_sync(SV_FULL, lsc, o));
-                lxx = fmaxf(lxx, __shfl_xor_sync(SV_FULL, lxx, o));
-            }
-            best_dropped = lsc; xx_dropped = lxx;
-            // two winners from different halves can share a lane field: sort (key, origin) as one 64-bit key
-            kkey_t wk = ((kkey_t)ak << 1) | (from2 ? 1ull : 0ull);
-            warp_sort32_desc(wk, lane);
-            ak = (unsigned)(wk >> 1);
-            from2 = (wk & 1ull) != 0ull;
-        }
         // fetch the entry this position now holds
         const int src = (int)(ak & 31u);
-        const int n = min(cnt, 32);
-        float sme = __shfl_sync(SV_FULL, ent.x, src);
-        int jme = __float_as_int(__shfl_sync(SV_FULL, ent.y, src));
+        const float sme = __shfl_sync(SV_FULL, ent.x, src);
+        const int jme = __float_as_int(__shfl_sync(SV_FULL, ent.y, src));
         float xj = __shfl_sync(SV_FULL, xe, src);
-        if (cnt > 32) {
-            const float s2 = __shfl_sync(SV_FULL, ent2.x, src);
-            const int j2 = __float_as_int(__shfl_sync(SV_FULL, ent2.y, src));
-            const float x2 = __shfl_sync(SV_FULL, xe2, src);
-            if (from2) { sme = s2; jme = j2; xj = x2; }
-        }
-        if (lane >= n) xj = 0.0f;
+        if (lane >= cnt) xj = 0.0f;
         jout = jme;
         // ---- neighbours in this order that the error bound does not separate ----
         const float snx = __shfl_down_sync(SV_FULL, sme, 1);
         const float xnx = __shfl_down_sync(SV_FULL, xj, 1);
         bool am = false;
-        if (lane + 1 < n) am = (sme - snx) <= 0.5f * p.eps * (2.0f * xxi + xj + xnx);
+        if (lane + 1 < cnt) am = (sme - snx) <= 0.5f * p.eps * (2.0f * xxi + xj + xnx);
         const unsigned amb = __ballot_sync(SV_FULL, am);
         unsigned rel = amb & ((1u << k) - 1u);       // pairs e <= k-1, then the runs continuing from them
         for (;;) {
@@ -651,86 +689,38 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
             if (!nx) break;
             rel |= nx;
         }
-        if (cnt > 32) {
-            // the dropped entries must be certainly worse than everything that can reach the first k positions
-            const int last = 32 - __clz(rel | (rel << 1) | ((1u << k) - 1u));   // one past the last position of interest
-            const float slast = __shfl_sync(SV_FULL, sme, last - 1);
-            float xkept = xj;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) xkept = fmaxf(xkept, __shfl_xor_sync(SV_FULL, xkept, o));
-            if (last >= 32 || (slast - best_dropped) <= 0.5f * p.eps * (2.0f * xxi + xkept + xx_dropped)) brute = true;
-        }
-        if (rel && !brute) {
+        if (rel) {
             st_exact = true;
-            const unsigned flagged = rel | (rel << 1);
-            const int T = __popc(flagged);
-            const unsigned lt = (1u << lane) - 1u;
-            const int myo = __popc(flagged & lt);
-            const bool mine = (flagged >> lane) & 1u;
-            unsigned sc = 0u;
-            const int nu = (C + 31) >> 5;
-            for (int ch0 = 0; ch0 < T; ch0 += p.xcap) {
-                __syncwarp();
-                if (ch0 == 0) {
-                    for (int u = 0; u < nu; ++u) {
-                        const int c = lane + 32 * u;
-                        if (c < C) cp_async4(arow + c, gtab[c] + rg * (long)gstr[c]);
-                    }
-                    if (lane < Cp - C) arow[C + lane] = 0.0f;            // zero padding of the float4 chains
-                }
-                unsigned m = flagged;
-                int o = -ch0;
-                while (m) {
-                    const int srcl = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (o >= 0 && o < p.xcap) {
-                        const long row = base + __shfl_sync(SV_FULL, jme, srcl);
-                        float* dstp = exb + o * Cp;
-                        for (int u = 0; u < nu; ++u) {
-                            const int c = lane + 32 * u;
-                            if (c < C) cp_async4(dstp + c, gtab[c] + row * (long)gstr[c]);
-                        }
-                        if (lane < Cp - C) dstp[C + lane] = 0.0f;
-                    }
-                    ++o;
-                }
-                cp_async_wait_all();
-                __syncwarp();
-                const int ol = myo - ch0;
-                if (mine && ol >= 0 && ol < p.xcap) {
-                    const float4* bp = reinterpret_cast<const float4*>(exb + ol * Cp);
-                    const float4* ap = reinterpret_cast<const float4*>(arow);
-                    float dot = 0.0f;      // channel ascending; the zero padding adds fmaf(0,0,x) == x
-                    for (int c4 = 0; c4 < (C + 3) >> 2; ++c4) {
-                        const float4 av = ap[c4], bv = bp[c4];
-                        dot = __fmaf_rn(av.x, bv.x, dot);
-                        dot = __fmaf_rn(av.y, bv.y, dot);
-                        dot = __fmaf_rn(av.z, bv.z, dot);
-                        dot = __fmaf_rn(av.w, bv.w, dot);
-                    }
-                    const float pe = exact_score(dot, xxi, xj);
-                    sc = (unsigned)(make_key(pe, 0) >> 32);
-                    emax = fmaxf(emax, fabsf(pe - 2.0f * sme) / (xxi + xj));     // 2*sme = tensor-core score
-                }
-            }
+            const unsigned sc = exact_keys(f, rel | (rel << 1), jme, xj, sme);
             // composite key: (run start asc, exact score desc, index asc); unflagged entries are their own run
             const unsigned starts = ~(rel << 1);
-            if (lane < n) {
+            kkey_t key = 0ull;
+            if (lane < cnt) {
                 const int seg = 31 - __clz(starts & ((2u << lane) - 1u));
                 key = ((kkey_t)(127 - seg) << 44) | ((kkey_t)sc << 12) | (kkey_t)(4095 - jme);
-            } else {
-                key = 0ull;
             }
             warp_sort32_desc(key, lane);
             jout = 4095 - (int)(key & 4095ull);
         }
-    }
-    if (brute) {
-        __syncwarp();
-        for (int c = lane; c < C; c += 32) arow[c] = sv_feat(p.in, rg, c);
-        __syncwarp();
-        brute_force_row(p, base, i, arow, xxs, lane, key);
-        jout = key_index(key);
+    } else {
+        // ---- more than 32 survivors: exact scores for all of them, 32 at a time, keep the best 32 ----
+        st_exact = true;
+        kkey_t best = 0ull;
+        for (int e0 = 0; e0 < cnt; e0 += 32) {
+            const int e = e0 + lane;
+            float2 ent = make_float2(0.0f, 0.0f);
+            if (e < cnt) ent = __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
+            const int jme = __float_as_int(ent.y);
+            const float xj = e < cnt ? __ldg(xxs + jme) : 0.0f;
+            const unsigned valid = __ballot_sync(SV_FULL, e < cnt);
+            const unsigned sc = exact_keys(f, valid, jme, xj, ent.x);
+            kkey_t key = e < cnt ? (((kkey_t)sc << 32) | (unsigned)(~jme)) : 0ull;     // == make_key(exact score, j)
+            warp_sort32_desc(key, lane);
+            const kkey_t rev = shfl_key(key, 31 - lane);
+            best = best > rev ? best : rev;          // upper half of the bitonic merge: the 32 best of the 64
+            warp_sort32_desc(best, lane);
+        }
+        jout = key_index(best);
     }
     if (lane < k) {
         const long o = rg * k + lane;
@@ -738,6 +728,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
         if (p.idx64) p.idx64[o] = (int64_t)jout;
     }
     if (p.stats) {
+        float emax = f.emax;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(SV_FULL, emax, o));
         if (lane == 0) {
@@ -745,6 +736,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
             if (st_exact) atomicAdd(&g_knn_tc_stats[1], 1ull);
             if (brute) atomicAdd(&g_knn_tc_stats[2], 1ull);
             atomicAdd(&g_knn_tc_stats[3], (unsigned long long)cnt);
+            if (cnt > 32 && !brute) atomicAdd(&g_knn_tc_stats[10], 1ull);
             if (emax > 0.0f) atomicMax(&g_knn_tc_stats[9], (unsigned long long)__float_as_uint(emax));
         }
     }

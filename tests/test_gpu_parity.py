@@ -110,7 +110,7 @@ def _tc_stats(reset=True):
     return list(out)
 
 
-@pytest.mark.parametrize("case", ["duplicates", "lattice", "offset", "all_equal", "ragged", "two_clusters"])
+@pytest.mark.parametrize("case", ["duplicates", "heavy_ties", "lattice", "offset", "all_equal", "ragged", "two_clusters"])
 def test_knn_tensor_core_path_adversarial(case, monkeypatch):
     """Shapes served by the tcgen05 filter (csrc/knn_tc.cu: N >= 64, k <= 24): exact ties (duplicated
     points, lattice), norms much larger than neighbour gaps, everything equal (queue overflow ->
@@ -123,6 +123,10 @@ def test_knn_tensor_core_path_adversarial(case, monkeypatch):
     if case == "duplicates":
         base = torch.randn((B, N // 4, C), generator=g)
         feat = base.repeat(1, 4, 1)[:, torch.randperm(N, generator=g)]
+    elif case == "heavy_ties":
+        B, N, C, k = 1, 640, 62, 20          # 16 distinct points x 40 copies: > 32 exact ties around every query
+        base = torch.randn((B, 16, C), generator=g)
+        feat = base.repeat(1, 40, 1)[:, torch.randperm(N, generator=g)]
     elif case == "lattice":
         B, N, C, k = 1, 343, 3, 20
         ax = torch.arange(7, dtype=torch.float32)
@@ -153,6 +157,8 @@ def test_knn_tensor_core_path_adversarial(case, monkeypatch):
     assert (tc == ref).all(), "%d rows differ" % int((tc != ref).any(-1).sum())
     if case == "all_equal":
         assert st[2] > 0      # every candidate reaches the threshold: the rows take the brute-force path
+    if case == "heavy_ties":
+        assert st[10] > 0 and st[2] == 0      # more than 32 survivors: every survivor re-scored exactly, no brute force
 
 
 def test_knn_tensor_core_error_model_on_model_features():

@@ -26,12 +26,13 @@ def knn(view, B, N, k, **kw):
         view.Cs + 3 * view.Cv, e0.elapsed_time(e1) * 1e3, 100.0 * st[1] / rows, st[2], st[3] / rows, err, *cyc))
     return r
 nv.knn = knn
+B = int(os.environ.get("KB", 32)); N = int(os.environ.get("KN", 1024)); SEED = int(os.environ.get("KSEED", 1002))
 for binary in (True, False):
     with contextlib.redirect_stdout(io.StringIO()):
         net = sv.SV_DGCNN_CLS(make_args(k=20, binary=binary), 40)
-    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=1002))
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=SEED))
     net = net.cuda().eval()
-    x = synthetic_clouds(32, 1024, 1002).cuda()
+    x = synthetic_clouds(B, N, SEED).cuda()
     print("binary" if binary else "fp")
     with torch.no_grad():
         net(x); print(" --"); net(x)
