@@ -117,10 +117,17 @@ def cpu_port_throughput(n_clouds, reps=1):
     return n_clouds / best, best
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all host threads it can
+    (set before the oracle's OpenMP runtime is loaded)."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     cores = os.cpu_count()
     v0, _ = cpu_port_throughput(4)
     n = int(min(64, max(4, round(2.0 * v0 / 4) * 4)))   # ~2 s of CPU work per step
@@ -285,7 +292,8 @@ def main():
                                "frac": algorithmic_bytes_per_cloud() * B / (ms * 1e-3) / 1e9 / hbm_peak}}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:             # rank 0 at N = 1 only (bench contract)
+        use_all_host_threads()
         v, dt = cpu_port_throughput(4)                      # probe, then a sample worth ~15 s of CPU work
         n_cpu = int(min(256, max(4, round(15.0 * v / 4) * 4)))
         v, dt = cpu_port_throughput(n_cpu)
