@@ -12,3 +12,4 @@ from .sv_pointnet_partseg import SV_PointNet_PSEG
 __all__ = ["SV_DGCNN_CLS", "SV_DGCNN_PSEG", "SV_PointNet_CLS", "SV_PointNet_PSEG", "SVBlock", "SVFuse", "SV_STNkd", "Vector2Scalar", "VectorBN", "Linear", "Conv1d",
            "knn", "get_graph_feature", "get_graph_feature_cross", "get_graph_feature_sv", "svpool", "svcat",
            "sv_layers", "sv_util"]
+from .graph import GraphedForward  # noqa: E402,F401

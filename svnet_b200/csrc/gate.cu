@@ -91,19 +91,32 @@ __global__ void __launch_bounds__(NT) gate_rows_cluster_kernel(const float* __re
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const long r_lo = rows * rank / CL, r_hi = rows * (rank + 1) / CL;
     const float* p = s + (long)b * rows * lds;
-    for (int c0 = 0; c0 < Cs; c0 += 32) {
-        const int c = c0 + lane;
-        float acc = 0.0f;
-        if (c < Cs)
-            for (long r = r_lo + rg; r < r_hi; r += 8) acc += p[r * lds + c];
-        part[rg * 32 + lane] = acc;
-        __syncthreads();
-        if (rg == 0 && c < Cs) {
-            float t = part[lane];
-            for (int g = 1; g < 8; ++g) t += part[g * 32 + lane];
-            psum[c] = t;
+    // one pass over this CTA's rows per 256-column super block: 8 independent accumulators per thread keep
+    // 8 x unroll loads in flight (the per-column summation order is unchanged: warp rg adds its rows in
+    // order, the warps are added in order, then the ranks)
+    for (int cb = 0; cb < Cs; cb += 256) {
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+#pragma unroll 2
+        for (long r = r_lo + rg; r < r_hi; r += 8) {
+            const float* pr = p + r * lds + cb + lane;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (cb + 32 * u + lane < Cs) acc[u] += pr[32 * u];
         }
-        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = cb + 32 * u + lane;
+            __syncthreads();
+            part[rg * 32 + lane] = acc[u];
+            __syncthreads();
+            if (rg == 0 && c < Cs) {
+                float t = part[lane];
+                for (int g = 1; g < 8; ++g) t += part[g * 32 + lane];
+                psum[c] = t;
+            }
+        }
     }
     cluster.sync();
     if (rank == 0) {
@@ -198,25 +211,37 @@ __global__ void __launch_bounds__(NT) gate_edge_cluster_kernel(svnet_view in, co
     }
     cluster.sync();   // every CTA is done reading remote histograms
     const float* p = in.s + (long)b * N * in.lds;
-    for (int c0 = 0; c0 < Cs; c0 += 32) {
-        const int c = c0 + lane;
-        float accd = 0.0f, accp = 0.0f;
-        if (c < Cs)
-            for (int r = r_lo + rg; r < r_hi; r += 8) {
-                const float t = p[(long)r * in.lds + c];
-                accd = fmaf((float)indeg[r - r_lo], t, accd);
-                accp += t;
-            }
-        part[rg * 32 + lane] = accd;
-        part[256 + rg * 32 + lane] = accp;
-        __syncthreads();
-        if (rg == 0 && c < Cs) {
-            float td = part[lane], tp = part[256 + lane];
-            for (int g = 1; g < 8; ++g) { td += part[g * 32 + lane]; tp += part[256 + g * 32 + lane]; }
-            psum[c] = td;
-            psum[Cs + c] = tp;
+    // one pass over the rows per 128-column super block (same summation order as a column-by-column walk)
+    for (int cb = 0; cb < Cs; cb += 128) {
+        float accd[4], accp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { accd[u] = 0.0f; accp[u] = 0.0f; }
+#pragma unroll 2
+        for (int r = r_lo + rg; r < r_hi; r += 8) {
+            const float* pr = p + (long)r * in.lds + cb + lane;
+            const float dg = (float)indeg[r - r_lo];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (cb + 32 * u + lane < Cs) {
+                    const float t = pr[32 * u];
+                    accd[u] = fmaf(dg, t, accd[u]);
+                    accp[u] += t;
+                }
         }
-        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = cb + 32 * u + lane;
+            __syncthreads();
+            part[rg * 32 + lane] = accd[u];
+            part[256 + rg * 32 + lane] = accp[u];
+            __syncthreads();
+            if (rg == 0 && c < Cs) {
+                float td = part[lane], tp = part[256 + lane];
+                for (int g = 1; g < 8; ++g) { td += part[g * 32 + lane]; tp += part[256 + g * 32 + lane]; }
+                psum[c] = td;
+                psum[Cs + c] = tp;
+            }
+        }
     }
     cluster.sync();
     if (rank == 0) {

@@ -9,20 +9,62 @@ from . import _native as nv
 
 
 MAX_POINTS_PER_PASS = int(os.environ.get("SVNET_MAX_POINTS", 1 << 19))
+SIDE_STREAM = os.environ.get("SVNET_SIDE_STREAM", "1") != "0"
+CONCURRENT_HALVES = os.environ.get("SVNET_TWO_STREAMS", "1") != "0"
+_SIDE = {}
+_IN_HALF = [False]
+
+
+def _side_stream(dev, which=0):
+    """Auxiliary CUDA streams per device: 0 = graph-independent tables, 1/2 = the two batch halves."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 def chunked(impl, x, extras=(), hooks=False):
     """Run ``impl(x_chunk, *extras_chunk)`` over cloud sub-batches so that the per-pass tables stay
     bounded (B*N <= MAX_POINTS_PER_PASS points; clouds are independent in eval mode).
-    Test hooks (forced indices / recording) disable chunking."""
+    A batch that fits one pass is split in two halves that run on two CUDA streams: kernels whose grids
+    leave SMs idle (the two-wave tensor-core kNN, the per-cloud gate / head kernels) overlap with the
+    other half's kernels.  Test hooks (forced indices / recording) disable both."""
     B, N = x.shape[0], x.shape[-1]
     per = max(1, MAX_POINTS_PER_PASS // max(N, 1))
-    if hooks or B <= per:
+    if hooks:
+        return impl(x, *extras)
+    if B <= per:
+        if CONCURRENT_HALVES and B >= 16 and x.is_cuda and not _IN_HALF[0]:
+            return _two_streams(impl, x, extras)
         return impl(x, *extras)
     outs = []
     for lo in range(0, B, per):
         outs.append(impl(x[lo:lo + per].contiguous(), *[e[lo:lo + per].contiguous() for e in extras]))
     return torch.cat(outs, dim=0)
+
+
+def _two_streams(impl, x, extras):
+    dev = x.device
+    cur = torch.cuda.current_stream()
+    B = x.shape[0]
+    h = (B + 1) // 2
+    parts = [(x[:h].contiguous(), [e[:h].contiguous() for e in extras]),
+             (x[h:].contiguous(), [e[h:].contiguous() for e in extras])]
+    outs = []
+    _IN_HALF[0] = True
+    try:
+        for i, (xc, ec) in enumerate(parts):
+            st = _side_stream(dev, 1 + i)
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                y = impl(xc, *ec)
+            y.record_stream(cur)
+            outs.append((st, y))
+    finally:
+        _IN_HALF[0] = False
+    for st, _ in outs:
+        cur.wait_stream(st)
+    return torch.cat([y for _, y in outs], dim=0)
 
 
 def _mview(s_out, v_out):
@@ -68,15 +110,26 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
     assert blk.in_dims == (2 * Cs, 2 * Cv), (blk.in_dims, Cs, Cv)
     dev = s_in.device
     view = nv.view_of(s_in, v_in)
+    # per-point tables for the vector branch (P | Q) do not depend on the graph: they run on a side
+    # stream next to the kNN kernels (whose second wave leaves SMs idle at B = 32)
+    Wpq, spq = blk.pq_weight()
+    PQ = torch.empty((R, 3, 2 * Cvo), dtype=torch.float32, device=dev)
+    cur = torch.cuda.current_stream()
+    side = _side_stream(dev) if (idx32 is None and SIDE_STREAM and not _IN_HALF[0]) else None
+    if side is not None:
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            nv.linear_rows(v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wpq, 2 * Cvo, PQ, 6 * Cvo, 2 * Cvo,
+                           sign_w=blk.linear2.bw, colscale=spq)
+    else:
+        nv.linear_rows(v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wpq, 2 * Cvo, PQ, 6 * Cvo, 2 * Cvo,
+                       sign_w=blk.linear2.bw, colscale=spq)
     if idx32 is None:
         idx32, _ = nv.knn(view, B, N, k)
     G1, G2 = blk.gate_weights()
     gate = nv.gate_edge(view, idx32, B, N, k, G1, G2)
-    # per-point tables for the vector branch: P | Q
-    Wpq, spq = blk.pq_weight()
-    PQ = torch.empty((R, 3, 2 * Cvo), dtype=torch.float32, device=dev)
-    nv.linear_rows(v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wpq, 2 * Cvo, PQ, 6 * Cvo, 2 * Cvo,
-                   sign_w=blk.linear2.bw, colscale=spq)
+    if side is not None:
+        cur.wait_stream(side)
     Wz, zs = blk.v2s.wz()
     a1, c1 = blk.bn1_folded()
     a2, c2 = blk.bn2.folded()

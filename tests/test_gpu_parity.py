@@ -636,3 +636,28 @@ def test_point_permutation_invariance_fp():
         y0 = net(x)
         y1 = net(x[:, :, perm].contiguous())
     assert_close(t2n(y1), t2n(y0), rtol=1e-3, atol=1e-4, what="permutation invariance")
+
+
+def test_graphed_forward_equals_eager():
+    """svnet_b200.GraphedForward (CUDA-graph replay, batch halves on two streams) returns exactly what the
+    eager single-stream forward returns, for new inputs of the captured shape, and rejects other shapes."""
+    import svnet_b200 as sv
+    from svnet_b200 import fused
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=20, binary=True), 40)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=3))
+    net = net.to(DEV).eval()
+    x0 = synthetic_clouds(16, 256, 11).to(DEV)
+    fast = sv.GraphedForward(net, x0)
+    for seed in (12, 13):
+        x = synthetic_clouds(16, 256, seed).to(DEV)
+        y_fast = fast(x).clone()
+        keep = fused.CONCURRENT_HALVES
+        fused.CONCURRENT_HALVES = False
+        try:
+            with torch.no_grad():
+                y = net(x)
+        finally:
+            fused.CONCURRENT_HALVES = keep
+        assert torch.equal(y_fast, y)
+    with pytest.raises(ValueError):
+        fast(synthetic_clouds(8, 256, 1).to(DEV))
