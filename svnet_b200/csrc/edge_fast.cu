@@ -15,6 +15,13 @@
 #include "common.cuh"
 #include <limits.h>
 
+#ifndef EDGE_MB_SMALL
+#define EDGE_MB_SMALL 4
+#endif
+#ifndef EDGE_MB_LARGE
+#define EDGE_MB_LARGE 3
+#endif
+
 namespace {
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
@@ -98,7 +105,7 @@ __device__ __forceinline__ void vector_branch(const svnet_edge_params& p, long r
 }
 
 template <int CS, int CV, int COUT, int CVO, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? 4 : 3) : 6) edge_bin_fast_kernel(svnet_edge_params p, int kp)
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDGE_MB_SMALL : EDGE_MB_LARGE) : 6) edge_bin_fast_kernel(svnet_edge_params p, int kp)
 {
     using S = Shape<CS, CV, COUT, CVO>;
     constexpr int EB = S::EB;

@@ -11,6 +11,7 @@ from . import _native as nv
 MAX_POINTS_PER_PASS = int(os.environ.get("SVNET_MAX_POINTS", 1 << 19))
 SIDE_STREAM = os.environ.get("SVNET_SIDE_STREAM", "1") != "0"
 CONCURRENT_HALVES = os.environ.get("SVNET_TWO_STREAMS", "1") != "0"
+N_SPLIT = max(2, int(os.environ.get("SVNET_STREAMS", "2")))      # sub-batches that run concurrently
 _SIDE = {}
 _IN_HALF = [False]
 
@@ -47,9 +48,9 @@ def _two_streams(impl, x, extras):
     dev = x.device
     cur = torch.cuda.current_stream()
     B = x.shape[0]
-    h = (B + 1) // 2
-    parts = [(x[:h].contiguous(), [e[:h].contiguous() for e in extras]),
-             (x[h:].contiguous(), [e[h:].contiguous() for e in extras])]
+    n = min(N_SPLIT, B // 8)
+    bounds = [B * i // n for i in range(n + 1)]
+    parts = [(x[lo:hi].contiguous(), [e[lo:hi].contiguous() for e in extras]) for lo, hi in zip(bounds[:-1], bounds[1:])]
     outs = []
     _IN_HALF[0] = True
     try:
