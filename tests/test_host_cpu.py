@@ -41,6 +41,19 @@ def test_argument_errors_without_gpu():
     with pytest.raises(RuntimeError):
         import svnet_b200 as sv
         sv.knn(torch.zeros(1, 3, 16), 4)  # CPU tensor: no fallback path exists
+    # workspace-based entry points: shape queries need no device; bad workspaces are rejected before any launch
+    lib.svnet_knn_workspace_bytes.restype = ctypes.c_size_t
+    lib.svnet_svfuse_pool_workspace.restype = ctypes.c_size_t
+    v.Cs, v.lds = 62, 62
+    assert lib.svnet_knn_workspace_bytes(ctypes.byref(v), 4, 1024, 20) > 0          # covered by the tensor-core path
+    assert lib.svnet_knn_workspace_bytes(ctypes.byref(v), 4, 1024, 40) == 0         # k > 24: CUDA-core kernel
+    assert lib.svnet_knn_workspace_bytes(ctypes.byref(v), 4, 32, 8) == 0            # N < 64
+    assert lib.svnet_svfuse_pool_workspace(2, 170, ctypes.c_long(1024)) > 0
+    rc = lib.svnet_svfuse_pool(None, 1, ctypes.c_long(8), None, None, None, None, 0, None, ctypes.c_size_t(0), None)
+    assert rc == -1 and b"svnet_svfuse_pool" in lib.svnet_last_error()
+    with pytest.raises(RuntimeError):
+        net = sv.SV_DGCNN_CLS(__import__("svnet_b200.synthetic", fromlist=["make_args"]).make_args(k=4, binary=True), 40).eval()
+        sv.GraphedForward(net, torch.zeros(1, 3, 16))     # CPU example input: no CPU path
 
 
 MODEL_FIXTURES = [("dgcnn_cls_bin", "SV_DGCNN_CLS"), ("dgcnn_cls_fp", "SV_DGCNN_CLS"), ("dgcnn_pseg_bin", "SV_DGCNN_PSEG"),
