@@ -223,6 +223,19 @@ int svnet_binlinear_rows(const uint32_t* bits, const uint32_t* mask, const int32
                          int act, const int32_t* cloud_dot, long rows_per_cloud, float* out, int ldo,
                          int32_t* out_i32, void* stream);
 
+/* Same result, bit for bit, with caller-owned scratch: with svnet_binlinear_workspace_bytes() bytes of
+ * workspace (16-byte aligned) the products run on the tcgen05 tensor cores -- ternary activations and
+ * +-1 weights are exact in bf16, the fp32 accumulators hold exact integers (csrc/binlinear_tc.cu).
+ * svnet_binlinear_workspace_bytes() returns 0 for shapes that stay on the popcount kernel
+ * (rows < 2048, K < 64, K > 640).  By default only calls of the form scale -> BN -> LeakyReLU on
+ * rows % 128 == 0 take the tensor-core path (lean epilogue, 2x the popcount kernel at conv5's shape);
+ * SVNET_BINLINEAR_TC=2 forces it for every covered call, =0 disables it. */
+size_t svnet_binlinear_workspace_bytes(long rows, int K, int Cout);
+int svnet_binlinear_rows_ws(const uint32_t* bits, const uint32_t* mask, const int32_t* nvalid, long rows, int K,
+                            const uint32_t* W1b, int Cout, const float* scale, const float* bias, const float* bn_a,
+                            const float* bn_c, int act, const int32_t* cloud_dot, long rows_per_cloud, float* out,
+                            int ldo, int32_t* out_i32, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Generic fp32 linear over (grouped) rows: C[m][n] = epi(sum_k A[m][k] * W[n][k]), sequential fmaf
  * chain over k (== oracle order).  Row m lives at A + (m / G)*lda_g + (m % G)*lda_x; same for C.
  *   sign_w: use sign(W) (binary weights, fp activations: sv_layers.py:43-49 with ba unset)

@@ -20,6 +20,7 @@ c_int, c_long, c_float, c_void_p = ctypes.c_int, ctypes.c_long, ctypes.c_float, 
 EXPORTS = [
     "svnet_version", "svnet_last_error", "svnet_pack_sign", "svnet_fold_bn", "svnet_knn",
     "svnet_knn_ws", "svnet_knn_workspace_bytes", "svnet_knn_tc_stats", "svnet_svfuse_pool", "svnet_svfuse_pool_workspace",
+    "svnet_binlinear_rows_ws", "svnet_binlinear_workspace_bytes",
     "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
@@ -76,6 +77,7 @@ def lib():
         l.svnet_last_error.restype = ctypes.c_char_p
         l.svnet_knn_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_svfuse_pool_workspace.restype = ctypes.c_size_t
+        l.svnet_binlinear_workspace_bytes.restype = ctypes.c_size_t
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
         if l.svnet_version() != 1:
@@ -262,10 +264,15 @@ def binlinear_rows(bits, mask, nvalid, K, W1b, Cout, scale=None, bias=None, bn=N
         out = torch.empty((rows, Cout), dtype=torch.float32, device=bits.device)
         ldo = Cout
     bn_a, bn_c = bn if bn is not None else (None, None)
-    _call("svnet_binlinear_rows", _ptr(bits), _ptr(mask), _ptr(nvalid), c_long(rows), c_int(K), _ptr(W1b),
-                                      c_int(Cout), _ptr(scale), _ptr(bias), _ptr(bn_a), _ptr(bn_c), c_int(act),
-                                      _ptr(cloud_dot), c_long(rows_per_cloud), _ptr(out), c_int(ldo or 0),
-                                      _ptr(res_i32), _stream())
+    # scratch for the expanded weights of the tensor-core path; 0 bytes -> popcount kernel
+    nbytes = int(lib().svnet_binlinear_workspace_bytes(c_long(rows), c_int(K), c_int(Cout)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=bits.device) if nbytes > 0 else None
+    _call("svnet_binlinear_rows_ws", _ptr(bits), _ptr(mask), _ptr(nvalid), c_long(rows), c_int(K), _ptr(W1b),
+                                         c_int(Cout), _ptr(scale), _ptr(bias), _ptr(bn_a), _ptr(bn_c), c_int(act),
+                                         _ptr(cloud_dot), c_long(rows_per_cloud), _ptr(out), c_int(ldo or 0),
+                                         _ptr(res_i32), _ptr(ws), ctypes.c_size_t(nbytes), _stream())
+    if nbytes > 0:
+        LAUNCHES[0] += 1
     return res_i32 if out_i32 else out
 
 

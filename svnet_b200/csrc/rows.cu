@@ -290,10 +290,16 @@ extern "C" int svnet_rows_prep(const svnet_view* in, long rows, const float* Wz,
     return SVNET_OK;
 }
 
-extern "C" int svnet_binlinear_rows(const uint32_t* bits, const uint32_t* mask, const int32_t* nvalid, long rows, int K,
-                                    const uint32_t* W1b, int Cout, const float* scale, const float* bias,
-                                    const float* bn_a, const float* bn_c, int act, const int32_t* cloud_dot,
-                                    long rows_per_cloud, float* out, int ldo, int32_t* out_i32, void* stream)
+int svnet_binlinear_tc_dispatch(const uint32_t* bits, const uint32_t* mask, long rows, int K, const uint32_t* W1b, int Cout,
+                                const float* scale, const float* bias, const float* bn_a, const float* bn_c, int act,
+                                const int32_t* cloud_dot, long rows_per_cloud, float* out, int ldo, int32_t* out_i32,
+                                void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+extern "C" int svnet_binlinear_rows_ws(const uint32_t* bits, const uint32_t* mask, const int32_t* nvalid, long rows, int K,
+                                       const uint32_t* W1b, int Cout, const float* scale, const float* bias,
+                                       const float* bn_a, const float* bn_c, int act, const int32_t* cloud_dot,
+                                       long rows_per_cloud, float* out, int ldo, int32_t* out_i32, void* workspace,
+                                       size_t workspace_bytes, void* stream)
 {
     SV_REQUIRE(bits && mask && nvalid && W1b, "svnet_binlinear_rows: null pointer");
     SV_REQUIRE(out || out_i32, "svnet_binlinear_rows: no output buffer");
@@ -302,10 +308,25 @@ extern "C" int svnet_binlinear_rows(const uint32_t* bits, const uint32_t* mask, 
     SV_REQUIRE((bn_a == nullptr) == (bn_c == nullptr), "svnet_binlinear_rows: bn_a/bn_c must come together");
     SV_REQUIRE(!cloud_dot || rows_per_cloud >= 1, "svnet_binlinear_rows: rows_per_cloud");
     if (rows == 0) return SVNET_OK;
+    if (workspace) {   // exact bf16 tensor-core path (binlinear_tc.cu) for the shapes it covers
+        const int handled = svnet_binlinear_tc_dispatch(bits, mask, rows, K, W1b, Cout, scale, bias, bn_a, bn_c, act, cloud_dot,
+                                                        rows_per_cloud, out, ldo, out_i32, workspace, workspace_bytes,
+                                                        sv_stream(stream));
+        if (handled != 0) return handled < 0 ? handled : SVNET_OK;
+    }
     dim3 grid(sv_cdiv(rows, BR), sv_cdiv(Cout, BO));
     binlinear_rows_kernel<<<grid, 256, 0, sv_stream(stream)>>>(bits, mask, nvalid, rows, (K + 31) / 32, W1b, Cout, scale,
                                                                bias, bn_a, bn_c, act, cloud_dot, rows_per_cloud, out, ldo,
                                                                out_i32);
     SV_CHECK_LAUNCH("svnet_binlinear_rows");
     return SVNET_OK;
+}
+
+extern "C" int svnet_binlinear_rows(const uint32_t* bits, const uint32_t* mask, const int32_t* nvalid, long rows, int K,
+                                    const uint32_t* W1b, int Cout, const float* scale, const float* bias,
+                                    const float* bn_a, const float* bn_c, int act, const int32_t* cloud_dot,
+                                    long rows_per_cloud, float* out, int ldo, int32_t* out_i32, void* stream)
+{
+    return svnet_binlinear_rows_ws(bits, mask, nvalid, rows, K, W1b, Cout, scale, bias, bn_a, bn_c, act, cloud_dot,
+                                   rows_per_cloud, out, ldo, out_i32, nullptr, 0, stream);
 }

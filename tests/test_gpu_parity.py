@@ -212,6 +212,37 @@ def test_rows_prep_fast_bits_equal_generic_and_oracle():
     assert (bits == pos.astype(np.uint8)).all() and (msk == nz.astype(np.uint8)).all()
 
 
+@pytest.mark.parametrize("rows,K,Cout", [(3000, 505, 512), (2048, 256, 128), (4100, 160, 40), (2500, 640, 300)])
+def test_binlinear_tensor_core_equals_popcount(rows, K, Cout, monkeypatch):
+    """csrc/binlinear_tc.cu (bf16 UMMAs, exact integers) against the XNOR/popcount kernel: integer dots and the
+    float epilogue (scale, bias, BN, LeakyReLU, per-cloud constant part) must be bit-identical."""
+    from svnet_b200 import _native as nv
+    x, W = rnd((rows, K), 21), rnd((Cout, K), 22)
+    beta = rnd((K,), 23, 0.1)
+    x[::3, ::5] = 0.0
+    beta[::5] = 0.0                                    # exact zeros -> mask plane
+    bits, mask, nvalid = nv.rows_prep(nv.view_of(cu(x), None), rows, beta=cu(beta), want_bits=True)
+    W1b = nv.pack_sign(cu(W))
+    scale, bias = cu(np.abs(rnd((Cout,), 24)) + 0.1), cu(rnd((Cout,), 25))
+    bn = (cu(rnd((Cout,), 26)), cu(rnd((Cout,), 27)))
+    rpc = 500
+    cloud = torch.randint(-50, 50, ((rows + rpc - 1) // rpc, Cout), dtype=torch.int32, device=DEV)
+    outs = {}
+    for tc in ("2", "0"):            # "2": every covered call on the tensor cores (default "1": lean epilogue only)
+        monkeypatch.setenv("SVNET_BINLINEAR_TC", tc)
+        assert (int(nv.lib().svnet_binlinear_workspace_bytes(rows, K, Cout)) > 0) == (tc == "2")
+        outs[tc] = (nv.binlinear_rows(bits, mask, nvalid, K, W1b, Cout, out_i32=True),
+                    nv.binlinear_rows(bits, mask, nvalid, K, W1b, Cout, scale=scale, bias=bias, bn=bn, act=nv.ACT_LEAKY),
+                    nv.binlinear_rows(bits, mask, nvalid, K, W1b, Cout, scale=scale, cloud_dot=cloud, rows_per_cloud=rpc),
+                    # scale + BN + LeakyReLU without bias: the lean epilogue when rows % 128 == 0
+                    nv.binlinear_rows(bits, mask, nvalid, K, W1b, Cout, scale=scale, bn=bn, act=nv.ACT_LEAKY))
+    for a, b in zip(outs["2"], outs["0"]):
+        assert torch.equal(a, b)
+    t = orc.sign_plane(x, beta).astype(np.int32)
+    ref = t @ np.sign(W).astype(np.int32).T
+    assert (t2n(outs["2"][0]) == ref).all()
+
+
 def test_svfuse_pool_equals_materialised_path():
     """svnet_svfuse_pool (v2s reduced on the fly) against rows_prep(u_out) + pool_rows: the max is exact,
     the mean differs only by the summation order."""
