@@ -236,6 +236,16 @@ int svnet_binlinear_rows_ws(const uint32_t* bits, const uint32_t* mask, const in
                             const float* bn_c, int act, const int32_t* cloud_dot, long rows_per_cloud, float* out,
                             int ldo, int32_t* out_i32, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Binarised Linear -> BN -> LeakyReLU fused with the per-cloud max / mean over the rows (tensor-core path
+ * only): the (rows, Cout) activation is never written.  SV_DGCNN_CLS pools conv5's scalar output right away
+ * (sv_dgcnn_cls.py:68-74).  rows_per_cloud % 128 == 0; svnet_binlinear_pool_workspace_bytes() returns 0 for
+ * shapes that are not covered (use svnet_binlinear_rows + svnet_pool_rows then). */
+size_t svnet_binlinear_pool_workspace_bytes(long rows, int K, int Cout, long rows_per_cloud);
+int svnet_binlinear_pool_ws(const uint32_t* bits, const uint32_t* mask, long rows, int K, const uint32_t* W1b, int Cout,
+                            const float* scale, const float* bn_a, const float* bn_c, long rows_per_cloud,
+                            float* max_out, float* mean_out, int ldo, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* Generic fp32 linear over (grouped) rows: C[m][n] = epi(sum_k A[m][k] * W[n][k]), sequential fmaf
  * chain over k (== oracle order).  Row m lives at A + (m / G)*lda_g + (m % G)*lda_x; same for C.
  *   sign_w: use sign(W) (binary weights, fp activations: sv_layers.py:43-49 with ba unset)

@@ -20,7 +20,8 @@ c_int, c_long, c_float, c_void_p = ctypes.c_int, ctypes.c_long, ctypes.c_float, 
 EXPORTS = [
     "svnet_version", "svnet_last_error", "svnet_pack_sign", "svnet_fold_bn", "svnet_knn",
     "svnet_knn_ws", "svnet_knn_workspace_bytes", "svnet_knn_tc_stats", "svnet_svfuse_pool", "svnet_svfuse_pool_workspace",
-    "svnet_binlinear_rows_ws", "svnet_binlinear_workspace_bytes",
+    "svnet_binlinear_rows_ws", "svnet_binlinear_workspace_bytes", "svnet_binlinear_pool_ws",
+    "svnet_binlinear_pool_workspace_bytes",
     "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
@@ -78,6 +79,7 @@ def lib():
         l.svnet_knn_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_svfuse_pool_workspace.restype = ctypes.c_size_t
         l.svnet_binlinear_workspace_bytes.restype = ctypes.c_size_t
+        l.svnet_binlinear_pool_workspace_bytes.restype = ctypes.c_size_t
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
         if l.svnet_version() != 1:
@@ -274,6 +276,21 @@ def binlinear_rows(bits, mask, nvalid, K, W1b, Cout, scale=None, bias=None, bn=N
     if nbytes > 0:
         LAUNCHES[0] += 1
     return res_i32 if out_i32 else out
+
+
+def binlinear_pool_workspace(rows, K, Cout, rows_per_cloud):
+    return int(lib().svnet_binlinear_pool_workspace_bytes(c_long(rows), c_int(K), c_int(Cout), c_long(rows_per_cloud)))
+
+
+def binlinear_pool(bits, mask, K, W1b, Cout, scale, bn, rows_per_cloud, max_out, mean_out, ldo):
+    """Binarised Linear -> BN -> LeakyReLU -> per-cloud max / mean, fused (tensor-core path only)."""
+    rows = bits.shape[0]
+    nbytes = binlinear_pool_workspace(rows, K, Cout, rows_per_cloud)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=bits.device)
+    _call("svnet_binlinear_pool_ws", _ptr(bits), _ptr(mask), c_long(rows), c_int(K), _ptr(W1b), c_int(Cout), _ptr(scale),
+          _ptr(bn[0]), _ptr(bn[1]), c_long(rows_per_cloud), _ptr(max_out), _ptr(mean_out), c_int(ldo), _ptr(ws),
+          ctypes.c_size_t(nbytes), _stream())
+    LAUNCHES[0] += 2
 
 
 def linear_rows(A, lda_g, lda_x, G, M, K, W, N, C, ldc_g, ldc_x, sign_w=False, colscale=None, bias=None, bn=None,

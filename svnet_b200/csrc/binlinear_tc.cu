@@ -152,9 +152,12 @@ struct bl_args {
     float* out;
     int ldo;
     int32_t* out_i32;
+    float* pool_partial;     // MODE 2: [tile][half][max | sum][Cout]
 };
 
-template <bool GENERIC>
+// MODE 0: generic epilogue; 1: scale -> BN -> LeakyReLU stores on full tiles; 2: the same values reduced to
+// per-tile column max / sum partials (global pooling fused, nothing else is written)
+template <int MODE>
 __global__ void __launch_bounds__(NTH, 1) binlinear_tc_kernel(bl_args p)
 {
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -252,6 +255,7 @@ __global__ void __launch_bounds__(NTH, 1) binlinear_tc_kernel(bl_args p)
             mbar_wait(tfull + buf, (uint32_t)((mt >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * TR + half * 64);
+            float vmax = -INFINITY, vsum = 0.0f;
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
                 float d[32];
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(NTH, 1) binlinear_tc_kernel(bl_args p)
                     if (lane == 0) mbar_arrive(tempty + buf);
                 }
                 const long rb = r0 + half * 64 + part * 32;
-                if (GENERIC) {
+                if (MODE == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const long r = rb + j;
@@ -274,6 +278,14 @@ __global__ void __launch_bounds__(NTH, 1) binlinear_tc_kernel(bl_args p)
                         if (p.bias) y = __fadd_rn(y, bi);
                         if (p.bn_a) y = __fadd_rn(__fmul_rn(y, a1), c1);
                         p.out[r * p.ldo + c] = sv_act(y, p.act);
+                    }
+                } else if (MODE == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float y = __fadd_rn(__fmul_rn(__fmul_rn(d[j], sc), a1), c1);
+                        y = y > 0.0f ? y : __fmul_rn(0.2f, y);
+                        vmax = fmaxf(vmax, y);
+                        vsum += y;
                     }
                 } else {
                     // scale -> BN -> LeakyReLU, full tile: no flags, no bounds checks inside the unrolled loop.
@@ -288,6 +300,11 @@ __global__ void __launch_bounds__(NTH, 1) binlinear_tc_kernel(bl_args p)
                         }
                     }
                 }
+            }
+            if (MODE == 2 && cok) {
+                float* pp = p.pool_partial + ((size_t)blockIdx.x * 2 + half) * 2 * p.Cout;
+                pp[c] = vmax;
+                pp[p.Cout + c] = vsum;
             }
         }
     }
@@ -346,13 +363,79 @@ int svnet_binlinear_tc_dispatch(const uint32_t* bits, const uint32_t* mask, long
     a.Wtc = static_cast<const unsigned char*>(workspace);
     a.scale = scale; a.bias = bias; a.bn_a = bn_a; a.bn_c = bn_c; a.act = act;
     a.cloud_dot = cloud_dot; a.rows_per_cloud = rows_per_cloud; a.out = out; a.ldo = ldo; a.out_i32 = out_i32;
+    a.pool_partial = nullptr;
     if (lean) {
-        SV_CUDA(cudaFuncSetAttribute(binlinear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        binlinear_tc_kernel<false><<<sv_cdiv(rows, TR), NTH, smem, st>>>(a);
+        SV_CUDA(cudaFuncSetAttribute(binlinear_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        binlinear_tc_kernel<1><<<sv_cdiv(rows, TR), NTH, smem, st>>>(a);
     } else {
-        SV_CUDA(cudaFuncSetAttribute(binlinear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        binlinear_tc_kernel<true><<<sv_cdiv(rows, TR), NTH, smem, st>>>(a);
+        SV_CUDA(cudaFuncSetAttribute(binlinear_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        binlinear_tc_kernel<0><<<sv_cdiv(rows, TR), NTH, smem, st>>>(a);
     }
     SV_CHECK_LAUNCH("svnet_binlinear_rows(tcgen05)");
     return 1;
+}
+
+// ---- binarised Linear + BN + LeakyReLU fused with the global max / mean pooling over the rows of a cloud
+//      (SV_DGCNN_CLS: conv5's scalar output is only ever pooled, sv_dgcnn_cls.py:68-74) ----
+namespace {
+__global__ void binlinear_pool_reduce_kernel(const float* __restrict__ partial, int tiles_per_cloud, int Cout, long rows_per_cloud,
+                                             float* __restrict__ max_out, float* __restrict__ mean_out, int ldo)
+{
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cout) return;
+    const float* p = partial + (size_t)b * tiles_per_cloud * 2 * 2 * Cout;
+    float mx = -INFINITY, sm = 0.0f;
+    for (int t = 0; t < tiles_per_cloud * 2; ++t) {        // fixed order: tile, then half
+        mx = fmaxf(mx, p[(size_t)t * 2 * Cout + c]);
+        sm += p[(size_t)t * 2 * Cout + Cout + c];
+    }
+    if (max_out) max_out[(size_t)b * ldo + c] = mx;
+    if (mean_out) mean_out[(size_t)b * ldo + c] = sm / (float)rows_per_cloud;
+}
+}  // namespace
+
+extern "C" size_t svnet_binlinear_pool_workspace_bytes(long rows, int K, int Cout, long rows_per_cloud)
+{
+    int MT, NKC;
+    size_t wb, smem;
+    if (rows_per_cloud < TR || (rows_per_cloud % TR) != 0 || (rows % rows_per_cloud) != 0) return 0;
+    if (!bl_plan(rows, K, Cout, &MT, &NKC, &wb, &smem)) return 0;
+    return wb + (size_t)(rows / TR) * 2 * 2 * Cout * sizeof(float);
+}
+
+extern "C" int svnet_binlinear_pool_ws(const uint32_t* bits, const uint32_t* mask, long rows, int K, const uint32_t* W1b,
+                                       int Cout, const float* scale, const float* bn_a, const float* bn_c,
+                                       long rows_per_cloud, float* max_out, float* mean_out, int ldo, void* workspace,
+                                       size_t workspace_bytes, void* stream)
+{
+    SV_REQUIRE(bits && mask && W1b && scale && bn_a && bn_c, "svnet_binlinear_pool_ws: null pointer");
+    SV_REQUIRE(max_out || mean_out, "svnet_binlinear_pool_ws: no output requested");
+    SV_REQUIRE(ldo >= Cout, "svnet_binlinear_pool_ws: ldo too small");
+    const size_t need = svnet_binlinear_pool_workspace_bytes(rows, K, Cout, rows_per_cloud);
+    SV_REQUIRE(need > 0, "svnet_binlinear_pool_ws: shape not covered (rows %ld, K %d, rows_per_cloud %ld)", rows, K, rows_per_cloud);
+    SV_REQUIRE(workspace && workspace_bytes >= need && !(reinterpret_cast<uintptr_t>(workspace) & 15),
+               "svnet_binlinear_pool_ws: workspace too small or misaligned");
+    int MT, NKC;
+    size_t wb, smem;
+    bl_plan(rows, K, Cout, &MT, &NKC, &wb, &smem);
+    cudaStream_t st = sv_stream(stream);
+    const int Kw = (K + 31) / 32;
+    binlinear_pack_w_kernel<<<sv_cdiv((long)MT * NKC * 8 * TCH, 256), 256, 0, st>>>(W1b, Kw, K, Cout, MT, NKC,
+                                                                                   static_cast<uint4*>(workspace));
+    SV_CHECK_LAUNCH("svnet_binlinear_pool_ws(pack)");
+    bl_args a;
+    a.bits = bits; a.mask = mask; a.rows = rows; a.Kw = Kw; a.Cout = Cout; a.MT = MT; a.NKC = NKC;
+    a.Wtc = static_cast<const unsigned char*>(workspace);
+    a.scale = scale; a.bias = nullptr; a.bn_a = bn_a; a.bn_c = bn_c; a.act = SVNET_ACT_LEAKY;
+    a.cloud_dot = nullptr; a.rows_per_cloud = rows_per_cloud; a.out = nullptr; a.ldo = 0; a.out_i32 = nullptr;
+    a.pool_partial = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + wb);
+    SV_CUDA(cudaFuncSetAttribute(binlinear_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    binlinear_tc_kernel<2><<<sv_cdiv(rows, TR), NTH, smem, st>>>(a);
+    SV_CHECK_LAUNCH("svnet_binlinear_pool_ws(tcgen05)");
+    const int B = (int)(rows / rows_per_cloud);
+    binlinear_pool_reduce_kernel<<<dim3(sv_cdiv(Cout, 128), B), 128, 0, st>>>(a.pool_partial, (int)(rows_per_cloud / TR), Cout,
+                                                                             rows_per_cloud, max_out, mean_out, ldo);
+    SV_CHECK_LAUNCH("svnet_binlinear_pool_ws(reduce)");
+    return SVNET_OK;
 }

@@ -62,9 +62,8 @@ class SV_DGCNN_CLS(nn.Module, _Cached):
         if record is None and 3 * C5v <= 512:
             # svfuse + global pools without the (B*N, 1022) table: scalars are pooled from conv5's own output,
             # v2s(v) is reduced on the fly (svnet_svfuse_pool)
-            s5 = torch.empty((B * N, C5s), dtype=torch.float32, device=dev)
-            self.conv5.forward_rows(s_cat, v_cat, B, N, s_out=s5, lds_out=C5s, v_out=v5)
-            nv.pool_rows(s5, C5s, C5s, B, N, want_max=True, want_mean=True, max_out=g, mean_out=g[:, Cf:], ldo=2 * Cf)
+            # (binary models: linear1 + BN + LeakyReLU + pooling run as one tensor-core kernel, svnet_binlinear_pool_ws)
+            self.conv5.forward_rows(s_cat, v_cat, B, N, v_out=v5, s_pool=(g, g[:, Cf:], 2 * Cf))
             Wz, zs = self.svfuse.v2s.wz()
             nv.svfuse_pool(v5, B, N, Wz, zs, g[:, C5s:], g[:, Cf + C5s:], 2 * Cf)
         else:

@@ -293,8 +293,11 @@ class SVBlock(nn.Module, _Cached):
         return self._packed("yab", (lin.weight,), build)
 
     # -- module-level forward over materialised rows --------------------------------------------
-    def forward_rows(self, s2d, v3, B, rows_per_cloud, s_out=None, lds_out=None, v_out=None):
-        """s2d (R, Cs) [row stride may exceed Cs], v3 (R, 3, Cv) strided.  Returns (s', v')."""
+    def forward_rows(self, s2d, v3, B, rows_per_cloud, s_out=None, lds_out=None, v_out=None, s_pool=None):
+        """s2d (R, Cs) [row stride may exceed Cs], v3 (R, 3, Cv) strided.  Returns (s', v').
+        ``s_pool`` = (max_out, mean_out, ldo): the scalar output is only needed pooled over each cloud's rows
+        (SV_DGCNN_CLS conv5) -- when the fused tensor-core kernel covers the shape s' is never written and
+        None is returned for it; otherwise s' is computed and pooled with svnet_pool_rows."""
         R = s2d.shape[0]
         Cs, Cv = self.in_dims
         Cso, Cvo = self.out_dims
@@ -304,14 +307,20 @@ class SVBlock(nn.Module, _Cached):
         Wz, zs = self.v2s.wz()
         view = nv.view_of(s2d, v3, Cs=Cs, Cv=Cv)
         bn1 = self.bn1_folded()
-        if s_out is None:
+        K = Cs + 3 * Cv
+        fused_pool = (s_pool is not None and self.binary and s_out is None
+                      and nv.binlinear_pool_workspace(R, K, Cso, rows_per_cloud) > 0)
+        if s_out is None and not fused_pool:
             s_out = torch.empty((R, Cso), dtype=torch.float32, device=dev)
             lds_out = Cso
-        K = Cs + 3 * Cv
         if self.binary:
             bits, mask, nvalid = nv.rows_prep(view, R, Wz=Wz, zscale=zs, beta=self.linear1.beta_vec(), want_bits=True)
-            nv.binlinear_rows(bits, mask, nvalid, K, self.linear1.sign_bits(), Cso, scale=self.linear1.scale_vec(),
-                              bn=bn1, act=nv.ACT_LEAKY, out=s_out, ldo=lds_out)
+            if fused_pool:
+                nv.binlinear_pool(bits, mask, K, self.linear1.sign_bits(), Cso, self.linear1.scale_vec(), bn1,
+                                  rows_per_cloud, s_pool[0], s_pool[1], s_pool[2])
+            else:
+                nv.binlinear_rows(bits, mask, nvalid, K, self.linear1.sign_bits(), Cso, scale=self.linear1.scale_vec(),
+                                  bn=bn1, act=nv.ACT_LEAKY, out=s_out, ldo=lds_out)
         else:
             u = torch.empty((R, K), dtype=torch.float32, device=dev)
             nv.rows_prep(view, R, Wz=Wz, zscale=zs, u_out=u, ldu=K)
@@ -324,6 +333,9 @@ class SVBlock(nn.Module, _Cached):
                        v_out.stride(0), v_out.stride(1), sign_w=lin2.bw,
                        colscale=lin2.scale_vec() if lin2.bw else None, bn=self.bn2.folded(), vbn=True, gate=gate,
                        groups_per_cloud=rows_per_cloud)
+        if s_pool is not None and not fused_pool:
+            nv.pool_rows(s_out, lds_out, Cso, B, rows_per_cloud, want_max=True, want_mean=True, max_out=s_pool[0],
+                         mean_out=s_pool[1], ldo=s_pool[2])
         return s_out, v_out
 
     def forward(self, x):

@@ -243,6 +243,29 @@ def test_binlinear_tensor_core_equals_popcount(rows, K, Cout, monkeypatch):
     assert (t2n(outs["2"][0]) == ref).all()
 
 
+def test_binlinear_pool_equals_linear_then_pool():
+    """svnet_binlinear_pool_ws (binarised Linear -> BN -> LeakyReLU -> per-cloud max | mean in one tensor-core
+    kernel) against svnet_binlinear_rows + svnet_pool_rows: the max is exact, the mean differs only by the
+    summation order."""
+    from svnet_b200 import _native as nv
+    B, N, K, Cout = 3, 1024, 505, 512
+    rows = B * N
+    x, W, beta = rnd((rows, K), 31), rnd((Cout, K), 32), rnd((K,), 33, 0.1)
+    bits, mask, nvalid = nv.rows_prep(nv.view_of(cu(x), None), rows, beta=cu(beta), want_bits=True)
+    W1b = nv.pack_sign(cu(W))
+    scale = cu(np.abs(rnd((Cout,), 34)) * 0.05 + 0.01)
+    bn = (cu(rnd((Cout,), 35)), cu(rnd((Cout,), 36)))
+    y = nv.binlinear_rows(bits, mask, nvalid, K, W1b, Cout, scale=scale, bn=bn, act=nv.ACT_LEAKY)
+    mx, mean = nv.pool_rows(y, Cout, Cout, B, N, want_max=True, want_mean=True)
+    assert nv.binlinear_pool_workspace(rows, K, Cout, N) > 0
+    g = torch.zeros((B, 2 * Cout + 8), device=DEV)
+    nv.binlinear_pool(bits, mask, K, W1b, Cout, scale, bn, N, g[:, 4:4 + Cout], g[:, 8 + Cout:], g.stride(0))
+    assert torch.equal(g[:, 4:4 + Cout], mx)
+    assert_close(t2n(g[:, 8 + Cout:8 + 2 * Cout]), t2n(mean), rtol=1e-5, atol=1e-6, what="binlinear_pool mean")
+    assert float(g[:, :4].abs().max()) == 0.0 and float(g[:, 4 + Cout:8 + Cout].abs().max()) == 0.0
+    assert nv.binlinear_pool_workspace(rows, K, Cout, 1000) == 0        # rows_per_cloud % 128 != 0: not covered
+
+
 def test_svfuse_pool_equals_materialised_path():
     """svnet_svfuse_pool (v2s reduced on the fly) against rows_prep(u_out) + pool_rows: the max is exact,
     the mean differs only by the summation order."""
