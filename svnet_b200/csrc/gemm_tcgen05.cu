@@ -211,10 +211,11 @@ __global__ void __launch_bounds__(NTH, 2) vlinear_tcgen05_kernel(svnet_gemm_para
                         cq[0] = w0; cq[p.ldc_x] = w1; cq[2L * p.ldc_x] = w2;
                         continue;
                     }
-                    const float nrm = __fadd_rn(
-                        __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0, w0), __fmul_rn(w1, w1)), __fmul_rn(w2, w2))), 1e-6f);
-                    const float nb = __fadd_rn(__fmul_rn(nrm, a2), c2);
-                    float sfac = __fdiv_rn(nb, nrm);
+                    // VectorBN: v * (bn(n) / n), n = |v| + 1e-6 (sv_layers.py:94-100).  Tolerance-level arithmetic
+                    // (norms are not bit-pinned): rsqrt / fast division instead of the IEEE sequences.
+                    const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0 * w0));
+                    const float nrm = (s2 > 0.0f ? s2 * rsqrtf(s2) : 0.0f) + 1e-6f;
+                    float sfac = a2 + __fdividef(c2, nrm);
                     if (p.gate) sfac *= __ldg(p.gate + (long)((unsigned)pnt / gpc) * p.N + c);
                     float* cp = p.C + pnt * p.ldc_g + c;
                     cp[0] = w0 * sfac;
