@@ -195,6 +195,11 @@ __global__ void __launch_bounds__(NTH, 2) vlinear_tcgen05_kernel(svnet_gemm_para
             const float a2 = (cok && p.vbn) ? p.bn_a[c] : 0.0f, c2 = (cok && p.vbn) ? p.bn_c[c] : 0.0f;
             const uint32_t tbase = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(mt * NCOL);
             const unsigned gpc = (unsigned)p.groups_per_cloud;
+            // the gate depends on (cloud, channel) only: one load per tile when the tile lies inside one cloud
+            // (always, when the rows per cloud are a multiple of the 32-point tile)
+            const long last_pt = (p0 + PTS - 1 < npoints ? p0 + PTS - 1 : npoints - 1);
+            const bool one_cloud = ((unsigned)p0 / gpc) == ((unsigned)last_pt / gpc);
+            const float gate_tile = (p.gate && cok && one_cloud) ? __ldg(p.gate + (long)((unsigned)p0 / gpc) * p.N + c) : 1.0f;
             for (int q0 = 0; q0 < PTS; q0 += 16) {
                 float vx[16], vy[16], vz[16];
                 tmem_ld16(tbase + q0, vx);
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(NTH, 2) vlinear_tcgen05_kernel(svnet_gemm_para
                     const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0 * w0));
                     const float nrm = (s2 > 0.0f ? s2 * rsqrtf(s2) : 0.0f) + 1e-6f;
                     float sfac = a2 + __fdividef(c2, nrm);
-                    if (p.gate) sfac *= __ldg(p.gate + (long)((unsigned)pnt / gpc) * p.N + c);
+                    if (p.gate) sfac *= one_cloud ? gate_tile : __ldg(p.gate + (long)((unsigned)pnt / gpc) * p.N + c);
                     float* cp = p.C + pnt * p.ldc_g + c;
                     cp[0] = w0 * sfac;
                     cp[p.ldc_x] = w1 * sfac;
