@@ -27,15 +27,37 @@ __device__ __forceinline__ void rf_wait() { asm volatile("cp.async.wait_all;\n" 
 __host__ __device__ inline int rf_cvp(int Cv) { return (Cv + 3) & ~3; }
 __host__ __device__ inline int rf_warp_floats(int Cv) { return 9 * rf_cvp(Cv) + 16 + 36; }
 
-// stage the vectors of up to three rows (all copies in flight), zero the channel padding once
+__device__ __forceinline__ void rf_cp_async8(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+
+// stage the vectors of up to three rows (all copies in flight); 8-byte copies when the view allows it
 __device__ __forceinline__ void stage_rows(const svnet_view& in, long r0, int ng, float* vsm, int Cv, int CvP, int lane)
 {
+    const bool wide = (((Cv | in.ldv | in.xs) & 1) == 0) && ((reinterpret_cast<uintptr_t>(in.v) & 7) == 0);
 #pragma unroll 1
     for (int x = 0; x < 3; ++x) {
-        const float* src = in.v + r0 * in.ldv + (long)x * in.xs;
-        float* dst = vsm + x * CvP;
-        for (int c = lane; c < Cv; c += 32)
-            for (int g = 0; g < ng; ++g) rf_cp_async4(dst + g * 3 * CvP + c, src + (long)g * in.ldv + c);
+        const float* s0 = in.v + r0 * in.ldv + (long)x * in.xs;
+        const float* s1 = s0 + in.ldv;
+        const float* s2 = s1 + in.ldv;
+        float* d0 = vsm + x * CvP;
+        float* d1 = d0 + 3 * CvP;
+        float* d2 = d1 + 3 * CvP;
+        if (wide) {
+            for (int c = 2 * lane; c < Cv; c += 64) {
+                rf_cp_async8(d0 + c, s0 + c);
+                if (ng > 1) rf_cp_async8(d1 + c, s1 + c);
+                if (ng > 2) rf_cp_async8(d2 + c, s2 + c);
+            }
+        } else {
+            for (int c = lane; c < Cv; c += 32) {
+                rf_cp_async4(d0 + c, s0 + c);
+                if (ng > 1) rf_cp_async4(d1 + c, s1 + c);
+                if (ng > 2) rf_cp_async4(d2 + c, s2 + c);
+            }
+        }
     }
 }
 
