@@ -38,8 +38,8 @@ def main():
         name = r[ix["Kernel Name"]]
         if "knn_pack_kernel" in name or ("knn_kernel" in name and "tc" not in name):
             pending = t
-        elif ("knn_tc_kernel" in name or "knn_finish_kernel" in name) and pending is not None:
-            pending += t
+        elif "knn_tc_kernel" in name or "knn_finish_kernel" in name:
+            pending = t if pending is None else pending + t      # (a capture may start after the pack kernel)
         elif "edge_xyz" in name:
             if pending is not None:
                 d["svnet_knn[layer1]"] = pending
