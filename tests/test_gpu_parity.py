@@ -715,3 +715,33 @@ def test_graphed_forward_equals_eager():
         assert torch.equal(y_fast, y)
     with pytest.raises(ValueError):
         fast(synthetic_clouds(8, 256, 1).to(DEV))
+
+
+@pytest.mark.parametrize("model", ["pseg", "pointnet"])
+def test_two_stream_halves_equal_single_stream(model):
+    """fused.chunked runs a batch of >= 16 clouds as two halves on two CUDA streams; clouds are independent in
+    eval mode, so the result must equal the single-stream forward exactly (also with an extra per-cloud input)."""
+    import svnet_b200 as sv
+    from svnet_b200 import fused
+    from svnet_b200.synthetic import one_hot_labels
+    B, N = 16, 256
+    x = synthetic_clouds(B, N, 21).to(DEV)
+    if model == "pseg":
+        net = quiet(sv.SV_DGCNN_PSEG, make_args(k=12, binary=True), 50)
+        extra = (one_hot_labels(B).to(DEV),)
+    else:
+        net = quiet(sv.SV_PointNet_CLS, make_args(k=12, binary=False), 40)
+        extra = ()
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=5))
+    net = net.to(DEV).eval()
+    keep = fused.CONCURRENT_HALVES
+    try:
+        with torch.no_grad():
+            fused.CONCURRENT_HALVES = True
+            y2 = net(x, *extra)
+            fused.CONCURRENT_HALVES = False
+            y1 = net(x, *extra)
+    finally:
+        fused.CONCURRENT_HALVES = keep
+    torch.cuda.synchronize()
+    assert y2.shape == y1.shape and torch.equal(y2, y1)
