@@ -94,7 +94,7 @@ int svnet_knn(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t
  * svnet_knn_workspace_bytes() bytes (16-byte aligned) the pairwise scores run on the tcgen05 tensor
  * cores as a FILTER (bf16 hi/mid/lo planes, fp32 accumulators in tensor memory) and every decision the
  * filter cannot certify is re-taken with the exact fp32 chain above (csrc/knn_tc.cu).
- * svnet_knn_workspace_bytes() returns 0 for shapes the tensor-core path does not cover (k > 24,
+ * svnet_knn_workspace_bytes() returns 0 for shapes the tensor-core path does not cover (k > 48,
  * N > 4096, N < 64, more than 160 channels); svnet_knn_ws then runs the CUDA-core kernel. */
 size_t svnet_knn_workspace_bytes(const svnet_view* in, int B, int N, int k);
 int svnet_knn_ws(const svnet_view* in, int B, int N, int k, int32_t* idx32, int64_t* idx64, void* workspace,

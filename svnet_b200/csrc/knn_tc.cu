@@ -1,5 +1,5 @@
 // K1-TC -- kNN graph construction with the pairwise scores on tcgen05 tensor cores.
-// Replaces sv_util.knn (reference models/utils/sv_util.py:19-25) for k <= 24, N <= 4096, C <= 160;
+// Replaces sv_util.knn (reference models/utils/sv_util.py:19-25) for k <= 48, 64 <= N <= 4096, C <= 160;
 // other shapes stay on the CUDA-core kernel in knn.cu.  Results are bit-identical to
 // oracle/svnet_oracle.c:orc_knn: the tensor cores only FILTER, every decision that the filter
 // cannot certify is re-taken with the oracle's exact fp32 fmaf chain.
@@ -52,7 +52,8 @@ constexpr int GM_BYTES = GROUPS * TM * 4;      // group maxima between the passe
 constexpr int FIN_WARPS = 8;                   // finish kernel: warps per CTA, one warp = one row
 constexpr int KMAX = 160;                      // padded channels
 constexpr int MAX_STAGES = 5;
-constexpr int KNN_TC_MAX_K = 24;
+constexpr int KNN_TC_MAX_K = 48;               // k <= 32: approximate-order finish; 33..48: every survivor re-scored
+                                               // (the 64-group threshold gets loose as k approaches 64)
 
 __device__ unsigned long long g_knn_tc_stats[12];
 
@@ -249,27 +250,31 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// brute-force exact selection of one row by one warp (queue overflow / degenerate inputs)
+// brute-force exact selection of one row by one warp (queue overflow / degenerate inputs); k <= 32 R
+template <int R>
 __device__ void brute_force_row(const knn_tc_args& p, long base, int i, const float* arow, const float* xxs, int lane,
-                                kkey_t& out)
+                                kkey_t (&out)[R])
 {
-    TopK<1> L;      // k <= KNN_TC_MAX_K <= 32
-    L.k[0] = 0ull;
+    TopK<R> L;
+#pragma unroll
+    for (int r = 0; r < R; ++r) L.k[r] = 0ull;
     const float xi = xxs[i];
     const int k = p.k;
     for (int j0 = 0; j0 < p.N; j0 += 32) {
         const int j = j0 + lane;
         kkey_t c = 0ull;
         if (j < p.N) c = make_key(exact_score(exact_dot(p.in, base + j, arow), xi, xxs[j]), j);
-        const kkey_t worst = shfl_key(L.k[0], k - 1);
+        kkey_t worst = shfl_key(L.k[0], (k - 1) & 31);
+        if (R > 1 && k > 32) worst = shfl_key(L.k[R - 1], (k - 1) & 31);
         unsigned m = __ballot_sync(SV_FULL, c > worst);
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
-            topk_insert<1>(L, shfl_key(c, src), lane);
+            topk_insert<R>(L, shfl_key(c, src), lane);
         }
     }
-    out = L.k[0];
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[r] = L.k[r];
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
@@ -656,9 +661,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
     if (brute) {
         for (int c = lane; c < C; c += 32) f.arow[c] = sv_feat(p.in, rg, c);
         __syncwarp();
-        kkey_t key;
-        brute_force_row(p, base, i, f.arow, xxs, lane, key);
-        jout = key_index(key);
+        kkey_t key[1];
+        brute_force_row<1>(p, base, i, f.arow, xxs, lane, key);
+        jout = key_index(key[0]);
     } else if (cnt <= 32) {
         // entry e of the row is half0[e] for e < c0, else half1[e - c0] (fetched by shuffle)
         float2 ent;
@@ -683,7 +688,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
         bool am = false;
         if (lane + 1 < cnt) am = (sme - snx) <= 0.5f * p.eps * (2.0f * xxi + xj + xnx);
         const unsigned amb = __ballot_sync(SV_FULL, am);
-        unsigned rel = amb & ((1u << k) - 1u);       // pairs e <= k-1, then the runs continuing from them
+        unsigned rel = amb & (k >= 32 ? 0xFFFFFFFFu : (1u << k) - 1u);       // pairs e <= k-1, then the runs continuing from them
         for (;;) {
             const unsigned nx = (rel << 1) & amb & ~rel;
             if (!nx) break;
@@ -739,6 +744,88 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
             if (cnt > 32 && !brute) atomicAdd(&g_knn_tc_stats[10], 1ull);
             if (emax > 0.0f) atomicMax(&g_knn_tc_stats[9], (unsigned long long)__float_as_uint(emax));
         }
+    }
+}
+
+// ---- finish kernel for 32 < k <= 48 (part segmentation, k = 40): every survivor is re-scored with the exact
+//      chain, 32 at a time, and merged into the best 64 (two sorted registers per lane) ----
+__global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_wide_kernel(knn_tc_args p)
+{
+    extern __shared__ __align__(16) float fin_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * FIN_WARPS + warp;
+    const long base = (long)b * p.N;
+    const long rg = base + i;
+    const int k = p.k;
+    const int C = p.in.Cs + 3 * p.in.Cv, Cp = fin_stride(C);
+    const float* xxs = p.xx + (size_t)b * p.NCB * TNB;
+    const float** gtab = reinterpret_cast<const float**>(fin_smem);
+    int* gstr = reinterpret_cast<int*>(gtab + KMAX);
+    for (int c = threadIdx.x; c < C; c += FIN_WARPS * 32) {
+        const int cc2 = c - p.in.Cs;
+        const int x = (cc2 >= p.in.Cv ? 1 : 0) + (cc2 >= 2 * p.in.Cv ? 1 : 0);
+        const bool in_s = c < p.in.Cs;
+        gtab[c] = in_s ? p.in.s + c : p.in.v + (long)x * p.in.xs + (cc2 - x * p.in.Cv);
+        gstr[c] = in_s ? p.in.lds : p.in.ldv;
+    }
+    __syncthreads();
+    if (i >= p.N) return;
+    fin_env f;
+    f.p = &p; f.gtab = gtab; f.gstr = gstr;
+    f.arow = fin_smem + FIN_TAB_FLOATS + (size_t)warp * ((1 + p.xcap) * Cp);
+    f.exb = f.arow + Cp;
+    f.base = base; f.rg = rg; f.C = C; f.Cp = Cp; f.lane = lane;
+    f.arow_loaded = false; f.emax = 0.0f;
+    f.xxi = __ldg(xxs + i);
+    const float2* q0 = p.gq + rg * 2 * CAPH;
+    const int2 cc = __ldg(reinterpret_cast<const int2*>(p.gqcnt) + rg);
+    const int c0 = cc.x, cnt = cc.x + cc.y;
+    const bool brute = !(cc.x <= CAPH && cc.y <= CAPH && cnt >= k);
+    kkey_t best[2] = {0ull, 0ull};
+    if (brute) {
+        for (int c = lane; c < C; c += 32) f.arow[c] = sv_feat(p.in, rg, c);
+        __syncwarp();
+        brute_force_row<2>(p, base, i, f.arow, xxs, lane, best);
+    } else {
+        for (int e0 = 0; e0 < cnt; e0 += 32) {
+            const int e = e0 + lane;
+            float2 ent = make_float2(0.0f, 0.0f);
+            if (e < cnt) ent = __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
+            const int jme = __float_as_int(ent.y);
+            const float xj = e < cnt ? __ldg(xxs + jme) : 0.0f;
+            const unsigned valid = __ballot_sync(SV_FULL, e < cnt);
+            const unsigned sc = exact_keys(f, valid, jme, xj, ent.x);
+            kkey_t key = e < cnt ? (((kkey_t)sc << 32) | (unsigned)(~jme)) : 0ull;     // == make_key(exact score, j)
+            warp_sort32_desc(key, lane);
+            // (best[0], best[1]) = the 64 best so far, sorted; merge the new 32 into the lower half, then the halves
+            kkey_t rev = shfl_key(key, 31 - lane);
+            kkey_t lo = best[1] > rev ? best[1] : rev;
+            warp_sort32_desc(lo, lane);
+            rev = shfl_key(lo, 31 - lane);
+            kkey_t hi = best[0] > rev ? best[0] : rev;
+            lo = best[0] > rev ? rev : best[0];
+            warp_sort32_desc(hi, lane);
+            warp_sort32_desc(lo, lane);
+            best[0] = hi; best[1] = lo;
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int pos = w * 32 + lane;
+        if (pos < k) {
+            const long o = rg * k + pos;
+            const int j = key_index(best[w]);
+            if (p.idx32) p.idx32[o] = j;
+            if (p.idx64) p.idx64[o] = (int64_t)j;
+        }
+    }
+    if (p.stats && lane == 0) {
+        atomicAdd(&g_knn_tc_stats[0], 1ull);
+        atomicAdd(&g_knn_tc_stats[1], 1ull);
+        if (brute) atomicAdd(&g_knn_tc_stats[2], 1ull);
+        atomicAdd(&g_knn_tc_stats[3], (unsigned long long)cnt);
+        if (cnt > 32 && !brute) atomicAdd(&g_knn_tc_stats[10], 1ull);
     }
 }
 
@@ -827,8 +914,13 @@ int svnet_knn_tc_dispatch(const svnet_view* in, int B, int N, int k, int32_t* id
     SV_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_tc_kernel<<<dim3(sv_cdiv(N, TM), B), NTHREADS, smem, st>>>(a);
     SV_CHECK_LAUNCH("svnet_knn(tcgen05)");
-    SV_CUDA(cudaFuncSetAttribute(knn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.fin_smem));
-    knn_finish_kernel<<<dim3(sv_cdiv(N, FIN_WARPS), B), FIN_WARPS * 32, pl.fin_smem, st>>>(a);
+    if (k <= 32) {
+        SV_CUDA(cudaFuncSetAttribute(knn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.fin_smem));
+        knn_finish_kernel<<<dim3(sv_cdiv(N, FIN_WARPS), B), FIN_WARPS * 32, pl.fin_smem, st>>>(a);
+    } else {
+        SV_CUDA(cudaFuncSetAttribute(knn_finish_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.fin_smem));
+        knn_finish_wide_kernel<<<dim3(sv_cdiv(N, FIN_WARPS), B), FIN_WARPS * 32, pl.fin_smem, st>>>(a);
+    }
     SV_CHECK_LAUNCH("svnet_knn(finish)");
     return 1;
 }

@@ -110,9 +110,10 @@ def _tc_stats(reset=True):
     return list(out)
 
 
-@pytest.mark.parametrize("case", ["duplicates", "heavy_ties", "lattice", "offset", "all_equal", "ragged", "two_clusters"])
+@pytest.mark.parametrize("case", ["duplicates", "heavy_ties", "lattice", "offset", "all_equal", "ragged", "two_clusters",
+                                  "k40", "k40_ties", "k32"])
 def test_knn_tensor_core_path_adversarial(case, monkeypatch):
-    """Shapes served by the tcgen05 filter (csrc/knn_tc.cu: N >= 64, k <= 24): exact ties (duplicated
+    """Shapes served by the tcgen05 filter (csrc/knn_tc.cu: N >= 64, k <= 48): exact ties (duplicated
     points, lattice), norms much larger than neighbour gaps, everything equal (queue overflow ->
     brute-force rows), N not a multiple of the 128/256 tiles.  Indices must equal the oracle's, and
     the CUDA-core kernel's, bit for bit; the counters prove that the tensor-core path ran."""
@@ -127,6 +128,16 @@ def test_knn_tensor_core_path_adversarial(case, monkeypatch):
         B, N, C, k = 1, 640, 62, 20          # 16 distinct points x 40 copies: > 32 exact ties around every query
         base = torch.randn((B, 16, C), generator=g)
         feat = base.repeat(1, 40, 1)[:, torch.randperm(N, generator=g)]
+    elif case == "k40":                      # part-segmentation shape: 32 < k <= 48 -> wide finish kernel
+        B, N, C, k = 2, 700, 80, 40
+        feat = torch.randn((B, N, C), generator=g) * 0.2 + 0.5
+    elif case == "k40_ties":
+        B, N, C, k = 1, 512, 16, 40
+        base = torch.randn((B, 64, C), generator=g)
+        feat = base.repeat(1, 8, 1)[:, torch.randperm(N, generator=g)]
+    elif case == "k32":
+        B, N, C, k = 1, 400, 62, 32
+        feat = torch.randn((B, N, C), generator=g)
     elif case == "lattice":
         B, N, C, k = 1, 343, 3, 20
         ax = torch.arange(7, dtype=torch.float32)

@@ -46,7 +46,8 @@ def test_argument_errors_without_gpu():
     lib.svnet_svfuse_pool_workspace.restype = ctypes.c_size_t
     v.Cs, v.lds = 62, 62
     assert lib.svnet_knn_workspace_bytes(ctypes.byref(v), 4, 1024, 20) > 0          # covered by the tensor-core path
-    assert lib.svnet_knn_workspace_bytes(ctypes.byref(v), 4, 1024, 40) == 0         # k > 24: CUDA-core kernel
+    assert lib.svnet_knn_workspace_bytes(ctypes.byref(v), 4, 1024, 40) > 0          # 32 < k <= 48: wide finish kernel
+    assert lib.svnet_knn_workspace_bytes(ctypes.byref(v), 4, 1024, 100) == 0        # k > 48: CUDA-core kernel
     assert lib.svnet_knn_workspace_bytes(ctypes.byref(v), 4, 32, 8) == 0            # N < 64
     assert lib.svnet_svfuse_pool_workspace(2, 170, ctypes.c_long(1024)) > 0
     rc = lib.svnet_svfuse_pool(None, 1, ctypes.c_long(8), None, None, None, None, 0, None, ctypes.c_size_t(0), None)
