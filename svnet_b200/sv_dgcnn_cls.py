@@ -71,10 +71,18 @@ class SV_DGCNN_CLS(nn.Module, _Cached):
             self.conv5.forward_rows(s_cat, v_cat, B, N, s_out=fused, lds_out=fused.stride(0), v_out=v5)
             self.svfuse.forward_rows(None, v5, out=fused)
             nv.pool_rows(fused, Cf, Cf, B, N, want_max=True, want_mean=True, max_out=g, mean_out=g[:, Cf:], ldo=2 * Cf)
-        # head: three chained layers in one kernel, one CTA per cloud
-        out = nv.head_fwd(g, [head_layer(self.linear1, folded_bn(self, "bn1"), nv.ACT_LEAKY),
-                              head_layer(self.linear2, folded_bn(self, "bn2"), nv.ACT_LEAKY),
-                              head_layer(self.linear3)])
+        # head: three chained layers in one kernel, one CTA per cloud.  The full-precision first layer
+        # (2044 x 512 fp32 weights) would be re-read by every cloud's CTA: run it as one GEMM over the batch.
+        if self.binary:
+            out = nv.head_fwd(g, [head_layer(self.linear1, folded_bn(self, "bn1"), nv.ACT_LEAKY),
+                                  head_layer(self.linear2, folded_bn(self, "bn2"), nv.ACT_LEAKY),
+                                  head_layer(self.linear3)])
+        else:
+            h1 = torch.empty((B, self.linear1.out_features), dtype=torch.float32, device=dev)
+            nv.linear_rows(g, g.stride(0), 0, 1, B, g.shape[1], self.linear1.weight.detach(), h1.shape[1], h1,
+                           h1.stride(0), 0, bn=folded_bn(self, "bn1"), act=nv.ACT_LEAKY)
+            out = nv.head_fwd(h1, [head_layer(self.linear2, folded_bn(self, "bn2"), nv.ACT_LEAKY),
+                                   head_layer(self.linear3)])
         if record is not None:
             record.update(fused=fused, glob=g)
         return out
