@@ -262,6 +262,13 @@ typedef struct {
     float* C; long ldc_g; int ldc_x;
 } svnet_gemm_params;
 int svnet_linear_rows(const svnet_gemm_params* p, void* stream);
+/* With svnet_linear_workspace_bytes(p) bytes of caller-owned scratch (16-byte aligned) a plain fp32 linear
+ * (G == 1, no sign_w / vbn / gate, M >= 2048, 32 <= N <= 512, K >= 32) runs on the tcgen05 tensor cores with
+ * both operands split exactly into three bf16 planes (six plane products, fp32 accumulation in tensor memory:
+ * fp32-level accuracy, different summation order -> tolerance-level, csrc/gemm_tc3.cu).  0 bytes: not covered,
+ * svnet_linear_rows_ws then behaves as svnet_linear_rows. */
+size_t svnet_linear_workspace_bytes(const svnet_gemm_params* p);
+int svnet_linear_rows_ws(const svnet_gemm_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Classification head, one CTA per cloud: up to three chained layers, each a binarised Linear
  * (W1b + beta [+ scale]) or an fp Linear (W [Cout][K], sign_w for binary weights / fp activations),

@@ -21,7 +21,7 @@ EXPORTS = [
     "svnet_version", "svnet_last_error", "svnet_pack_sign", "svnet_fold_bn", "svnet_knn",
     "svnet_knn_ws", "svnet_knn_workspace_bytes", "svnet_knn_tc_stats", "svnet_svfuse_pool", "svnet_svfuse_pool_workspace",
     "svnet_binlinear_rows_ws", "svnet_binlinear_workspace_bytes", "svnet_binlinear_pool_ws",
-    "svnet_binlinear_pool_workspace_bytes",
+    "svnet_binlinear_pool_workspace_bytes", "svnet_linear_rows_ws", "svnet_linear_workspace_bytes",
     "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
@@ -80,6 +80,7 @@ def lib():
         l.svnet_svfuse_pool_workspace.restype = ctypes.c_size_t
         l.svnet_binlinear_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_binlinear_pool_workspace_bytes.restype = ctypes.c_size_t
+        l.svnet_linear_workspace_bytes.restype = ctypes.c_size_t
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
         if l.svnet_version() != 1:
@@ -309,7 +310,12 @@ def linear_rows(A, lda_g, lda_x, G, M, K, W, N, C, ldc_g, ldc_x, sign_w=False, c
     p.gate = gate.data_ptr() if gate is not None else 0
     p.groups_per_cloud = groups_per_cloud
     p.C, p.ldc_g, p.ldc_x = C.data_ptr(), ldc_g, ldc_x
-    _call("svnet_linear_rows", ctypes.byref(p), _stream())
+    # scratch for the split weights of the three-plane tensor-core path (plain fp32 linears over many rows)
+    nbytes = int(lib().svnet_linear_workspace_bytes(ctypes.byref(p)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=C.device) if nbytes > 0 else None
+    _call("svnet_linear_rows_ws", ctypes.byref(p), _ptr(ws), ctypes.c_size_t(nbytes), _stream())
+    if nbytes > 0:
+        LAUNCHES[0] += 1
 
 
 def vector_bn_rows(v, bn_a, bn_c):

@@ -8,6 +8,8 @@
 
 int svnet_signlinear_tc_dispatch(const svnet_gemm_params* p, cudaStream_t st);
 int svnet_vlinear_tcgen05_dispatch(const svnet_gemm_params* p, cudaStream_t st);
+size_t svnet_linear_tc3_workspace(const svnet_gemm_params* p);
+int svnet_linear_tc3_dispatch(const svnet_gemm_params* p, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 namespace {
 
@@ -122,7 +124,14 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(svnet_gemm_params p)
 
 }  // namespace
 
+extern "C" size_t svnet_linear_workspace_bytes(const svnet_gemm_params* p) { return svnet_linear_tc3_workspace(p); }
+
 extern "C" int svnet_linear_rows(const svnet_gemm_params* p, void* stream)
+{
+    return svnet_linear_rows_ws(p, nullptr, 0, stream);
+}
+
+extern "C" int svnet_linear_rows_ws(const svnet_gemm_params* p, void* workspace, size_t workspace_bytes, void* stream)
 {
     SV_REQUIRE(p, "svnet_linear_rows: null params");
     SV_REQUIRE(p->A && p->W && p->C, "svnet_linear_rows: null pointer");
@@ -135,6 +144,11 @@ extern "C" int svnet_linear_rows(const svnet_gemm_params* p, void* stream)
     }
     if (p->M == 0) return SVNET_OK;
     cudaStream_t st = sv_stream(stream);
+    if (workspace) {   // plain fp32 linear over many rows: three-plane bf16 tcgen05 kernel (gemm_tc3.cu)
+        const int h = svnet_linear_tc3_dispatch(p, workspace, workspace_bytes, st);
+        if (h < 0) return h;
+        if (h == 1) return SVNET_OK;
+    }
     {   // binary-weight vector linear + VectorBN: tcgen05 / TMEM kernel (gemm_tcgen05.cu)
         const int h = svnet_vlinear_tcgen05_dispatch(p, st);
         if (h < 0) return h;

@@ -277,6 +277,36 @@ def test_binlinear_pool_equals_linear_then_pool():
     assert nv.binlinear_pool_workspace(rows, K, Cout, 1000) == 0        # rows_per_cloud % 128 != 0: not covered
 
 
+@pytest.mark.parametrize("rows,K,N", [(3000, 505, 512), (2048, 62, 64), (5000, 300, 100), (4096, 32, 40)])
+def test_linear_three_plane_tensor_core_matches_cuda_core(rows, K, N, monkeypatch):
+    """csrc/gemm_tc3.cu (fp32 linear as six bf16 plane products on tcgen05) against the CUDA-core GEMM with the
+    oracle's sequential chain: fp32-level agreement (the summation order differs), all epilogue options."""
+    from svnet_b200 import _native as nv
+    A, W = cu(rnd((rows, K + 3), 41)), cu(rnd((N, K), 42, 0.2))
+    bias, scale = cu(rnd((N,), 43)), cu(np.abs(rnd((N,), 44)) + 0.5)
+    bn = (cu(rnd((N,), 45)), cu(rnd((N,), 46)))
+    outs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("SVNET_LINEAR_TC", tc)
+        res = []
+        for kw in (dict(), dict(bias=bias, bn=bn, act=nv.ACT_RELU), dict(colscale=scale, bn=bn, act=nv.ACT_LEAKY)):
+            C = torch.full((rows, N + 5), 7.0, device=DEV)
+            nv.linear_rows(A, A.stride(0), 0, 1, rows, K, W, N, C, C.stride(0), 0, **kw)
+            res.append(C)
+        outs[tc] = res
+    ref = t2n(A[:, :K]).astype(np.float64) @ t2n(W).astype(np.float64).T
+    for a, b in zip(outs["1"], outs["0"]):
+        assert torch.equal(a[:, N:], b[:, N:])                      # columns beyond N untouched
+        assert_close(t2n(a[:, :N]), t2n(b[:, :N]), rtol=1e-4, atol=1e-4, what="tc3 vs cuda-core")
+    # accuracy against fp64: the tensor cores truncate when they accumulate, so the error grows with the number
+    # of accumulation steps (6 per 16 channels) -- about 1e-5 of the row/column norms, 10x the fp32 chain
+    scale = np.linalg.norm(t2n(A[:, :K]), axis=1, keepdims=True) * np.linalg.norm(t2n(W), axis=1)[None, :]
+    err_tc = (np.abs(t2n(outs["1"][0][:, :N]) - ref) / scale).max()
+    err_cc = (np.abs(t2n(outs["0"][0][:, :N]) - ref) / scale).max()
+    print("relative error vs fp64: tensor cores %.2e, fp32 chain %.2e" % (err_tc, err_cc))
+    assert err_tc < 2e-6, (err_tc, err_cc)
+
+
 def test_svfuse_pool_equals_materialised_path():
     """svnet_svfuse_pool (v2s reduced on the fly) against rows_prep(u_out) + pool_rows: the max is exact,
     the mean differs only by the summation order."""
