@@ -4,10 +4,11 @@
 // (hi + mid + lo = the fp32 value) and six plane products (h*h, h*m, m*h, m*m, h*l, l*h) are accumulated
 // in fp32 tensor memory; the dropped products are < 2^-20 of |a||w| per term.  The summation order differs
 // from the CUDA-core kernel's sequential chain (gemm.cu), so this path is tolerance-level (1e-5 relative,
-// far inside the 1e-3 / 1e-4 contract of the fp models); it is taken for rows >= 2048 only.
+// far inside the 1e-3 / 1e-4 contract of the fp models).  It is chosen by (K, N) only, never by the row count,
+// so that a cloud's result does not depend on the batch it is in.
 //
-//   D[c][r] = sum_k W[c][k] * a[r][k]        M = 128 channels per tile (<= 4 tiles: the whole 512-column
-//                                            tensor memory), N = 128 rows per CTA, K = 16 per UMMA
+//   D[c][r] = sum_k W[c][k] * a[r][k]        M = 128 channels per tile (two accumulators per tile, two tiles per
+//                                            CTA: the whole 512-column tensor memory), N = 128 rows, K = 16 per UMMA
 //   * weights     : split once per call into [tile][k-chunk 32][plane][k-block 4][128 channels][8 bf16]
 //                   (24 KB per chunk), streamed through an mbarrier ring with cp.async.bulk
 //   * activations : the CTA's 128 rows are split chunk by chunk into the same layout (double buffered in
@@ -147,7 +148,7 @@ __global__ void gemm_tc3_pack_w_kernel(const float* __restrict__ W, int ldw, int
 struct tc3_args {
     const float* A;
     long lda, rows;
-    int K, N, MT, NKC;
+    int K, N, MT, NKC;       // MT = channel tiles handled by one CTA (blockIdx.y selects the group)
     const unsigned char* Wtc;
     const float* colscale;
     const float* bias;
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc3_kernel(tc3_args p)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long r0 = (long)blockIdx.x * TR;
+    const int mt0 = blockIdx.y * MT;         // first channel tile of this CTA
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc3_kernel(tc3_args p)
                 for (int mt = 0; mt < MT; ++mt, ++t) {
                     if (t >= STAGES) mbar_wait(empty + s, ph ^ 1u);
                     mbar_expect_tx(full + s, CHUNK_BYTES);
-                    bulk_g2s(Ring + (size_t)s * CHUNK_BYTES, p.Wtc + ((size_t)mt * NKC + kc) * CHUNK_BYTES, CHUNK_BYTES, full + s);
+                    bulk_g2s(Ring + (size_t)s * CHUNK_BYTES, p.Wtc + ((size_t)(mt0 + mt) * NKC + kc) * CHUNK_BYTES, CHUNK_BYTES, full + s);
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
         }
@@ -220,17 +222,22 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc3_kernel(tc3_args p)
                     mbar_wait(full + s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint64_t ad = adesc0 + (uint64_t)((s * CHUNK_BYTES) >> 4);
-                    const uint32_t dcol = tmem_base + (uint32_t)(mt * TR);
+                    // two accumulators per channel tile: the tensor cores truncate when they accumulate, so the
+                    // large h*h products get an accumulator of their own (K/16 steps instead of 6K/16) and the five
+                    // small products (2^-8 and below) share the other one, where the same truncation is 2^-8 smaller
+                    const uint32_t dmain = tmem_base + (uint32_t)(mt * 2 * TR);
+                    const uint32_t dsmall = dmain + (uint32_t)TR;
 #pragma unroll
                     for (int ks = 0; ks < KC / 16; ++ks) {
                         const uint64_t off = (uint64_t)((2 * ks * KB_BYTES) >> 4);
-                        // plane products, small terms first: h*l, l*h, m*m, h*m, m*h, h*h  (A = weights, B = activations)
-                        umma_bf16(dcol, ad + off, bd + off + P2, idesc, (kc == 0 && ks == 0) ? 0u : 1u);
-                        umma_bf16(dcol, ad + off + P2, bd + off, idesc, 1u);
-                        umma_bf16(dcol, ad + off + P1, bd + off + P1, idesc, 1u);
-                        umma_bf16(dcol, ad + off, bd + off + P1, idesc, 1u);
-                        umma_bf16(dcol, ad + off + P1, bd + off, idesc, 1u);
-                        umma_bf16(dcol, ad + off, bd + off, idesc, 1u);
+                        const uint32_t first = (kc == 0 && ks == 0) ? 0u : 1u;
+                        // (A = weights, B = activations) small terms: h*l, l*h, m*m, h*m, m*h
+                        umma_bf16(dsmall, ad + off, bd + off + P2, idesc, first);
+                        umma_bf16(dsmall, ad + off + P2, bd + off, idesc, 1u);
+                        umma_bf16(dsmall, ad + off + P1, bd + off + P1, idesc, 1u);
+                        umma_bf16(dsmall, ad + off, bd + off + P1, idesc, 1u);
+                        umma_bf16(dsmall, ad + off + P1, bd + off, idesc, 1u);
+                        umma_bf16(dmain, ad + off, bd + off, idesc, first);
                     }
                     umma_commit(empty + s);
                     if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -274,16 +281,19 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc3_kernel(tc3_args p)
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const int q4 = warp & 3, half = warp >> 2;
         for (int mt = 0; mt < MT; ++mt) {
-            const int c = mt * TCH + q4 * 32 + lane;
+            const int c = (mt0 + mt) * TCH + q4 * 32 + lane;
             const bool cok = c < p.N;
             const float cs = (cok && p.colscale) ? p.colscale[c] : 1.0f;
             const float bi = (cok && p.bias) ? p.bias[c] : 0.0f;
             const float a1 = (cok && p.bn_a) ? p.bn_a[c] : 1.0f, c1 = (cok && p.bn_a) ? p.bn_c[c] : 0.0f;
-            const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * TR + half * 64);
+            const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(mt * 2 * TR + half * 64);
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
-                float d[32];
+                float d[32], ds[32];
                 tmem_ld32(trow + (uint32_t)(part * 32), d);
+                tmem_ld32(trow + (uint32_t)(TR + part * 32), ds);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) d[j] += ds[j];
                 const long rb = r0 + half * 64 + part * 32;
                 if (!cok) continue;
                 float* op = p.C + rb * p.ldc + c;
@@ -309,7 +319,9 @@ bool tc3_plan(const svnet_gemm_params* p, int* MT, int* NKC, size_t* wbytes, siz
     const char* on = getenv("SVNET_LINEAR_TC");
     if (on && on[0] == '0') return false;
     if (p->G != 1 || p->sign_w || p->vbn || p->gate) return false;
-    if (p->M < 2048 || p->K < 32 || p->N < 32 || p->N > MT_MAX * TCH) return false;
+    // The choice must not depend on the number of rows: this path rounds differently from the CUDA-core chain,
+    // and a cloud's result has to be the same bits whatever batch (or batch shard) it is part of.
+    if (p->M < 1 || p->K < 32 || p->K > 4096 || p->N < 32 || p->N > MT_MAX * TCH) return false;
     *NKC = (p->K + KC - 1) / KC;
     *MT = (p->N + TCH - 1) / TCH;
     *wbytes = (size_t)*MT * *NKC * CHUNK_BYTES;
@@ -338,12 +350,16 @@ int svnet_linear_tc3_dispatch(const svnet_gemm_params* p, void* workspace, size_
                                                                                   static_cast<unsigned char*>(workspace));
     SV_CHECK_LAUNCH("svnet_linear_rows(pack)");
     tc3_args a;
-    a.A = p->A; a.lda = p->lda_g; a.rows = p->M; a.K = p->K; a.N = p->N; a.MT = MT; a.NKC = NKC;
+    // two accumulators per channel tile -> at most two tiles per CTA (512 tensor-memory columns); with few row
+    // tiles one channel tile per CTA so that more SMs take part (the activations are staged per CTA)
+    const int row_tiles = sv_cdiv(p->M, TR);
+    const int mt_per_cta = row_tiles >= 64 ? (MT < 2 ? MT : 2) : 1;
+    a.A = p->A; a.lda = p->lda_g; a.rows = p->M; a.K = p->K; a.N = p->N; a.MT = mt_per_cta; a.NKC = NKC;
     a.Wtc = static_cast<const unsigned char*>(workspace);
     a.colscale = p->colscale; a.bias = p->bias; a.bn_a = p->bn_a; a.bn_c = p->bn_c; a.act = p->act;
     a.C = p->C; a.ldc = p->ldc_g;
     SV_CUDA(cudaFuncSetAttribute(gemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc3_kernel<<<sv_cdiv(p->M, TR), NTH, smem, st>>>(a);
+    gemm_tc3_kernel<<<dim3(row_tiles, sv_cdiv(MT, mt_per_cta)), NTH, smem, st>>>(a);
     SV_CHECK_LAUNCH("svnet_linear_rows(tcgen05 x3)");
     return 1;
 }

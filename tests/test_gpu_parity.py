@@ -277,7 +277,8 @@ def test_binlinear_pool_equals_linear_then_pool():
     assert nv.binlinear_pool_workspace(rows, K, Cout, 1000) == 0        # rows_per_cloud % 128 != 0: not covered
 
 
-@pytest.mark.parametrize("rows,K,N", [(3000, 505, 512), (2048, 62, 64), (5000, 300, 100), (4096, 32, 40)])
+@pytest.mark.parametrize("rows,K,N", [(3000, 505, 512), (2048, 62, 64), (5000, 300, 100), (4096, 32, 40), (2100, 640, 130),
+                                      (32, 2044, 512), (200, 1022, 300)])
 def test_linear_three_plane_tensor_core_matches_cuda_core(rows, K, N, monkeypatch):
     """csrc/gemm_tc3.cu (fp32 linear as six bf16 plane products on tcgen05) against the CUDA-core GEMM with the
     oracle's sequential chain: fp32-level agreement (the summation order differs), all epilogue options."""
