@@ -163,3 +163,60 @@ def test_checkpoint_helpers(tmp_path):
     R = random_rotations(5, generator=torch.Generator().manual_seed(1))
     eye = torch.eye(3).expand(5, 3, 3)
     assert torch.allclose(R @ R.transpose(1, 2), eye, atol=1e-5) and torch.allclose(torch.linalg.det(R), torch.ones(5), atol=1e-5)
+
+
+def test_dataset_readers_without_h5py(tmp_path):
+    """the npz readers return what the reference's HDF5 readers return (data.py:71-115,
+    186-201, 260-300, 302-340) -- same globbing of shards, dtypes, item tuples and partition behaviour."""
+    from svnet_b200 import data as D
+    rng = np.random.default_rng(7)
+    mn = tmp_path / "modelnet40_ply_hdf5_2048"
+    mn.mkdir()
+    shards = []
+    for i in range(2):
+        pts, lab = rng.standard_normal((5, 2048, 3)).astype("float64"), rng.integers(0, 40, (5, 1)).astype("uint8")
+        np.savez(mn / f"ply_data_test{i}.npz", data=pts, label=lab)
+        shards.append((pts, lab))
+    np.savez(mn / "ply_data_train0.npz", data=shards[0][0][:2], label=shards[0][1][:2])
+    ds = D.ModelNet40(num_points=1024, data_dir=str(tmp_path), partition="test")
+    assert len(ds) == 10 and ds.data.dtype == np.float32 and ds.label.dtype == np.int64
+    cloud, label = ds[7]
+    assert cloud.shape == (1024, 3) and np.array_equal(cloud, shards[1][0][2, :1024].astype("float32")) and label[0] == shards[1][1][2, 0]
+    # train items: the reference's draw order (scale, shift, then an in-place shuffle of the points)
+    tr = D.ModelNet40(num_points=64, data_dir=str(tmp_path), partition="train")
+    np.random.seed(3)
+    got, _ = tr[1]
+    np.random.seed(3)
+    want = D.translate_pointcloud(tr.data[1][:64])
+    np.random.shuffle(want)
+    assert np.array_equal(got, want)
+
+    sp = tmp_path / "shapenet_part_seg_hdf5_data"
+    sp.mkdir()
+    for name, n in (("ply_data_train0", 4), ("ply_data_val0", 3), ("ply_data_test0", 6)):
+        np.savez(sp / (name + ".npz"), data=rng.standard_normal((n, 2048, 3)).astype("float32"),
+                 label=(np.arange(n) % 3).reshape(n, 1).astype("uint8"), pid=rng.integers(0, 50, (n, 2048)).astype("uint8"))
+    te = D.ShapeNetPart(num_points=2048, data_dir=str(tmp_path), partition="test")
+    assert len(te) == 6 and te.seg_num_all == 50 and te.seg_start_index == 0
+    pts, lab, seg = te[0]
+    assert pts.shape == (2048, 3) and seg.shape == (2048,) and seg.dtype == np.int64 and lab.shape == (1,)
+    tv = D.ShapeNetPart(num_points=256, data_dir=str(tmp_path), partition="trainval")
+    assert len(tv) == 7
+    pts, _, seg = tv[2]                                # shuffled, but every point keeps its part id
+    base = {tuple(p): s for p, s in zip(tv.data[2][:256], tv.seg[2][:256])}
+    assert all(base[tuple(p)] == s for p, s in zip(pts, seg))
+    bag = D.ShapeNetPart(num_points=2048, data_dir=str(tmp_path), partition="test", class_choice="bag")
+    assert len(bag) == 2 and bag.seg_num_all == 2 and bag.seg_start_index == 4 and (bag.label == 1).all()
+
+    so = tmp_path / "h5_files" / "main_split"
+    so.mkdir(parents=True)
+    np.savez(so / "test_objectdataset.npz", data=rng.standard_normal((3, 2048, 3)).astype("float32"), label=np.arange(3))
+    sc = D.ScanObjectNNCls(num_points=1024, data_dir=str(tmp_path), partition="test")
+    pts, lab = sc[1]
+    assert pts.shape == (1024, 3) and lab == 1 and {tuple(p) for p in pts} <= {tuple(p) for p in sc.points[1]}
+    with pytest.raises(ValueError):
+        D.ScanObjectNNCls(num_points=1024, data_dir=str(tmp_path), partition="val")
+    with pytest.raises(FileNotFoundError):
+        D.ModelNet40(num_points=1024, data_dir=str(tmp_path / "nowhere"), partition="test")
+    unit = D.pc_normalize(shards[0][0][0])
+    assert abs(np.linalg.norm(unit, axis=1).max() - 1.0) < 1e-12 and np.abs(unit.mean(0)).max() < 1e-12
