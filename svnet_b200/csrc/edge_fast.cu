@@ -297,10 +297,12 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
             for (int t = 0; t < S::TS; ++t)
                 cmis[oo] += __popc((cpos[t] ^ W1b[(S::TS + t) * COUT + lane + 32 * (ob + oo)]) & cnz[t]);
         }
-        for (int eb = 0; eb < k; eb += EB) {
-            int acc[EB][S::OPP];
+        // PEB edges per accumulation round: 20 accumulators stay in registers (40 spilled inside the loop)
+        constexpr int PEB = (S::OPP == 2) ? EB / 2 : EB;
+        for (int eb = 0; eb < k; eb += PEB) {
+            int acc[PEB][S::OPP];
 #pragma unroll
-            for (int e = 0; e < EB; ++e)
+            for (int e = 0; e < PEB; ++e)
 #pragma unroll
                 for (int oo = 0; oo < S::OPP; ++oo) acc[e][oo] = 0;
 #pragma unroll
@@ -309,21 +311,29 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
                 uint32_t wv[S::OPP];
 #pragma unroll
                 for (int oo = 0; oo < S::OPP; ++oo) wv[oo] = W1b[wd * COUT + lane + 32 * (ob + oo)];
-                const uint4* Ap = reinterpret_cast<const uint4*>(A + wd * kp + eb);
-                const uint4* Mp = reinterpret_cast<const uint4*>(M + wd * kp + eb);
+                constexpr int VW = (PEB % 4 == 0) ? 4 : 2;       // 16-byte loads when the round allows (kp % 4 == 0)
+                const uint32_t* Ap = A + wd * kp + eb;
+                const uint32_t* Mp = M + wd * kp + eb;
 #pragma unroll
-                for (int e4 = 0; e4 < EB / 4; ++e4) {
-                    const uint4 a4 = Ap[e4], m4 = Mp[e4];
-                    const uint32_t av[4] = {a4.x, a4.y, a4.z, a4.w};
-                    const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
+                for (int ev = 0; ev < PEB / VW; ++ev) {
+                    uint32_t av[VW], mv[VW];
+                    if constexpr (VW == 4) {
+                        const uint4 a4 = reinterpret_cast<const uint4*>(Ap)[ev], m4 = reinterpret_cast<const uint4*>(Mp)[ev];
+                        av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+                        mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
+                    } else {
+                        const uint2 a2 = reinterpret_cast<const uint2*>(Ap)[ev], m2 = reinterpret_cast<const uint2*>(Mp)[ev];
+                        av[0] = a2.x; av[1] = a2.y;
+                        mv[0] = m2.x; mv[1] = m2.y;
+                    }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                    for (int u = 0; u < VW; ++u)
 #pragma unroll
-                        for (int oo = 0; oo < S::OPP; ++oo) acc[e4 * 4 + u][oo] += __popc((av[u] ^ wv[oo]) & mv[u]);
+                        for (int oo = 0; oo < S::OPP; ++oo) acc[ev * VW + u][oo] += __popc((av[u] ^ wv[oo]) & mv[u]);
                 }
             }
 #pragma unroll
-            for (int e = 0; e < EB; ++e) {
+            for (int e = 0; e < PEB; ++e) {
                 if (eb + e < k) {
                     const int nv = nvalid[eb + e];
 #pragma unroll

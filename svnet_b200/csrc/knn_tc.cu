@@ -860,6 +860,10 @@ static bool knn_tc_plan(const svnet_view* in, int B, int N, int k, knn_tc_plan_t
     pl->NCB = sv_cdiv(N, TNB);
     pl->NKC = sv_cdiv(C, KCH);
     int s = MAX_STAGES;
+    if (const char* st = getenv("SVNET_KNN_STAGES")) {    // tuning aid: fewer ring stages leave shared memory to co-resident kernels
+        const int v = atoi(st);
+        if (v >= 2 && v <= MAX_STAGES) s = v;
+    }
     const size_t limit = 227 * 1024;
     while (s > 2 && knn_tc_smem(pl->NCB, pl->NKC, s) > limit) --s;
     if (knn_tc_smem(pl->NCB, pl->NKC, s) > limit) return false;
