@@ -190,6 +190,12 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
 #pragma unroll
             for (int t = 0; t < S::TS; ++t) sv[e][t] = __ldg(sj + 32 * t);
         }
+        // the ballot words are warp-uniform: lane e keeps those of edge eb + e and stores them once
+        // (a lane-0 store per word costs an address and a predicated store each)
+        unsigned mp[S::TS], mn[S::TS];
+        int mnv = 0;
+#pragma unroll
+        for (int t = 0; t < S::TS; ++t) mp[t] = mn[t] = 0u;
 #pragma unroll
         for (int e = 0; e < EB; ++e) {
             if (eb + e < k) {
@@ -200,10 +206,15 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
                     const unsigned pos = __ballot_sync(SV_FULL, u > 0.0f);
                     const unsigned nz = __ballot_sync(SV_FULL, u != 0.0f);
                     nv += __popc(nz);
-                    if (lane == 0) { A[t * kp + eb + e] = pos; M[t * kp + eb + e] = nz; }
+                    if (lane == e) { mp[t] = pos; mn[t] = nz; }
                 }
-                if (lane == 0) nvalid[eb + e] = nv;
+                if (lane == e) mnv = nv;
             }
+        }
+        if (lane < EB && eb + lane < k) {
+#pragma unroll
+            for (int t = 0; t < S::TS; ++t) { A[t * kp + eb + lane] = mp[t]; M[t * kp + eb + lane] = mn[t]; }
+            nvalid[eb + lane] = mnv;
         }
     }
     cp_async_wait_all();
@@ -248,23 +259,36 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
 #pragma unroll
         for (int t = 0; t < S::QW; ++t) qsrc[t] = wbase + qoff[t];
         const float* z = zb;
-#pragma unroll 2
-        for (int e = 0; e < k; ++e, z += 9) {
-            int nv = 0;
+        for (int e0 = 0; e0 < k; e0 += 32) {        // lane e - e0 keeps the words of edge e (see P1)
+            const int en = min(32, k - e0);
+            unsigned mp[S::QW], mn[S::QW];
+            int mnv = 0;
 #pragma unroll
-            for (int t = 0; t < S::QW; ++t) {
-                const float* src = qsrc[t];
-                qsrc[t] += qstr[t];
-                float q = __fmul_rn(src[0], z[zoff[t]]);
-                q = __fmaf_rn(src[S::XS], z[3 + zoff[t]], q);
-                q = __fmaf_rn(src[2 * S::XS], z[6 + zoff[t]], q);
-                const float u = qok[t] ? __fadd_rn(q, beta[2 * S::TS + t]) : 0.0f;
-                const unsigned pos = __ballot_sync(SV_FULL, u > 0.0f);
-                const unsigned nz = __ballot_sync(SV_FULL, u != 0.0f);
-                nv += __popc(nz);
-                if (lane == 0) { A[(2 * S::TS + t) * kp + e] = pos; M[(2 * S::TS + t) * kp + e] = nz; }
+            for (int t = 0; t < S::QW; ++t) mp[t] = mn[t] = 0u;
+#pragma unroll 2
+            for (int el = 0; el < en; ++el, z += 9) {
+                const bool me = lane == el;
+                int nv = 0;
+#pragma unroll
+                for (int t = 0; t < S::QW; ++t) {
+                    const float* src = qsrc[t];
+                    qsrc[t] += qstr[t];
+                    float q = __fmul_rn(src[0], z[zoff[t]]);
+                    q = __fmaf_rn(src[S::XS], z[3 + zoff[t]], q);
+                    q = __fmaf_rn(src[2 * S::XS], z[6 + zoff[t]], q);
+                    const float u = qok[t] ? __fadd_rn(q, beta[2 * S::TS + t]) : 0.0f;
+                    const unsigned pos = __ballot_sync(SV_FULL, u > 0.0f);
+                    const unsigned nz = __ballot_sync(SV_FULL, u != 0.0f);
+                    nv += __popc(nz);
+                    if (me) { mp[t] = pos; mn[t] = nz; }
+                }
+                if (me) mnv = nv;
             }
-            if (lane == 0) nvalid[e] += nv;
+            if (lane < en) {
+#pragma unroll
+                for (int t = 0; t < S::QW; ++t) { A[(2 * S::TS + t) * kp + e0 + lane] = mp[t]; M[(2 * S::TS + t) * kp + e0 + lane] = mn[t]; }
+                nvalid[e0 + lane] += mnv;
+            }
         }
     }
     __syncwarp();
