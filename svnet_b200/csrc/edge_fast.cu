@@ -29,6 +29,10 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
 }
+__device__ __forceinline__ void cp_async4_s(unsigned smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc));
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 template <int CS, int CV, int COUT, int CVO>
@@ -72,12 +76,13 @@ __device__ __forceinline__ void vector_branch(const svnet_edge_params& p, long r
         float sum[3] = {0.0f, 0.0f, 0.0f};
         if (active) {
             const float* pi = p.PQ + r * 3 * LDP + c;
+            const float* pq0 = p.PQ + cbase * 3 * LDP + c;      // row offsets inside a cloud fit 32 bits (launch guard)
             const float d_i[3] = {__ldg(pi + CVO) - __ldg(pi), __ldg(pi + LDP + CVO) - __ldg(pi + LDP),
                                   __ldg(pi + 2 * LDP + CVO) - __ldg(pi + 2 * LDP)};      // Q_i - P_i
             const float a2 = __ldg(p.bn2_a + c), c2 = __ldg(p.bn2_c + c);
 #pragma unroll 4
             for (int e = g; e < k; e += ng) {
-                const float* pj = p.PQ + (cbase + nidx[e]) * 3 * LDP + c;
+                const float* pj = pq0 + (unsigned)nidx[e] * (unsigned)(3 * LDP);
                 const float w0 = __ldg(pj) + d_i[0], w1 = __ldg(pj + LDP) + d_i[1], w2 = __ldg(pj + 2 * LDP) + d_i[2];
                 const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0 * w0));
                 const float n = (s2 > 0.0f ? s2 * rsqrtf(s2) : 0.0f) + 1e-6f;
@@ -128,10 +133,13 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
     float* vc = wbase + ((2 * S::KW * kp + 2 * kp + 3) & ~3);     // [3][XS] centre vectors
     float* ves = vc + 3 * S::XS;                                  // [kp][3][XS] neighbour - centre
     float* zb = ves + kp * S::ES;                                 // [kp][9]
-    __syncthreads();
-
+    // the CTA-wide barrier for the staged weights comes after P0/P1 (which do not read them), so the
+    // staging latency hides behind the gathers; warps past the end wait there and leave
     const long r = (long)blockIdx.x * WARPS + warp;
-    if (r >= (long)p.B * p.N) return;
+    if (r >= (long)p.B * p.N) {
+        __syncthreads();
+        return;
+    }
     const int b = (int)(r / p.N);
     const long cbase = (long)b * p.N;
     const int k = p.k;
@@ -176,17 +184,30 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
     // ---- P1: gather all k neighbour rows: vectors by cp.async straight into shared memory, scalars
     //      into registers (EB rows in flight); one latency exposure for both.  Then S1 sign words by
     //      ballot and the vector differences in place ----
-    for (int e = 0; e < k; ++e) {
-        const float* vj = p.in.v + (cbase + nidx[e]) * p.in.ldv;
+    {
+        unsigned sdst[S::TV];
+        const float* vsrc[S::TV];
 #pragma unroll
-        for (int t = 0; t < S::TV; ++t)
-            if (voff[t] >= 0) cp_async4(ves + e * S::ES + vso[t], vj + voff[t]);
+        for (int t = 0; t < S::TV; ++t) {
+            sdst[t] = (unsigned)__cvta_generic_to_shared(ves + vso[t]);
+            vsrc[t] = p.in.v + cbase * p.in.ldv + (voff[t] >= 0 ? voff[t] : 0);
+        }
+        const unsigned ldv = (unsigned)p.in.ldv;
+#pragma unroll 4
+        for (int e = 0; e < k; ++e) {
+            const unsigned off = (unsigned)nidx[e] * ldv;       // < 2^31 (launch guard)
+#pragma unroll
+            for (int t = 0; t < S::TV; ++t)
+                if (voff[t] >= 0) cp_async4_s(sdst[t] + (unsigned)(e * S::ES * 4), vsrc[t] + off);
+        }
     }
+    const float* sbase = p.in.s + cbase * p.in.lds + lane;
+    const unsigned lds = (unsigned)p.in.lds;
     for (int eb = 0; eb < k; eb += EB) {
         float sv[EB][S::TS];
 #pragma unroll
         for (int e = 0; e < EB; ++e) {
-            const float* sj = p.in.s + (cbase + nidx[eb + e]) * p.in.lds + lane;   // padded slots read row 0
+            const float* sj = sbase + (unsigned)nidx[eb + e] * lds;   // padded slots read row 0
 #pragma unroll
             for (int t = 0; t < S::TS; ++t) sv[e][t] = __ldg(sj + 32 * t);
         }
@@ -226,6 +247,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
     }
     __syncwarp();
 
+    __syncthreads();          // Wz / W1b staged (see the top of the kernel)
     // ---- P2: frames z[e][x][m]: one sequential chain per (edge, x, m), 32 chains per round ----
     const bool use_zscale = p.zscale != nullptr;
     for (int task = lane; task < k * 9; task += 32) {
@@ -433,11 +455,22 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_fp_fast
     __syncwarp();
 
     // ---- P1: neighbour vectors by cp.async, differences in place ----
-    for (int e = 0; e < k; ++e) {
-        const float* vj = p.in.v + (cbase + nidx[e]) * p.in.ldv;
+    {
+        unsigned sdst[S::TV];
+        const float* vsrc[S::TV];
 #pragma unroll
-        for (int t = 0; t < S::TV; ++t)
-            if (voff[t] >= 0) cp_async4(ves + e * S::ES + vso[t], vj + voff[t]);
+        for (int t = 0; t < S::TV; ++t) {
+            sdst[t] = (unsigned)__cvta_generic_to_shared(ves + vso[t]);
+            vsrc[t] = p.in.v + cbase * p.in.ldv + (voff[t] >= 0 ? voff[t] : 0);
+        }
+        const unsigned ldv = (unsigned)p.in.ldv;
+#pragma unroll 4
+        for (int e = 0; e < k; ++e) {
+            const unsigned off = (unsigned)nidx[e] * ldv;       // < 2^31 (launch guard)
+#pragma unroll
+            for (int t = 0; t < S::TV; ++t)
+                if (voff[t] >= 0) cp_async4_s(sdst[t] + (unsigned)(e * S::ES * 4), vsrc[t] + off);
+        }
     }
     cp_async_wait_all();
     __syncwarp();
@@ -509,7 +542,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_fp_fast
             float acc[EB][S::OPP];
 #pragma unroll
             for (int e = 0; e < EB; ++e) {
-                const float* yj = p.Yab + (cbase + nidx[eb + e]) * 2 * COUT + lane + 32 * ob;
+                const float* yj = p.Yab + cbase * 2 * COUT + (unsigned)nidx[eb + e] * (unsigned)(2 * COUT) + lane + 32 * ob;
 #pragma unroll
                 for (int oo = 0; oo < S::OPP; ++oo) acc[e][oo] = __ldg(yj + 32 * oo) + yi[oo];
             }
@@ -608,6 +641,9 @@ int svnet_edge_fast_dispatch(const svnet_edge_params* p, cudaStream_t st)
 {
     const int cs = p->in.Cs, cv = p->in.Cv, co = p->Cout, cvo = p->Cvo;
     int rc = 1;
+    // the specialised kernels address rows inside a cloud with 32-bit element offsets
+    const long widest = p->in.ldv > p->in.lds ? p->in.ldv : p->in.lds;
+    if ((long)p->N * (widest > 6l * cvo ? widest : 6l * cvo) >= (1l << 31) || (long)p->N * 2 * co >= (1l << 31)) return 0;
     if (!p->binary) {
 #define FCASE(A, Bv, C, D) if (cs == A && cv == Bv && co == C && cvo == D) { rc = launch_fp_fast<A, Bv, C, D>(p, st); return rc == SVNET_OK ? 1 : rc; }
         FCASE(32, 10, 32, 10)
