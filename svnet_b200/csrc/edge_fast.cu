@@ -24,17 +24,6 @@
 
 namespace {
 
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async4_s(unsigned smem_dst, const void* gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
 template <int CS, int CV, int COUT, int CVO>
 struct Shape {
     static constexpr int CVE = 2 * CV;
@@ -181,35 +170,26 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
     for (int i = lane; i < S::KW * kp; i += 32) { A[i] = 0u; M[i] = 0u; }
     __syncwarp();
 
-    // ---- P1: gather all k neighbour rows: vectors by cp.async straight into shared memory, scalars
-    //      into registers (EB rows in flight); one latency exposure for both.  Then S1 sign words by
-    //      ballot and the vector differences in place ----
-    {
-        unsigned sdst[S::TV];
-        const float* vsrc[S::TV];
-#pragma unroll
-        for (int t = 0; t < S::TV; ++t) {
-            sdst[t] = (unsigned)__cvta_generic_to_shared(ves + vso[t]);
-            vsrc[t] = p.in.v + cbase * p.in.ldv + (voff[t] >= 0 ? voff[t] : 0);
-        }
-        const unsigned ldv = (unsigned)p.in.ldv;
-#pragma unroll 4
-        for (int e = 0; e < k; ++e) {
-            const unsigned off = (unsigned)nidx[e] * ldv;       // < 2^31 (launch guard)
-#pragma unroll
-            for (int t = 0; t < S::TV; ++t)
-                if (voff[t] >= 0) cp_async4_s(sdst[t] + (unsigned)(e * S::ES * 4), vsrc[t] + off);
-        }
-    }
+    // ---- P1: gather the neighbour rows into registers, PB rows in flight per round (scalars and vectors
+    //      of a round share one latency exposure); S1 sign words by ballot, vector differences to
+    //      shared memory.  (cp.async costs four issue slots apiece here -- ptxas pads every LDGSTS
+    //      with three dummy LDS -- plus a second pass for the subtraction.) ----
+    constexpr int PB = (S::TV + S::TS <= 2) ? EB : EB / 2;
     const float* sbase = p.in.s + cbase * p.in.lds + lane;
-    const unsigned lds = (unsigned)p.in.lds;
-    for (int eb = 0; eb < k; eb += EB) {
-        float sv[EB][S::TS];
+    const unsigned lds = (unsigned)p.in.lds, ldv = (unsigned)p.in.ldv;   // row offsets inside a cloud fit 32 bits (launch guard)
+    const float* vsrc[S::TV];
 #pragma unroll
-        for (int e = 0; e < EB; ++e) {
-            const float* sj = sbase + (unsigned)nidx[eb + e] * lds;   // padded slots read row 0
+    for (int t = 0; t < S::TV; ++t) vsrc[t] = p.in.v + cbase * p.in.ldv + (voff[t] >= 0 ? voff[t] : 0);
+    for (int eb = 0; eb < k; eb += PB) {
+        float sv[PB][S::TS], vv[PB][S::TV];
+#pragma unroll
+        for (int e = 0; e < PB; ++e) {
+            const unsigned j = (unsigned)nidx[eb + e];            // padded slots read row 0
+            const float* sj = sbase + j * lds;
 #pragma unroll
             for (int t = 0; t < S::TS; ++t) sv[e][t] = __ldg(sj + 32 * t);
+#pragma unroll
+            for (int t = 0; t < S::TV; ++t) vv[e][t] = __ldg(vsrc[t] + j * ldv);
         }
         // the ballot words are warp-uniform: lane e keeps those of edge eb + e and stores them once
         // (a lane-0 store per word costs an address and a predicated store each)
@@ -218,7 +198,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
 #pragma unroll
         for (int t = 0; t < S::TS; ++t) mp[t] = mn[t] = 0u;
 #pragma unroll
-        for (int e = 0; e < EB; ++e) {
+        for (int e = 0; e < PB; ++e) {
             if (eb + e < k) {
                 int nv = ncen;
 #pragma unroll
@@ -230,20 +210,16 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
                     if (lane == e) { mp[t] = pos; mn[t] = nz; }
                 }
                 if (lane == e) mnv = nv;
+#pragma unroll
+                for (int t = 0; t < S::TV; ++t)
+                    if (voff[t] >= 0) ves[(eb + e) * S::ES + vso[t]] = __fsub_rn(vv[e][t], vi[t]);
             }
         }
-        if (lane < EB && eb + lane < k) {
+        if (lane < PB && eb + lane < k) {
 #pragma unroll
             for (int t = 0; t < S::TS; ++t) { A[t * kp + eb + lane] = mp[t]; M[t * kp + eb + lane] = mn[t]; }
             nvalid[eb + lane] = mnv;
         }
-    }
-    cp_async_wait_all();
-    __syncwarp();
-    for (int e = 0; e < k; ++e) {
-#pragma unroll
-        for (int t = 0; t < S::TV; ++t)
-            if (voff[t] >= 0) ves[e * S::ES + vso[t]] = __fsub_rn(ves[e * S::ES + vso[t]], vi[t]);
     }
     __syncwarp();
 
@@ -454,30 +430,29 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_fp_fast
     for (int i = lane; i < KQ * kp; i += 32) qs[i] = 0.0f;   // padded edge slots stay zero
     __syncwarp();
 
-    // ---- P1: neighbour vectors by cp.async, differences in place ----
+    // ---- P1: neighbour vectors through registers (EB rows in flight), differences to shared memory ----
     {
-        unsigned sdst[S::TV];
+        const unsigned ldv = (unsigned)p.in.ldv;                 // row offsets inside a cloud fit 32 bits (launch guard)
         const float* vsrc[S::TV];
 #pragma unroll
-        for (int t = 0; t < S::TV; ++t) {
-            sdst[t] = (unsigned)__cvta_generic_to_shared(ves + vso[t]);
-            vsrc[t] = p.in.v + cbase * p.in.ldv + (voff[t] >= 0 ? voff[t] : 0);
-        }
-        const unsigned ldv = (unsigned)p.in.ldv;
-#pragma unroll 4
-        for (int e = 0; e < k; ++e) {
-            const unsigned off = (unsigned)nidx[e] * ldv;       // < 2^31 (launch guard)
+        for (int t = 0; t < S::TV; ++t) vsrc[t] = p.in.v + cbase * p.in.ldv + (voff[t] >= 0 ? voff[t] : 0);
+        for (int eb = 0; eb < k; eb += EB) {
+            float vv[EB][S::TV];
 #pragma unroll
-            for (int t = 0; t < S::TV; ++t)
-                if (voff[t] >= 0) cp_async4_s(sdst[t] + (unsigned)(e * S::ES * 4), vsrc[t] + off);
-        }
-    }
-    cp_async_wait_all();
-    __syncwarp();
-    for (int e = 0; e < k; ++e) {
+            for (int e = 0; e < EB; ++e) {
+                const unsigned j = (unsigned)nidx[eb + e];        // padded slots read row 0
 #pragma unroll
-        for (int t = 0; t < S::TV; ++t)
-            if (voff[t] >= 0) ves[e * S::ES + vso[t]] = __fsub_rn(ves[e * S::ES + vso[t]], vi[t]);
+                for (int t = 0; t < S::TV; ++t) vv[e][t] = __ldg(vsrc[t] + j * ldv);
+            }
+#pragma unroll
+            for (int e = 0; e < EB; ++e) {
+                if (eb + e < k) {
+#pragma unroll
+                    for (int t = 0; t < S::TV; ++t)
+                        if (voff[t] >= 0) ves[(eb + e) * S::ES + vso[t]] = __fsub_rn(vv[e][t], vi[t]);
+                }
+            }
+        }
     }
     __syncwarp();
 
