@@ -47,6 +47,19 @@ struct Shape {
 // e = g, g+G, ...; partial sums meet by shuffle), so CVO = 10 keeps 30 lanes busy instead of 10.
 // Tolerance-level arithmetic (norms and mean pools are not bit-pinned): rsqrt /
 // fast division instead of the IEEE sequences.
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int CVO>
 __device__ __forceinline__ void vector_branch(const svnet_edge_params& p, long r, int b, long cbase, const int* nidx, int k, int lane)
 {
@@ -74,8 +87,7 @@ __device__ __forceinline__ void vector_branch(const svnet_edge_params& p, long r
                 const float* pj = pq0 + (unsigned)nidx[e] * (unsigned)(3 * LDP);
                 const float w0 = __ldg(pj) + d_i[0], w1 = __ldg(pj + LDP) + d_i[1], w2 = __ldg(pj + 2 * LDP) + d_i[2];
                 const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0 * w0));
-                const float n = (s2 > 0.0f ? s2 * rsqrtf(s2) : 0.0f) + 1e-6f;
-                const float t = a2 + __fdividef(c2, n);          // (n a2 + c2) / n
+                const float t = fmaf(c2, fast_rcp(fast_sqrt(s2) + 1e-6f), a2);      // (n a2 + c2) / n,  n = |w| + 1e-6
                 sum[0] = fmaf(w0, t, sum[0]);
                 sum[1] = fmaf(w1, t, sum[1]);
                 sum[2] = fmaf(w2, t, sum[2]);
@@ -113,15 +125,15 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
     for (int i = threadIdx.x; i < 3 * S::CVE; i += blockDim.x) Wz[i] = p.Wz[i];
     for (int i = threadIdx.x; i < S::KW * COUT; i += blockDim.x) W1b[i] = p.W1b[i];
     // ---- per warp ----
-    const int per_warp = ((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3;
+    const int per_warp = ((2 * S::KW * kp + 2 * kp + 3) & ~3) + kp * 12 + 3 * S::XS + kp * S::ES;
     float* wbase = smem_raw + ((SHARED + 3) & ~3) + (size_t)warp * ((per_warp + 3) & ~3);
     uint32_t* A = reinterpret_cast<uint32_t*>(wbase);            // [KW][kp]   (16B aligned rows: kp % 4 == 0)
     uint32_t* M = A + S::KW * kp;                                 // [KW][kp]
     int* nvalid = reinterpret_cast<int*>(M + S::KW * kp);         // [kp]
     int* nidx = nvalid + kp;                                      // [kp]
-    float* vc = wbase + ((2 * S::KW * kp + 2 * kp + 3) & ~3);     // [3][XS] centre vectors
+    float* zb = wbase + ((2 * S::KW * kp + 2 * kp + 3) & ~3);     // [kp][3 m][4]: frame columns, 16-byte aligned
+    float* vc = zb + kp * 12;                                     // [3][XS] centre vectors
     float* ves = vc + 3 * S::XS;                                  // [kp][3][XS] neighbour - centre
-    float* zb = ves + kp * S::ES;                                 // [kp][9]
     // the CTA-wide barrier for the staged weights comes after P0/P1 (which do not read them), so the
     // staging latency hides behind the gathers; warps past the end wait there and leave
     const long r = (long)blockIdx.x * WARPS + warp;
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
 #pragma unroll
         for (int d = 0; d < CV; ++d) acc = __fmaf_rn(cv[d], wz[CV + d], acc);
         if (use_zscale) acc = __fmul_rn(acc, __ldg(p.zscale + m));
-        zb[task] = acc;
+        zb[e * 12 + m * 4 + x] = acc;
     }
     __syncwarp();
 
@@ -249,7 +261,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
         for (int t = 0; t < S::QW; ++t) {
             const int tq = 32 * t + lane, d = tq / 3, m = tq - d * 3;
             qok[t] = tq < 6 * CV;
-            zoff[t] = m;
+            zoff[t] = 4 * m;
             if (d < CV) { qoff[t] = (int)(ves - wbase) + d; qstr[t] = S::ES; }
             else { qoff[t] = (int)(vc - wbase) + (qok[t] ? d - CV : 0); qstr[t] = 0; }
         }
@@ -264,16 +276,17 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
 #pragma unroll
             for (int t = 0; t < S::QW; ++t) mp[t] = mn[t] = 0u;
 #pragma unroll 2
-            for (int el = 0; el < en; ++el, z += 9) {
+            for (int el = 0; el < en; ++el, z += 12) {
                 const bool me = lane == el;
                 int nv = 0;
 #pragma unroll
                 for (int t = 0; t < S::QW; ++t) {
                     const float* src = qsrc[t];
                     qsrc[t] += qstr[t];
-                    float q = __fmul_rn(src[0], z[zoff[t]]);
-                    q = __fmaf_rn(src[S::XS], z[3 + zoff[t]], q);
-                    q = __fmaf_rn(src[2 * S::XS], z[6 + zoff[t]], q);
+                    const float4 zz = *reinterpret_cast<const float4*>(z + zoff[t]);     // column m of the frame
+                    float q = __fmul_rn(src[0], zz.x);
+                    q = __fmaf_rn(src[S::XS], zz.y, q);
+                    q = __fmaf_rn(src[2 * S::XS], zz.z, q);
                     const float u = qok[t] ? __fadd_rn(q, beta[2 * S::TS + t]) : 0.0f;
                     const unsigned pos = __ballot_sync(SV_FULL, u > 0.0f);
                     const unsigned nz = __ballot_sync(SV_FULL, u != 0.0f);
@@ -360,7 +373,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
                     const int nv = nvalid[eb + e];
 #pragma unroll
                     for (int oo = 0; oo < S::OPP; ++oo) {
-                        const int dot = nv - 2 * (acc[e][oo] + cmis[oo]);
+                        const int dot = nv - 2 * acc[e][oo];          // the centre words' share comes off after the loop
                         dmax[oo] = max(dmax[oo], dot);
                         dmin[oo] = min(dmin[oo], dot);
                     }
@@ -371,8 +384,8 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
         for (int oo = 0; oo < S::OPP; ++oo) {
             const int o = lane + 32 * (ob + oo);
             const float sc = __ldg(p.scale1 + o), a1 = __ldg(p.bn1_a + o), c1 = __ldg(p.bn1_c + o);
-            float y0 = __fadd_rn(__fmul_rn(__fmul_rn((float)dmax[oo], sc), a1), c1);
-            float y1 = __fadd_rn(__fmul_rn(__fmul_rn((float)dmin[oo], sc), a1), c1);
+            float y0 = __fadd_rn(__fmul_rn(__fmul_rn((float)(dmax[oo] - 2 * cmis[oo]), sc), a1), c1);
+            float y1 = __fadd_rn(__fmul_rn(__fmul_rn((float)(dmin[oo] - 2 * cmis[oo]), sc), a1), c1);
             y0 = y0 > 0.0f ? y0 : __fmul_rn(0.2f, y0);
             y1 = y1 > 0.0f ? y1 : __fmul_rn(0.2f, y1);
             p.out.s[r * p.out.lds + o] = fmaxf(y0, y1);
@@ -397,13 +410,13 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_fp_fast
     float* Wz = smem_raw;                                   // [3][CVE], CTA-shared
     constexpr int SHARED = (3 * S::CVE + 3) & ~3;
     for (int i = threadIdx.x; i < 3 * S::CVE; i += blockDim.x) Wz[i] = p.Wz[i];
-    const int per_warp = (KQ * kp + 3 * S::XS + kp * S::ES + kp * 9 + 3 + kp + 3) & ~3;
+    const int per_warp = (KQ * kp + kp * 12 + 3 * S::XS + kp * S::ES + kp + 3) & ~3;
     float* wbase = smem_raw + SHARED + (size_t)warp * per_warp;
     float* qs = wbase;                                      // [KQ][kp]  (16B aligned rows: kp % 4 == 0)
-    float* vc = qs + KQ * kp;                               // [3][XS]
+    float* zb = qs + KQ * kp;                               // [kp][3 m][4]: frame columns, 16-byte aligned
+    float* vc = zb + kp * 12;                               // [3][XS]
     float* ves = vc + 3 * S::XS;                            // [kp][3][XS]
-    float* zb = ves + kp * S::ES;                           // [kp][9]
-    int* nidx = reinterpret_cast<int*>(zb + kp * 9 + 3);    // [kp]
+    int* nidx = reinterpret_cast<int*>(ves + kp * S::ES);   // [kp]
     __syncthreads();
 
     const long r = (long)blockIdx.x * WARPS + warp;
@@ -468,7 +481,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_fp_fast
 #pragma unroll
         for (int d = 0; d < CV; ++d) acc = __fmaf_rn(cv[d], wz[CV + d], acc);
         if (p.zscale) acc = __fmul_rn(acc, __ldg(p.zscale + m));
-        zb[task] = acc;
+        zb[e * 12 + m * 4 + x] = acc;
     }
     __syncwarp();
 
@@ -482,20 +495,21 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? 2 : 4) edge_fp_fast
         for (int t = 0; t < QT; ++t) {
             const int tq = 32 * t + lane, d = tq / 3, m = tq - d * 3;
             qok[t] = tq < KQ;
-            zoff[t] = m;
+            zoff[t] = 4 * m;
             if (d < CV) { qsrc[t] = ves + d; qstr[t] = S::ES; }
             else { qsrc[t] = vc + (qok[t] ? d - CV : 0); qstr[t] = 0; }
         }
         const float* z = zb;
 #pragma unroll 2
-        for (int e = 0; e < k; ++e, z += 9) {
+        for (int e = 0; e < k; ++e, z += 12) {
 #pragma unroll
             for (int t = 0; t < QT; ++t) {
                 const float* src = qsrc[t];
                 qsrc[t] += qstr[t];
-                float q = __fmul_rn(src[0], z[zoff[t]]);
-                q = __fmaf_rn(src[S::XS], z[3 + zoff[t]], q);
-                q = __fmaf_rn(src[2 * S::XS], z[6 + zoff[t]], q);
+                const float4 zz = *reinterpret_cast<const float4*>(z + zoff[t]);         // column m of the frame
+                float q = __fmul_rn(src[0], zz.x);
+                q = __fmaf_rn(src[S::XS], zz.y, q);
+                q = __fmaf_rn(src[2 * S::XS], zz.z, q);
                 if (qok[t]) qs[(32 * t + lane) * kp + e] = q;
             }
         }
@@ -567,7 +581,7 @@ int launch_fp_fast(const svnet_edge_params* p, cudaStream_t st)
     constexpr int KQ = 6 * CV;
     const int kp = ((p->k + EB - 1) / EB) * EB;
     constexpr int SHARED = (3 * S::CVE + 3) & ~3;
-    const int per_warp = (KQ * kp + 3 * S::XS + kp * S::ES + kp * 9 + 3 + kp + 3) & ~3;
+    const int per_warp = (KQ * kp + kp * 12 + 3 * S::XS + kp * S::ES + kp + 3) & ~3;
     const long P = (long)p->B * p->N;
     auto smem_for = [&](int warps) { return sizeof(float) * (size_t)(SHARED + warps * per_warp); };
     if (smem_for(8) <= 100 * 1024) {
@@ -591,7 +605,7 @@ int launch_fast(const svnet_edge_params* p, cudaStream_t st)
     constexpr int EB = S::EB;
     const int kp = ((p->k + EB - 1) / EB) * EB;
     constexpr int SHARED = 3 * S::CVE + ((3 * S::CVE) & 1) + S::KW * COUT;
-    const int per_warp = ((((2 * S::KW * kp + 2 * kp + 3) & ~3) + 3 * S::XS + kp * S::ES + kp * 9 + 3) + 3) & ~3;
+    const int per_warp = ((((2 * S::KW * kp + 2 * kp + 3) & ~3) + kp * 12 + 3 * S::XS + kp * S::ES) + 3) & ~3;
     const long P = (long)p->B * p->N;
     auto smem_for = [&](int warps) { return sizeof(float) * (size_t)(((SHARED + 3) & ~3) + warps * per_warp); };
     if (smem_for(8) <= 72 * 1024) {
