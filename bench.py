@@ -343,7 +343,10 @@ def main():
         "clocks": clocks,
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
-        "gpu_launches": launches,
+        # kernels of libsvnet_b200.so inside the timed region: K replays of the captured forward (two batch
+        # halves); the eager single-stream pass used for the per-kernel events launches `eager` per step
+        "gpu_launches": fast.kernels_per_replay * args.steps,
+        "gpu_launches_per_step": {"graph_replay": fast.kernels_per_replay, "eager_single_stream": launches},
         "roofline": roofline,
         "cpu_baseline": cpu,
     }

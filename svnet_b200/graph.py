@@ -28,9 +28,12 @@ class GraphedForward:
                 model(*self.static_in)
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        from . import _native as nv
         self.graph = torch.cuda.CUDAGraph()
+        l0 = nv.LAUNCHES[0]
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.static_out = model(*self.static_in)
+        self.kernels_per_replay = nv.LAUNCHES[0] - l0     # kernels of this library inside one replay
 
     def __call__(self, *inputs):
         if len(inputs) != len(self.static_in):
