@@ -193,7 +193,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # The step is the public inference call: svnet_b200.GraphedForward(net, example) captures the forward
-    # once (CUDA graph with the two batch halves on two streams) and replays it per batch.
+    # once (CUDA graph with the batch split into four sub-batches on four streams) and replays it per batch.
     fast = sv.GraphedForward(net, x_dev)
 
     def step(xin):
@@ -338,13 +338,13 @@ def main():
         "dtype": "f32 (+u32 XNOR/popcount for the binarised linears; exact bf16x3 tcgen05 filter in front of the fp32 kNN)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B, "n_points": N_POINTS, "k": K_NN,
                    "parallelism": "batch-sharded x%d, all-gather of logits" % world,
-                   "call": "svnet_b200.GraphedForward(net, batch): CUDA-graph replay, batch halves on two streams",
+                   "call": "svnet_b200.GraphedForward(net, batch): CUDA-graph replay, four sub-batches of 8 clouds on four streams",
                    "l2": "flushed between steps (256 MiB memset, untimed)"},
         "clocks": clocks,
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
-        # kernels of libsvnet_b200.so inside the timed region: K replays of the captured forward (two batch
-        # halves); the eager single-stream pass used for the per-kernel events launches `eager` per step
+        # kernels of libsvnet_b200.so inside the timed region: K replays of the captured forward (four
+        # sub-batches); the eager single-stream pass used for the per-kernel events launches `eager` per step
         "gpu_launches": fast.kernels_per_replay * args.steps,
         "gpu_launches_per_step": {"graph_replay": fast.kernels_per_replay, "eager_single_stream": launches},
         "roofline": roofline,

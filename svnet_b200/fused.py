@@ -11,13 +11,13 @@ from . import _native as nv
 MAX_POINTS_PER_PASS = int(os.environ.get("SVNET_MAX_POINTS", 1 << 19))
 SIDE_STREAM = os.environ.get("SVNET_SIDE_STREAM", "1") != "0"
 CONCURRENT_HALVES = os.environ.get("SVNET_TWO_STREAMS", "1") != "0"
-N_SPLIT = max(2, int(os.environ.get("SVNET_STREAMS", "2")))      # sub-batches that run concurrently
+N_SPLIT = max(2, int(os.environ.get("SVNET_STREAMS", "4")))      # sub-batches that run concurrently
 _SIDE = {}
 _IN_HALF = [False]
 
 
 def _side_stream(dev, which=0):
-    """Auxiliary CUDA streams per device: 0 = graph-independent tables, 1/2 = the two batch halves."""
+    """Auxiliary CUDA streams per device: 0 = graph-independent tables, 1.. = the concurrent sub-batches."""
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=dev)
@@ -27,9 +27,9 @@ def _side_stream(dev, which=0):
 def chunked(impl, x, extras=(), hooks=False):
     """Run ``impl(x_chunk, *extras_chunk)`` over cloud sub-batches so that the per-pass tables stay
     bounded (B*N <= MAX_POINTS_PER_PASS points; clouds are independent in eval mode).
-    A batch that fits one pass is split in two halves that run on two CUDA streams: kernels whose grids
-    leave SMs idle (the two-wave tensor-core kNN, the per-cloud gate / head kernels) overlap with the
-    other half's kernels.  Test hooks (forced indices / recording) disable both."""
+    A batch that fits one pass is split into up to N_SPLIT sub-batches (at least 8 clouds each) that run on
+    their own CUDA streams: kernels whose grids leave SMs idle (the tensor-core kNN, the per-cloud
+    gate / head kernels) overlap with the other sub-batches' kernels.  Test hooks (forced indices / recording) disable both."""
     B, N = x.shape[0], x.shape[-1]
     per = max(1, MAX_POINTS_PER_PASS // max(N, 1))
     if hooks:

@@ -1,6 +1,6 @@
 """CUDA-graph replay of an SV model forward (inference): one capture per input shape, then every
-batch is a device-side replay -- no per-kernel launch cost, and the two batch halves that
-`fused.chunked` puts on two streams really overlap (eager enqueueing serialises them on the host).
+batch is a device-side replay -- no per-kernel launch cost, and the sub-batches that
+`fused.chunked` puts on separate streams really overlap (eager enqueueing serialises them on the host).
 
     net = svnet_b200.SV_DGCNN_CLS(args, 40).cuda().eval(); net.load_state_dict(...)
     fast = svnet_b200.GraphedForward(net, example_batch)      # same signature as net(...)
