@@ -12,6 +12,7 @@ MAX_POINTS_PER_PASS = int(os.environ.get("SVNET_MAX_POINTS", 1 << 19))
 SIDE_STREAM = os.environ.get("SVNET_SIDE_STREAM", "1") != "0"
 CONCURRENT_HALVES = os.environ.get("SVNET_TWO_STREAMS", "1") != "0"
 N_SPLIT = max(2, int(os.environ.get("SVNET_STREAMS", "4")))      # sub-batches that run concurrently
+MIN_CLOUDS = max(1, int(os.environ.get("SVNET_MIN_CLOUDS", "8")))  # ... of at least this many clouds
 _SIDE = {}
 _IN_HALF = [False]
 
@@ -48,7 +49,7 @@ def _two_streams(impl, x, extras):
     dev = x.device
     cur = torch.cuda.current_stream()
     B = x.shape[0]
-    n = min(N_SPLIT, B // 8)
+    n = min(N_SPLIT, B // MIN_CLOUDS)
     bounds = [B * i // n for i in range(n + 1)]
     parts = [(x[lo:hi].contiguous(), [e[lo:hi].contiguous() for e in extras]) for lo, hi in zip(bounds[:-1], bounds[1:])]
     outs = []
