@@ -315,38 +315,42 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
         }
     }
 
-    // ---- P4: XNOR/popcount linear1, lanes = output channels (OPP per lane per pass) ----
+    // ---- P4: XNOR/popcount linear1, lanes = output channels (PO per lane per pass; all four groups of a
+    //      128-channel layer in one pass, so every sign / mask word is read once) ----
+    constexpr int PO = (S::OPT == 4) ? 4 : S::OPP;
+    constexpr int NWD = S::KW - S::TS;                       // words that differ per edge
+    // PEB edges per accumulation round: at most 20 accumulators, so they stay in registers (40 were
+    // spilled inside the loop)
+    constexpr int PEB = (PO == 4) ? 4 : (PO == 2) ? EB / 2 : EB;
+    constexpr int VW = (PEB % 4 == 0) ? 4 : 2;               // 16-byte loads when the round allows (kp % 4 == 0)
 #pragma unroll 1
-    for (int ob = 0; ob < S::OPT; ob += S::OPP) {
+    for (int ob = 0; ob < S::OPT; ob += PO) {
         // y = leaky(bn(scale * dot)) is a monotone function of the integer dot (every fp32 rounding is
         // monotone), so max over the edges of y is y(max dot) or y(min dot): keep integer extremes and
         // run the float epilogue once per output channel -- bit-identical to taking the max of all y.
-        int dmax[S::OPP], dmin[S::OPP];
-        int cmis[S::OPP];   // mismatches of the centre words (identical for all edges of this point)
+        int dmax[PO], dmin[PO];
+        int cmis[PO];   // mismatches of the centre words (identical for all edges of this point)
+        uint32_t wv[NWD][PO];
 #pragma unroll
-        for (int oo = 0; oo < S::OPP; ++oo) {
+        for (int oo = 0; oo < PO; ++oo) {
             dmax[oo] = INT_MIN;
             dmin[oo] = INT_MAX;
             cmis[oo] = 0;
 #pragma unroll
             for (int t = 0; t < S::TS; ++t)
                 cmis[oo] += __popc((cpos[t] ^ W1b[(S::TS + t) * COUT + lane + 32 * (ob + oo)]) & cnz[t]);
+#pragma unroll
+            for (int w = 0; w < NWD; ++w) wv[w][oo] = W1b[(w < S::TS ? w : w + S::TS) * COUT + lane + 32 * (ob + oo)];
         }
-        // PEB edges per accumulation round: 20 accumulators stay in registers (40 spilled inside the loop)
-        constexpr int PEB = (S::OPP == 2) ? EB / 2 : EB;
         for (int eb = 0; eb < k; eb += PEB) {
-            int acc[PEB][S::OPP];
+            int acc[PEB][PO];
 #pragma unroll
             for (int e = 0; e < PEB; ++e)
 #pragma unroll
-                for (int oo = 0; oo < S::OPP; ++oo) acc[e][oo] = 0;
+                for (int oo = 0; oo < PO; ++oo) acc[e][oo] = 0;
 #pragma unroll
-            for (int wd = 0; wd < S::KW; ++wd) {
-                if (wd >= S::TS && wd < 2 * S::TS) continue;  // centre words: cmis
-                uint32_t wv[S::OPP];
-#pragma unroll
-                for (int oo = 0; oo < S::OPP; ++oo) wv[oo] = W1b[wd * COUT + lane + 32 * (ob + oo)];
-                constexpr int VW = (PEB % 4 == 0) ? 4 : 2;       // 16-byte loads when the round allows (kp % 4 == 0)
+            for (int w = 0; w < NWD; ++w) {
+                const int wd = w < S::TS ? w : w + S::TS;     // the centre words are in cmis
                 const uint32_t* Ap = A + wd * kp + eb;
                 const uint32_t* Mp = M + wd * kp + eb;
 #pragma unroll
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
 #pragma unroll
                     for (int u = 0; u < VW; ++u)
 #pragma unroll
-                        for (int oo = 0; oo < S::OPP; ++oo) acc[ev * VW + u][oo] += __popc((av[u] ^ wv[oo]) & mv[u]);
+                        for (int oo = 0; oo < PO; ++oo) acc[ev * VW + u][oo] += __popc((av[u] ^ wv[w][oo]) & mv[u]);
                 }
             }
 #pragma unroll
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
                 if (eb + e < k) {
                     const int nv = nvalid[eb + e];
 #pragma unroll
-                    for (int oo = 0; oo < S::OPP; ++oo) {
+                    for (int oo = 0; oo < PO; ++oo) {
                         const int dot = nv - 2 * acc[e][oo];          // the centre words' share comes off after the loop
                         dmax[oo] = max(dmax[oo], dot);
                         dmin[oo] = min(dmin[oo], dot);
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDG
             }
         }
 #pragma unroll
-        for (int oo = 0; oo < S::OPP; ++oo) {
+        for (int oo = 0; oo < PO; ++oo) {
             const int o = lane + 32 * (ob + oo);
             const float sc = __ldg(p.scale1 + o), a1 = __ldg(p.bn1_a + o), c1 = __ldg(p.bn1_c + o);
             float y0 = __fadd_rn(__fmul_rn(__fmul_rn((float)(dmax[oo] - 2 * cmis[oo]), sc), a1), c1);
