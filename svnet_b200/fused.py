@@ -45,12 +45,17 @@ def chunked(impl, x, extras=(), hooks=False):
     return torch.cat(outs, dim=0)
 
 
+def split_bounds(B):
+    """Contiguous sub-batch boundaries: up to N_SPLIT sub-batches of at least MIN_CLOUDS clouds."""
+    n = max(1, min(N_SPLIT, B // MIN_CLOUDS))
+    return [B * i // n for i in range(n + 1)]
+
+
 def _two_streams(impl, x, extras):
     dev = x.device
     cur = torch.cuda.current_stream()
     B = x.shape[0]
-    n = min(N_SPLIT, B // MIN_CLOUDS)
-    bounds = [B * i // n for i in range(n + 1)]
+    bounds = split_bounds(B)
     parts = [(x[lo:hi].contiguous(), [e[lo:hi].contiguous() for e in extras]) for lo, hi in zip(bounds[:-1], bounds[1:])]
     outs = []
     _IN_HALF[0] = True

@@ -220,3 +220,14 @@ def test_dataset_readers_without_h5py(tmp_path):
         D.ModelNet40(num_points=1024, data_dir=str(tmp_path / "nowhere"), partition="test")
     unit = D.pc_normalize(shards[0][0][0])
     assert abs(np.linalg.norm(unit, axis=1).max() - 1.0) < 1e-12 and np.abs(unit.mean(0)).max() < 1e-12
+
+
+def test_sub_batch_bounds_cover_the_batch():
+    """fused.chunked splits a batch into contiguous sub-batches that run concurrently (clouds are
+    independent in eval mode): every cloud exactly once, none smaller than the minimum."""
+    from svnet_b200 import fused
+    for B in (16, 17, 31, 32, 33, 100, 256, 4096):
+        b = fused.split_bounds(B)
+        assert b[0] == 0 and b[-1] == B and all(lo < hi for lo, hi in zip(b[:-1], b[1:]))
+        assert len(b) - 1 <= fused.N_SPLIT and min(hi - lo for lo, hi in zip(b[:-1], b[1:])) >= fused.MIN_CLOUDS
+    assert fused.split_bounds(fused.MIN_CLOUDS - 1 or 1) == [0, fused.MIN_CLOUDS - 1 or 1]
