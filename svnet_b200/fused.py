@@ -2,6 +2,7 @@
 into the C-ABI parameter blocks of the fused kernels.  No arithmetic happens here.
 """
 import os
+import threading
 
 import torch
 
@@ -14,7 +15,11 @@ CONCURRENT_HALVES = os.environ.get("SVNET_TWO_STREAMS", "1") != "0"
 N_SPLIT = max(2, int(os.environ.get("SVNET_STREAMS", "4")))      # sub-batches that run concurrently
 MIN_CLOUDS = max(1, int(os.environ.get("SVNET_MIN_CLOUDS", "8")))  # ... of at least this many clouds
 _SIDE = {}
-_IN_HALF = [False]
+class _State(threading.local):       # per thread: DataParallel drives one forward per device thread
+    in_sub_batch = False
+
+
+_STATE = _State()
 
 
 def _side_stream(dev, which=0):
@@ -36,7 +41,7 @@ def chunked(impl, x, extras=(), hooks=False):
     if hooks:
         return impl(x, *extras)
     if B <= per:
-        if CONCURRENT_HALVES and B >= 16 and x.is_cuda and not _IN_HALF[0]:
+        if CONCURRENT_HALVES and B >= 16 and x.is_cuda and not _STATE.in_sub_batch:
             return _two_streams(impl, x, extras)
         return impl(x, *extras)
     outs = []
@@ -58,7 +63,7 @@ def _two_streams(impl, x, extras):
     bounds = split_bounds(B)
     parts = [(x[lo:hi].contiguous(), [e[lo:hi].contiguous() for e in extras]) for lo, hi in zip(bounds[:-1], bounds[1:])]
     outs = []
-    _IN_HALF[0] = True
+    _STATE.in_sub_batch = True
     try:
         for i, (xc, ec) in enumerate(parts):
             st = _side_stream(dev, 1 + i)
@@ -68,7 +73,7 @@ def _two_streams(impl, x, extras):
             y.record_stream(cur)
             outs.append((st, y))
     finally:
-        _IN_HALF[0] = False
+        _STATE.in_sub_batch = False
     for st, _ in outs:
         cur.wait_stream(st)
     return torch.cat([y for _, y in outs], dim=0)
@@ -122,7 +127,7 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
     Wpq, spq = blk.pq_weight()
     PQ = torch.empty((R, 3, 2 * Cvo), dtype=torch.float32, device=dev)
     cur = torch.cuda.current_stream()
-    side = _side_stream(dev) if (idx32 is None and SIDE_STREAM and not _IN_HALF[0]) else None
+    side = _side_stream(dev) if (idx32 is None and SIDE_STREAM and not _STATE.in_sub_batch) else None
     if side is not None:
         side.wait_stream(cur)
         with torch.cuda.stream(side):
