@@ -312,8 +312,14 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(dom[0])
     except Exception:
         pass
+    limiter = None
+    try:  # what the same capture says limits that kernel (issue slots, not DRAM: DESIGN.md section 4)
+        limiter = json.load(open(os.path.join(ROOT, "profiles", "limiters.json"))).get(dom[0])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "limiter_ncu": limiter,
                 "kernel_ms": dom[1], "algorithmic_bytes_per_launch": dom[2],
                 "clouds_per_launch": Bl,
                 "timed": "eager single-stream pass of the same %d steps (events cannot bracket kernels inside the graph replay)" % args.steps,

@@ -56,6 +56,21 @@ def main():
             d["svnet_knn[layer%d]" % (i + 2)] = kn
     d = dict(sorted(d.items()))
     json.dump(d, open(os.path.join(ROOT, "profiles", "dram_traffic.json"), "w"), indent=1)
+    # what limits the edge kernels (bench.py quotes it next to the HBM fraction): issue-slot and DRAM utilisation
+    lim = {}
+    edge_rows = {}
+    for r in body:
+        name = r[ix["Kernel Name"]]
+        if "edge_bin_fast" in name or "edge_fp_fast" in name:
+            edge_rows[name.split("kernel<")[1].split(">")[0]] = r
+    for i, sh in enumerate(sorted(edge_rows, key=lambda sh: [int(v) for v in sh.split(",")[:4]])):
+        r = edge_rows[sh]
+        lim["svnet_svblock_edge_fwd[layer%d]" % (i + 2)] = {
+            "issue_slot_pct": float(r[ix["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+            "dram_pct": float(r[ix["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
+            "warp_instructions": float(r[ix["smsp__inst_executed.sum"]].replace(",", "")),
+            "source": "profiles/%s_ncu_full_all_kernels.md" % tag}
+    json.dump(lim, open(os.path.join(ROOT, "profiles", "limiters.json"), "w"), indent=1)
     for src, dst in (("launches_r1.csv", tag + "_launches.csv"), ("bench_r1.json", tag + "_bench.json")):
         p = os.path.join(ROOT, "gpurun_out", src)
         if os.path.exists(p):
