@@ -11,8 +11,11 @@ Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in 
 same metric through the public nn.Module call with pinned HOST buffers (H2D of the clouds and D2H
 of the logits inside the timed region).  `roofline` is for the dominant kernel, timed live with
 CUDA events on its launch stream; `cpu_baseline` is the oracle port (C + OpenMP) on the host cores.
-`--impl reference` times that CPU port alone (the reference is pure Python/PyTorch and
-/root/reference does not exist on the GPU box).
+`--impl reference` times the UNMODIFIED reference forward (oracle/_ref, staged by oracle/make_ref.sh:
+the reference's own models/*.py, stock PyTorch on the host cores, all threads) on the same config.
+Extra keys of our line: `gpu_eager_reference` (the same reference modules on cuda: stock eager fp32),
+`extra.cfg3` / `extra.cfg4` (BASELINE.json configs[2] / configs[3], batch-sharded over the ranks: strong
+scaling, cfg4 with the all-gather of the per-point logits inside the timed region).
 """
 import argparse
 import contextlib
@@ -28,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B_PER_GPU, N_POINTS, K_NN, N_CLASS, SEED = 32, 1024, 20, 40, 1002
+# the logits all-gather as a node of the replayed CUDA graph (0: host-launched after every replay)
+GRAPH_ALLGATHER = os.environ.get("SVNET_GRAPH_ALLGATHER", "1") != "0"
 METRIC = "SV-DGCNN clouds/sec (1024 pts, k=20)"
 WORKLOAD = "SV-DGCNN binary ModelNet40 cls forward, B=32/GPU, N=1024, k=20, synthetic clouds + synthetic checkpoint"
 
@@ -52,6 +57,13 @@ def edge_kernel_bytes_per_cloud(layer, N=N_POINTS, k=K_NN):
 
 def knn_kernel_bytes_per_cloud(layer, N=N_POINTS, k=K_NN):
     return 4 * N * F_L[layer] + 4 * N * k
+
+
+def bench_config(world):
+    """`config` of the JSON line -- the same object in both arms (ours / reference)."""
+    return {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "n_points": N_POINTS, "k": K_NN,
+            "parallelism": "batch-sharded x%d, all-gather of logits" % world,
+            "l2": "GPU arm: flushed between steps (256 MiB memset, untimed)"}
 
 
 class ClockSampler:
@@ -123,34 +135,160 @@ def use_all_host_threads():
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
 
 
+def reference_model(device="cpu", kind="SV_DGCNN_CLS", k=K_NN, binary=True, ncls=N_CLASS, seed=SEED):
+    """The unmodified reference model (oracle/_ref/models, models/sv_dgcnn_cls.py:22-82) with the
+    same synthetic checkpoint as the CUDA arm."""
+    import torch
+    from oracle import reference
+    from svnet_b200.synthetic import make_args, synthetic_state_dict
+    ref = reference.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = getattr(ref, kind)(make_args(k=k, binary=binary), ncls)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=seed))
+    return net.to(device).eval()
+
+
+def reference_cpu_throughput(n_clouds, steps, warmup, budget_s=240.0):
+    """Reference PyTorch forward on the host cores, all threads: `steps` timed forwards of `n_clouds`
+    clouds each (the per-step sample shrinks only if the probe says the run would exceed `budget_s`)."""
+    import torch
+    from svnet_b200.synthetic import synthetic_clouds
+    torch.set_num_threads(os.cpu_count())
+    net = reference_model("cpu")
+    with torch.no_grad():
+        xp = synthetic_clouds(4, N_POINTS, SEED)
+        net(xp)                                     # page in, thread pool
+        t0 = time.perf_counter()
+        net(xp)
+        per_cloud = (time.perf_counter() - t0) / 4
+        n = n_clouds
+        while n > 4 and per_cloud * n * (steps + warmup) > budget_s:
+            n //= 2
+        x = synthetic_clouds(n, N_POINTS, SEED)
+        per_step = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            y = net(x)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                per_step.append(dt)
+    assert bool(torch.isfinite(y).all())
+    return n, per_step
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     use_all_host_threads()
     cores = os.cpu_count()
-    v0, _ = cpu_port_throughput(4)
-    n = int(min(64, max(4, round(2.0 * v0 / 4) * 4)))   # ~2 s of CPU work per step
-    per_step = []
-    for i in range(args.warmup + args.steps):
-        v, dt = cpu_port_throughput(n)
-        if i >= args.warmup:
-            per_step.append(dt)
-        if sum(per_step) > 150:  # keep the whole run within a few minutes
-            break
+    from oracle import reference
+    if reference.available():
+        n, per_step = reference_cpu_throughput(B_PER_GPU, args.steps, args.warmup)
+        kind = "reference"
+        what = ("%d clouds per step; unmodified reference forward (oracle/_ref/models, models/sv_dgcnn_cls.py:46-82), "
+                "stock PyTorch CPU, torch.set_num_threads(%d)" % (n, cores))
+    else:   # oracle/_ref not staged on this box: fall back to the C + OpenMP restatement (still a CPU arm)
+        v0, _ = cpu_port_throughput(4)
+        n = int(min(64, max(4, round(2.0 * v0 / 4) * 4)))
+        per_step = [cpu_port_throughput(n)[1] for _ in range(args.warmup + args.steps)][args.warmup:]
+        kind = "port"
+        what = "%d clouds per step, oracle C port with OpenMP (oracle/_ref missing)" % n
     ms = 1e3 * sum(per_step) / len(per_step)
     value = n / (ms / 1e3)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": args.gpus,
         "steps": len(per_step), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "%d clouds per step" % n},
-        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": cores, "kind": "port",
-                         "sample": "%d clouds of the same workload per step, oracle C port with OpenMP" % n},
+        "config": bench_config(max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": cores, "kind": kind, "sample": what},
         "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out))
+
+
+PSEG_BYTES_PER_CLOUD = 25.76e6     # SURVEY.md 8(d), N=2048, k=40
+
+
+def extra_config(sv, kind, margs, ncls, seed, global_batch, n_points, world, rank, dev, timed, gather, steps=5):
+    """One of BASELINE.json's other configs: `global_batch` clouds split contiguously over the ranks
+    (strong scaling), eager public call, device-resident inputs, L2 flushed between steps; `gather`
+    puts the NCCL all-gather of the per-point logits inside the timed region (cfg4)."""
+    import torch
+    import torch.distributed as dist
+    from svnet_b200 import parallel
+    from svnet_b200.synthetic import make_args, one_hot_labels, synthetic_clouds, synthetic_state_dict
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = getattr(sv, kind)(make_args(**margs), ncls)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=seed))
+    net = net.to(dev).eval()
+    lo, hi = parallel.shard_bounds(global_batch, world, rank)
+    per = hi - lo
+    # the rank's shard only (a 128 x 2048-point batch is generated per rank, not replicated)
+    x = synthetic_clouds(per, n_points, seed + 17 * rank).to(dev)
+    ins = (x, one_hot_labels(global_batch)[lo:hi].to(dev)) if kind == "SV_DGCNN_PSEG" else (x,)
+    out_all = None
+    ag_ms = None
+
+    def fwd():
+        y = net(*ins)
+        if gather and world > 1:
+            dist.all_gather_into_tensor(out_all, y)
+        return y
+    y = net(*ins)
+    if gather and world > 1:
+        assert per * world == global_batch
+        out_all = torch.empty((global_batch,) + tuple(y.shape[1:]), dtype=y.dtype, device=dev)
+    for _ in range(2):
+        fwd()
+    ms = timed(fwd, steps)
+    if gather and world > 1:
+        ag_ms = timed(lambda: dist.all_gather_into_tensor(out_all, y), steps)
+    res = {"global_batch": global_batch, "per_rank_batch": per, "n_points": n_points, "k": margs["k"],
+           "binary": margs["binary"], "model": kind, "scaling": "strong", "steps": steps,
+           "ms_per_step": ms, "clouds_per_s": global_batch / (ms * 1e-3), "call": "eager net(x) per rank"}
+    if gather:
+        res["allgather_ms"] = ag_ms
+        res["allgather_bytes_per_rank"] = int(y.numel() * 4) if world > 1 else 0
+    bytes_per_cloud = PSEG_BYTES_PER_CLOUD if kind == "SV_DGCNN_PSEG" else algorithmic_bytes_per_cloud(n_points, margs["k"])
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    res["roofline_frac_whole_step"] = bytes_per_cloud * per / (ms * 1e-3) / 1e9 / peak
+    del net, x, ins, out_all
+    torch.cuda.empty_cache()
+    return res
+
+
+def gpu_eager_reference(dev, x_dev, steps=5):
+    """the unmodified reference modules on cuda (stock PyTorch eager, fp32, TF32
+    off) on the same batch -- the GPU implementation the new kernels must beat."""
+    import torch
+    from oracle import reference
+    if not reference.available():
+        return {"unavailable": "oracle/_ref not staged"}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    net = reference_model(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            net(x_dev)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for e0, e1 in ev:
+            e0.record()
+            net(x_dev)
+            e1.record()
+        torch.cuda.synchronize()
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev) / steps
+    peak_mb = torch.cuda.max_memory_allocated(dev) / 2 ** 20
+    del net
+    torch.cuda.empty_cache()
+    return {"value": x_dev.shape[0] / (ms * 1e-3), "unit": "clouds/s", "ms_per_step": ms, "steps": steps,
+            "what": "unmodified reference forward (oracle/_ref/models) on the same B200, stock PyTorch eager, fp32, TF32 off, "
+                    "B=%d device-resident" % x_dev.shape[0], "max_memory_allocated_mib": peak_mb}
 
 
 def main():
@@ -160,6 +298,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra.cfg3 / extra.cfg4 / gpu_eager_reference")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
@@ -194,11 +333,12 @@ def main():
 
     # The step is the public inference call: svnet_b200.GraphedForward(net, example) captures the forward
     # once (CUDA graph with the batch split into four sub-batches on four streams) and replays it per batch.
-    fast = sv.GraphedForward(net, x_dev)
+    in_graph = world > 1 and GRAPH_ALLGATHER
+    fast = sv.GraphedForward(net, x_dev, epilogue=(lambda y: dist.all_gather_into_tensor(gathered, y)) if in_graph else None)
 
     def step(xin):
         y = fast(xin)
-        if world > 1:
+        if world > 1 and not in_graph:
             dist.all_gather_into_tensor(gathered, y)
         return y
 
@@ -278,6 +418,18 @@ def main():
             e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
 
+        # ---- the other configs north_star names, batch-sharded over the ranks (strong scaling) ----
+        extra = {}
+        if not args.no_extra:
+            extra["cfg3"] = extra_config(sv, "SV_DGCNN_CLS", dict(k=20, binary=False), 15, 1003, 256, 1024, world, rank, dev,
+                                         timed, gather=False)
+            extra["cfg4"] = extra_config(sv, "SV_DGCNN_PSEG", dict(k=40, binary=True), 50, 1004, 128, 2048, world, rank, dev,
+                                         timed, gather=True)
+        # ---- the unmodified reference modules on the same GPU (stock PyTorch eager, fp32, TF32 off) ----
+        eager_ref = None
+        if rank == 0 and not args.no_extra:
+            eager_ref = gpu_eager_reference(dev, x_dev)
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -332,20 +484,29 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:             # rank 0 at N = 1 only (bench contract)
         use_all_host_threads()
-        v, dt = cpu_port_throughput(4)                      # probe, then a sample worth ~15 s of CPU work
-        n_cpu = int(min(256, max(4, round(15.0 * v / 4) * 4)))
+        from oracle import reference
+        v, dt = cpu_port_throughput(4)                      # probe, then a sample worth ~5 s of CPU work
+        n_cpu = int(min(128, max(4, round(5.0 * v / 4) * 4)))
         v, dt = cpu_port_throughput(n_cpu)
-        cpu = {"value": v, "unit": "clouds/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d clouds of the same workload (N=1024, k=20), oracle C port with OpenMP, %.1f s" % (n_cpu, dt)}
+        port = {"value": v, "unit": "clouds/s", "kind": "port",
+                "sample": "%d clouds of the same workload (N=1024, k=20), oracle C port with OpenMP, %.1f s" % (n_cpu, dt)}
+        if reference.available():
+            n_ref, per_step = reference_cpu_throughput(B_PER_GPU, 2, 1, budget_s=45.0)
+            best = min(per_step)
+            cpu = {"value": n_ref / best, "unit": "clouds/s", "cores": os.cpu_count(), "kind": "reference",
+                   "sample": "%d clouds of the same workload per forward, best of %d after 1 warm-up (%.1f s each); unmodified "
+                             "reference forward (oracle/_ref/models), stock PyTorch CPU, all host threads" % (n_ref, len(per_step), best),
+                   "port": port}
+        else:
+            cpu = dict(port, cores=os.cpu_count())
 
     out = {
         "metric": METRIC, "value": world * B / (ms * 1e-3), "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (+u32 XNOR/popcount for the binarised linears; exact bf16x3 tcgen05 filter in front of the fp32 kNN)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * B, "n_points": N_POINTS, "k": K_NN,
-                   "parallelism": "batch-sharded x%d, all-gather of logits" % world,
-                   "call": "svnet_b200.GraphedForward(net, batch): CUDA-graph replay, four sub-batches of 8 clouds on four streams",
-                   "l2": "flushed between steps (256 MiB memset, untimed)"},
+        "config": bench_config(world),
+        "call": "svnet_b200.GraphedForward(net, batch): CUDA-graph replay, four sub-batches of 8 clouds on four streams"
+                + ("; the logits all-gather is captured in the same graph" if (world > 1 and GRAPH_ALLGATHER) else ""),
         "clocks": clocks,
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
@@ -355,6 +516,8 @@ def main():
         "gpu_launches_per_step": {"graph_replay": fast.kernels_per_replay, "eager_single_stream": launches},
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "gpu_eager_reference": eager_ref,
+        "extra": extra,
     }
     print(json.dumps(out))
 

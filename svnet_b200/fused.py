@@ -178,11 +178,6 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
     return idx32
 
 
-def point_block(blk, s_in, v_in, B, rows_per_cloud, s_out=None, lds_out=None, v_out=None):
-    """Per-row SVBlock (conv5, PointNet blocks): thin alias of SVBlock.forward_rows."""
-    return blk.forward_rows(s_in, v_in, B, rows_per_cloud, s_out=s_out, lds_out=lds_out, v_out=v_out)
-
-
 def dgcnn_trunk(model, x, forced_idx=None, record=None):
     """Edge layers 1..4 shared by SV_DGCNN_CLS / SV_DGCNN_PSEG (sv_dgcnn_cls.py:47-67,
     sv_dgcnn_partseg.py:81-103).  Returns the svcat table (s_cat (B*N, sum Cs), v_cat (B*N, 3, sum Cv));

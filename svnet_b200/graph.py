@@ -7,12 +7,18 @@ batch is a device-side replay -- no per-kernel launch cost, and the sub-batches 
     logits = fast(batch)                                       # valid until the next call
 
 Shapes are static: a batch of another shape raises (build a second GraphedForward for it).
+
+``epilogue`` (optional callable ``y -> anything``) runs inside the capture right after the forward, on the
+capture stream: multi-GPU callers pass the NCCL all-gather of the outputs here
+(``lambda y: dist.all_gather_into_tensor(all_y, y)``) so that the collective is a node of the same graph
+instead of a host-launched kernel behind every replay.  It is also run in the warm-up passes, so the
+communicator exists before the capture starts.
 """
 import torch
 
 
 class GraphedForward:
-    def __init__(self, model, *example_inputs, warmup=2):
+    def __init__(self, model, *example_inputs, warmup=2, epilogue=None):
         if model.training:
             raise RuntimeError("GraphedForward captures the inference path: call model.eval() first")
         for t in example_inputs:
@@ -25,7 +31,9 @@ class GraphedForward:
         side.wait_stream(cur)
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(max(1, warmup)):          # allocator / lazy weight packing settle before the capture
-                model(*self.static_in)
+                y = model(*self.static_in)
+                if epilogue is not None:
+                    epilogue(y)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         from . import _native as nv
@@ -33,6 +41,8 @@ class GraphedForward:
         l0 = nv.LAUNCHES[0]
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.static_out = model(*self.static_in)
+            if epilogue is not None:
+                epilogue(self.static_out)
         self.kernels_per_replay = nv.LAUNCHES[0] - l0     # kernels of this library inside one replay
 
     def __call__(self, *inputs):

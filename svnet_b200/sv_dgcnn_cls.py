@@ -18,7 +18,7 @@ from .fused import chunked, dgcnn_trunk
 from .sv_layers import Linear, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, folded_bn, head_layer
 
 
-class SV_DGCNN_CLS(nn.Module, _Cached):
+class SV_DGCNN_CLS(_Cached, nn.Module):
     def __init__(self, args, num_class=40):
         super(SV_DGCNN_CLS, self).__init__()
         self.k = args.k

@@ -33,12 +33,12 @@ def _get_visible_value(divisor=8):
 _V = _get_visible_value(8)
 
 
-class _Seq(nn.Sequential, _Cached):
+class _Seq(_Cached, nn.Sequential):
     """nn.Sequential(conv, BatchNorm1d, act) with a cached folded BN (keys '0', '1' as in the reference)."""
 
     def bn_folded(self):
         bn = self[1]
-        return self._packed("fold", (bn.weight, bn.bias, bn.running_mean, bn.running_var), lambda: nv.fold_bn(bn))
+        return self._packed("fold", ("1.weight", "1.bias", "1.running_mean", "1.running_var"), lambda: nv.fold_bn(bn))
 
 
 class SV_DGCNN_PSEG(nn.Module):

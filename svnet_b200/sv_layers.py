@@ -26,22 +26,74 @@ def _inference_only(m):
                            % type(m).__name__)
 
 
-def _sig(tensors):
-    return tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+def _resolve(module, path):
+    """'linear.weight' -> module.linear.weight ('1.weight' indexes an nn.Sequential)."""
+    obj = module
+    for part in path.split("."):
+        obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
+    return obj
 
 
 class _Cached:
-    """Mixin: cache of derived (packed) tensors keyed on the parameters' versions."""
+    """Mixin (first base, before the nn.Module class): cache of derived (packed) tensors -- sign bit-planes,
+    folded BatchNorm affines, re-laid-out weight slices -- keyed on (what, device) and validated against the
+    source parameters' (data_ptr, _version).
+
+    * ``deps`` are attribute paths relative to the module, resolved on the *source* module: under
+      nn.DataParallel every forward runs on fresh replicas whose parameters are new broadcast copies
+      (main_cls_dgcnn.py:125); replicas remember their source (`_replicate_for_data_parallel`) and share its
+      cache, so each device packs once, not once per forward.
+    * Entries carry the CUDA event of their producer kernels: a consumer on another stream (the concurrent
+      sub-batches of `fused.chunked`) waits on it until the event has been seen complete once.
+    * In-place writes through ``.data`` do not bump ``_version``: ``load_state_dict`` and ``.to()/.cuda()``
+      invalidate the cache here; after any other in-place surgery call ``invalidate_packed()``.
+    """
 
     def _packed(self, key, deps, builder):
-        cache = self.__dict__.setdefault("_sv_cache", {})
-        sig = _sig(deps)
-        hit = cache.get(key)
+        src = self.__dict__.get("_sv_src")
+        owner = self if src is None else src
+        cache = owner.__dict__.setdefault("_sv_cache", {})
+        tensors = [_resolve(owner, d) for d in deps]
+        dev = _resolve(self, deps[0]).device
+        sig = tuple((t.data_ptr(), t._version) for t in tensors)
+        k = (key, dev)
+        hit = cache.get(k)
         if hit is None or hit[0] != sig:
             with torch.no_grad():
-                hit = (sig, builder())
-            cache[key] = hit
+                val = builder()
+            ev = None
+            if dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+            hit = [sig, val, ev]
+            cache[k] = hit
+            _Cached.BUILDS += 1
+        elif hit[2] is not None and not torch.cuda.is_current_stream_capturing():
+            if hit[2].query():
+                hit[2] = None                     # producers retired: no ordering needed any more
+            else:
+                torch.cuda.current_stream(dev).wait_event(hit[2])
         return hit[1]
+
+    BUILDS = 0          # builder invocations (tests count re-packs with it)
+
+    def invalidate_packed(self):
+        """Drop every cached packed tensor of this module and its children."""
+        for m in self.modules() if isinstance(self, nn.Module) else [self]:
+            m.__dict__.pop("_sv_cache", None)
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica.__dict__["_sv_src"] = self.__dict__.get("_sv_src", self)
+        return replica
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.__dict__.pop("_sv_cache", None)
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_sv_cache", None)
+        return super()._apply(fn, *args, **kwargs)
 
 
 def _rows2d(x):
@@ -50,7 +102,7 @@ def _rows2d(x):
     return x.view(-1, x.shape[-1])
 
 
-class Linear(nn.Linear, _Cached):
+class Linear(_Cached, nn.Linear):
     """sv_layers.py:20-53.  bw: binarise weights, ba: binarise activations (sign(x + beta))."""
 
     def __init__(self, in_channels, out_channels, bias, bw=False, ba=False):
@@ -63,16 +115,16 @@ class Linear(nn.Linear, _Cached):
 
     # -- packed forms ---------------------------------------------------------------------------
     def sign_bits(self):
-        return self._packed("bits", (self.weight,), lambda: nv.pack_sign(self.weight.detach()))
+        return self._packed("bits", ("weight",), lambda: nv.pack_sign(self.weight.detach()))
 
     def scale_vec(self):
-        return self._packed("scale", (self.scale,), lambda: self.scale.detach().reshape(-1).contiguous())
+        return self._packed("scale", ("scale",), lambda: self.scale.detach().reshape(-1).contiguous())
 
     def beta_vec(self):
-        return self._packed("beta", (self.beta,), lambda: self.beta.detach().reshape(-1).contiguous())
+        return self._packed("beta", ("beta",), lambda: self.beta.detach().reshape(-1).contiguous())
 
     def sign_weight(self):
-        return self._packed("signw", (self.weight,), lambda: torch.sign(self.weight.detach()).contiguous())
+        return self._packed("signw", ("weight",), lambda: torch.sign(self.weight.detach()).contiguous())
 
     # -- forward --------------------------------------------------------------------------------
     def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE, out=None, ldo=None):
@@ -100,7 +152,7 @@ class Linear(nn.Linear, _Cached):
         return y.view(shape_x[:-1] + (y.shape[-1],))
 
 
-class Conv1d(nn.Conv1d, _Cached):
+class Conv1d(_Cached, nn.Conv1d):
     """sv_layers.py:55-78: kernel-1 convolution on (B, C, N), always bw & ba when ``binary``."""
 
     def __init__(self, in_channels, out_channels, binary=False):
@@ -112,17 +164,17 @@ class Conv1d(nn.Conv1d, _Cached):
             self.scale = nn.Parameter(torch.ones(1, out_channels, 1) / math.sqrt(in_channels))
 
     def weight2d(self):
-        return self._packed("w2d", (self.weight,), lambda: self.weight.detach()[:, :, 0].contiguous())
+        return self._packed("w2d", ("weight",), lambda: self.weight.detach()[:, :, 0].contiguous())
 
     def sign_bits(self, lo=0, hi=None):
-        return self._packed(("bits", lo, hi), (self.weight,),
+        return self._packed(("bits", lo, hi), ("weight",),
                             lambda: nv.pack_sign(self.weight.detach()[:, lo:hi, 0].contiguous()))
 
     def scale_vec(self):
-        return self._packed("scale", (self.scale,), lambda: self.scale.detach().reshape(-1).contiguous())
+        return self._packed("scale", ("scale",), lambda: self.scale.detach().reshape(-1).contiguous())
 
     def beta_vec(self):
-        return self._packed("beta", (self.beta,), lambda: self.beta.detach().reshape(-1).contiguous())
+        return self._packed("beta", ("beta",), lambda: self.beta.detach().reshape(-1).contiguous())
 
     def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE, cloud=None, rows_per_cloud=1):
         """x2d (rows, Kp) -> (rows, Cout).  ``cloud`` (B, Kc), if given, holds per-cloud-constant
@@ -157,7 +209,7 @@ class Conv1d(nn.Conv1d, _Cached):
         return y.view(B, N, -1).transpose(1, 2).contiguous()
 
 
-class VectorBN(nn.Module, _Cached):
+class VectorBN(_Cached, nn.Module):
     """sv_layers.py:81-102: rescale each 3-vector by BatchNorm1d(|v|)/|v|."""
 
     def __init__(self, dim):
@@ -166,7 +218,7 @@ class VectorBN(nn.Module, _Cached):
 
     def folded(self):
         bn = self.bn
-        return self._packed("fold", (bn.weight, bn.bias, bn.running_mean, bn.running_var), lambda: nv.fold_bn(bn))
+        return self._packed("fold", ("bn.weight", "bn.bias", "bn.running_mean", "bn.running_var"), lambda: nv.fold_bn(bn))
 
     def forward(self, v):
         _inference_only(self)
@@ -177,11 +229,11 @@ class VectorBN(nn.Module, _Cached):
 def folded_bn(owner, name):
     """Folded eval affine of ``owner.<name>`` (an nn.BatchNorm1d), cached on ``owner``."""
     bn = getattr(owner, name)
-    return owner._packed("fold_" + name, (bn.weight, bn.bias, bn.running_mean, bn.running_var),
+    return owner._packed("fold_" + name, tuple(name + "." + a for a in ("weight", "bias", "running_mean", "running_var")),
                          lambda: nv.fold_bn(bn))
 
 
-class Vector2Scalar(nn.Module, _Cached):
+class Vector2Scalar(_Cached, nn.Module):
     """sv_layers.py:104-129: invariant scalars s[d*m+j] = sum_i v[i,d] * (v W^T)[i,j]."""
 
     def __init__(self, v_dim, multi, binary=False, trans_back=False):
@@ -196,7 +248,7 @@ class Vector2Scalar(nn.Module, _Cached):
         lin = self.linear
         if lin.bw:
             return lin.sign_weight(), lin.scale_vec()
-        return self._packed("wz", (lin.weight,), lambda: lin.weight.detach().contiguous()), None
+        return self._packed("wz", ("linear.weight",), lambda: lin.weight.detach().contiguous()), None
 
     def forward_rows(self, v3, u_out=None, ldu=None, want_z=False):
         """v3 (rows, 3, C) strided view -> u (rows, 3C) written to u_out (row stride ldu)."""
@@ -235,7 +287,7 @@ class VectorReLU(nn.Module):
         raise NotImplementedError("VectorReLU is unused by the SV models (reference sv_layers.py:131-149)")
 
 
-class SVBlock(nn.Module, _Cached):
+class SVBlock(_Cached, nn.Module):
     """sv_layers.py:151-196.  ``forward`` is the materialised (module-level) path over rows; the
     DGCNN models call the fused edge kernels instead (sv_dgcnn_cls.py in this package)."""
 
@@ -277,7 +329,7 @@ class SVBlock(nn.Module, _Cached):
             Wc = torch.cat([W[:, :half], W[:, half:]], dim=0).contiguous()
             sc = torch.cat([lin.scale.detach().reshape(-1)] * 2).contiguous() if lin.bw else None
             return Wc, sc
-        deps = (lin.weight, lin.scale) if lin.bw else (lin.weight,)
+        deps = ("linear2.weight", "linear2.scale") if lin.bw else ("linear2.weight",)
         return self._packed("pq", deps, build)
 
     def yab_weight(self):
@@ -290,7 +342,7 @@ class SVBlock(nn.Module, _Cached):
             Wab = torch.cat([W[:, :cs], W[:, cs:2 * cs]], dim=0).contiguous()
             Wq_t = W[:, 2 * cs:].t().contiguous()
             return Wab, Wq_t
-        return self._packed("yab", (lin.weight,), build)
+        return self._packed("yab", ("linear1.weight",), build)
 
     # -- module-level forward over materialised rows --------------------------------------------
     def forward_rows(self, s2d, v3, B, rows_per_cloud, s_out=None, lds_out=None, v_out=None, s_pool=None):
@@ -379,6 +431,7 @@ class SVFuse(nn.Module):
         shape of s: B, N_points, [k,] s_dim
         shape of v: B, N_points, [k,] 3, v_dim
         '''
+        _inference_only(self)
         s, v = x
         s, v = s.contiguous(), v.contiguous()
         lead = s.shape[:-1]

@@ -97,7 +97,7 @@ class SVPointNetEncoder(nn.Module):
         return out
 
 
-class SV_PointNet_CLS(nn.Module, _Cached):
+class SV_PointNet_CLS(_Cached, nn.Module):
     def __init__(self, args, num_class=40):
         super(SV_PointNet_CLS, self).__init__()
         self.binary = args.binary

@@ -124,7 +124,7 @@ def _worker(rank, world, port, batch, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("batch", [8, 5])
+@pytest.mark.parametrize("batch", [8, 5, 1])
 def test_sharded_inference_gloo_world2(batch):
     """N>1 path on CPU: batch sharding + all-gather reproduce the unsharded result on every rank."""
     import torch.multiprocessing as mp
@@ -231,3 +231,36 @@ def test_sub_batch_bounds_cover_the_batch():
         assert b[0] == 0 and b[-1] == B and all(lo < hi for lo, hi in zip(b[:-1], b[1:]))
         assert len(b) - 1 <= fused.N_SPLIT and min(hi - lo for lo, hi in zip(b[:-1], b[1:])) >= fused.MIN_CLOUDS
     assert fused.split_bounds(fused.MIN_CLOUDS - 1 or 1) == [0, fused.MIN_CLOUDS - 1 or 1]
+
+
+def test_packed_cache_keys_replicas_on_their_source_and_invalidates():
+    """The packed-weight cache: nn.DataParallel replicas (fresh parameter copies every forward) resolve their
+    dependencies on the source module, so nothing is re-packed per forward; load_state_dict / .to() and
+    invalidate_packed() drop stale entries (in-place writes through .data do not bump _version)."""
+    import svnet_b200 as sv
+    from svnet_b200.sv_layers import _Cached
+    lin = sv.Linear(8, 4, bias=False, bw=True, ba=True).eval()
+    n0 = _Cached.BUILDS
+    a = lin.scale_vec()
+    assert _Cached.BUILDS == n0 + 1 and lin.scale_vec() is a and _Cached.BUILDS == n0 + 1
+    # what torch.nn.parallel.replicate does for every forward
+    rep = lin._replicate_for_data_parallel()
+    rep._parameters = {k: torch.nn.Parameter(v.detach().clone()) for k, v in lin._parameters.items() if v is not None}
+    assert rep.__dict__["_sv_src"] is lin
+    assert rep.scale_vec() is a and _Cached.BUILDS == n0 + 1          # same device: the source's entry, no build
+    rep2 = rep._replicate_for_data_parallel()
+    assert rep2.__dict__["_sv_src"] is lin
+    # stale-data protection
+    lin.scale.data.fill_(3.0)                                          # no version bump
+    assert lin.scale_vec() is a
+    lin.invalidate_packed()
+    assert float(lin.scale_vec()[0]) == 3.0
+    b = lin.scale_vec()
+    lin.load_state_dict(lin.state_dict())
+    assert lin.scale_vec() is not b
+    blk = quiet(sv.SVBlock, (8, 2), (4, 2), True).eval()
+    w1, _ = blk.pq_weight()
+    blk.double().float()                                               # _apply invalidates children too
+    assert blk.pq_weight()[0] is not w1
+    seq = quiet(sv.SV_DGCNN_PSEG, make_args(k=4, binary=True), 50)     # '1.weight' paths of the nn.Sequential blocks
+    assert seq.conv8._packed("probe", ("1.weight",), lambda: 1) == 1

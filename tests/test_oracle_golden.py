@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import svnet_oracle as orc
-from tests.util import assert_close, golden, golden_state_dict, knn_is_valid, max_abs
+from tests.util import assert_close, golden, golden_state_dict, knn_is_valid, max_abs, quiet
 from svnet_b200.synthetic import synthetic_state_dict
 import torch
 
@@ -124,3 +124,22 @@ def test_models_match_reference(name, fn, with_label):
     if all((rec["idx"][i] == g["idx%d" % i]).all() for i in range(nidx)):
         assert_close(y, g["logits"], what=name + " logits")
         assert (y.argmax(1) == g["logits"].argmax(1)).all()
+
+
+def test_svblock_binary_sign_plane_matches_reference():
+    """The q-channel sign planes (v2s output + beta, the fragile ones of SURVEY.md 7.3.2) of a binary
+    SVBlock as the reference recorded them (make_golden.py: `svb_bin_sign`) against the oracle."""
+    import svnet_b200 as sv
+    g = golden("layers")
+    blk = quiet(sv.SVBlock, (64, 20), (32, 10), True)
+    sd = _layer_sd(blk.state_dict(), 41)
+    P = orc.Params(sd)
+    s, v = g["svb_bin_s"], g["svb_bin_v"]
+    u = np.concatenate([s, orc.p_v2s(P.sub("v2s"), v)], axis=-1)
+    sign = orc.sign_plane(u, P.get("linear1.beta"))
+    ref = g["svb_bin_sign"]
+    assert sign.shape == ref.shape and ref.shape[-1] == 64 + 60
+    assert (sign == ref).all(), "%d of %d sign values differ" % ((sign != ref).sum(), ref.size)
+    so, vo = orc.svblock(P, (s, v))
+    assert_close(so, g["svb_bin_so"], rtol=1e-5, atol=1e-5)
+    assert_close(vo, g["svb_bin_vo"], rtol=1e-4, atol=1e-5)
