@@ -33,8 +33,10 @@ def test_full_size_parity_with_reference_forward(cfg):
         # kNN: identical rows, or a differing row is a swap / boundary exchange between candidates whose
         # exact scores agree to a few fp32 ulps of the operands' squared norms
         assert st["unexplained_rows"] == 0, st
-        assert st["row_agree"] >= 0.97, st
-        assert st["set_agree"] >= 0.99, st
+        # measured (profiles/r2a_ref_parity.json): rows 0.992-1.0 at k=20, 0.963-0.9998 at k=40 (twice the adjacent
+        # pairs per row, denser features); sets 0.9968-1.0; worst explained gap 1.0e-6 of the norms
+        assert st["row_agree"] >= 0.94, st
+        assert st["set_agree"] >= 0.995, st
         # pooled per-point features of the layer (teacher-forced on the reference's inputs and graph)
         assert st["pooled_v_out_of_tol"] <= 1e-4, st
         assert st["pooled_s_out_of_tol"] <= (2e-3 if kw["binary"] and st["layer"] > 1 else 1e-4), st
