@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SVNET_ABI_VERSION 1
+#define SVNET_ABI_VERSION 2
 
 /* error codes */
 #define SVNET_OK 0
@@ -196,8 +196,22 @@ typedef struct {
     /* optional parity taps (may be NULL): per edge sign words / nonzero-mask words [B*N*k][Kw] */
     uint32_t* dbg_bits;
     uint32_t* dbg_mask;
+    /* optional, binary layers: with both set (and a covered shape, svnet_edge_tc_weight_bytes() > 0) linear1 runs on the
+     * tcgen05 tensor cores (csrc/edge_tc.cu): ternary activations are written as fp8 e4m3 bytes straight into the UMMA
+     * operand, +-1 weights likewise, fp32 accumulators in tensor memory hold the exact integer dot products. */
+    const unsigned char* W1tc; /* svnet_edge_tc_pack_w() of conv.linear1.weight, svnet_edge_tc_weight_bytes() bytes, 16-byte aligned */
+    float* ftab;               /* scratch, svnet_edge_tc_table_bytes(B*N) bytes, 16-byte aligned: per-point frame tables */
 } svnet_edge_params;
 int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream);
+
+/* Tensor-core variant of the binary edge layers (sv_layers.py:36-49 on sv_util.py:90-116's edge features).
+ * svnet_edge_tc_weight_bytes() is 0 for shapes / k the kernel does not cover (covered: the six edge-layer shapes of
+ * SV_DGCNN_CLS / SV_DGCNN_PSEG at k = 20 or 40; SVNET_EDGE_TC=0 disables the path).  svnet_edge_tc_pack_w() turns
+ * conv.linear1.weight [Cout][2Cs + 6Cv] (row stride ldw) into sign bytes in the kernel's operand layout; exact zeros
+ * follow sign(0) = 0 (sv_layers.py:45). */
+size_t svnet_edge_tc_weight_bytes(int Cs, int Cv, int Cout, int Cvo, int k);
+size_t svnet_edge_tc_table_bytes(long points);
+int svnet_edge_tc_pack_w(const float* W1, int ldw, int Cs, int Cv, int Cout, unsigned char* out, void* stream);
 
 /* ---- per-row building blocks (conv5, PointNet per-point blocks, heads, module-level API) ---- */
 

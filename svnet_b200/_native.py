@@ -25,6 +25,7 @@ EXPORTS = [
     "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
+    "svnet_edge_tc_weight_bytes", "svnet_edge_tc_table_bytes", "svnet_edge_tc_pack_w",
 ]
 
 
@@ -45,7 +46,7 @@ class EdgeParams(ctypes.Structure):
                 ("Wz", c_void_p), ("zscale", c_void_p), ("beta", c_void_p), ("W1b", c_void_p), ("scale1", c_void_p),
                 ("Yab", c_void_p), ("W1q_t", c_void_p), ("bn1_a", c_void_p), ("bn1_c", c_void_p), ("Cout", c_int),
                 ("PQ", c_void_p), ("bn2_a", c_void_p), ("bn2_c", c_void_p), ("gate", c_void_p), ("Cvo", c_int),
-                ("out", View), ("dbg_bits", c_void_p), ("dbg_mask", c_void_p)]
+                ("out", View), ("dbg_bits", c_void_p), ("dbg_mask", c_void_p), ("W1tc", c_void_p), ("ftab", c_void_p)]
 
 
 class GemmParams(ctypes.Structure):
@@ -81,9 +82,11 @@ def lib():
         l.svnet_binlinear_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_binlinear_pool_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_linear_workspace_bytes.restype = ctypes.c_size_t
+        l.svnet_edge_tc_weight_bytes.restype = ctypes.c_size_t
+        l.svnet_edge_tc_table_bytes.restype = ctypes.c_size_t
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
-        if l.svnet_version() != 1:
+        if l.svnet_version() != 2:
             raise RuntimeError("svnet_b200: ABI version mismatch")
         _lib = l
     return _lib
@@ -240,6 +243,28 @@ def edge_xyz_fwd(params):
 
 def svblock_edge_fwd(params):
     _call("svnet_svblock_edge_fwd", ctypes.byref(params), _stream())
+    if params.W1tc and params.ftab:
+        LAUNCHES[0] += 1     # tensor-core path = frame-table kernel + tcgen05 edge kernel
+
+
+def edge_tc_weight_bytes(Cs, Cv, Cout, Cvo, k):
+    """0 when the tensor-core edge kernel does not cover the layer (svnet_edge_tc_weight_bytes)."""
+    return int(lib().svnet_edge_tc_weight_bytes(c_int(Cs), c_int(Cv), c_int(Cout), c_int(Cvo), c_int(k)))
+
+
+def edge_tc_pack_w(W1, Cs, Cv):
+    """conv.linear1.weight (Cout, 2Cs + 6Cv) -> e4m3 sign bytes in the UMMA operand layout of csrc/edge_tc.cu."""
+    W1 = _dev(W1)
+    assert W1.dim() == 2 and W1.stride(1) == 1
+    Cout = W1.shape[0]
+    nbytes = (2 * Cs + 8 * Cv + 31) // 32 * 32 * 128
+    out = torch.empty(nbytes, dtype=torch.uint8, device=W1.device)
+    _call("svnet_edge_tc_pack_w", _ptr(W1), c_int(W1.stride(0)), c_int(Cs), c_int(Cv), c_int(Cout), _ptr(out), _stream())
+    return out
+
+
+def edge_tc_table_bytes(points):
+    return int(lib().svnet_edge_tc_table_bytes(c_long(points)))
 
 
 def rows_prep(view, rows, Wz=None, zscale=None, beta=None, u_out=None, ldu=0, z_out=None, want_bits=False,

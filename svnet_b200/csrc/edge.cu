@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 int svnet_edge_fast_dispatch(const svnet_edge_params* p, cudaStream_t st);
+int svnet_edge_tc_dispatch(const svnet_edge_params* p, cudaStream_t st);
 
 namespace {
 
@@ -391,7 +392,11 @@ extern "C" int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream)
         // SVNET_EDGE_GENERIC=1 forces the generic kernel (tests cover both)
         const char* force = getenv("SVNET_EDGE_GENERIC");
         if (!(force && force[0] == '1')) {
-            const int h = svnet_edge_fast_dispatch(p, sv_stream(stream));
+            // tensor-core kernel when the caller supplied its packed weights and table scratch (edge_tc.cu)
+            int h = svnet_edge_tc_dispatch(p, sv_stream(stream));
+            if (h < 0) return h;
+            if (h == 1) return SVNET_OK;
+            h = svnet_edge_fast_dispatch(p, sv_stream(stream));
             if (h < 0) return h;
             if (h == 1) return SVNET_OK;
         }

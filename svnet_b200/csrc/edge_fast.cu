@@ -13,6 +13,7 @@
 //   P4  XNOR/popcount linear1 (lanes = output channels), BN, LeakyReLU, max over edges
 //   P5  vector branch from the per-point P|Q table, VectorBN, gate, mean over edges
 #include "common.cuh"
+#include "edge_vector.cuh"
 #include <limits.h>
 
 #ifndef EDGE_MB_SMALL
@@ -41,74 +42,6 @@ struct Shape {
     static_assert(CS % 32 == 0 && COUT % 32 == 0, "scalar widths must be multiples of 32");
 };
 
-
-// ---- P5: vector branch from the per-point P|Q table: w_e = (P_j - P_i) + Q_i, VectorBN, gate, mean over
-// the edges.  Channels beyond a multiple of 32 are spread over lane groups (group g takes the edges
-// e = g, g+G, ...; partial sums meet by shuffle), so CVO = 10 keeps 30 lanes busy instead of 10.
-// Tolerance-level arithmetic (norms and mean pools are not bit-pinned): rsqrt /
-// fast division instead of the IEEE sequences.
-__device__ __forceinline__ float fast_sqrt(float x)
-{
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float fast_rcp(float x)
-{
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-template <int CVO>
-__device__ __forceinline__ void vector_branch(const svnet_edge_params& p, long r, int b, long cbase, const int* nidx, int k, int lane)
-{
-    constexpr int LDP = 2 * CVO;
-    const float inv_k = 1.0f / (float)k;
-    constexpr int FULL = CVO / 32;                 // passes with 32 channels, one edge group
-    constexpr int R = CVO % 32;                    // remainder channels
-    constexpr int G = R > 0 ? 32 / R : 1;          // edge groups of the remainder pass
-#pragma unroll
-    for (int pass = 0; pass < FULL + (R > 0 ? 1 : 0); ++pass) {
-        const bool rem = pass == FULL;
-        const int g = rem ? lane / R : 0;
-        const int c = rem ? FULL * 32 + lane % (R > 0 ? R : 1) : pass * 32 + lane;
-        const int ng = rem ? G : 1;
-        const bool active = !rem || g < G;
-        float sum[3] = {0.0f, 0.0f, 0.0f};
-        if (active) {
-            const float* pi = p.PQ + r * 3 * LDP + c;
-            const float* pq0 = p.PQ + cbase * 3 * LDP + c;      // row offsets inside a cloud fit 32 bits (launch guard)
-            const float d_i[3] = {__ldg(pi + CVO) - __ldg(pi), __ldg(pi + LDP + CVO) - __ldg(pi + LDP),
-                                  __ldg(pi + 2 * LDP + CVO) - __ldg(pi + 2 * LDP)};      // Q_i - P_i
-            const float a2 = __ldg(p.bn2_a + c), c2 = __ldg(p.bn2_c + c);
-#pragma unroll 4
-            for (int e = g; e < k; e += ng) {
-                const float* pj = pq0 + (unsigned)nidx[e] * (unsigned)(3 * LDP);
-                const float w0 = __ldg(pj) + d_i[0], w1 = __ldg(pj + LDP) + d_i[1], w2 = __ldg(pj + 2 * LDP) + d_i[2];
-                const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0 * w0));
-                const float t = fmaf(c2, fast_rcp(fast_sqrt(s2) + 1e-6f), a2);      // (n a2 + c2) / n,  n = |w| + 1e-6
-                sum[0] = fmaf(w0, t, sum[0]);
-                sum[1] = fmaf(w1, t, sum[1]);
-                sum[2] = fmaf(w2, t, sum[2]);
-            }
-        }
-        if (rem && G > 1) {
-#pragma unroll
-            for (int x = 0; x < 3; ++x) {
-                float tot = sum[x];
-#pragma unroll
-                for (int gg = 1; gg < G; ++gg) tot += __shfl_sync(SV_FULL, sum[x], (lane % (R > 0 ? R : 1)) + gg * R);
-                sum[x] = tot;
-            }
-        }
-        if (active && g == 0) {
-            const float gt = p.gate[(long)b * CVO + c] * inv_k;
-#pragma unroll
-            for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + c] = sum[x] * gt;
-        }
-    }
-}
 
 template <int CS, int CV, int COUT, int CVO, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8) ? ((COUT <= 64) ? EDGE_MB_SMALL : EDGE_MB_LARGE) : 6) edge_bin_fast_kernel(svnet_edge_params p, int kp)

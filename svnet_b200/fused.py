@@ -158,6 +158,12 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
         beta, W1b, sc = lin.beta_vec(), lin.sign_bits(), lin.scale_vec()
         p.beta, p.W1b, p.scale1 = beta.data_ptr(), W1b.data_ptr(), sc.data_ptr()
         keep += [beta, W1b, sc]
+        if nv.edge_tc_weight_bytes(Cs, Cv, Cout, Cvo, k) > 0:
+            # linear1 on the tensor cores (csrc/edge_tc.cu): fp8 sign bytes of the weights + per-point frame-table scratch
+            W1tc = blk.edge_tc_weight()
+            ftab = torch.empty(nv.edge_tc_table_bytes(R) // 4, dtype=torch.float32, device=dev)
+            p.W1tc, p.ftab = W1tc.data_ptr(), ftab.data_ptr()
+            keep += [W1tc, ftab]
     else:
         Wab, Wq_t = blk.yab_weight()
         Yab = torch.empty((R, 2 * Cout), dtype=torch.float32, device=dev)

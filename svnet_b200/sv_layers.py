@@ -332,6 +332,11 @@ class SVBlock(_Cached, nn.Module):
         deps = ("linear2.weight", "linear2.scale") if lin.bw else ("linear2.weight",)
         return self._packed("pq", deps, build)
 
+    def edge_tc_weight(self):
+        """linear1's sign bytes (fp8 e4m3) in the operand layout of the tensor-core edge kernel."""
+        cs, cv = self.in_dims[0] // 2, self.in_dims[1] // 2
+        return self._packed("w1tc", ("linear1.weight",), lambda: nv.edge_tc_pack_w(self.linear1.weight.detach(), cs, cv))
+
     def yab_weight(self):
         """fp linear1 split: ([W1a; W1b] (2*Cout, Cs_pt), W1q^T (6Cv_pt... = 3*Cv_e, Cout))."""
         lin = self.linear1

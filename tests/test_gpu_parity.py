@@ -787,3 +787,81 @@ def test_two_stream_halves_equal_single_stream(model):
         fused.CONCURRENT_HALVES = keep
     torch.cuda.synchronize()
     assert y2.shape == y1.shape and torch.equal(y2, y1)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core edge kernel (csrc/edge_tc.cu) against the XNOR/popcount kernel and against itself
+# ------------------------------------------------------------------------------------------------
+def _run_edge_layer(blk, s_in, v_in, idx32, B, N, k, tc):
+    import os
+    from svnet_b200 import fused
+    Cout, Cvo = blk.out_dims
+    s_out = torch.empty((B * N, Cout), device=DEV)
+    v_out = torch.empty((B * N, 3, Cvo), device=DEV)
+    taps = {}
+    old = os.environ.get("SVNET_EDGE_TC")
+    os.environ["SVNET_EDGE_TC"] = "1" if tc else "0"
+    try:
+        with torch.no_grad():
+            fused.sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=idx32, taps=taps)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            del os.environ["SVNET_EDGE_TC"]
+        else:
+            os.environ["SVNET_EDGE_TC"] = old
+    return s_out, v_out, taps
+
+
+@pytest.mark.parametrize("Cs,Cv,Cout,Cvo,k,B,N", [
+    (32, 10, 32, 10, 20, 2, 256), (32, 10, 64, 21, 20, 1, 100), (64, 21, 128, 42, 20, 2, 256),
+    (32, 16, 32, 16, 40, 1, 130), (32, 16, 64, 24, 40, 2, 128), (64, 24, 128, 40, 40, 1, 256),
+    (64, 21, 128, 42, 40, 1, 96), (32, 16, 64, 24, 20, 1, 64)])
+def test_edge_tensor_core_kernel(Cs, Cv, Cout, Cvo, k, B, N):
+    """linear1 of the binary edge layers on tcgen05 (fp8 ternary operands, exact integer accumulators):
+    * the pooled scalars equal, bit for bit, what the kernel's own sign bytes (read back through the taps) give
+      under integer arithmetic and the float epilogue chain -- operand layout, K permutation, descriptors,
+      accumulators and epilogue are all covered by this;
+    * the s-channel signs equal the popcount kernel's exactly; q-channel signs (frames from the per-point
+      table) may differ only where |q + beta| is at rounding level;
+    * the vector branch is the same code: identical at k = 20, summation-order tolerance at k = 40."""
+    import svnet_b200 as sv
+    from svnet_b200 import _native as nv
+    if nv.edge_tc_weight_bytes(Cs, Cv, Cout, Cvo, k) == 0:
+        pytest.skip("tensor-core edge path disabled")
+    blk = quiet(sv.SVBlock, (2 * Cs, 2 * Cv), (Cout, Cvo), True)
+    blk.load_state_dict(synthetic_state_dict(blk.state_dict(), seed=77 + Cs + Cv))
+    blk = blk.to(DEV).eval()
+    R = B * N
+    s_in = cu(rnd((R, Cs), 3))
+    v_in = cu(rnd((R, 3, Cv), 4))
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(0, N, (B, N, k), generator=g, dtype=torch.int32)
+    idx[:, :, 0] = torch.arange(N, dtype=torch.int32)            # the self edge: exact zeros in the difference channels
+    idx32 = idx.to(DEV)
+    s_tc, v_tc, taps_tc = _run_edge_layer(blk, s_in, v_in, idx32, B, N, k, tc=True)
+    s_pc, v_pc, taps_pc = _run_edge_layer(blk, s_in, v_in, idx32, B, N, k, tc=False)
+    K = 2 * Cs + 6 * Cv
+    bt, mt = _unpack(t2n(taps_tc["bits"]), K), _unpack(t2n(taps_tc["mask"]), K)
+    bp, mp = _unpack(t2n(taps_pc["bits"]), K), _unpack(t2n(taps_pc["mask"]), K)
+    t_tc = np.where(mt == 1, np.where(bt == 1, 1, -1), 0).astype(np.int32)           # (R*k, K)
+    t_pc = np.where(mp == 1, np.where(bp == 1, 1, -1), 0).astype(np.int32)
+    assert (t_tc[:, :2 * Cs] == t_pc[:, :2 * Cs]).all(), "s-channel signs differ"
+    assert (t_tc[:, :Cs].reshape(R, k, Cs)[:, 0] == np.sign(t2n(blk.linear1.beta)[0, :Cs])).all()   # self edge: sign(0 + beta)
+    nd = int((t_tc != t_pc).sum())
+    assert nd <= 1e-4 * t_tc.size, "%d of %d signs differ" % (nd, t_tc.size)
+    # pooled scalars from the kernel's own signs: integer dot, then the kernel's float chain
+    W = np.sign(t2n(blk.linear1.weight)).astype(np.int32)                             # (Cout, K)
+    dot = (t_tc @ W.T).reshape(R, k, Cout)
+    sc = t2n(blk.linear1.scale).reshape(-1).astype(np.float32)
+    a1, c1 = (t2n(t).astype(np.float32) for t in blk.bn1_folded())
+    y = (dot.astype(np.float32) * sc).astype(np.float32)
+    y = ((y * a1).astype(np.float32) + c1).astype(np.float32)
+    y = np.where(y > 0, y, (np.float32(0.2) * y).astype(np.float32))
+    assert (t2n(s_tc) == y.max(axis=1)).all(), "pooled scalars differ from the integer recomputation"
+    if nd == 0:
+        assert torch.equal(s_tc, s_pc)
+    if k == 20:
+        assert torch.equal(v_tc, v_pc)
+    else:
+        assert_close(t2n(v_tc), t2n(v_pc), rtol=1e-5, atol=1e-6, what="vector branch")
