@@ -200,7 +200,10 @@ typedef struct {
      * tcgen05 tensor cores (csrc/edge_tc.cu): ternary activations are written as fp8 e4m3 bytes straight into the UMMA
      * operand, +-1 weights likewise, fp32 accumulators in tensor memory hold the exact integer dot products. */
     const unsigned char* W1tc; /* svnet_edge_tc_pack_w() of conv.linear1.weight, svnet_edge_tc_weight_bytes() bytes, 16-byte aligned */
-    float* ftab;               /* scratch, svnet_edge_tc_table_bytes(B*N) bytes, 16-byte aligned: per-point frame tables */
+    const float* tab4;         /* [B*N][svnet_edge_tc_table_cols(Cv, Cvo)][4], 16-byte aligned: per-point table of (x, y, z, 0)
+                                * columns [P (Cvo) | Q (Cvo) | T (3) | U (3) | v (Cv)] -- P | Q as in `PQ` (which may then be NULL),
+                                * T = v Wz[:, :Cv]^T zscale, U = v Wz[:, Cv:]^T zscale (frames z_e = T_j + U_i - T_i), v = the layer
+                                * input vectors; one svnet_linear_rows call with `c4` set produces it */
 } svnet_edge_params;
 int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream);
 
@@ -210,7 +213,7 @@ int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream);
  * conv.linear1.weight [Cout][2Cs + 6Cv] (row stride ldw) into sign bytes in the kernel's operand layout; exact zeros
  * follow sign(0) = 0 (sv_layers.py:45). */
 size_t svnet_edge_tc_weight_bytes(int Cs, int Cv, int Cout, int Cvo, int k);
-size_t svnet_edge_tc_table_bytes(long points);
+int svnet_edge_tc_table_cols(int Cv, int Cvo);
 int svnet_edge_tc_pack_w(const float* W1, int ldw, int Cs, int Cv, int Cout, unsigned char* out, void* stream);
 
 /* ---- per-row building blocks (conv5, PointNet per-point blocks, heads, module-level API) ---- */
@@ -274,6 +277,8 @@ typedef struct {
     const float* colscale; const float* bias; const float* bn_a; const float* bn_c; int act;
     int vbn; const float* gate; long groups_per_cloud;
     float* C; long ldc_g; int ldc_x;
+    int c4;  /* != 0 (needs G == 3, no vbn; tcgen05 path only): the three rows of group g are stored as one float4
+              * (x, y, z, 0) per column at C + g*ldc_g + 4*n (ldc_x unused) -- the table layout of the tensor-core edge kernel */
 } svnet_gemm_params;
 int svnet_linear_rows(const svnet_gemm_params* p, void* stream);
 /* With svnet_linear_workspace_bytes(p) bytes of caller-owned scratch (16-byte aligned) a plain fp32 linear

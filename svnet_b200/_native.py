@@ -25,7 +25,7 @@ EXPORTS = [
     "svnet_graph_feature_xyz", "svnet_graph_feature_sv", "svnet_gate_rows", "svnet_gate_edge", "svnet_gate_xyz",
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
-    "svnet_edge_tc_weight_bytes", "svnet_edge_tc_table_bytes", "svnet_edge_tc_pack_w",
+    "svnet_edge_tc_weight_bytes", "svnet_edge_tc_table_cols", "svnet_edge_tc_pack_w",
 ]
 
 
@@ -46,7 +46,7 @@ class EdgeParams(ctypes.Structure):
                 ("Wz", c_void_p), ("zscale", c_void_p), ("beta", c_void_p), ("W1b", c_void_p), ("scale1", c_void_p),
                 ("Yab", c_void_p), ("W1q_t", c_void_p), ("bn1_a", c_void_p), ("bn1_c", c_void_p), ("Cout", c_int),
                 ("PQ", c_void_p), ("bn2_a", c_void_p), ("bn2_c", c_void_p), ("gate", c_void_p), ("Cvo", c_int),
-                ("out", View), ("dbg_bits", c_void_p), ("dbg_mask", c_void_p), ("W1tc", c_void_p), ("ftab", c_void_p)]
+                ("out", View), ("dbg_bits", c_void_p), ("dbg_mask", c_void_p), ("W1tc", c_void_p), ("tab4", c_void_p)]
 
 
 class GemmParams(ctypes.Structure):
@@ -54,7 +54,7 @@ class GemmParams(ctypes.Structure):
                 ("M", c_long), ("N", c_int), ("K", c_int), ("sign_w", c_int), ("colscale", c_void_p),
                 ("bias", c_void_p), ("bn_a", c_void_p), ("bn_c", c_void_p), ("act", c_int), ("vbn", c_int),
                 ("gate", c_void_p), ("groups_per_cloud", c_long), ("C", c_void_p), ("ldc_g", c_long),
-                ("ldc_x", c_int)]
+                ("ldc_x", c_int), ("c4", c_int)]
 
 
 class HeadLayer(ctypes.Structure):
@@ -83,7 +83,6 @@ def lib():
         l.svnet_binlinear_pool_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_linear_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_edge_tc_weight_bytes.restype = ctypes.c_size_t
-        l.svnet_edge_tc_table_bytes.restype = ctypes.c_size_t
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
         if l.svnet_version() != 2:
@@ -243,8 +242,6 @@ def edge_xyz_fwd(params):
 
 def svblock_edge_fwd(params):
     _call("svnet_svblock_edge_fwd", ctypes.byref(params), _stream())
-    if params.W1tc and params.ftab:
-        LAUNCHES[0] += 1     # tensor-core path = frame-table kernel + tcgen05 edge kernel
 
 
 def edge_tc_weight_bytes(Cs, Cv, Cout, Cvo, k):
@@ -263,8 +260,8 @@ def edge_tc_pack_w(W1, Cs, Cv):
     return out
 
 
-def edge_tc_table_bytes(points):
-    return int(lib().svnet_edge_tc_table_bytes(c_long(points)))
+def edge_tc_table_cols(Cv, Cvo):
+    return int(lib().svnet_edge_tc_table_cols(c_int(Cv), c_int(Cvo)))
 
 
 def rows_prep(view, rows, Wz=None, zscale=None, beta=None, u_out=None, ldu=0, z_out=None, want_bits=False,
@@ -320,7 +317,7 @@ def binlinear_pool(bits, mask, K, W1b, Cout, scale, bn, rows_per_cloud, max_out,
 
 
 def linear_rows(A, lda_g, lda_x, G, M, K, W, N, C, ldc_g, ldc_x, sign_w=False, colscale=None, bias=None, bn=None,
-                act=ACT_NONE, vbn=False, gate=None, groups_per_cloud=1):
+                act=ACT_NONE, vbn=False, gate=None, groups_per_cloud=1, c4=False):
     """Raw generic linear; A and C are tensors whose data_ptr() is the first element addressed."""
     p = GemmParams()
     p.A, p.lda_g, p.lda_x, p.G = A.data_ptr(), lda_g, lda_x, G
@@ -335,6 +332,7 @@ def linear_rows(A, lda_g, lda_x, G, M, K, W, N, C, ldc_g, ldc_x, sign_w=False, c
     p.gate = gate.data_ptr() if gate is not None else 0
     p.groups_per_cloud = groups_per_cloud
     p.C, p.ldc_g, p.ldc_x = C.data_ptr(), ldc_g, ldc_x
+    p.c4 = 1 if c4 else 0
     # scratch for the split weights of the three-plane tensor-core path (plain fp32 linears over many rows)
     nbytes = int(lib().svnet_linear_workspace_bytes(ctypes.byref(p)))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=C.device) if nbytes > 0 else None

@@ -380,8 +380,8 @@ int launch_edge(const svnet_edge_params* p, cudaStream_t st)
 extern "C" int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream)
 {
     SV_REQUIRE(p, "svnet_svblock_edge_fwd: null params");
-    SV_REQUIRE(p->in.s && p->in.v && p->idx && p->Wz && p->bn1_a && p->bn1_c && p->PQ && p->bn2_a && p->bn2_c &&
-                   p->gate && p->out.s && p->out.v,
+    SV_REQUIRE(p->in.s && p->in.v && p->idx && p->Wz && p->bn1_a && p->bn1_c && (p->PQ || (p->tab4 && p->W1tc)) && p->bn2_a &&
+                   p->bn2_c && p->gate && p->out.s && p->out.v,
                "svnet_svblock_edge_fwd: null pointer");
     SV_REQUIRE(p->in.Cs >= 1 && p->in.Cv >= 1 && p->B >= 0 && p->N >= 1 && p->k >= 1 && p->Cout >= 1 && p->Cvo >= 1,
                "svnet_svblock_edge_fwd: bad shape");
@@ -396,6 +396,7 @@ extern "C" int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream)
             int h = svnet_edge_tc_dispatch(p, sv_stream(stream));
             if (h < 0) return h;
             if (h == 1) return SVNET_OK;
+            SV_REQUIRE(p->PQ, "svnet_svblock_edge_fwd: layer not covered by the tensor-core kernel and no PQ table given");
             h = svnet_edge_fast_dispatch(p, sv_stream(stream));
             if (h < 0) return h;
             if (h == 1) return SVNET_OK;

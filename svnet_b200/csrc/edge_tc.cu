@@ -4,7 +4,11 @@
 // sign words, the popcount loop and nvalid disappear:
 //
 //   * every lane writes the ternary value sign(u + beta) of its channel straight into the UMMA B operand as an
-//     fp8 e4m3 byte ({-1, 0, +1} are exact: 0xB8, 0x00, 0x38), K-major canonical layout, no swizzle; the K
+//     fp8 e4m3 byte, K-major canonical layout, no swizzle.  The byte comes from one saturating conversion of two
+//     values at a time (cvt.rn.satfinite.e4m3x2.f32): u + beta is computed times 2^80 (frames and betas are
+//     pre-scaled by that power of two, which commutes with every fp32 rounding), so any non-zero value saturates
+//     to +-448 (0x7E / 0xFE) and an exact zero stays zero -- the accumulators hold 448 x the integer dot product
+//     (|.| < 2^24, exact) and the epilogue divides it out exactly.  Weights are +-1 (0x38 / 0xB8), 0 for padding.  The K
 //     positions are permuted so that a lane's values sit in one 32-bit word (weights are permuted the same
 //     way at pack time -- a dot product does not care):
 //         scalar section  pos = 2*TS*lane + t        t <  TS: s_j - s_i channel 32t + lane
@@ -17,8 +21,12 @@
 //     the k columns of a point and applies scale -> BN -> LeakyReLU once per (point, channel) -- the same
 //     monotone-chain argument and the same float sequence as edge_fast.cu, so given equal signs the pooled
 //     scalars are bit-identical;
-//   * the 3x3 frames come from a per-point table: z_e = T_j + (U_i - T_i) with T = v Wz[:, :Cv]^T zscale,
-//     U = v Wz[:, Cv:]^T zscale (frame_table_kernel) instead of 9k sequential chains per point.  This changes
+//   * everything a point contributes to its neighbours' edges comes from ONE per-point table of float4 columns
+//     (x, y, z, 0), written by one tcgen05 vector linear (gemm_tcgen05.cu, `c4` layout) over the layer input v:
+//         [P (Cvo) | Q (Cvo) | T (3) | U (3) | v (Cv)]      P | Q: vector branch, w_e = P_j + (Q_i - P_i)
+//     T = v Wz[:, :Cv]^T zscale, U = v Wz[:, Cv:]^T zscale: the 3x3 frames are z_e = T_j + (U_i - T_i) instead of
+//     9k sequential chains per point; v itself comes through identity weight rows (exact), so that every gather
+//     is one 16-byte load per (edge, lane).  This changes
 //     the q channels' contract from "the oracle's summation chain" to tolerance level: a sign can differ from
 //     the reference's where |q + beta| is at rounding level (tests/test_gpu_reference.py counts and bounds
 //     them); the s channels (one exact subtraction) stay bit-exact;
@@ -37,7 +45,15 @@ constexpr int ROWS_PAD = 163;    // rows per k-block slab: 4 * 163 = 12 (mod 32)
 constexpr int EPW = 20;          // edges per warp
 constexpr int NWARP = 8;
 constexpr int TMEM_COLS = 256;   // power of two >= ROWS
-constexpr int FT = 24;           // frame table floats per point: T[m][4] | U[m][4]
+#ifndef EDGE_TC_PB
+#define EDGE_TC_PB 10            // q-section passes whose gathers are in flight together
+#endif
+#ifndef EDGE_TC_VB
+#define EDGE_TC_VB 10            // vector-branch edges whose gathers are in flight together
+#endif
+#ifndef EDGE_TC_SB
+#define EDGE_TC_SB 10            // scalar-section edges whose gathers are in flight together
+#endif
 
 template <int CS, int CV, int COUT, int CVO, int KE>
 struct TC {
@@ -53,7 +69,9 @@ struct TC {
     static constexpr int KBB = ROWS_PAD * 16;      // ... of the activation operand
     static constexpr int A_BYTES = NKB * KBA;
     static constexpr int B_BYTES = NKB * KBB;
-    static constexpr int WARP_FLOATS = EPW * 12 + 32;                 // frames [e][m][4] + neighbour indices
+    static constexpr int WARP_FLOATS = EPW * 12;                      // frames [e][m][4]
+    static constexpr int NC = 2 * CVO + 6 + CV;    // float4 columns of the per-point table: P | Q | T | U | v
+    static constexpr int TQ0 = CVO, TT0 = 2 * CVO, TU0 = 2 * CVO + 3, TV0 = 2 * CVO + 6;
     static constexpr int VPART = (WPP > 1) ? NWARP * 3 * CVO : 0;     // partial vector sums
     static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + sizeof(float) * (NWARP * WARP_FLOATS + VPART) + 16;
     static_assert(KE % EPW == 0 && NWARP % WPP == 0 && NP * KE == ROWS, "tile shape");
@@ -121,49 +139,52 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8])
 }
 
 // ---- K positions (shared by the weight packer, the taps and the producer lanes) -------------------------------
-// reference channel c of u = [s_j - s_i | s_i | q(3*ds + m)] -> byte position inside an operand row
+// reference channel c of u = [s_j - s_i | s_i | q(3*ds + m)] -> byte position inside an operand row.
+// TS = 2: a lane holds the channel pair (2l, 2l + 1) (one 8-byte load per neighbour row); TS = 1: channel l.
 __host__ __device__ inline int tc_pos(int c, int CS, int TS)
 {
     if (c < 2 * CS) {
         const int half = c >= CS ? 1 : 0, cc = c - half * CS;
-        return 2 * TS * (cc & 31) + half * TS + (cc >> 5);
+        return (TS == 2) ? 4 * (cc >> 1) + 2 * half + (cc & 1) : 2 * cc + half;
     }
     const int qi = c - 2 * CS;
     return 2 * CS + 4 * (qi / 3) + (qi % 3);
 }
-
-// ---- per-point frame table: T[m][x] = zs[m] * sum_d v[x][d] Wz[m][d], U[m][x] likewise on Wz[m][CV + d] ------
-template <int CV>
-__global__ void frame_table_kernel(const float* __restrict__ v, int ldv, int xs, long points, const float* __restrict__ Wz,
-                                   const float* __restrict__ zscale, float* __restrict__ ftab)
+// inverse: byte position -> reference channel, -1 for padding
+__host__ __device__ inline int tc_chan(int pos, int CS, int TS, int CV)
 {
-    __shared__ float w[6 * CV];
-    for (int i = threadIdx.x; i < 6 * CV; i += blockDim.x) w[i] = Wz[i];       // [m][2CV]
-    __syncthreads();
-    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= points * 3) return;
-    const long r = t / 3;
-    const int x = (int)(t - r * 3);
-    const float* vr = v + r * ldv + x * xs;
-    float a[3] = {0.0f, 0.0f, 0.0f}, u[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int d = 0; d < CV; ++d) {
-        const float vv = __ldg(vr + d);
-#pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            a[m] = __fmaf_rn(vv, w[m * 2 * CV + d], a[m]);
-            u[m] = __fmaf_rn(vv, w[m * 2 * CV + CV + d], u[m]);
-        }
+    if (pos < 2 * CS) {
+        if (TS == 2) return ((pos >> 1) & 1) * CS + 2 * (pos >> 2) + (pos & 1);
+        return (pos & 1) * CS + (pos >> 1);
     }
-    float* o = ftab + r * FT;
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {
-        const float zs = zscale ? __ldg(zscale + m) : 1.0f;
-        o[m * 4 + x] = __fmul_rn(a[m], zs);
-        o[12 + m * 4 + x] = __fmul_rn(u[m], zs);
-        if (x == 0) { o[m * 4 + 3] = 0.0f; o[12 + m * 4 + 3] = 0.0f; }
-    }
+    const int q = pos - 2 * CS, ds = q >> 2, m = q & 3;
+    return (m < 3 && ds < 2 * CV) ? 2 * CS + 3 * ds + m : -1;
 }
+
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// two pre-scaled values -> two saturated e4m3 bytes: lo -> bits 0..7, hi -> bits 8..15
+__device__ __forceinline__ uint32_t sat2(float lo, float hi)
+{
+    unsigned short r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;\n" : "=h"(r) : "f"(hi), "f"(lo));
+    return (uint32_t)r;
+}
+constexpr float TSCALE = 1.2089258196146292e24f;      // 2^80: |u| >= 2^-71 saturates, |u| < 2^47 cannot overflow
+constexpr float TMAG_INV = 1.0f / 448.0f;             // accumulators are 448 x integer
 
 // ---- weights: fp32 W1 [COUT][K] -> e4m3 sign bytes in the canonical K-major operand layout [k-block][128][16],
 // K positions permuted by tc_pos, zero rows / columns for padding; sign(0) = 0 needs no special case here
@@ -174,15 +195,7 @@ __global__ void edge_tc_pack_w_kernel(const float* __restrict__ W1, int ldw, int
     const int K = 2 * CS + 6 * CV;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int b = i & 15, ch = (i >> 4) & 127, kb = i >> 11;
-        const int pos = kb * 16 + b;
-        int c = -1;
-        if (pos < 2 * CS) {
-            const int l = pos / (2 * TS), t = pos - l * 2 * TS;
-            c = (t < TS) ? 32 * t + l : CS + 32 * (t - TS) + l;
-        } else {
-            const int q = pos - 2 * CS, ds = q >> 2, m = q & 3;
-            if (m < 3 && ds < 2 * CV) c = 2 * CS + 3 * ds + m;
-        }
+        const int c = tc_chan(kb * 16 + b, CS, TS, CV);
         unsigned char val = 0;
         if (c >= 0 && c < K && ch < COUT) {
             const float w = __ldg(W1 + (long)ch * ldw + c);
@@ -198,73 +211,181 @@ struct QSection {
     static constexpr int GE = 32 / NDS;
     static constexpr int PASSES = (EPW + GE - 1) / GE;
     static constexpr bool ANY_DIFF = DS0 < CV;
-    int ds, esub, d;
+    static constexpr int PB = ANY_DIFF ? (PASSES < EDGE_TC_PB ? PASSES : EDGE_TC_PB) : 1;
+    int esub;
     bool lane_on, is_diff;
     float bq[3];
-    float vi[3];
-    uint32_t boff;
+    float4 vi;
+    uint32_t bst;              // shared address of this lane's word in operand row 0 of the warp
+    const float4* vcol;        // this lane's v column in the cloud's table (row 0)
 
-    __device__ __forceinline__ void init(const svnet_edge_params& p, int lane)
+    __device__ __forceinline__ void init(const svnet_edge_params& p, int lane, uint32_t brow0)
     {
         esub = lane / NDS;
-        ds = DS0 + lane % NDS;
+        const int ds = DS0 + lane % NDS;
         lane_on = lane < GE * NDS && ds < 2 * CV;
         is_diff = ds < CV;
-        d = is_diff ? ds : ds - CV;
-        if (!lane_on) d = 0;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) bq[m] = lane_on ? __ldg(p.beta + 2 * S::TS * 32 + 3 * ds + m) : 0.0f;
+        for (int m = 0; m < 3; ++m) bq[m] = lane_on ? __ldg(p.beta + 2 * S::TS * 32 + 3 * ds + m) * TSCALE : 0.0f;
         const int pos = S::KQ0 + 4 * ds;
-        boff = (uint32_t)((pos >> 4) * S::KBB + (pos & 15));
+        bst = brow0 + (uint32_t)((pos >> 4) * S::KBB + (pos & 15));
     }
-    __device__ __forceinline__ void centre(const float* vrow, int xs)
+    // tabc: table of the cloud, trow: table row of the centre point
+    __device__ __forceinline__ void centre(const float4* tabc, const float4* trow, int lane)
+    {
+        const int ds = DS0 + lane % NDS;
+        const int d = lane_on ? (is_diff ? ds : ds - CV) : 0;
+        vcol = tabc + S::TV0 + d;
+        vi = __ldg(trow + S::TV0 + d);
+    }
+    // my_j: neighbour index of edge `lane` of this warp; zb: shared address of the frames [e][m][4].
+    // PB passes per round: all their gathers are issued before the first use (one L2 latency per round).
+    __device__ __forceinline__ void run(int my_j, uint32_t zb) const
+    {
+#pragma unroll 1
+        for (int p0 = 0; p0 < PASSES; p0 += PB) {
+            float4 nb[PB];
+            if (ANY_DIFF) {
+#pragma unroll
+                for (int i = 0; i < PB; ++i) {
+                    const int e = (p0 + i) * GE + esub;
+                    const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, (lane_on && e < EPW) ? e : 0);
+                    nb[i] = is_diff ? __ldg(vcol + (size_t)j * S::NC) : vi;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                const int e = (p0 + i) * GE + esub;
+                const bool on = lane_on && e < EPW;
+                const int es = on ? e : 0;
+                float ve[3];
+                if (ANY_DIFF) {
+                    ve[0] = is_diff ? __fsub_rn(nb[i].x, vi.x) : vi.x;
+                    ve[1] = is_diff ? __fsub_rn(nb[i].y, vi.y) : vi.y;
+                    ve[2] = is_diff ? __fsub_rn(nb[i].z, vi.z) : vi.z;
+                } else {
+                    ve[0] = vi.x; ve[1] = vi.y; ve[2] = vi.z;
+                }
+                float u[3];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const float4 z = lds128(zb + (uint32_t)(es * 48 + m * 16));        // frame column m, times 2^80
+                    float q = __fmul_rn(ve[0], z.x);
+                    q = __fmaf_rn(ve[1], z.y, q);
+                    q = __fmaf_rn(ve[2], z.z, q);
+                    u[m] = __fadd_rn(q, bq[m]);
+                }
+                const uint32_t w = __byte_perm(sat2(u[0], u[1]), sat2(u[2], 0.0f), 0x5410);
+                if (on) sts32(bst + (uint32_t)(es * 16), w);
+            }
+        }
+    }
+};
+
+// ---- vector branch on the float4 table: w_e = P_j + (Q_i - P_i), VectorBN, gate, mean over the edges (see
+// edge_vector.cuh for the arithmetic; here every gather is one 16-byte load and VB rows are in flight per round).
+// The first round's gathers are issued by prefetch() before the tile barrier, so that their latency hides
+// behind the barrier and the MMA issue.
+template <typename S, int CVO>
+struct VBranch {
+    static constexpr int VB = EDGE_TC_VB;
+    static constexpr int FULL = CVO / 32, R = CVO % 32, G = R > 0 ? 32 / R : 1, NPASS = FULL + (R > 0 ? 1 : 0);
+    struct Lane {
+        bool rem, active;
+        int graw, g, c, ng, cc;
+    };
+    static __device__ __forceinline__ Lane lane_of(int pass, int lane)
+    {
+        Lane L;
+        L.rem = pass == FULL;
+        L.graw = L.rem ? lane / (R > 0 ? R : 1) : 0;
+        L.active = !L.rem || L.graw < G;
+        L.g = L.active ? L.graw : 0;            // idle lanes walk the same rounds (the index shuffles are warp-wide)
+        L.c = L.rem ? FULL * 32 + lane % (R > 0 ? R : 1) : pass * 32 + lane;
+        L.ng = L.rem ? G : 1;
+        L.cc = L.active ? L.c : 0;
+        return L;
+    }
+    float4 w0[VB], pi0, qi0;
+
+    __device__ __forceinline__ void load_round(float4 (&w)[VB], const float4* pcol, int my_j, int e0, int ng) const
     {
 #pragma unroll
-        for (int x = 0; x < 3; ++x) vi[x] = __ldg(vrow + x * xs + d);
+        for (int i = 0; i < VB; ++i) {
+            const int e = e0 + i * ng;
+            const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, e < EPW ? e : 0);
+            w[i] = __ldg(pcol + (size_t)j * S::NC);
+        }
     }
-    // my_j: neighbour index of edge `lane` of this warp; vcloud: v table of the cloud; zb: frames [e][m][4]
-    __device__ __forceinline__ void run(int my_j, const float* vcloud, unsigned ldv, int xs, const float* zb, unsigned char* brow0)
+    __device__ __forceinline__ void prefetch(const float4* tabc, const float4* trow, int my_j, int lane)
     {
-#pragma unroll 5
-        for (int pass = 0; pass < PASSES; ++pass) {
-            const int e = pass * GE + esub;
-            const bool on = lane_on && e < EPW;
-            const int es = on ? e : 0;
-            float ve[3];
-            if (ANY_DIFF) {
-                const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, es);
-                const float* vj = vcloud + j * ldv + d;
+        const Lane L = lane_of(0, lane);
+        pi0 = __ldg(trow + L.cc);
+        qi0 = __ldg(trow + S::TQ0 + L.cc);
+        load_round(w0, tabc + L.cc, my_j, L.g, L.ng);
+    }
+    __device__ __forceinline__ void run(const svnet_edge_params& p, long r, int b, const float4* tabc, const float4* trow, int my_j,
+                                        int ktot, int lane, float* partial) const
+    {
+        const float inv_k = 1.0f / (float)ktot;
+#pragma unroll
+        for (int pass = 0; pass < NPASS; ++pass) {
+            const Lane L = lane_of(pass, lane);
+            float sum[3] = {0.0f, 0.0f, 0.0f};
+            const float4 pi = pass == 0 ? pi0 : __ldg(trow + L.cc), qi = pass == 0 ? qi0 : __ldg(trow + S::TQ0 + L.cc);
+            const float d0 = qi.x - pi.x, d1 = qi.y - pi.y, d2 = qi.z - pi.z;
+            const float a2 = __ldg(p.bn2_a + L.cc), c2 = __ldg(p.bn2_c + L.cc);
+            const float4* pcol = tabc + L.cc;
+            auto consume = [&](const float4 (&w)[VB], int e0) {
+#pragma unroll
+                for (int i = 0; i < VB; ++i) {
+                    if (e0 + i * L.ng < EPW) {
+                        const float w0_ = w[i].x + d0, w1 = w[i].y + d1, w2 = w[i].z + d2;
+                        const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0_ * w0_));
+                        const float t = fmaf(c2, fast_rcp(fast_sqrt(s2) + 1e-6f), a2);      // (n a2 + c2) / n,  n = |w| + 1e-6
+                        sum[0] = fmaf(w0_, t, sum[0]);
+                        sum[1] = fmaf(w1, t, sum[1]);
+                        sum[2] = fmaf(w2, t, sum[2]);
+                    }
+                }
+            };
+            int e0 = L.g;
+            if (pass == 0) {
+                consume(w0, e0);
+                e0 += L.ng * VB;
+            }
+#pragma unroll 1
+            for (; e0 < EPW; e0 += L.ng * VB) {
+                float4 w[VB];
+                load_round(w, pcol, my_j, e0, L.ng);
+                consume(w, e0);
+            }
+            if (L.rem && G > 1) {
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
-                    const float nb = is_diff ? __ldg(vj + x * xs) : 0.0f;
-                    ve[x] = is_diff ? __fsub_rn(nb, vi[x]) : vi[x];
+                    float tot = sum[x];
+#pragma unroll
+                    for (int gg = 1; gg < G; ++gg) tot += __shfl_sync(SV_FULL, sum[x], (lane % (R > 0 ? R : 1)) + gg * R);
+                    sum[x] = tot;
                 }
-            } else {
-#pragma unroll
-                for (int x = 0; x < 3; ++x) ve[x] = vi[x];
             }
-            const float4* z4 = reinterpret_cast<const float4*>(zb + es * 12);
-            uint32_t nzw = 0, b[3];
+            if (L.active && L.graw == 0) {
+                if (partial) {
 #pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                const float4 z = z4[m];
-                float q = __fmul_rn(ve[0], z.x);
-                q = __fmaf_rn(ve[1], z.y, q);
-                q = __fmaf_rn(ve[2], z.z, q);
-                const float u = __fadd_rn(q, bq[m]);
-                b[m] = __float_as_uint(u);
-                nzw |= (u != 0.0f) ? (0x38u << (8 * m)) : 0u;
+                    for (int x = 0; x < 3; ++x) partial[x * CVO + L.c] = sum[x];
+                } else {
+                    const float gt = p.gate[(long)b * CVO + L.c] * inv_k;
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + L.c] = sum[x] * gt;
+                }
             }
-            // sign bytes: top byte of each float -> bytes 0..2, keep bit 7
-            const uint32_t sg = __byte_perm(__byte_perm(b[0], b[1], 0x0073), b[2], 0x0710) & 0x00808080u;
-            if (on) *reinterpret_cast<uint32_t*>(brow0 + es * 16 + boff) = sg | nzw;
         }
     }
 };
 
 template <int CS, int CV, int COUT, int CVO, int KE>
 __global__ void __launch_bounds__(NWARP * 32, 2)
-edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, const float* __restrict__ ftab, int ntiles)
+edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, const float4* __restrict__ tab4, int ntiles)
 {
     using S = TC<CS, CV, COUT, CVO, KE>;
     constexpr int TS = S::TS;
@@ -298,25 +419,25 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
     const uint32_t tmem_base = *tmem_slot;
 
     // ---- per-lane constants ----
-    float* zb = wsm + warp * S::WARP_FLOATS;                       // [EPW][3 m][4]
-    int* nidx = reinterpret_cast<int*>(zb + EPW * 12);             // [EPW] (+ padding to 32)
+    const uint32_t zb = smem_u32(wsm + warp * S::WARP_FLOATS);     // frames [EPW][3 m][4]
     const int pt_in_tile = warp / S::WPP, e0 = (warp % S::WPP) * EPW;
-    unsigned char* brow0 = Bs + (size_t)(warp * EPW) * 16;         // first operand row of this warp
+    const uint32_t brow0 = smem_u32(Bs) + (uint32_t)(warp * EPW) * 16u;     // first operand row of this warp
+    // scalar word of this lane: TS = 2: channels (2l, 2l+1) -> K positions 4l .. 4l+3; TS = 1: channel l -> 2l, 2l+1
     float bs[TS], bc[TS];
 #pragma unroll
     for (int t = 0; t < TS; ++t) {
-        bs[t] = __ldg(p.beta + 32 * t + lane);
-        bc[t] = __ldg(p.beta + CS + 32 * t + lane);
+        const int c = (TS == 2) ? 2 * lane + t : lane;
+        bs[t] = __ldg(p.beta + c) * TSCALE;
+        bc[t] = __ldg(p.beta + CS + c);
     }
-    // scalar word of this lane: K positions 2*TS*lane .. +2*TS-1
-    const uint32_t soff = (uint32_t)(((2 * TS * lane) >> 4) * S::KBB + ((2 * TS * lane) & 15));
+    const uint32_t sst = brow0 + (uint32_t)(((2 * TS * lane) >> 4) * S::KBB + ((2 * TS * lane) & 15));
     constexpr int S0N = (2 * CV >= 32) ? 32 : ((CV <= 16) ? CV : 2 * CV);       // first section
     constexpr int S1N = (2 * CV > 32) ? 2 * CV - 32 : ((CV <= 16 && 2 * CV < 32) ? CV : 0);
     constexpr int S1_0 = (2 * CV > 32) ? 32 : CV;
     QSection<S, CV, 0, S0N> q0;
     QSection<S, CV, S1_0, (S1N > 0 ? S1N : 1)> q1;
-    q0.init(p, lane);
-    if (S1N > 0) q1.init(p, lane);
+    q0.init(p, lane, brow0);
+    if (S1N > 0) q1.init(p, lane, brow0);
     // epilogue role: TMEM lane quarter = output channels, column group = points
     const int q4 = warp & 3, grp = warp >> 2;
     const int oc = q4 * 32 + lane;
@@ -325,77 +446,105 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
     if (epi_on) { sc1 = __ldg(p.scale1 + oc); a1 = __ldg(p.bn1_a + oc); c1 = __ldg(p.bn1_c + oc); }
     const int m_lane = lane % 3, e_lane = lane / 3;                // frame tasks: 10 edges x 3 columns per round
 
+    // neighbour indices of the first tile (later tiles are prefetched one iteration ahead)
+    int next_j = 0;
+    {
+        const long r = (long)blockIdx.x * S::NP + pt_in_tile;
+        if (blockIdx.x < ntiles && r < total && lane < EPW) next_j = __ldg(p.idx + r * KE + e0 + lane);
+    }
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long r = (long)tile * S::NP + pt_in_tile;
         const bool valid = r < total;
+        const int my_j = next_j;
+        {
+            const long rn = r + (long)gridDim.x * S::NP;
+            next_j = (tile + gridDim.x < ntiles && rn < total && lane < EPW) ? __ldg(p.idx + rn * KE + e0 + lane) : 0;
+        }
         int b = 0;
-        long cbase = 0;
-        int my_j = 0;
+        const float4* tabc = tab4;
+        const float4* trow = tab4;
         if (valid) {
             b = (int)(r / p.N);
-            cbase = (long)b * p.N;
-            my_j = lane < EPW ? __ldg(p.idx + r * KE + e0 + lane) : 0;
-            if (lane < EPW) nidx[lane] = my_j;
-            // ---- frames z_e[x][m] = T_j + (U_i - T_i), stored [e][m][x (4)] ----
-            {
-                const float4 ti = __ldg(reinterpret_cast<const float4*>(ftab + r * FT) + m_lane);
-                const float4 ui = __ldg(reinterpret_cast<const float4*>(ftab + r * FT + 12) + m_lane);
-                const float4 di = make_float4(ui.x - ti.x, ui.y - ti.y, ui.z - ti.z, 0.0f);
+            const long cbase = (long)b * p.N;
+            tabc = tab4 + cbase * S::NC;
+            trow = tab4 + r * S::NC;
+            // ---- issue: frame gathers, centre rows, first half of the neighbour scalars ----
+            const float4 ti = __ldg(trow + S::TT0 + m_lane), ui = __ldg(trow + S::TU0 + m_lane);
+            float4 tj[2];
 #pragma unroll
-                for (int rd = 0; rd < 2; ++rd) {
-                    const int e = rd * 10 + e_lane;
-                    const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, e < EPW ? e : 0);
-                    if (lane < 30) {
-                        const float4 tj = __ldg(reinterpret_cast<const float4*>(ftab + (cbase + j) * FT) + m_lane);
-                        reinterpret_cast<float4*>(zb)[e * 3 + m_lane] = make_float4(tj.x + di.x, tj.y + di.y, tj.z + di.z, 0.0f);
-                    }
-                }
+            for (int rd = 0; rd < 2; ++rd) {
+                const int e = rd * 10 + e_lane;
+                const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, e < EPW ? e : 0);
+                tj[rd] = __ldg(tabc + (size_t)j * S::NC + S::TT0 + m_lane);
             }
-            // ---- scalar section: centre bytes once, one word per edge ----
+            const float* srow = p.in.s + r * p.in.lds;
             float si[TS];
-            uint32_t cw = 0;
-#pragma unroll
-            for (int t = 0; t < TS; ++t) {
-                si[t] = __ldg(p.in.s + r * p.in.lds + 32 * t + lane);
-                const float u = __fadd_rn(si[t], bc[t]);
-                cw |= ((u != 0.0f ? 0x38u : 0u) | ((__float_as_uint(u) >> 24) & 0x80u)) << (8 * (TS + t));
+            if (TS == 2) {
+                const float2 t2 = __ldg(reinterpret_cast<const float2*>(srow) + lane);
+                si[0] = t2.x; si[TS - 1] = t2.y;
+            } else {
+                si[0] = __ldg(srow + lane);
             }
+            q0.centre(tabc, trow, lane);
+            if (S1N > 0) q1.centre(tabc, trow, lane);
+            const float* sbase = p.in.s + cbase * p.in.lds + TS * lane;
+            const unsigned lds = (unsigned)p.in.lds;
+            // centre bytes (identical for all edges of the point): TS = 2 -> bytes 2, 3 of the word; TS = 1 -> byte 1
+            uint32_t cw;
             {
-                const float* sbase = p.in.s + cbase * p.in.lds + lane;
-                const unsigned lds = (unsigned)p.in.lds;
-#pragma unroll 5
-                for (int e = 0; e < EPW; ++e) {
-                    const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, e);
-                    const float* sj = sbase + j * lds;
-                    uint32_t w = cw;
+                const float uc0 = __fadd_rn(si[0], bc[0]) * TSCALE, uc1 = __fadd_rn(si[TS - 1], bc[TS - 1]) * TSCALE;
+                cw = (TS == 2) ? (sat2(uc0, uc1) << 16) : ((sat2(uc0, 0.0f) & 0xFFu) << 8);
+            }
+            // ---- scalar section: one word per edge, EDGE_TC_SB neighbour rows in flight per round ----
+#pragma unroll 1
+            for (int eb = 0; eb < EPW; eb += EDGE_TC_SB) {
+                float sv[EDGE_TC_SB][TS];
 #pragma unroll
-                    for (int t = 0; t < TS; ++t) {
-                        const float u = __fadd_rn(__fsub_rn(__ldg(sj + 32 * t), si[t]), bs[t]);
-                        w |= ((u != 0.0f ? 0x38u : 0u) | ((__float_as_uint(u) >> 24) & 0x80u)) << (8 * t);
+                for (int i = 0; i < EDGE_TC_SB; ++i) {
+                    const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, eb + i);
+                    const float* sj = sbase + (size_t)j * lds;
+                    if (TS == 2) {
+                        const float2 t2 = __ldg(reinterpret_cast<const float2*>(sj));
+                        sv[i][0] = t2.x; sv[i][TS - 1] = t2.y;
+                    } else {
+                        sv[i][0] = __ldg(sj);
                     }
-                    if (TS == 2) *reinterpret_cast<uint32_t*>(brow0 + e * 16 + soff) = w;
-                    else *reinterpret_cast<uint16_t*>(brow0 + e * 16 + soff) = (uint16_t)w;
+                }
+                if (eb == 0) {
+                    // frames z_e[x][m] = T_j + (U_i - T_i), stored [e][m][x (4)]; they are needed after the scalar section
+                    if (lane < 30) {
+#pragma unroll
+                        for (int rd = 0; rd < 2; ++rd)
+                            sts128(zb + (uint32_t)((rd * 10 + e_lane) * 48 + m_lane * 16),
+                                   make_float4((tj[rd].x + (ui.x - ti.x)) * TSCALE, (tj[rd].y + (ui.y - ti.y)) * TSCALE,
+                                               (tj[rd].z + (ui.z - ti.z)) * TSCALE, 0.0f));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < EDGE_TC_SB; ++i) {
+                    const float u0 = __fmaf_rn(__fsub_rn(sv[i][0], si[0]), TSCALE, bs[0]);
+                    const float u1 = (TS == 2) ? __fmaf_rn(__fsub_rn(sv[i][TS - 1], si[TS - 1]), TSCALE, bs[TS - 1]) : 0.0f;
+                    const uint32_t w = cw | ((TS == 2) ? sat2(u0, u1) : (sat2(u0, 0.0f) & 0xFFu));
+                    if (TS == 2) sts32(sst + (uint32_t)((eb + i) * 16), w);
+                    else sts16(sst + (uint32_t)((eb + i) * 16), w);
                 }
             }
-            // ---- q sections ----
-            const float* vrow = p.in.v + r * p.in.ldv;
-            const float* vcloud = p.in.v + cbase * p.in.ldv;
-            q0.centre(vrow, p.in.xs);
-            if (S1N > 0) q1.centre(vrow, p.in.xs);
             __syncwarp();                                      // frames visible to the whole warp
-            q0.run(my_j, vcloud, (unsigned)p.in.ldv, p.in.xs, zb, brow0);
-            if (S1N > 0) q1.run(my_j, vcloud, (unsigned)p.in.ldv, p.in.xs, zb, brow0);
+            // ---- q sections ----
+            q0.run(my_j, zb);
+            if (S1N > 0) q1.run(my_j, zb);
             if (p.dbg_bits) {
                 // parity taps: rebuild the reference-ordered sign / mask words from the operand bytes
                 __syncwarp();
+                const unsigned char* brow = Bs + (size_t)(warp * EPW) * 16;
                 for (int e = 0; e < EPW; ++e)
                     for (int w = 0; w < S::KW; ++w) {
                         const int c = 32 * w + lane;
                         unsigned char byte = 0;
                         if (c < S::K) {
                             const int pos = tc_pos(c, CS, TS);
-                            byte = brow0[e * 16 + (pos >> 4) * S::KBB + (pos & 15)];
+                            byte = brow[e * 16 + (pos >> 4) * S::KBB + (pos & 15)];
                         }
                         const unsigned nz = __ballot_sync(SV_FULL, (byte & 0x7F) != 0);
                         const unsigned pos_w = __ballot_sync(SV_FULL, (byte & 0x7F) != 0 && !(byte & 0x80));
@@ -406,6 +555,9 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
                     }
             }
         }
+        // first vector-branch gathers go out before the barrier
+        VBranch<S, CVO> vb;
+        if (valid) vb.prefetch(tabc, trow, my_j, lane);
         // ---- tile complete: generic-proxy writes -> tensor-core reads ----
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -426,10 +578,7 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
             __syncwarp();
         }
         // ---- vector branch while the tensor core works ----
-        if (valid) {
-            if (S::WPP == 1) vector_branch<CVO>(p, r, b, cbase, nidx, EPW, lane);
-            else vector_branch<CVO>(p, r, b, cbase, nidx, EPW, lane, vpart + warp * 3 * CVO);
-        }
+        if (valid) vb.run(p, r, b, tabc, trow, my_j, KE, lane, S::WPP == 1 ? nullptr : vpart + warp * 3 * CVO);
         if (S::WPP > 1) {
             __syncthreads();
             if (valid && e0 == 0) vector_branch_combine<CVO, S::WPP>(p, r, b, vpart + warp * 3 * CVO, 3 * CVO, KE, lane);
@@ -464,6 +613,8 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
                     }
                 }
                 if (rr < total) {
+                    dmax = rintf(dmax * TMAG_INV);               // 448 x integer -> the integer, exactly
+                    dmin = rintf(dmin * TMAG_INV);
                     float y0 = __fadd_rn(__fmul_rn(__fmul_rn(dmax, sc1), a1), c1);
                     float y1 = __fadd_rn(__fmul_rn(__fmul_rn(dmin, sc1), a1), c1);
                     y0 = y0 > 0.0f ? y0 : __fmul_rn(0.2f, y0);
@@ -491,16 +642,14 @@ int sm_count()
 }
 
 template <int CS, int CV, int COUT, int CVO, int KE>
-int launch_tc(const svnet_edge_params* p, const unsigned char* W1tc, float* ftab, cudaStream_t st)
+int launch_tc(const svnet_edge_params* p, cudaStream_t st)
 {
     using S = TC<CS, CV, COUT, CVO, KE>;
     const long total = (long)p->B * p->N;
-    frame_table_kernel<CV><<<sv_cdiv(total * 3, 256), 256, 0, st>>>(p->in.v, p->in.ldv, p->in.xs, total, p->Wz, p->zscale, ftab);
-    SV_CHECK_LAUNCH("svnet_svblock_edge_fwd(frame table)");
     const int ntiles = sv_cdiv(total, S::NP);
     const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
     SV_CUDA(cudaFuncSetAttribute(edge_bin_tc_kernel<CS, CV, COUT, CVO, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-    edge_bin_tc_kernel<CS, CV, COUT, CVO, KE><<<grid, NWARP * 32, S::SMEM, st>>>(*p, W1tc, ftab, ntiles);
+    edge_bin_tc_kernel<CS, CV, COUT, CVO, KE><<<grid, NWARP * 32, S::SMEM, st>>>(*p, p->W1tc, reinterpret_cast<const float4*>(p->tab4), ntiles);
     SV_CHECK_LAUNCH("svnet_svblock_edge_fwd(tcgen05)");
     return SVNET_OK;
 }
@@ -512,6 +661,8 @@ bool tc_covered(int cs, int cv, int co, int cvo, int k)
 {
     const char* off = getenv("SVNET_EDGE_TC");
     if (off && off[0] == '0') return false;
+    const char* tc = getenv("SVNET_TCGEN05");          // the per-point table comes from the tcgen05 vector linear
+    if (tc && tc[0] == '0') return false;
     if (k != 20 && k != 40) return false;
     for (const tc_shape& s : kShapes)
         if (s.cs == cs && s.cv == cv && s.co == co && s.cvo == cvo) return true;
@@ -526,7 +677,7 @@ extern "C" size_t svnet_edge_tc_weight_bytes(int Cs, int Cv, int Cout, int Cvo, 
     return (size_t)((2 * Cs + 8 * Cv + 31) / 32 * 32) * 128;
 }
 
-extern "C" size_t svnet_edge_tc_table_bytes(long points) { return (size_t)points * FT * sizeof(float); }
+extern "C" int svnet_edge_tc_table_cols(int Cv, int Cvo) { return 2 * Cvo + 6 + Cv; }
 
 extern "C" int svnet_edge_tc_pack_w(const float* W1, int ldw, int Cs, int Cv, int Cout, unsigned char* out, void* stream)
 {
@@ -542,15 +693,15 @@ extern "C" int svnet_edge_tc_pack_w(const float* W1, int ldw, int Cs, int Cv, in
 // Returns 1 if the tensor-core kernel handled the layer, 0 if the caller must use another kernel, < 0 on error.
 int svnet_edge_tc_dispatch(const svnet_edge_params* p, cudaStream_t st)
 {
-    if (!p->binary || !p->W1tc || !p->ftab) return 0;
+    if (!p->binary || !p->W1tc || !p->tab4) return 0;
     const int cs = p->in.Cs, cv = p->in.Cv, co = p->Cout, cvo = p->Cvo, k = p->k;
     if (!tc_covered(cs, cv, co, cvo, k)) return 0;
-    const long widest = p->in.ldv > p->in.lds ? p->in.ldv : p->in.lds;
-    if ((long)p->N * (widest > 6l * cvo ? widest : 6l * cvo) >= (1l << 31)) return 0;     // 32-bit row offsets inside a cloud
-    if ((reinterpret_cast<uintptr_t>(p->W1tc) & 15) || (reinterpret_cast<uintptr_t>(p->ftab) & 15)) return 0;
+    if ((long)p->N * p->in.lds >= (1l << 31)) return 0;        // 32-bit row offsets inside a cloud
+    if ((reinterpret_cast<uintptr_t>(p->W1tc) & 15) || (reinterpret_cast<uintptr_t>(p->tab4) & 15)) return 0;
+    if ((reinterpret_cast<uintptr_t>(p->in.s) & 7) || (p->in.lds & 1)) return 0;   // 8-byte loads of the scalar rows
     int rc = 0;
 #define TCASE(A, Bv, C, D, KE) \
-    if (cs == A && cv == Bv && co == C && cvo == D && k == KE) { rc = launch_tc<A, Bv, C, D, KE>(p, p->W1tc, p->ftab, st); return rc == SVNET_OK ? 1 : rc; }
+    if (cs == A && cv == Bv && co == C && cvo == D && k == KE) { rc = launch_tc<A, Bv, C, D, KE>(p, st); return rc == SVNET_OK ? 1 : rc; }
     TCASE(32, 10, 32, 10, 20)
     TCASE(32, 10, 64, 21, 20)
     TCASE(64, 21, 128, 42, 20)

@@ -23,7 +23,7 @@ __device__ __forceinline__ float fast_rcp(float x)
     return y;
 }
 
-template <int CVO>
+template <int CVO, int VB = 0>
 __device__ __forceinline__ void vector_branch(const svnet_edge_params& p, long r, int b, long cbase, const int* nidx, int k, int lane,
                                               float* partial = nullptr)
 {
@@ -48,6 +48,30 @@ __device__ __forceinline__ void vector_branch(const svnet_edge_params& p, long r
             const float d_i[3] = {__ldg(pi + CVO) - __ldg(pi), __ldg(pi + LDP + CVO) - __ldg(pi + LDP),
                                   __ldg(pi + 2 * LDP + CVO) - __ldg(pi + 2 * LDP)};      // Q_i - P_i
             const float a2 = __ldg(p.bn2_a + c), c2 = __ldg(p.bn2_c + c);
+            if constexpr (VB > 0) {
+                // VB neighbour rows in flight per round (the gathers are L2 latency: one exposure per round)
+                for (int e0 = g; e0 < k; e0 += ng * VB) {
+                    float w[VB][3];
+#pragma unroll
+                    for (int i = 0; i < VB; ++i) {
+                        const int e = e0 + i * ng;
+                        const float* pj = pq0 + (unsigned)nidx[e < k ? e : 0] * (unsigned)(3 * LDP);
+#pragma unroll
+                        for (int x = 0; x < 3; ++x) w[i][x] = __ldg(pj + x * LDP);
+                    }
+#pragma unroll
+                    for (int i = 0; i < VB; ++i) {
+                        if (e0 + i * ng < k) {
+                            const float w0 = w[i][0] + d_i[0], w1 = w[i][1] + d_i[1], w2 = w[i][2] + d_i[2];
+                            const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0 * w0));
+                            const float t = fmaf(c2, fast_rcp(fast_sqrt(s2) + 1e-6f), a2);
+                            sum[0] = fmaf(w0, t, sum[0]);
+                            sum[1] = fmaf(w1, t, sum[1]);
+                            sum[2] = fmaf(w2, t, sum[2]);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll 4
             for (int e = g; e < k; e += ng) {
                 const float* pj = pq0 + (unsigned)nidx[e] * (unsigned)(3 * LDP);
@@ -57,6 +81,7 @@ __device__ __forceinline__ void vector_branch(const svnet_edge_params& p, long r
                 sum[0] = fmaf(w0, t, sum[0]);
                 sum[1] = fmaf(w1, t, sum[1]);
                 sum[2] = fmaf(w2, t, sum[2]);
+            }
             }
         }
         if (rem && G > 1) {

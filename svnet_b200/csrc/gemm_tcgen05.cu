@@ -212,6 +212,10 @@ __global__ void __launch_bounds__(NTH, 2) vlinear_tcgen05_kernel(svnet_gemm_para
                     if (!cok || pnt >= npoints) continue;
                     const float w0 = __fmul_rn(vx[e], cs), w1 = __fmul_rn(vy[e], cs), w2 = __fmul_rn(vz[e], cs);
                     if (!p.vbn) {   // plain table (P|Q of the fused edge kernel)
+                        if (p.c4) {   // one (x, y, z, 0) column per (point, channel): 512 contiguous bytes per warp
+                            *reinterpret_cast<float4*>(p.C + pnt * p.ldc_g + 4 * c) = make_float4(w0, w1, w2, 0.0f);
+                            continue;
+                        }
                         float* cq = p.C + pnt * p.ldc_g + c;
                         cq[0] = w0; cq[p.ldc_x] = w1; cq[2L * p.ldc_x] = w2;
                         continue;
@@ -244,6 +248,7 @@ int svnet_vlinear_tcgen05_dispatch(const svnet_gemm_params* p, cudaStream_t st)
     if (on && on[0] == '0') return 0;                         // SVNET_TCGEN05=0 falls back to mma.sync / CUDA cores
     if (!p->sign_w || p->G != 3 || p->M % 3 != 0) return 0;
     if (p->K > 96 || p->N > 256 || p->bias || p->act != SVNET_ACT_NONE || (!p->vbn && p->bn_a)) return 0;
+    if (p->c4 && (p->vbn || (p->ldc_g & 3) || (reinterpret_cast<uintptr_t>(p->C) & 15))) return 0;
     const int Kpad = (p->K + 15) / 16 * 16;
     const int MT = (p->N + 127) / 128;
     const long npoints = p->M / 3;

@@ -122,20 +122,29 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
     assert blk.in_dims == (2 * Cs, 2 * Cv), (blk.in_dims, Cs, Cv)
     dev = s_in.device
     view = nv.view_of(s_in, v_in)
-    # per-point tables for the vector branch (P | Q) do not depend on the graph: they run on a side
-    # stream next to the kNN kernels (whose second wave leaves SMs idle at B = 32)
-    Wpq, spq = blk.pq_weight()
-    PQ = torch.empty((R, 3, 2 * Cvo), dtype=torch.float32, device=dev)
+    # per-point tables do not depend on the graph: they run on a side stream next to the kNN kernels (whose second
+    # wave leaves SMs idle at B = 32).  Tensor-core edge kernel (csrc/edge_tc.cu): one float4 table
+    # [P | Q | T | U | v]; other kernels: the P | Q table of the vector branch.
+    use_tc = blk.binary and nv.edge_tc_weight_bytes(Cs, Cv, Cout, Cvo, k) > 0
     cur = torch.cuda.current_stream()
     side = _side_stream(dev) if (idx32 is None and SIDE_STREAM and not _STATE.in_sub_batch) else None
+    if use_tc:
+        Wt, cst = blk.edge_tc_table_weight()
+        NC = Wt.shape[0]
+        table = torch.empty((R, NC, 4), dtype=torch.float32, device=dev)
+        args = (v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wt, NC, table, 4 * NC, 0)
+        kw = dict(sign_w=True, colscale=cst, c4=True)
+    else:
+        Wpq, spq = blk.pq_weight()
+        table = torch.empty((R, 3, 2 * Cvo), dtype=torch.float32, device=dev)
+        args = (v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wpq, 2 * Cvo, table, 6 * Cvo, 2 * Cvo)
+        kw = dict(sign_w=blk.linear2.bw, colscale=spq)
     if side is not None:
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            nv.linear_rows(v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wpq, 2 * Cvo, PQ, 6 * Cvo, 2 * Cvo,
-                           sign_w=blk.linear2.bw, colscale=spq)
+            nv.linear_rows(*args, **kw)
     else:
-        nv.linear_rows(v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wpq, 2 * Cvo, PQ, 6 * Cvo, 2 * Cvo,
-                       sign_w=blk.linear2.bw, colscale=spq)
+        nv.linear_rows(*args, **kw)
     if idx32 is None:
         idx32, _ = nv.knn(view, B, N, k)
     G1, G2 = blk.gate_weights()
@@ -152,18 +161,17 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
     p.binary = 1 if blk.binary else 0
     p.Wz = Wz.data_ptr()
     p.zscale = zs.data_ptr() if zs is not None else 0
-    keep = [gate, PQ, Wz, zs, a1, c1, a2, c2]
+    keep = [gate, table, Wz, zs, a1, c1, a2, c2]
     if blk.binary:
         lin = blk.linear1
         beta, W1b, sc = lin.beta_vec(), lin.sign_bits(), lin.scale_vec()
         p.beta, p.W1b, p.scale1 = beta.data_ptr(), W1b.data_ptr(), sc.data_ptr()
         keep += [beta, W1b, sc]
-        if nv.edge_tc_weight_bytes(Cs, Cv, Cout, Cvo, k) > 0:
-            # linear1 on the tensor cores (csrc/edge_tc.cu): fp8 sign bytes of the weights + per-point frame-table scratch
+        if use_tc:
+            # linear1 on the tensor cores: fp8 sign bytes of the weights
             W1tc = blk.edge_tc_weight()
-            ftab = torch.empty(nv.edge_tc_table_bytes(R) // 4, dtype=torch.float32, device=dev)
-            p.W1tc, p.ftab = W1tc.data_ptr(), ftab.data_ptr()
-            keep += [W1tc, ftab]
+            p.W1tc, p.tab4 = W1tc.data_ptr(), table.data_ptr()
+            keep += [W1tc]
     else:
         Wab, Wq_t = blk.yab_weight()
         Yab = torch.empty((R, 2 * Cout), dtype=torch.float32, device=dev)
@@ -171,7 +179,8 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
         p.Yab, p.W1q_t = Yab.data_ptr(), Wq_t.data_ptr()
         keep += [Yab, Wq_t]
     p.bn1_a, p.bn1_c, p.Cout = a1.data_ptr(), c1.data_ptr(), Cout
-    p.PQ, p.bn2_a, p.bn2_c, p.gate, p.Cvo = PQ.data_ptr(), a2.data_ptr(), c2.data_ptr(), gate.data_ptr(), Cvo
+    p.PQ = 0 if use_tc else table.data_ptr()
+    p.bn2_a, p.bn2_c, p.gate, p.Cvo = a2.data_ptr(), c2.data_ptr(), gate.data_ptr(), Cvo
     p.out = _mview(s_out, v_out)
     if taps is not None and blk.binary:
         Kw = (2 * Cs + 6 * Cv + 31) // 32

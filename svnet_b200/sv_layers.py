@@ -332,6 +332,22 @@ class SVBlock(_Cached, nn.Module):
         deps = ("linear2.weight", "linear2.scale") if lin.bw else ("linear2.weight",)
         return self._packed("pq", deps, build)
 
+    def edge_tc_table_weight(self):
+        """Weights / column scales of the per-point table of the tensor-core edge kernel (csrc/edge_tc.cu):
+        rows [W2a | W2b | Wz[:, :Cv] | Wz[:, Cv:] | I] over the Cv input vector channels (binary blocks only)."""
+        lin, v2s = self.linear2, self.v2s.linear
+
+        def build():
+            W = lin.weight.detach()
+            cv = W.shape[1] // 2
+            Wz = v2s.weight.detach()
+            eye = torch.eye(cv, dtype=W.dtype, device=W.device)
+            Wt = torch.cat([W[:, :cv], W[:, cv:], Wz[:, :cv], Wz[:, cv:], eye], dim=0).contiguous()
+            sc2, zs = lin.scale.detach().reshape(-1), v2s.scale.detach().reshape(-1)
+            cs = torch.cat([sc2, sc2, zs, zs, torch.ones(cv, dtype=W.dtype, device=W.device)]).contiguous()
+            return Wt, cs
+        return self._packed("tc_tab", ("linear2.weight", "linear2.scale", "v2s.linear.weight", "v2s.linear.scale"), build)
+
     def edge_tc_weight(self):
         """linear1's sign bytes (fp8 e4m3) in the operand layout of the tensor-core edge kernel."""
         cs, cv = self.in_dims[0] // 2, self.in_dims[1] // 2
