@@ -14,7 +14,9 @@
 //                 read their rows with tcgen05.ld (lane = query row) -- no shuffles, no atomics:
 //       pass A  : 64 running group maxima per row of a LOWER bound of the score; the k-th largest
 //                 group maximum is a lower bound L of the row's k-th best score (k distinct
-//                 candidates reach it) and leaves ~k+5..10 survivors;
+//                 candidates reach it) and leaves ~k+5..10 survivors.  A lower bound may be loose, so this
+//                 pass runs only the three largest plane products (h*h, h*m, m*h: error ~2^-15 |a||b|, its
+//                 own eps) and streams only the hi and mid planes -- half the tensor work of pass B;
 //       pass B  : candidates whose UPPER bound reaches L are queued (approximate score, index);
 //       finish  : a warp sorts a row's survivors by approximate score; neighbours in that order
 //                 whose scores differ by more than the error bound are certainly ordered; runs of
@@ -232,7 +234,9 @@ __device__ __forceinline__ float exact_score(float dot, float xxi, float xxj)
 struct knn_tc_args {
     svnet_view in;
     int N, k, NCB, NKC, stages;
-    float eps;                   // |p_ij - q_ij| <= eps * (xx_i + xx_j)
+    float eps;                   // |p_ij - q_ij| <= eps * (xx_i + xx_j), six plane products (pass B, finish)
+    float epsA;                  // the same bound for the three-product scores of pass A
+    int passA3;                  // pass A with three plane products (0: six, tuning aid SVNET_KNN_PASSA=6)
     const unsigned char* pack;
     const float* xx;             // [B][NCB*256]
     float2* gq;                  // survivor queues [B*N rows][2 halves][CAPH] of (half-scale score, index bits)
@@ -335,8 +339,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
                 const unsigned char* bsrc = cloud_pack + (size_t)cb * NKC * B_CHUNK;
                 for (int kc = 0; kc < NKC; ++kc, ++t) {
                     if (t >= S) mbar_wait(empty + s, ph ^ 1u);
-                    mbar_expect_tx(full + s, B_CHUNK);
-                    bulk_g2s(Ring + (size_t)s * B_CHUNK, bsrc + (size_t)kc * B_CHUNK, B_CHUNK, full + s);
+                    const uint32_t bytes = (it >= NB || !p.passA3) ? B_CHUNK : 2 * B_PLANE;     // pass A reads the hi and mid planes only
+                    mbar_expect_tx(full + s, bytes);
+                    bulk_g2s(Ring + (size_t)s * B_CHUNK, bsrc + (size_t)kc * B_CHUNK, bytes, full + s);
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
             }
@@ -362,11 +367,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
                     const uint64_t ad = adesc0 + (uint64_t)((kc * A_CHUNK) >> 4);
                     const uint64_t bd = bdesc0 + (uint64_t)((s * B_CHUNK) >> 4);
                     constexpr uint64_t A1 = A_PLANE >> 4, A2 = (2 * A_PLANE) >> 4, B1 = B_PLANE >> 4, B2 = (2 * B_PLANE) >> 4;
-                    // plane products, small terms first: h*l, l*h, m*m, h*m, m*h, h*h
-                    umma_bf16(dcol, ad, bd + B2, idesc, kc == 0 ? 0u : 1u);
-                    umma_bf16(dcol, ad + A2, bd, idesc, 1u);
-                    umma_bf16(dcol, ad + A1, bd + B1, idesc, 1u);
-                    umma_bf16(dcol, ad, bd + B1, idesc, 1u);
+                    // plane products, small terms first: h*l, l*h, m*m, h*m, m*h, h*h (pass A: the last three)
+                    if (it >= NB || !p.passA3) {
+                        umma_bf16(dcol, ad, bd + B2, idesc, kc == 0 ? 0u : 1u);
+                        umma_bf16(dcol, ad + A2, bd, idesc, 1u);
+                        umma_bf16(dcol, ad + A1, bd + B1, idesc, 1u);
+                        umma_bf16(dcol, ad, bd + B1, idesc, 1u);
+                    } else {
+                        umma_bf16(dcol, ad, bd + B1, idesc, kc == 0 ? 0u : 1u);
+                    }
                     umma_bf16(dcol, ad + A1, bd, idesc, 1u);
                     umma_bf16(dcol, ad, bd, idesc, 1u);
                     umma_commit(empty + s);     // the stage may be refilled once these MMAs have read it
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
         const bool row_ok = (i0 + row) < p.N;
         const float xi = xxs[i0 + row];
         const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * (TNB / 2));
-        const float CA = -0.5f * (1.0f + p.eps), CB = -0.5f * (1.0f - p.eps);
+        const float CA = -0.5f * (1.0f + p.epsA), CB = -0.5f * (1.0f - p.eps);
 
         float m[32];
 #pragma unroll
@@ -427,8 +436,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
 #pragma unroll
                     for (int i = 1; i < GROUPS; ++i)
                         if (i == k - 1) Lp = v[i];
-                    // hi_ij >= lower bound of the k-th score  <=>  V_ij >= Lp - eps*xx_i (minus fp32 slack)
-                    const float r = Lp - p.eps * xi - 9.5367431640625e-7f * (fabsf(Lp) + xi);
+                    // upper bound (pass B, eps) >= lower bound of the k-th score (pass A, epsA)
+                    //   <=>  V_ij >= Lp - (eps + epsA)/2 * xx_i (minus fp32 slack)
+                    const float r = Lp - 0.5f * (p.eps + p.epsA) * xi - 9.5367431640625e-7f * (fabsf(Lp) + xi);
                     thr[row] = row_ok ? r : INFINITY;
                 }
                 scan_bar();
@@ -844,6 +854,15 @@ float knn_tc_eps(int C)
     return 1.5f * (NKC * 7.2e-7f + C * 3.0e-8f + 8.0e-7f);
 }
 
+// three plane products (h*h, h*m, m*h).  The split truncates: |m| < 2^-7 |a|, |l| < 2^-15 |a| per element, so the
+// dropped h*l + l*h + m*m (+ smaller) terms are below (2*2^-15 + 2^-14 + 2^-21) |a||b| <= 6.2e-5 (xx_i + xx_j);
+// accumulation as above; x1.5 safety
+float knn_tc_eps3(int C)
+{
+    const int NKC = (C + KCH - 1) / KCH;
+    return 1.5f * (6.2e-5f + NKC * 3.6e-7f + C * 3.0e-8f + 8.0e-7f);
+}
+
 }  // namespace
 
 struct knn_tc_plan_t {
@@ -903,6 +922,11 @@ int svnet_knn_tc_dispatch(const svnet_view* in, int B, int N, int k, int32_t* id
     knn_tc_args a;
     a.in = *in; a.N = N; a.k = k; a.NCB = pl.NCB; a.NKC = pl.NKC; a.stages = pl.stages; a.xcap = pl.xcap;
     a.eps = knn_tc_eps(in->Cs + 3 * in->Cv);
+    a.epsA = knn_tc_eps3(in->Cs + 3 * in->Cv);
+    a.passA3 = 1;
+    if (const char* pa = getenv("SVNET_KNN_PASSA")) {
+        if (pa[0] == '6') { a.passA3 = 0; a.epsA = a.eps; }
+    }
     {
         const char* sv = getenv("SVNET_KNN_TC_STATS");
         a.stats = (sv && sv[0] == '1') ? 1 : 0;
