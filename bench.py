@@ -129,6 +129,12 @@ def cpu_port_throughput(n_clouds, reps=1):
     return n_clouds / best, best
 
 
+def dbg(msg):
+    """stage marker on stderr (SVNET_BENCH_DEBUG=1): where a multi-rank run stops, if it does"""
+    if os.environ.get("SVNET_BENCH_DEBUG", "0") != "0":
+        print("[bench rank %s %.1fs] %s" % (os.environ.get("RANK", "0"), time.time() % 1000, msg), file=sys.stderr, flush=True)
+
+
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all host threads it can
     (set before the oracle's OpenMP runtime is loaded)."""
@@ -334,6 +340,7 @@ def main():
     # The step is the public inference call: svnet_b200.GraphedForward(net, example) captures the forward
     # once (CUDA graph with the batch split into four sub-batches on four streams) and replays it per batch.
     in_graph = world > 1 and GRAPH_ALLGATHER
+    dbg("model ready, capturing (all-gather in graph: %s)" % in_graph)
     fast = sv.GraphedForward(net, x_dev, epilogue=(lambda y: dist.all_gather_into_tensor(gathered, y)) if in_graph else None)
 
     def step(xin):
@@ -369,6 +376,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
+    dbg("captured")
     with torch.no_grad():
         sampler = ClockSampler(local)
         if rank == 0:
@@ -378,13 +386,15 @@ def main():
         barrier()
         if rank == 0:
             t_wait = time.time()
-            while not sampler.rows and time.time() - t_wait < 3.0:   # nvidia-smi start-up (no collective here)
-                fast(x_dev)
+            while not sampler.rows and time.time() - t_wait < 3.0:   # nvidia-smi start-up; rank 0 only, so no collective:
+                net(x_dev)                                           # the eager forward (the graph may hold the all-gather)
             torch.cuda.synchronize()
             sampler.rows.clear()
         barrier()
         # ---- device-resident throughput (graph replay of the public call) ----
+        dbg("warm-up done")
         ms = timed(lambda: step(x_dev), args.steps)
+        dbg("graph steps timed")
         # ---- the same K steps eagerly, with the dominant C-ABI calls bracketed by CUDA events on their
         #      launch stream (events cannot bracket kernels inside a graph replay) ----
         from svnet_b200 import fused as sv_fused
@@ -414,9 +424,11 @@ def main():
         def e2e_step():
             y = step(x_host)                     # pinned host -> static input (H2D) -> replay
             y_host.copy_(y, non_blocking=True)
+        dbg("eager steps timed")
         for _ in range(3):
             e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
+        dbg("e2e timed")
 
         # ---- the other configs north_star names, batch-sharded over the ranks (strong scaling) ----
         extra = {}
@@ -426,14 +438,30 @@ def main():
             extra["cfg4"] = extra_config(sv, "SV_DGCNN_PSEG", dict(k=40, binary=True), 50, 1004, 128, 2048, world, rank, dev,
                                          timed, gather=True)
         # ---- the unmodified reference modules on the same GPU (stock PyTorch eager, fp32, TF32 off) ----
+        dbg("extras done")
         eager_ref = None
         if rank == 0 and not args.no_extra:
             eager_ref = gpu_eager_reference(dev, x_dev)
+        dbg("eager reference done")
 
-    if world > 1:
-        dist.destroy_process_group()
+    # Teardown.  A CUDA graph that holds NCCL kernels keeps the communicator busy: destroy_process_group() then
+    # never returns (seen at N = 2).  Drop the graph first; ranks other than 0 are done here, rank 0 prints its line
+    # and every rank leaves through finish() (which skips the communicator teardown in that case).
+    kernels_per_replay = fast.kernels_per_replay
+    fast = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+
+    def finish():
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            if in_graph:
+                os._exit(0)
+            dist.destroy_process_group()
     if rank != 0:
-        return
+        return finish()
 
     peaks = {}
     try:
@@ -512,14 +540,15 @@ def main():
                 "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
         # kernels of libsvnet_b200.so inside the timed region: K replays of the captured forward (four
         # sub-batches); the eager single-stream pass used for the per-kernel events launches `eager` per step
-        "gpu_launches": fast.kernels_per_replay * args.steps,
-        "gpu_launches_per_step": {"graph_replay": fast.kernels_per_replay, "eager_single_stream": launches},
+        "gpu_launches": kernels_per_replay * args.steps,
+        "gpu_launches_per_step": {"graph_replay": kernels_per_replay, "eager_single_stream": launches},
         "roofline": roofline,
         "cpu_baseline": cpu,
         "gpu_eager_reference": eager_ref,
         "extra": extra,
     }
     print(json.dumps(out))
+    finish()
 
 
 if __name__ == "__main__":
