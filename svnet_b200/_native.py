@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvnet_b200.so")
+LIB_PATH = os.environ.get("SVNET_LIB") or os.path.join(_HERE, "libsvnet_b200.so")   # SVNET_LIB: developer A/B builds
 _lib = None
 
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2

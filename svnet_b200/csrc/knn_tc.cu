@@ -641,7 +641,6 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
     const int k = p.k;
     const int C = p.in.Cs + 3 * p.in.Cv, Cp = fin_stride(C);
     const float* xxs = p.xx + (size_t)b * p.NCB * TNB;
-    // gather table shared by the CTA: channel c -> (address of that channel in row 0, row stride)
     const float** gtab = reinterpret_cast<const float**>(fin_smem);
     int* gstr = reinterpret_cast<int*>(gtab + KMAX);
     for (int c = threadIdx.x; c < C; c += FIN_WARPS * 32) {
@@ -668,35 +667,97 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
     const bool brute = !(cc.x <= CAPH && cc.y <= CAPH && cnt >= k);
     bool st_exact = false;
     int jout = 0;
+    // ---- the row's survivors as one entry per lane (the approximate-order path needs at most 32) ----
+    float2 ent = make_float2(0.0f, 0.0f);
+    int n = cnt;
+    bool fast = !brute && cnt <= 32;
+    if (fast) {
+        // entry e of the row is half0[e] for e < c0, else half1[e - c0] (fetched by shuffle)
+        const int sl = (lane - c0) & 31;
+        const float a1 = __shfl_sync(SV_FULL, h1.x, sl), b1 = __shfl_sync(SV_FULL, h1.y, sl);
+        ent = lane < c0 ? h0 : make_float2(a1, b1);
+    } else if (!brute) {
+        // ---- 33 .. 128 survivors: the group-maxima threshold of the scan kernel was loose for this row.  With the
+        // survivors' own scores the bound is much tighter: T = k-th largest LOWER bound (q - delta) over the
+        // survivors is a lower bound of the k-th best exact score; entries whose UPPER bound (q + delta) is below T
+        // are out.  Usually that leaves <= 32, which take the approximate-order path. ----
+        float2 en[4];
+        float up[4];
+        unsigned lk[4];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int e = s4 * 32 + lane;
+            en[s4] = make_float2(0.0f, 0.0f);
+            up[s4] = -INFINITY;
+            lk[s4] = 0u;
+            if (e < cnt) {
+                en[s4] = __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
+                const float dl = 0.5f * p.eps * (xxi + __ldg(xxs + __float_as_int(en[s4].y)));
+                const float dlt = dl + 4.76837158203125e-7f * (fabsf(en[s4].x) + dl);      // fp32 slack of these two operations
+                up[s4] = en[s4].x + dlt;
+                const unsigned fb = __float_as_uint((en[s4].x - dlt) + 0.0f);
+                lk[s4] = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);                    // order-preserving, > 0
+            }
+        }
+        // the 32 largest lower bounds: sort each register, then bitonic half-cleaners + merges
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+            if (s4 * 32 < cnt) warp_sort32_desc_u32(lk[s4], lane);
+        unsigned top = lk[0];
+#pragma unroll
+        for (int s4 = 1; s4 < 4; ++s4) {
+            if (s4 * 32 < cnt) {
+                top = max(top, __shfl_sync(SV_FULL, lk[s4], 31 - lane));
+                warp_sort32_desc_u32(top, lane);
+            }
+        }
+        const unsigned tk = __shfl_sync(SV_FULL, top, k - 1);       // k <= 32 in this kernel
+        const unsigned tb = (tk & 0x80000000u) ? (tk & 0x7FFFFFFFu) : ~tk;
+        const float T = __uint_as_float(tb);
+        unsigned keep[4];
+        int kept = 0;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            keep[s4] = __ballot_sync(SV_FULL, up[s4] >= T);
+            kept += __popc(keep[s4]);
+        }
+        if (kept <= 32 && kept >= k) {
+            float2* scratch = reinterpret_cast<float2*>(f.exb);        // per-warp staging area (>= 64 floats)
+            int before = 0;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                if ((keep[s4] >> lane) & 1u) scratch[before + __popc(keep[s4] & ((1u << lane) - 1u))] = en[s4];
+                before += __popc(keep[s4]);
+            }
+            __syncwarp();
+            if (lane < kept) ent = scratch[lane];
+            __syncwarp();
+            n = kept;
+            fast = true;
+        }
+    }
     if (brute) {
         for (int c = lane; c < C; c += 32) f.arow[c] = sv_feat(p.in, rg, c);
         __syncwarp();
         kkey_t key[1];
         brute_force_row<1>(p, base, i, f.arow, xxs, lane, key);
         jout = key_index(key[0]);
-    } else if (cnt <= 32) {
-        // entry e of the row is half0[e] for e < c0, else half1[e - c0] (fetched by shuffle)
-        float2 ent;
-        {
-            const int sl = (lane - c0) & 31;
-            const float a1 = __shfl_sync(SV_FULL, h1.x, sl), b1 = __shfl_sync(SV_FULL, h1.y, sl);
-            ent = lane < c0 ? h0 : make_float2(a1, b1);
-        }
-        const float xe = lane < cnt ? __ldg(xxs + __float_as_int(ent.y)) : 0.0f;      // norm of the entry's point
-        unsigned ak = lane < cnt ? approx_key(ent.x, lane) : (unsigned)lane;
+    } else if (fast) {
+        const float xe = lane < n ? __ldg(xxs + __float_as_int(ent.y)) : 0.0f;      // norm of the entry's point
+        unsigned ak = lane < n ? approx_key(ent.x, lane) : (unsigned)lane;
         warp_sort32_desc_u32(ak, lane);
         // fetch the entry this position now holds
         const int src = (int)(ak & 31u);
         const float sme = __shfl_sync(SV_FULL, ent.x, src);
         const int jme = __float_as_int(__shfl_sync(SV_FULL, ent.y, src));
         float xj = __shfl_sync(SV_FULL, xe, src);
-        if (lane >= cnt) xj = 0.0f;
+        if (lane >= n) xj = 0.0f;
         jout = jme;
         // ---- neighbours in this order that the error bound does not separate ----
         const float snx = __shfl_down_sync(SV_FULL, sme, 1);
         const float xnx = __shfl_down_sync(SV_FULL, xj, 1);
         bool am = false;
-        if (lane + 1 < cnt) am = (sme - snx) <= 0.5f * p.eps * (2.0f * xxi + xj + xnx);
+        if (lane + 1 < n) am = (sme - snx) <= 0.5f * p.eps * (2.0f * xxi + xj + xnx);
         const unsigned amb = __ballot_sync(SV_FULL, am);
         unsigned rel = amb & (k >= 32 ? 0xFFFFFFFFu : (1u << k) - 1u);       // pairs e <= k-1, then the runs continuing from them
         for (;;) {
@@ -710,7 +771,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
             // composite key: (run start asc, exact score desc, index asc); unflagged entries are their own run
             const unsigned starts = ~(rel << 1);
             kkey_t key = 0ull;
-            if (lane < cnt) {
+            if (lane < n) {
                 const int seg = 31 - __clz(starts & ((2u << lane) - 1u));
                 key = ((kkey_t)(127 - seg) << 44) | ((kkey_t)sc << 12) | (kkey_t)(4095 - jme);
             }
@@ -894,9 +955,10 @@ static bool knn_tc_plan(const svnet_view* in, int B, int N, int k, knn_tc_plan_t
     pl->cnt_bytes = ((size_t)B * N * 2 * sizeof(int) + a256) & ~a256;
     const int Cp = fin_stride(C);
     pl->xcap = Cp <= 68 ? 12 : 8;
+    if (pl->xcap * Cp < 64) pl->xcap = (64 + Cp - 1) / Cp;     // the staging area doubles as a 32-entry scratch (finish kernel: prune)
     if (const char* xc = getenv("SVNET_KNN_XCAP")) {      // tuning aid
         const int v = atoi(xc);
-        if (v >= 2 && v <= 32) pl->xcap = v;
+        if (v >= 2 && v <= 32 && v * Cp >= 64) pl->xcap = v;
     }
     pl->fin_smem = ((size_t)FIN_TAB_FLOATS + (size_t)FIN_WARPS * ((1 + pl->xcap) * Cp)) * sizeof(float);
     return true;
