@@ -40,23 +40,27 @@
 
 namespace {
 
-constexpr int ROWS = 160;        // edge rows per tile (UMMA N)
-constexpr int ROWS_PAD = 163;    // rows per k-block slab: 4 * 163 = 12 (mod 32) words -> conflict-free word stores
+// tile = NW warps x 20 edge rows (UMMA N = 160 or 240); rows per k-block slab = N + 3: 4 * (N + 3) = 12 (mod 32) words
+// -> conflict-free word stores
 constexpr int EPW = 20;          // edges per warp
-constexpr int NWARP = 8;
-constexpr int TMEM_COLS = 256;   // power of two >= ROWS
-#ifndef EDGE_TC_PB
-#define EDGE_TC_PB 10            // q-section passes whose gathers are in flight together
+constexpr int TMEM_COLS = 256;   // power of two >= rows per tile
+// Launch shape: NW warps per CTA (2 CTAs per SM) and BT = neighbour rows whose gathers are in flight together per
+// round (q-section passes, vector-branch edges, scalar-section edges).  8 warps leave 128 registers per thread
+// (BT = 10); 12 warps leave 85 (BT = 5) but hide more latency with warps.
+#ifndef EDGE_TC_NW_SMALL
+#define EDGE_TC_NW_SMALL 8       // layers whose tile fits twice per SM with 12 warps (conv2 / conv3 shapes)
 #endif
-#ifndef EDGE_TC_VB
-#define EDGE_TC_VB 10            // vector-branch edges whose gathers are in flight together
+#ifndef EDGE_TC_BT_SMALL
+#define EDGE_TC_BT_SMALL 10
 #endif
-#ifndef EDGE_TC_SB
-#define EDGE_TC_SB 10            // scalar-section edges whose gathers are in flight together
+#ifndef EDGE_TC_BT_LARGE
+#define EDGE_TC_BT_LARGE 10
 #endif
 
-template <int CS, int CV, int COUT, int CVO, int KE>
+template <int CS, int CV, int COUT, int CVO, int KE, int NW, int BT_>
 struct TC {
+    static constexpr int NWARP = NW, BT = BT_;
+    static constexpr int ROWS = NW * EPW, ROWS_PAD = ROWS + 3;
     static constexpr int TS = CS / 32;
     static constexpr int WPP = KE / EPW;           // warps per point
     static constexpr int NP = NWARP / WPP;         // points per tile
@@ -74,7 +78,7 @@ struct TC {
     static constexpr int TQ0 = CVO, TT0 = 2 * CVO, TU0 = 2 * CVO + 3, TV0 = 2 * CVO + 6;
     static constexpr int VPART = (WPP > 1) ? NWARP * 3 * CVO : 0;     // partial vector sums
     static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + sizeof(float) * (NWARP * WARP_FLOATS + VPART) + 16;
-    static_assert(KE % EPW == 0 && NWARP % WPP == 0 && NP * KE == ROWS, "tile shape");
+    static_assert(KE % EPW == 0 && NWARP % WPP == 0 && NP * KE == ROWS && ROWS <= TMEM_COLS && ROWS % 16 == 0 && NW % 4 == 0, "tile shape");
     static_assert(CS % 32 == 0 && COUT % 32 == 0 && COUT <= 128 && TS <= 2, "scalar widths");
 };
 
@@ -211,7 +215,7 @@ struct QSection {
     static constexpr int GE = 32 / NDS;
     static constexpr int PASSES = (EPW + GE - 1) / GE;
     static constexpr bool ANY_DIFF = DS0 < CV;
-    static constexpr int PB = ANY_DIFF ? (PASSES < EDGE_TC_PB ? PASSES : EDGE_TC_PB) : 1;
+    static constexpr int PB = ANY_DIFF ? (PASSES < S::BT ? PASSES : S::BT) : 1;
     int esub;
     bool lane_on, is_diff;
     float bq[3];
@@ -288,7 +292,7 @@ struct QSection {
 // behind the barrier and the MMA issue.
 template <typename S, int CVO>
 struct VBranch {
-    static constexpr int VB = EDGE_TC_VB;
+    static constexpr int VB = S::BT;
     static constexpr int FULL = CVO / 32, R = CVO % 32, G = R > 0 ? 32 / R : 1, NPASS = FULL + (R > 0 ? 1 : 0);
     struct Lane {
         bool rem, active;
@@ -383,12 +387,12 @@ struct VBranch {
     }
 };
 
-template <int CS, int CV, int COUT, int CVO, int KE>
-__global__ void __launch_bounds__(NWARP * 32, 2)
+template <int CS, int CV, int COUT, int CVO, int KE, int NW, int BT>
+__global__ void __launch_bounds__(NW * 32, 2)
 edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, const float4* __restrict__ tab4, int ntiles)
 {
-    using S = TC<CS, CV, COUT, CVO, KE>;
-    constexpr int TS = S::TS;
+    using S = TC<CS, CV, COUT, CVO, KE, NW, BT>;
+    constexpr int TS = S::TS, NWARP = NW, ROWS = S::ROWS, SB = (BT < EPW && EPW % BT == 0) ? BT : EPW / 2;
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* As = smraw;
     unsigned char* Bs = As + S::A_BYTES;
@@ -496,12 +500,12 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
                 const float uc0 = __fadd_rn(si[0], bc[0]) * TSCALE, uc1 = __fadd_rn(si[TS - 1], bc[TS - 1]) * TSCALE;
                 cw = (TS == 2) ? (sat2(uc0, uc1) << 16) : ((sat2(uc0, 0.0f) & 0xFFu) << 8);
             }
-            // ---- scalar section: one word per edge, EDGE_TC_SB neighbour rows in flight per round ----
+            // ---- scalar section: one word per edge, SB neighbour rows in flight per round ----
 #pragma unroll 1
-            for (int eb = 0; eb < EPW; eb += EDGE_TC_SB) {
-                float sv[EDGE_TC_SB][TS];
+            for (int eb = 0; eb < EPW; eb += SB) {
+                float sv[SB][TS];
 #pragma unroll
-                for (int i = 0; i < EDGE_TC_SB; ++i) {
+                for (int i = 0; i < SB; ++i) {
                     const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, eb + i);
                     const float* sj = sbase + (size_t)j * lds;
                     if (TS == 2) {
@@ -522,7 +526,7 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < EDGE_TC_SB; ++i) {
+                for (int i = 0; i < SB; ++i) {
                     const float u0 = __fmaf_rn(__fsub_rn(sv[i][0], si[0]), TSCALE, bs[0]);
                     const float u1 = (TS == 2) ? __fmaf_rn(__fsub_rn(sv[i][TS - 1], si[TS - 1]), TSCALE, bs[TS - 1]) : 0.0f;
                     const uint32_t w = cw | ((TS == 2) ? sat2(u0, u1) : (sat2(u0, 0.0f) & 0xFFu));
@@ -588,7 +592,7 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
         phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         if (epi_on) {
-            constexpr int PPW = S::NP / 2;                          // points per epilogue warp
+            constexpr int PPW = S::NP / (NWARP / 4);                // points per epilogue warp
 #pragma unroll 1
             for (int pp = 0; pp < PPW; ++pp) {
                 const int pt = grp * PPW + pp;
@@ -644,12 +648,15 @@ int sm_count()
 template <int CS, int CV, int COUT, int CVO, int KE>
 int launch_tc(const svnet_edge_params* p, cudaStream_t st)
 {
-    using S = TC<CS, CV, COUT, CVO, KE>;
+    // 12-warp tiles where two of them fit one SM's shared memory (the conv4 shapes do not: K = 320)
+    constexpr bool SMALL = 2 * (TC<CS, CV, COUT, CVO, KE, EDGE_TC_NW_SMALL, EDGE_TC_BT_SMALL>::SMEM + 1024) <= 228 * 1024;
+    constexpr int NW = SMALL ? EDGE_TC_NW_SMALL : 8, BT = SMALL ? EDGE_TC_BT_SMALL : EDGE_TC_BT_LARGE;
+    using S = TC<CS, CV, COUT, CVO, KE, NW, BT>;
     const long total = (long)p->B * p->N;
     const int ntiles = sv_cdiv(total, S::NP);
     const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
-    SV_CUDA(cudaFuncSetAttribute(edge_bin_tc_kernel<CS, CV, COUT, CVO, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
-    edge_bin_tc_kernel<CS, CV, COUT, CVO, KE><<<grid, NWARP * 32, S::SMEM, st>>>(*p, p->W1tc, reinterpret_cast<const float4*>(p->tab4), ntiles);
+    SV_CUDA(cudaFuncSetAttribute(edge_bin_tc_kernel<CS, CV, COUT, CVO, KE, NW, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+    edge_bin_tc_kernel<CS, CV, COUT, CVO, KE, NW, BT><<<grid, NW * 32, S::SMEM, st>>>(*p, p->W1tc, reinterpret_cast<const float4*>(p->tab4), ntiles);
     SV_CHECK_LAUNCH("svnet_svblock_edge_fwd(tcgen05)");
     return SVNET_OK;
 }
