@@ -44,7 +44,7 @@ def main():
             if pending is not None:
                 d["svnet_knn[layer1]"] = pending
             pending = None
-        elif "edge_bin_fast" in name or "svblock_edge_kernel" in name or "edge_fp_fast" in name:
+        elif "edge_bin_fast" in name or "svblock_edge_kernel" in name or "edge_fp_fast" in name or "edge_bin_tc" in name:
             shape = name.split("kernel<")[1].split(">")[0] if "kernel<" in name else "0, 0, 0, 0"
             d["_edge_" + shape] = (t, pending)
             pending = None
@@ -56,22 +56,45 @@ def main():
             d["svnet_knn[layer%d]" % (i + 2)] = kn
     d = dict(sorted(d.items()))
     json.dump(d, open(os.path.join(ROOT, "profiles", "dram_traffic.json"), "w"), indent=1)
-    # what limits the edge kernels (bench.py quotes it next to the HBM fraction): issue-slot and DRAM utilisation
+    # what limits the hot kernels (bench.py quotes it next to the HBM fraction): the compute-side roofline --
+    # issue-slot, tensor-pipe, L1 / L2 and DRAM utilisation as ncu measured them
+    def col(r, key, default=None):
+        try:
+            return float(r[ix[key]].replace(",", ""))
+        except (KeyError, ValueError):
+            return default
     lim = {}
     edge_rows = {}
+    knn_rows = []          # (tc kernel row, finish kernel row) per layer, in launch order
+    cur = {}
     for r in body:
         name = r[ix["Kernel Name"]]
-        if "edge_bin_fast" in name or "edge_fp_fast" in name:
+        if "edge_bin_fast" in name or "edge_fp_fast" in name or "edge_bin_tc" in name:
             edge_rows[name.split("kernel<")[1].split(">")[0]] = r
+        if "knn_tc_kernel" in name:
+            cur = {"tc": r}
+        elif "knn_finish" in name and "tc" in cur:
+            cur["fin"] = r
+            knn_rows.append(cur)
+            cur = {}
+
+    def entry(r):
+        return {"kernel": r[ix["Kernel Name"]].split("(")[0].replace("void <unnamed>::", ""),
+                "time_us": col(r, "gpu__time_duration.sum"),
+                "issue_slot_pct": col(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "tensor_pipe_pct": col(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                "l1tex_pct": col(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+                "l2_pct": col(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                "dram_pct": col(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                "warps_active_pct": col(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "warp_instructions": col(r, "smsp__inst_executed.sum"),
+                "source": "profiles/%s_ncu_full_all_kernels.md" % tag}
     for i, sh in enumerate(sorted(edge_rows, key=lambda sh: [int(v) for v in sh.split(",")[:4]])):
-        r = edge_rows[sh]
-        lim["svnet_svblock_edge_fwd[layer%d]" % (i + 2)] = {
-            "issue_slot_pct": float(r[ix["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
-            "dram_pct": float(r[ix["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
-            "warp_instructions": float(r[ix["smsp__inst_executed.sum"]].replace(",", "")),
-            "source": "profiles/%s_ncu_full_all_kernels.md" % tag}
+        lim["svnet_svblock_edge_fwd[layer%d]" % (i + 2)] = entry(edge_rows[sh])
+    for i, kr in enumerate(knn_rows[:4]):
+        lim["svnet_knn[layer%d]" % (i + 1)] = {"score_kernel": entry(kr["tc"]), "finish_kernel": entry(kr["fin"])}
     json.dump(lim, open(os.path.join(ROOT, "profiles", "limiters.json"), "w"), indent=1)
-    for src, dst in (("launches_r1.csv", tag + "_launches.csv"), ("bench_r1.json", tag + "_bench.json")):
+    for src, dst in ((tag + "_launches.csv", tag + "_launches.csv"), (tag + "_bench.json", tag + "_bench.json")):
         p = os.path.join(ROOT, "gpurun_out", src)
         if os.path.exists(p):
             shutil.copy(p, os.path.join(ROOT, "profiles", dst))
