@@ -483,9 +483,13 @@ def main():
                 for i in range(n_layers)]
     knn_ms = per_layer("svnet_knn_ws", 4)
     edge_ms = per_layer("svnet_svblock_edge_fwd", 3)
-    cand = [("svnet_knn[layer%d]" % (i + 1), knn_ms[i], knn_kernel_bytes_per_cloud(i) * Bl) for i in range(4)]
-    cand += [("svnet_svblock_edge_fwd[layer%d]" % (i + 2), edge_ms[i], edge_kernel_bytes_per_cloud(i + 1) * Bl) for i in range(3)]
+    # Candidates for "the dominant kernel" are single kernels: each edge layer is one kernel launch; a kNN call is
+    # three kernels (pack, tcgen05 score, finish -- the largest of them is below the layer-4 edge kernel, see the ncu
+    # launch list under profiles/), so the calls are listed in `calls` but the roofline is quoted for a kernel.
+    calls = [("svnet_knn[layer%d]" % (i + 1), knn_ms[i], knn_kernel_bytes_per_cloud(i) * Bl) for i in range(4)]
+    cand = [("svnet_svblock_edge_fwd[layer%d]" % (i + 2), edge_ms[i], edge_kernel_bytes_per_cloud(i + 1) * Bl) for i in range(3)]
     dom = max(cand, key=lambda c: c[1])
+    cand = calls + cand
     achieved = dom[2] / (dom[1] * 1e-3) / 1e9
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture

@@ -51,6 +51,9 @@ constexpr int GM_BYTES = GROUPS * TM * 4;      // group maxima between the passe
 #ifndef FIN_MIN_BLOCKS
 #define FIN_MIN_BLOCKS 6
 #endif
+#ifndef FIN_WIDE_MIN_BLOCKS
+#define FIN_WIDE_MIN_BLOCKS 4                  // two entries per lane: 64 registers per thread
+#endif
 constexpr int FIN_WARPS = 8;                   // finish kernel: warps per CTA, one warp = one row
 constexpr int KMAX = 160;                      // padded channels
 constexpr int MAX_STAGES = 5;
@@ -539,6 +542,28 @@ __device__ __forceinline__ void warp_sort32_desc_u32(unsigned& key, int lane)
         }
     }
 }
+
+// 64 keys in two registers per lane (position = slot * 32 + lane), descending
+__device__ __forceinline__ void warp_sort64_desc_u32(unsigned& k0, unsigned& k1, int lane)
+{
+    warp_sort32_desc_u32(k0, lane);
+    warp_sort32_desc_u32(k1, lane);
+    const unsigned r = __shfl_sync(SV_FULL, k1, 31 - lane);     // k0 ++ reverse(k1) is bitonic: one half-cleaner, then
+    k1 = min(k0, r);                                            // each half is bitonic again and the upper half dominates
+    k0 = max(k0, r);
+    warp_sort32_desc_u32(k0, lane);
+    warp_sort32_desc_u32(k1, lane);
+}
+__device__ __forceinline__ void warp_sort64_desc(kkey_t& k0, kkey_t& k1, int lane)
+{
+    warp_sort32_desc(k0, lane);
+    warp_sort32_desc(k1, lane);
+    const kkey_t r = shfl_key(k1, 31 - lane);
+    const kkey_t hi = k0 > r ? k0 : r, lo = k0 > r ? r : k0;
+    k0 = hi; k1 = lo;
+    warp_sort32_desc(k0, lane);
+    warp_sort32_desc(k1, lane);
+}
 // approximate-order key: order-preserving map of the score with the low 5 bits replaced by the lane
 // that holds the entry (the lost bits are far below the error bound of the score); 0 = empty
 __device__ __forceinline__ unsigned approx_key(float s, int lane)
@@ -820,7 +845,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
 
 // ---- finish kernel for 32 < k <= 48 (part segmentation, k = 40): every survivor is re-scored with the exact
 //      chain, 32 at a time, and merged into the best 64 (two sorted registers per lane) ----
-__global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_wide_kernel(knn_tc_args p)
+__global__ void __launch_bounds__(FIN_WARPS * 32, FIN_WIDE_MIN_BLOCKS) knn_finish_wide_kernel(knn_tc_args p)
 {
     extern __shared__ __align__(16) float fin_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -858,6 +883,143 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_wid
         for (int c = lane; c < C; c += 32) f.arow[c] = sv_feat(p.in, rg, c);
         __syncwarp();
         brute_force_row<2>(p, base, i, f.arow, xxs, lane, best);
+    }
+    // ---- 65 .. 128 survivors: prune with the survivors' own bounds first (see knn_finish_kernel): T = k-th largest
+    // lower bound; entries whose upper bound is below T are out; what is left usually fits the two-entry path ----
+    int n = cnt;
+    bool pruned = false;
+    float2* scratch = reinterpret_cast<float2*>(f.exb);         // per-warp staging area (>= 128 floats, see the plan)
+    if (!brute && cnt > 64) {
+        float2 en4[4];
+        float up[4];
+        unsigned lk[4];
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int e = s4 * 32 + lane;
+            en4[s4] = make_float2(0.0f, 0.0f);
+            up[s4] = -INFINITY;
+            lk[s4] = 0u;
+            if (e < cnt) {
+                en4[s4] = __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
+                const float dl = 0.5f * p.eps * (f.xxi + __ldg(xxs + __float_as_int(en4[s4].y)));
+                const float dlt = dl + 4.76837158203125e-7f * (fabsf(en4[s4].x) + dl);
+                up[s4] = en4[s4].x + dlt;
+                const unsigned fb = __float_as_uint((en4[s4].x - dlt) + 0.0f);
+                lk[s4] = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+            }
+        }
+        warp_sort64_desc_u32(lk[0], lk[1], lane);
+        warp_sort64_desc_u32(lk[2], lk[3], lane);
+        // the 64 largest of the 128: half-cleaner against the reversed second list, then sort
+        const unsigned r0 = __shfl_sync(SV_FULL, lk[3], 31 - lane), r1 = __shfl_sync(SV_FULL, lk[2], 31 - lane);
+        unsigned t0 = max(lk[0], r0), t1 = max(lk[1], r1);
+        warp_sort64_desc_u32(t0, t1, lane);
+        const unsigned tk = __shfl_sync(SV_FULL, (k - 1) < 32 ? t0 : t1, (k - 1) & 31);
+        const float T = __uint_as_float((tk & 0x80000000u) ? (tk & 0x7FFFFFFFu) : ~tk);
+        unsigned keep[4];
+        int kept = 0;
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            keep[s4] = __ballot_sync(SV_FULL, up[s4] >= T);
+            kept += __popc(keep[s4]);
+        }
+        if (kept <= 64 && kept >= k) {
+            int before = 0;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                if ((keep[s4] >> lane) & 1u) scratch[before + __popc(keep[s4] & ((1u << lane) - 1u))] = en4[s4];
+                before += __popc(keep[s4]);
+            }
+            __syncwarp();
+            n = kept;
+            pruned = true;
+        }
+    }
+    if (brute) {
+    } else if (n <= 64) {
+        // ---- approximate-order path with two entries per lane (as knn_finish_kernel, positions 0..63): sort by the
+        // tensor-core score; neighbours in that order which the error bound separates are certainly ordered; runs of
+        // closer scores that touch the first k positions are re-scored with the exact chain ----
+        float2 en[2];
+        float xe[2];
+        unsigned ak[2];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+            const int e = s2 * 32 + lane;
+            en[s2] = make_float2(0.0f, 0.0f);
+            xe[s2] = 0.0f;
+            ak[s2] = (unsigned)(s2 * 32 + lane);                   // empty slots: keys 0..63, below every real key
+            if (e < n) {
+                en[s2] = pruned ? scratch[e] : __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
+                xe[s2] = __ldg(xxs + __float_as_int(en[s2].y));
+                const unsigned fb = __float_as_uint(en[s2].x + 0.0f);
+                const unsigned hi = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+                ak[s2] = ((hi & ~63u) | (unsigned)(s2 * 32 + lane)) | 64u * (hi < 128u);
+            }
+        }
+        __syncwarp();                                   // the scratch entries are in registers now (exact_keys reuses the area)
+        warp_sort64_desc_u32(ak[0], ak[1], lane);
+        float sme[2], xj[2];
+        int jme[2];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+            // fetch the entry that position s2 * 32 + lane now holds: source (slot, lane) in the low 6 bits
+            const int sl = (int)(ak[s2] & 31u), ss = (int)((ak[s2] >> 5) & 1u);
+            const float a0 = __shfl_sync(SV_FULL, en[0].x, sl), a1 = __shfl_sync(SV_FULL, en[1].x, sl);
+            const float b0 = __shfl_sync(SV_FULL, en[0].y, sl), b1 = __shfl_sync(SV_FULL, en[1].y, sl);
+            const float x0 = __shfl_sync(SV_FULL, xe[0], sl), x1 = __shfl_sync(SV_FULL, xe[1], sl);
+            sme[s2] = ss ? a1 : a0;
+            jme[s2] = __float_as_int(ss ? b1 : b0);
+            xj[s2] = (s2 * 32 + lane < n) ? (ss ? x1 : x0) : 0.0f;
+        }
+        // neighbours in this order that the error bound does not separate (position p against p + 1)
+        unsigned long long amb = 0ull;
+        {
+            float snx[2], xnx[2];
+            snx[0] = __shfl_down_sync(SV_FULL, sme[0], 1);
+            xnx[0] = __shfl_down_sync(SV_FULL, xj[0], 1);
+            snx[1] = __shfl_down_sync(SV_FULL, sme[1], 1);
+            xnx[1] = __shfl_down_sync(SV_FULL, xj[1], 1);
+            const float s10 = __shfl_sync(SV_FULL, sme[1], 0), x10 = __shfl_sync(SV_FULL, xj[1], 0);
+            if (lane == 31) { snx[0] = s10; xnx[0] = x10; }
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                bool am = false;
+                if (s2 * 32 + lane + 1 < n) am = (sme[s2] - snx[s2]) <= 0.5f * p.eps * (2.0f * f.xxi + xj[s2] + xnx[s2]);
+                amb |= (unsigned long long)__ballot_sync(SV_FULL, am) << (32 * s2);
+            }
+        }
+        unsigned long long rel = amb & ((1ull << k) - 1ull);          // pairs p <= k-1, then the runs continuing from them
+        for (;;) {
+            const unsigned long long nx = (rel << 1) & amb & ~rel;
+            if (!nx) break;
+            rel |= nx;
+        }
+        int jout[2] = {jme[0], jme[1]};
+        if (rel) {
+            const unsigned long long flagged = rel | (rel << 1);
+            unsigned sc[2];
+            sc[0] = exact_keys(f, (unsigned)flagged, jme[0], xj[0], sme[0]);
+            sc[1] = exact_keys(f, (unsigned)(flagged >> 32), jme[1], xj[1], sme[1]);
+            // composite key: (run start asc, exact score desc, index asc); unflagged entries are their own run
+            const unsigned long long starts = ~(rel << 1);
+            kkey_t key[2] = {0ull, 0ull};
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int pos = s2 * 32 + lane;
+                if (pos < n) {
+                    const unsigned long long below = pos == 63 ? ~0ull : ((2ull << pos) - 1ull);
+                    const int seg = 63 - __clzll((long long)(starts & below));
+                    key[s2] = ((kkey_t)(127 - seg) << 44) | ((kkey_t)sc[s2] << 12) | (kkey_t)(4095 - jme[s2]);
+                }
+            }
+            warp_sort64_desc(key[0], key[1], lane);
+            jout[0] = 4095 - (int)(key[0] & 4095ull);
+            jout[1] = 4095 - (int)(key[1] & 4095ull);
+        }
+        // hand the ordered indices to the common store below as keys (only the index part is read)
+        best[0] = (kkey_t)(unsigned)(~jout[0]);
+        best[1] = (kkey_t)(unsigned)(~jout[1]);
     } else {
         for (int e0 = 0; e0 < cnt; e0 += 32) {
             const int e = e0 + lane;
@@ -955,10 +1117,13 @@ static bool knn_tc_plan(const svnet_view* in, int B, int N, int k, knn_tc_plan_t
     pl->cnt_bytes = ((size_t)B * N * 2 * sizeof(int) + a256) & ~a256;
     const int Cp = fin_stride(C);
     pl->xcap = Cp <= 68 ? 12 : 8;
-    if (pl->xcap * Cp < 64) pl->xcap = (64 + Cp - 1) / Cp;     // the staging area doubles as a 32-entry scratch (finish kernel: prune)
+    {   // the staging area doubles as a scratch for the pruned entries (32 entries, k <= 32; 64 entries, k > 32)
+        const int need = k > 32 ? 128 : 64;
+        if (pl->xcap * Cp < need) pl->xcap = (need + Cp - 1) / Cp;
+    }
     if (const char* xc = getenv("SVNET_KNN_XCAP")) {      // tuning aid
         const int v = atoi(xc);
-        if (v >= 2 && v <= 32 && v * Cp >= 64) pl->xcap = v;
+        if (v >= 2 && v <= 32 && v * Cp >= (k > 32 ? 128 : 64)) pl->xcap = v;
     }
     pl->fin_smem = ((size_t)FIN_TAB_FLOATS + (size_t)FIN_WARPS * ((1 + pl->xcap) * Cp)) * sizeof(float);
     return true;
