@@ -104,10 +104,17 @@ class SV_DGCNN_PSEG(nn.Module):
         nv.pool_rows(v5, 3 * C5v, 3 * C5v, B, N, want_max=False, want_mean=True, mean_out=vp)
         s6, v6 = self.conv6.forward_rows(sp, vp, B, 1)
         x_pool, _ = self.svfuse2.forward_rows(s6, v6)                             # (B, 520)
-        f3, _ = self.svfuse3.forward_rows(s5, v5)                                 # (R, 1016)
-        C3 = f3.shape[1]
+        # svfuse3 + max over points (sv_dgcnn_partseg.py:110-111) without the (R, 1016) table: the scalar half is the
+        # max of s5 that conv6's input already needed (sp), v2s(v5) is reduced on the fly (svnet_svfuse_pool)
+        C3 = C5s + 3 * C5v
         glob = torch.empty((B, C3 + x_pool.shape[1] + 64), dtype=torch.float32, device=dev)
-        nv.pool_rows(f3, C3, C3, B, N, want_max=True, max_out=glob, ldo=glob.shape[1])
+        if 3 * C5v <= 512:
+            glob[:, :C5s].copy_(sp)
+            Wz3, zs3 = self.svfuse3.v2s.wz()
+            nv.svfuse_pool(v5, B, N, Wz3, zs3, glob[:, C5s:], None, glob.shape[1])
+        else:
+            f3, _ = self.svfuse3.forward_rows(s5, v5)                             # (R, 1016)
+            nv.pool_rows(f3, C3, C3, B, N, want_max=True, max_out=glob, ldo=glob.shape[1])
         glob[:, C3:C3 + x_pool.shape[1]].copy_(x_pool)
         lab = dense_rows(self.conv7[0].weight, l.reshape(B, -1).contiguous().float(), bn=self.conv7.bn_folded(),
                          act=nv.ACT_LEAKY)
