@@ -15,6 +15,9 @@ COLS = [
     ("smsp__inst_executed.sum", "warp-inst"),
     ("dram__bytes_read.sum", "dram rd"),
     ("dram__bytes_write.sum", "dram wr"),
+    ("dram__bytes.sum.per_second", "dram B/s"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex%"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
     ("lts__t_bytes.sum", "L2 bytes"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),

@@ -24,8 +24,16 @@ def main():
     ix = {h: i for i, h in enumerate(hdr)}
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
+    rate = {"byte/s": 1, "Kbyte/s": 1e3, "Mbyte/s": 1e6, "Gbyte/s": 1e9, "Tbyte/s": 1e12}
+    tunit = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+
     def nbytes(r, key):
-        return float(r[ix[key]].replace(",", "")) * mult[units[ix[key]]]
+        if key in ix:
+            return float(r[ix[key]].replace(",", "")) * mult[units[ix[key]]]
+        if key == "dram__bytes_read.sum":      # section-limited capture: total DRAM bytes = rate x duration (read + write)
+            bi, ti = ix["dram__bytes.sum.per_second"], ix["gpu__time_duration.sum"]
+            return float(r[bi].replace(",", "")) * rate[units[bi]] * float(r[ti].replace(",", "")) * tunit[units[ti]]
+        return 0.0
     # A kNN call = pack + tcgen05 + finish kernels (or the CUDA-core knn_kernel); it belongs to the layer
     # of the next edge kernel in launch order.  Edge layers are told apart by their template shapes, so a
     # capture that starts mid-forward or covers more than one forward still maps correctly.
