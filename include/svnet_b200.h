@@ -216,6 +216,13 @@ size_t svnet_edge_tc_weight_bytes(int Cs, int Cv, int Cout, int Cvo, int k);
 int svnet_edge_tc_table_cols(int Cv, int Cvo);
 int svnet_edge_tc_pack_w(const float* W1, int ldw, int Cs, int Cv, int Cout, unsigned char* out, void* stream);
 
+/* Multi-GPU: all-gather of the per-rank outputs -- `count_per_rank` floats from `local` of every rank into
+ * `all` (rank-major) -- on the caller's ncclComm_t and stream; replaces nn.DataParallel's gather
+ * (main_cls_dgcnn.py:125, main_partseg_dgcnn.py:116).  The library resolves ncclAllGather at the first call from the NCCL
+ * already loaded in the process (PyTorch's) or from libnccl.so.2; it does not link against NCCL.  Inside an
+ * ncclGroupStart/End pair when one thread drives several devices. */
+int svnet_allgather_logits(void* nccl_comm, const float* local, float* all, size_t count_per_rank, void* stream);
+
 /* ---- per-row building blocks (conv5, PointNet per-point blocks, heads, module-level API) ---- */
 
 /* u = [s | v2s(v)] for every row (sv_layers.py:185-186 / SVFuse :218-219), rows handled three at a

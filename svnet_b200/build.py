@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsvnet_b200.so")
 SOURCES = ["misc.cu", "knn.cu", "knn_tc.cu", "gate.cu", "edge_xyz.cu", "edge.cu", "edge_fast.cu", "edge_tc.cu", "rows.cu",
-           "rows_fast.cu", "binlinear_tc.cu", "gemm.cu", "gemm_tc.cu", "gemm_tcgen05.cu", "gemm_tc3.cu", "head.cu"]
+           "rows_fast.cu", "binlinear_tc.cu", "gemm.cu", "gemm_tc.cu", "gemm_tcgen05.cu", "gemm_tc3.cu", "head.cu", "collective.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -51,7 +51,7 @@ def build_native(force=False, verbose=False):
         list(ex.map(run, jobs))
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in SOURCES]
     if jobs or force or _stale(LIB, objs):
-        run([nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + objs)
+        run([nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 

@@ -57,6 +57,7 @@ constexpr int GM_BYTES = GROUPS * TM * 4;      // group maxima between the passe
 constexpr int FIN_WARPS = 8;                   // finish kernel: warps per CTA, one warp = one row
 constexpr int KMAX = 160;                      // padded channels
 constexpr int MAX_STAGES = 5;
+constexpr int KNN_PASSA3_MAX_N = 1024;         // threshold pass with three plane products up to this cloud size
 constexpr int KNN_TC_MAX_K = 48;               // k <= 32: approximate-order finish; 33..48: every survivor re-scored
                                                // (the 64-group threshold gets loose as k approaches 64)
 
@@ -1150,10 +1151,14 @@ int svnet_knn_tc_dispatch(const svnet_view* in, int B, int N, int k, int32_t* id
     a.in = *in; a.N = N; a.k = k; a.NCB = pl.NCB; a.NKC = pl.NKC; a.stages = pl.stages; a.xcap = pl.xcap;
     a.eps = knn_tc_eps(in->Cs + 3 * in->Cv);
     a.epsA = knn_tc_eps3(in->Cs + 3 * in->Cv);
-    a.passA3 = 1;
+    // the three-product bound is ~6x looser: fine while neighbours are sparse relative to it, but at large N the
+    // survivor queues overflow into the brute-force path (N = 4096: kNN 13 ms instead of 4 ms per 32 clouds)
+    a.passA3 = N <= KNN_PASSA3_MAX_N ? 1 : 0;
     if (const char* pa = getenv("SVNET_KNN_PASSA")) {
-        if (pa[0] == '6') { a.passA3 = 0; a.epsA = a.eps; }
+        if (pa[0] == '6') a.passA3 = 0;
+        if (pa[0] == '3') a.passA3 = 1;
     }
+    if (!a.passA3) a.epsA = a.eps;
     {
         const char* sv = getenv("SVNET_KNN_TC_STATS");
         a.stats = (sv && sv[0] == '1') ? 1 : 0;

@@ -50,30 +50,60 @@ class _Cached:
     """
 
     def _packed(self, key, deps, builder):
-        src = self.__dict__.get("_sv_src")
-        owner = self if src is None else src
-        cache = owner.__dict__.setdefault("_sv_cache", {})
-        tensors = [_resolve(owner, d) for d in deps]
-        dev = _resolve(self, deps[0]).device
+        d = self.__dict__
+        src = d.get("_sv_src")
+        if src is None:
+            # fast path (every forward): one dict lookup, then the cached dependency tensors' (data_ptr, _version)
+            cache = d.get("_sv_cache")
+            if cache is None:
+                cache = d["_sv_cache"] = {}
+            hit = cache.get(key)
+            if hit is not None:
+                ok = True
+                for t, (ptr, ver) in zip(hit[3], hit[0]):
+                    if t._version != ver or t.data_ptr() != ptr:
+                        ok = False
+                        break
+                if ok:
+                    if hit[2] is not None:
+                        self._order_after(hit)
+                    return hit[1]
+            owner, k = self, key
+            tensors = [_resolve(self, dep) for dep in deps]
+        else:
+            # nn.DataParallel replica: dependencies are the source module's parameters, one slot per device
+            owner = src
+            cache = owner.__dict__.setdefault("_sv_cache", {})
+            tensors = [_resolve(owner, dep) for dep in deps]
+            dev = _resolve(self, deps[0]).device
+            k = key if dev == tensors[0].device else (key, dev)     # the replica on the source's device shares its slot
+            hit = cache.get(k)
+            if hit is not None and hit[0] == tuple((t.data_ptr(), t._version) for t in tensors):
+                if hit[2] is not None:
+                    self._order_after(hit)
+                return hit[1]
         sig = tuple((t.data_ptr(), t._version) for t in tensors)
-        k = (key, dev)
-        hit = cache.get(k)
-        if hit is None or hit[0] != sig:
-            with torch.no_grad():
-                val = builder()
-            ev = None
-            if dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(dev))
-            hit = [sig, val, ev]
-            cache[k] = hit
-            _Cached.BUILDS += 1
-        elif hit[2] is not None and not torch.cuda.is_current_stream_capturing():
-            if hit[2].query():
-                hit[2] = None                     # producers retired: no ordering needed any more
-            else:
-                torch.cuda.current_stream(dev).wait_event(hit[2])
-        return hit[1]
+        with torch.no_grad():
+            val = builder()
+        ev = None
+        dev = _resolve(self, deps[0]).device
+        if dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+        cache[k] = [sig, val, ev, tensors]
+        _Cached.BUILDS += 1
+        return val
+
+    @staticmethod
+    def _order_after(hit):
+        """Consumers on another stream wait for the producer kernels of a packed tensor until they have retired once."""
+        if torch.cuda.is_current_stream_capturing():
+            return
+        ev = hit[2]
+        if ev.query():
+            hit[2] = None
+        else:
+            torch.cuda.current_stream().wait_event(ev)
 
     BUILDS = 0          # builder invocations (tests count re-packs with it)
 

@@ -53,3 +53,35 @@ def test_sharded_equals_unsharded_bit_for_bit_nccl():
     res = json.loads(line)
     assert res["world"] == 2
     assert all(v["bit_identical_on_every_rank"] for v in res.values() if isinstance(v, dict)), res
+
+
+def test_c_abi_allgather_on_raw_nccl_communicators():
+    """svnet_allgather_logits (the C-ABI face of the path's one collective) on ncclComm_t handles made with
+    ncclCommInitAll, one thread driving both devices inside a group call."""
+    import ctypes
+    from svnet_b200 import _native as nv
+    lib = nv.lib()
+    nccl = ctypes.CDLL(None)                         # torch has NCCL loaded; same symbols the library resolves
+    if not hasattr(nccl, "ncclCommInitAll"):
+        nccl = ctypes.CDLL("libnccl.so.2")
+    comms = (ctypes.c_void_p * 2)()
+    devs = (ctypes.c_int * 2)(0, 1)
+    assert nccl.ncclCommInitAll(comms, 2, devs) == 0
+    count = 5 * 40
+    local = [torch.arange(count, dtype=torch.float32, device="cuda:%d" % r) + 1000.0 * r for r in range(2)]
+    out = [torch.zeros(2 * count, dtype=torch.float32, device="cuda:%d" % r) for r in range(2)]
+    assert nccl.ncclGroupStart() == 0
+    for r in range(2):
+        with torch.cuda.device(r):
+            rc = lib.svnet_allgather_logits(ctypes.c_void_p(comms[r]), ctypes.c_void_p(local[r].data_ptr()),
+                                            ctypes.c_void_p(out[r].data_ptr()), ctypes.c_size_t(count),
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            assert rc == 0, lib.svnet_last_error().decode()
+    assert nccl.ncclGroupEnd() == 0
+    for r in range(2):
+        torch.cuda.synchronize(r)
+    want = torch.cat([t.cpu() for t in local])
+    for r in range(2):
+        assert torch.equal(out[r].cpu(), want)
+    for r in range(2):
+        nccl.ncclCommDestroy(ctypes.c_void_p(comms[r]))

@@ -49,9 +49,9 @@ def main():
         ms = time_ms(lambda: net(x, l))
         out["cfg4 SV-DGCNN binary pseg B=16/GPU N=2048 k=40"] = {"ms": ms, "clouds_per_s": 16 / ms * 1e3}
         net = build(sv.SV_DGCNN_CLS, make_args(k=20, binary=True), 40, 1005)
-        for B, N in [(32, 1024), (128, 1024), (512, 1024), (32, 2048), (128, 2048), (32, 4096), (128, 4096)]:
+        for B, N in [(32, 1024), (128, 1024), (512, 1024), (2048, 1024), (4096, 1024), (32, 2048), (128, 2048), (512, 2048), (32, 4096), (128, 4096)]:
             x = synthetic_clouds(B, N, 1005).cuda()
-            ms = time_ms(lambda: net(x), reps=3)
+            ms = time_ms(lambda: net(x), reps=3 if B <= 512 else 2)
             out["cfg5 SV-DGCNN binary cls B=%d N=%d k=20" % (B, N)] = {"ms": ms, "clouds_per_s": B / ms * 1e3}
         net = build(sv.SV_PointNet_CLS, make_args(k=20, binary=False), 40, 1001)
         x = synthetic_clouds(32, 1024, 1001).cuda()
