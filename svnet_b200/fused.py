@@ -36,6 +36,10 @@ def chunked(impl, x, extras=(), hooks=False):
     A batch that fits one pass is split into up to N_SPLIT sub-batches (at least 8 clouds each) that run on
     their own CUDA streams: kernels whose grids leave SMs idle (the tensor-core kNN, the per-cloud
     gate / head kernels) overlap with the other sub-batches' kernels.  Test hooks (forced indices / recording) disable both."""
+    if x.is_cuda and x.device.index != torch.cuda.current_device():
+        # scratch tensors and the launch stream follow the current device: make it the input's device
+        with torch.cuda.device(x.device):
+            return chunked(impl, x, extras, hooks)
     B, N = x.shape[0], x.shape[-1]
     per = max(1, MAX_POINTS_PER_PASS // max(N, 1))
     if hooks:

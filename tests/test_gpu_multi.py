@@ -85,3 +85,18 @@ def test_c_abi_allgather_on_raw_nccl_communicators():
         assert torch.equal(out[r].cpu(), want)
     for r in range(2):
         nccl.ncclCommDestroy(ctypes.c_void_p(comms[r]))
+
+
+def test_model_on_second_device_while_first_is_current():
+    """A model moved with .to('cuda:1') while cuda:0 is the current device must launch on cuda:1 (scratch and stream
+    follow the input's device) and give the same bits as on cuda:0."""
+    import svnet_b200 as sv
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=20, binary=True), 40)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=11))
+    x = synthetic_clouds(2, 256, 11)
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        y0 = net.to("cuda:0").eval()(x.to("cuda:0")).cpu()
+        y1 = net.to("cuda:1").eval()(x.to("cuda:1")).cpu()
+    assert torch.cuda.current_device() == 0
+    assert torch.equal(y0, y1)
