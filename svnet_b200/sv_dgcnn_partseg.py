@@ -94,13 +94,20 @@ class SV_DGCNN_PSEG(nn.Module):
         R = B * N
         dev = x.device
         s_cat, v_cat = dgcnn_trunk(self, x, forced_idx, record)
-        x_fine, _ = self.svfuse1.forward_rows(s_cat, v_cat)                       # (R, 544)
-        s5, v5 = self.conv5.forward_rows(s_cat, v_cat, B, N)                      # (R,512), (R,3,168)
-        # global branch: svpool over points -> conv6 -> svfuse2
         C5s, C5v = self.conv5.out_dims
+        fuse3 = 3 * C5v <= 512             # svfuse3 + max pooling without the (R, 1016) table (svnet_svfuse_pool)
+        # svfuse1's output only feeds conv8: a binary conv8 takes its sign words straight from (s_cat, v_cat)
+        lean_fine = self.binary and record is None
+        x_fine = None if lean_fine else self.svfuse1.forward_rows(s_cat, v_cat)[0]          # (R, 544)
+        # global branch: svpool over points -> conv6 -> svfuse2.  Per point only v5 is needed further on (with fuse3):
+        # the binary conv5 pools its scalar output in the epilogue of its tensor-core linear and never writes it
         sp = torch.empty((B, C5s), dtype=torch.float32, device=dev)
         vp = torch.empty((B, 3, C5v), dtype=torch.float32, device=dev)
-        nv.pool_rows(s5, C5s, C5s, B, N, want_max=True, want_mean=False, max_out=sp)
+        if fuse3:
+            s5, v5 = self.conv5.forward_rows(s_cat, v_cat, B, N, s_pool=(sp, None, C5s))    # s5 is None on the fused path
+        else:
+            s5, v5 = self.conv5.forward_rows(s_cat, v_cat, B, N)                  # (R,512), (R,3,168)
+            nv.pool_rows(s5, C5s, C5s, B, N, want_max=True, want_mean=False, max_out=sp)
         nv.pool_rows(v5, 3 * C5v, 3 * C5v, B, N, want_max=False, want_mean=True, mean_out=vp)
         s6, v6 = self.conv6.forward_rows(sp, vp, B, 1)
         x_pool, _ = self.svfuse2.forward_rows(s6, v6)                             # (B, 520)
@@ -108,7 +115,7 @@ class SV_DGCNN_PSEG(nn.Module):
         # max of s5 that conv6's input already needed (sp), v2s(v5) is reduced on the fly (svnet_svfuse_pool)
         C3 = C5s + 3 * C5v
         glob = torch.empty((B, C3 + x_pool.shape[1] + 64), dtype=torch.float32, device=dev)
-        if 3 * C5v <= 512:
+        if fuse3:
             glob[:, :C5s].copy_(sp)
             Wz3, zs3 = self.svfuse3.v2s.wz()
             nv.svfuse_pool(v5, B, N, Wz3, zs3, glob[:, C5s:], None, glob.shape[1])
@@ -120,7 +127,12 @@ class SV_DGCNN_PSEG(nn.Module):
                          act=nv.ACT_LEAKY)
         glob[:, C3 + x_pool.shape[1]:].copy_(lab)
         # segmentation head on rows; glob is constant per cloud
-        h = self.conv8[0].forward_rows(x_fine, bn=self.conv8.bn_folded(), act=nv.ACT_LEAKY, cloud=glob, rows_per_cloud=N)
+        if lean_fine:
+            Wz1, zs1 = self.svfuse1.v2s.wz()
+            h = self.conv8[0].forward_rows(None, bn=self.conv8.bn_folded(), act=nv.ACT_LEAKY, cloud=glob, rows_per_cloud=N,
+                                           sv_in=(nv.view_of(s_cat, v_cat), R, Wz1, zs1))
+        else:
+            h = self.conv8[0].forward_rows(x_fine, bn=self.conv8.bn_folded(), act=nv.ACT_LEAKY, cloud=glob, rows_per_cloud=N)
         h = self.conv9[0].forward_rows(h, bn=self.conv9.bn_folded(), act=nv.ACT_LEAKY)
         h = self.conv10[0].forward_rows(h, bn=self.conv10.bn_folded(), act=nv.ACT_LEAKY)
         out = dense_rows(self.conv11.weight, h)                                   # (R, num_part)

@@ -206,12 +206,19 @@ class Conv1d(_Cached, nn.Conv1d):
     def beta_vec(self):
         return self._packed("beta", ("beta",), lambda: self.beta.detach().reshape(-1).contiguous())
 
-    def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE, cloud=None, rows_per_cloud=1):
+    def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE, cloud=None, rows_per_cloud=1, sv_in=None):
         """x2d (rows, Kp) -> (rows, Cout).  ``cloud`` (B, Kc), if given, holds per-cloud-constant
         leading input channels (the ``repeat(1, 1, num_points)`` block of sv_dgcnn_partseg.py:118):
         the layer input is [cloud[row // rows_per_cloud] | x2d[row]] and the constant part of every
-        dot product is reduced once per cloud instead of once per point."""
-        rows, Kp = x2d.shape
+        dot product is reduced once per cloud instead of once per point.
+        ``sv_in`` = (view, rows, Wz, zscale) replaces x2d by SVFuse's output [s | v2s(v)] of that view (binary layers
+        only): the sign words come straight from (s, v), the float table is never written."""
+        if sv_in is not None:
+            assert self.binary and x2d is None
+            view, rows, Wz_in, zs_in = sv_in
+            Kp = view.Cs + 3 * view.Cv
+        else:
+            rows, Kp = x2d.shape
         Cout = self.out_channels
         Kc = cloud.shape[1] if cloud is not None else 0
         assert Kc + Kp == self.in_channels, (Kc, Kp, self.in_channels)
@@ -221,7 +228,10 @@ class Conv1d(_Cached, nn.Conv1d):
             if cloud is not None:
                 cb, cm, cn = nv.rows_prep(nv.view_of(cloud, None), cloud.shape[0], beta=beta[:Kc], want_bits=True)
                 cdot = nv.binlinear_rows(cb, cm, cn, Kc, self.sign_bits(0, Kc), Cout, out_i32=True)
-            bits, mask, nvalid = nv.rows_prep(nv.view_of(x2d, None), rows, beta=beta[Kc:], want_bits=True)
+            if sv_in is not None:
+                bits, mask, nvalid = nv.rows_prep(view, rows, Wz=Wz_in, zscale=zs_in, beta=beta[Kc:], want_bits=True)
+            else:
+                bits, mask, nvalid = nv.rows_prep(nv.view_of(x2d, None), rows, beta=beta[Kc:], want_bits=True)
             return nv.binlinear_rows(bits, mask, nvalid, Kp, self.sign_bits(Kc, Kc + Kp), Cout, scale=self.scale_vec(),
                                      bn=bn, act=act, cloud_dot=cdot, rows_per_cloud=rows_per_cloud)
         if cloud is not None:
@@ -437,8 +447,8 @@ class SVBlock(_Cached, nn.Module):
                        colscale=lin2.scale_vec() if lin2.bw else None, bn=self.bn2.folded(), vbn=True, gate=gate,
                        groups_per_cloud=rows_per_cloud)
         if s_pool is not None and not fused_pool:
-            nv.pool_rows(s_out, lds_out, Cso, B, rows_per_cloud, want_max=True, want_mean=True, max_out=s_pool[0],
-                         mean_out=s_pool[1], ldo=s_pool[2])
+            nv.pool_rows(s_out, lds_out, Cso, B, rows_per_cloud, want_max=s_pool[0] is not None,
+                         want_mean=s_pool[1] is not None, max_out=s_pool[0], mean_out=s_pool[1], ldo=s_pool[2])
         return s_out, v_out
 
     def forward(self, x):
