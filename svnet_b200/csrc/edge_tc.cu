@@ -216,7 +216,7 @@ struct QSection {
     static constexpr int PASSES = (EPW + GE - 1) / GE;
     static constexpr bool ANY_DIFF = DS0 < CV;
     static constexpr int PB = ANY_DIFF ? (PASSES < S::BT ? PASSES : S::BT) : 1;
-    int esub;
+    int esub, dcol;
     bool lane_on, is_diff;
     float bq[3];
     float4 vi;
@@ -233,14 +233,13 @@ struct QSection {
         for (int m = 0; m < 3; ++m) bq[m] = lane_on ? __ldg(p.beta + 2 * S::TS * 32 + 3 * ds + m) * TSCALE : 0.0f;
         const int pos = S::KQ0 + 4 * ds;
         bst = brow0 + (uint32_t)((pos >> 4) * S::KBB + (pos & 15));
+        dcol = S::TV0 + (lane_on ? (is_diff ? ds : ds - CV) : 0);
     }
     // tabc: table of the cloud, trow: table row of the centre point
-    __device__ __forceinline__ void centre(const float4* tabc, const float4* trow, int lane)
+    __device__ __forceinline__ void centre(const float4* tabc, const float4* trow)
     {
-        const int ds = DS0 + lane % NDS;
-        const int d = lane_on ? (is_diff ? ds : ds - CV) : 0;
-        vcol = tabc + S::TV0 + d;
-        vi = __ldg(trow + S::TV0 + d);
+        vcol = tabc + dcol;
+        vi = __ldg(trow + dcol);
     }
     // my_j: neighbour index of edge `lane` of this warp; zb: shared address of the frames [e][m][4].
     // PB passes per round: all their gathers are issued before the first use (one L2 latency per round).
@@ -310,7 +309,18 @@ struct VBranch {
         L.cc = L.active ? L.c : 0;
         return L;
     }
-    float4 w0[VB], pi0, qi0;
+    float4 w0[VB], pi[NPASS], qi[NPASS];
+    float a2[NPASS], c2[NPASS], gt[NPASS];
+
+    __device__ __forceinline__ void init(const svnet_edge_params& p, int lane)
+    {
+#pragma unroll
+        for (int pass = 0; pass < NPASS; ++pass) {
+            const Lane L = lane_of(pass, lane);
+            a2[pass] = __ldg(p.bn2_a + L.cc);
+            c2[pass] = __ldg(p.bn2_c + L.cc);
+        }
+    }
 
     __device__ __forceinline__ void load_round(float4 (&w)[VB], const float4* pcol, int my_j, int e0, int ng) const
     {
@@ -321,11 +331,16 @@ struct VBranch {
             w[i] = __ldg(pcol + (size_t)j * S::NC);
         }
     }
-    __device__ __forceinline__ void prefetch(const float4* tabc, const float4* trow, int my_j, int lane)
+    __device__ __forceinline__ void prefetch(const svnet_edge_params& p, int b, const float4* tabc, const float4* trow, int my_j, int lane)
     {
+#pragma unroll
+        for (int pass = 0; pass < NPASS; ++pass) {
+            const Lane L = lane_of(pass, lane);
+            pi[pass] = __ldg(trow + L.cc);
+            qi[pass] = __ldg(trow + S::TQ0 + L.cc);
+            gt[pass] = __ldg(p.gate + (long)b * CVO + L.cc);
+        }
         const Lane L = lane_of(0, lane);
-        pi0 = __ldg(trow + L.cc);
-        qi0 = __ldg(trow + S::TQ0 + L.cc);
         load_round(w0, tabc + L.cc, my_j, L.g, L.ng);
     }
     __device__ __forceinline__ void run(const svnet_edge_params& p, long r, int b, const float4* tabc, const float4* trow, int my_j,
@@ -336,9 +351,8 @@ struct VBranch {
         for (int pass = 0; pass < NPASS; ++pass) {
             const Lane L = lane_of(pass, lane);
             float sum[3] = {0.0f, 0.0f, 0.0f};
-            const float4 pi = pass == 0 ? pi0 : __ldg(trow + L.cc), qi = pass == 0 ? qi0 : __ldg(trow + S::TQ0 + L.cc);
-            const float d0 = qi.x - pi.x, d1 = qi.y - pi.y, d2 = qi.z - pi.z;
-            const float a2 = __ldg(p.bn2_a + L.cc), c2 = __ldg(p.bn2_c + L.cc);
+            const float d0 = qi[pass].x - pi[pass].x, d1 = qi[pass].y - pi[pass].y, d2 = qi[pass].z - pi[pass].z;
+            const float a2p = a2[pass], c2p = c2[pass];
             const float4* pcol = tabc + L.cc;
             auto consume = [&](const float4 (&w)[VB], int e0) {
 #pragma unroll
@@ -346,7 +360,7 @@ struct VBranch {
                     if (e0 + i * L.ng < EPW) {
                         const float w0_ = w[i].x + d0, w1 = w[i].y + d1, w2 = w[i].z + d2;
                         const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0_ * w0_));
-                        const float t = fmaf(c2, fast_rcp(fast_sqrt(s2) + 1e-6f), a2);      // (n a2 + c2) / n,  n = |w| + 1e-6
+                        const float t = fmaf(c2p, fast_rcp(fast_sqrt(s2) + 1e-6f), a2p);      // (n a2 + c2) / n,  n = |w| + 1e-6
                         sum[0] = fmaf(w0_, t, sum[0]);
                         sum[1] = fmaf(w1, t, sum[1]);
                         sum[2] = fmaf(w2, t, sum[2]);
@@ -378,9 +392,9 @@ struct VBranch {
 #pragma unroll
                     for (int x = 0; x < 3; ++x) partial[x * CVO + L.c] = sum[x];
                 } else {
-                    const float gt = p.gate[(long)b * CVO + L.c] * inv_k;
+                    const float g = gt[pass] * inv_k;
 #pragma unroll
-                    for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + L.c] = sum[x] * gt;
+                    for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + L.c] = sum[x] * g;
                 }
             }
         }
@@ -450,6 +464,8 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
     if (epi_on) { sc1 = __ldg(p.scale1 + oc); a1 = __ldg(p.bn1_a + oc); c1 = __ldg(p.bn1_c + oc); }
     const int m_lane = lane % 3, e_lane = lane / 3;                // frame tasks: 10 edges x 3 columns per round
 
+    VBranch<S, CVO> vb;
+    vb.init(p, lane);
     // neighbour indices of the first tile (later tiles are prefetched one iteration ahead)
     int next_j = 0;
     {
@@ -490,8 +506,8 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
             } else {
                 si[0] = __ldg(srow + lane);
             }
-            q0.centre(tabc, trow, lane);
-            if (S1N > 0) q1.centre(tabc, trow, lane);
+            q0.centre(tabc, trow);
+            if (S1N > 0) q1.centre(tabc, trow);
             const float* sbase = p.in.s + cbase * p.in.lds + TS * lane;
             const unsigned lds = (unsigned)p.in.lds;
             // centre bytes (identical for all edges of the point): TS = 2 -> bytes 2, 3 of the word; TS = 1 -> byte 1
@@ -560,8 +576,7 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
             }
         }
         // first vector-branch gathers go out before the barrier
-        VBranch<S, CVO> vb;
-        if (valid) vb.prefetch(tabc, trow, my_j, lane);
+        if (valid) vb.prefetch(p, b, tabc, trow, my_j, lane);
         // ---- tile complete: generic-proxy writes -> tensor-core reads ----
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
