@@ -4,7 +4,9 @@
 //
 // Formulation (transposed so that the epilogue is thread-local and stores are coalesced):
 //     D[c][x*32 + p] = sum_k  Wsign[c][k] * v[p][x][k]          M = channels, N = 3 x 32 points
-//   * "A" operand  = sign(W) as bf16 +-1, [M_TILES*128 rows][Kpad], staged once per CTA
+//   * "A" operand  = sign(W) as bf16 +-1, [M_TILES*128 rows][Kpad], staged once per CTA; full-precision weights
+//                    (fp SV models, `sign_w` == 0) as three bf16 planes hi+mid+lo like the activations, and the six
+//                    plane products down to 2^-16 |a||w| (h*l, l*h, m*m, h*m, m*h, h*h), small terms first
 //   * "B" operand  = activations, split EXACTLY into three bf16 planes hi+mid+lo (8+8+8 mantissa
 //                    bits), [96 rows][Kpad] per plane; every plane*weight product is exact, the
 //                    tensor core only reorders the fp32 summation
@@ -60,42 +62,59 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 }
 
 // smem: Ws [KB][MT*128 rows][8] bf16 | Bs [3 planes][KB][96 rows (+1 pad)][8] bf16 | mbarrier | tmem base
-__global__ void __launch_bounds__(NTH, 2) vlinear_tcgen05_kernel(svnet_gemm_params p, int Kpad, int MT, int ntiles,
-                                                                 int* __restrict__ err_flag)
+template <int WP>
+__global__ void __launch_bounds__(NTH, WP == 1 ? 2 : 1) vlinear_tcgen05_kernel(svnet_gemm_params p, int Kpad, int MT, int ntiles,
+                                                                              int* __restrict__ err_flag)
 {
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int KB = Kpad / 8;                       // 8-element (16 B) k-blocks
     const int WROWS = MT * 128;
     const uint32_t KBS_W = WROWS * 16;             // bytes between k-blocks of the weight operand
     const uint32_t KBS_B = NCOL * 16 + 16;         // bytes between k-blocks of one activation plane (+16: bank spread)
-    unsigned char* Ws = smraw;
-    unsigned char* Bs = Ws + (size_t)KB * KBS_W;
+    unsigned char* Ws = smraw;                     // WP weight planes
+    const size_t wplane_bytes = (size_t)KB * KBS_W;
+    unsigned char* Bs = Ws + (size_t)WP * wplane_bytes;
     const size_t plane_bytes = (size_t)KB * KBS_B;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(Bs + 3 * plane_bytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- one-time: weights -> bf16 +-1 in the canonical layout; barrier; tensor memory ----
+    // ---- one-time: weights -> bf16 (+-1, or three exact planes) in the canonical layout; barrier; tensor memory ----
     for (int i = tid; i < WROWS * KB; i += NTH) {
         const int row = i % WROWS, kb = i / WROWS;
-        uint32_t w4[4];
+        uint32_t w4[WP][4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-            uint32_t lohi = 0;
+            uint32_t pl[WP];
+#pragma unroll
+            for (int q = 0; q < WP; ++q) pl[q] = 0;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int k = kb * 8 + h * 2 + e;
-                unsigned short v = 0;
-                if (row < p.N && k < p.K) {
-                    const float w = __ldg(p.W + (long)row * p.ldw + k);
-                    v = (w > 0.0f) ? 0x3F80 : ((w < 0.0f) ? 0xBF80 : 0);
+                float w = 0.0f;
+                if (row < p.N && k < p.K) w = __ldg(p.W + (long)row * p.ldw + k);
+                if (WP == 1) {
+                    const unsigned short v = (w > 0.0f) ? 0x3F80 : ((w < 0.0f) ? 0xBF80 : 0);
+                    pl[0] |= (uint32_t)v << (16 * e);
+                } else {
+                    const uint32_t hb = __float_as_uint(w) & 0xFFFF0000u;
+                    const float r1 = w - __uint_as_float(hb);
+                    const uint32_t mb = __float_as_uint(r1) & 0xFFFF0000u;
+                    const float r2 = r1 - __uint_as_float(mb);
+                    const uint32_t lb = __float_as_uint(r2) & 0xFFFF0000u;
+                    pl[0] |= (hb >> 16) << (16 * e);
+                    pl[WP > 1 ? 1 : 0] |= (mb >> 16) << (16 * e);
+                    pl[WP > 2 ? 2 : 0] |= (lb >> 16) << (16 * e);
                 }
-                lohi |= (uint32_t)v << (16 * e);
             }
-            w4[h] = lohi;
+#pragma unroll
+            for (int q = 0; q < WP; ++q) w4[q][h] = pl[q];
         }
-        *reinterpret_cast<uint4*>(Ws + (size_t)kb * KBS_W + (size_t)row * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+#pragma unroll
+        for (int q = 0; q < WP; ++q)
+            *reinterpret_cast<uint4*>(Ws + q * wplane_bytes + (size_t)kb * KBS_W + (size_t)row * 16) =
+                make_uint4(w4[q][0], w4[q][1], w4[q][2], w4[q][3]);
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar)));
@@ -155,13 +174,18 @@ __global__ void __launch_bounds__(NTH, 2) vlinear_tcgen05_kernel(svnet_gemm_para
 
         // ---- one thread issues all MMAs of the tile, then commits to the mbarrier ----
         if (tid == 0) {
+            // (weight plane, activation plane) products, small terms first; sign weights: one weight plane
+            constexpr int NPROD = WP == 1 ? 3 : 6;
+            const int apl1[3] = {2, 1, 0};
+            const int wpl3[6] = {0, 2, 1, 0, 1, 0}, apl3[6] = {2, 0, 1, 1, 0, 0};      // h*l, l*h, m*m, h*m, m*h, h*h
             for (int mt = 0; mt < MT; ++mt) {
                 uint32_t first = 1;
-                for (int pl = 2; pl >= 0; --pl) {        // small planes first
+                for (int pr = 0; pr < NPROD; ++pr) {
+                    const int wq = WP == 1 ? 0 : wpl3[pr], aq = WP == 1 ? apl1[pr] : apl3[pr];
                     for (int ks = 0; ks < Kpad / 16; ++ks) {
-                        const uint64_t adesc = make_desc(smem_u32(Ws) + (uint32_t)(2 * ks) * KBS_W + (uint32_t)mt * 128 * 16,
-                                                         KBS_W, 128);
-                        const uint64_t bdesc = make_desc(smem_u32(Bs) + (uint32_t)(pl * plane_bytes) + (uint32_t)(2 * ks) * KBS_B,
+                        const uint64_t adesc = make_desc(smem_u32(Ws) + (uint32_t)(wq * wplane_bytes) + (uint32_t)(2 * ks) * KBS_W +
+                                                             (uint32_t)mt * 128 * 16, KBS_W, 128);
+                        const uint64_t bdesc = make_desc(smem_u32(Bs) + (uint32_t)(aq * plane_bytes) + (uint32_t)(2 * ks) * KBS_B,
                                                          KBS_B, 128);
                         umma_bf16(tmem_base + (uint32_t)(mt * NCOL), adesc, bdesc, idesc, first ? 0u : 1u);
                         first = 0;
@@ -246,18 +270,33 @@ int svnet_vlinear_tcgen05_dispatch(const svnet_gemm_params* p, cudaStream_t st)
 {
     const char* on = getenv("SVNET_TCGEN05");
     if (on && on[0] == '0') return 0;                         // SVNET_TCGEN05=0 falls back to mma.sync / CUDA cores
-    if (!p->sign_w || p->G != 3 || p->M % 3 != 0) return 0;
+    if (p->G != 3 || p->M % 3 != 0) return 0;
     if (p->K > 96 || p->N > 256 || p->bias || p->act != SVNET_ACT_NONE || (!p->vbn && p->bn_a)) return 0;
     if (p->c4 && (p->vbn || (p->ldc_g & 3) || (reinterpret_cast<uintptr_t>(p->C) & 15))) return 0;
+    if (!p->sign_w) {
+        // full-precision weights: three weight planes.  Only where a caller needs this kernel's epilogues (the float4
+        // table layout, VectorBN + gate); plain tables stay on the fp32 chain kernel (their bits are part of the
+        // fp models' parity record), SVNET_VLINEAR_FP_TC=0 switches the path off.
+        const char* fp = getenv("SVNET_VLINEAR_FP_TC");
+        if (fp && fp[0] == '0') return 0;
+        if (!p->c4 && !p->vbn) return 0;
+    }
+    const int WP = p->sign_w ? 1 : 3;
     const int Kpad = (p->K + 15) / 16 * 16;
     const int MT = (p->N + 127) / 128;
     const long npoints = p->M / 3;
     const int ntiles = (int)((npoints + PTS - 1) / PTS);
-    const size_t smem = (size_t)(Kpad / 8) * (MT * 128) * 16 + (size_t)3 * (Kpad / 8) * (NCOL * 16 + 16) + 64;
+    const size_t smem = (size_t)WP * (Kpad / 8) * (MT * 128) * 16 + (size_t)3 * (Kpad / 8) * (NCOL * 16 + 16) + 64;
     if (smem > 220 * 1024) return 0;
-    SV_CUDA(cudaFuncSetAttribute(vlinear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = ntiles < 296 ? ntiles : 296;
-    vlinear_tcgen05_kernel<<<grid, NTH, smem, st>>>(*p, Kpad, MT, ntiles, nullptr);
+    const int per_sm = WP == 1 ? 2 : 1;
+    const int grid = ntiles < 148 * per_sm ? ntiles : 148 * per_sm;
+    if (WP == 1) {
+        SV_CUDA(cudaFuncSetAttribute(vlinear_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vlinear_tcgen05_kernel<1><<<grid, NTH, smem, st>>>(*p, Kpad, MT, ntiles, nullptr);
+    } else {
+        SV_CUDA(cudaFuncSetAttribute(vlinear_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vlinear_tcgen05_kernel<3><<<grid, NTH, smem, st>>>(*p, Kpad, MT, ntiles, nullptr);
+    }
     SV_CHECK_LAUNCH("svnet_linear_rows(tcgen05)");
     return 1;
 }
