@@ -49,7 +49,7 @@ constexpr int CAPH = 64;                       // survivor queue capacity per (r
 constexpr int GROUPS = 64;
 constexpr int GM_BYTES = GROUPS * TM * 4;      // group maxima between the passes
 #ifndef FIN_MIN_BLOCKS
-#define FIN_MIN_BLOCKS 6
+#define FIN_MIN_BLOCKS 5
 #endif
 #ifndef FIN_WIDE_MIN_BLOCKS
 #define FIN_WIDE_MIN_BLOCKS 4                  // two entries per lane: 64 registers per thread
@@ -143,7 +143,7 @@ __device__ __forceinline__ void scan_bar() { asm volatile("bar.sync 1, %0;\n" ::
 // warp 0 also runs the sequential norm chains from the tile.
 constexpr int PACK_ROWS = 32;
 __global__ void __launch_bounds__(256) knn_pack_kernel(svnet_view in, int N, int NCB, int NKC, unsigned char* __restrict__ pack,
-                                                       float* __restrict__ xx)
+                                                       float* __restrict__ xx, float* __restrict__ xf, int C4)
 {
     extern __shared__ float tile[];                 // [32 rows][Kpad + 1]
     const int b = blockIdx.y;
@@ -178,6 +178,16 @@ __global__ void __launch_bounds__(256) knn_pack_kernel(svnet_view in, int N, int
         for (int c = 0; c < C; ++c) nrm = __fmaf_rn(tr[c], tr[c], nrm);
         xx[(size_t)b * NCB * TNB + r] = r < N ? nrm : INFINITY;
     }
+    {   // fp32 copy of the rows in chain order, C4 = C rounded up to 4 floats per row (zero padded): the finish
+        // kernel's exact chains gather candidate rows from it with 16-byte loads
+        const int q4n = C4 >> 2;
+        float4* xfd = reinterpret_cast<float4*>(xf + ((size_t)b * NCB * TNB + r0) * C4);
+        for (int item = tid; item < PACK_ROWS * q4n; item += 256) {
+            const int rr = item / q4n, q = item - rr * q4n;
+            const float* a = tile + rr * ld + 4 * q;
+            xfd[item] = make_float4(a[0], a[1], a[2], a[3]);
+        }
+    }
     const int cb = r0 / TNB, rin = r0 % TNB;
     unsigned char* dst0 = pack + ((size_t)(b * NCB + cb) * NKC) * B_CHUNK + (size_t)rin * 16;
     for (int item = tid; item < PACK_ROWS * 2 * NKC; item += 256) {
@@ -209,26 +219,6 @@ __global__ void __launch_bounds__(256) knn_pack_kernel(svnet_view in, int N, int
     }
 }
 
-// ---- exact oracle chain: dot over channels ascending [s | v x0 | v x1 | v x2] ------------------
-__device__ __forceinline__ float exact_dot(const svnet_view& in, long rowj, const float* __restrict__ arow)
-{
-    float dot = 0.0f;
-    int c = 0;
-    if (in.Cs > 0) {
-        const float* ps = in.s + rowj * in.lds;
-#pragma unroll 8
-        for (int d = 0; d < in.Cs; ++d) dot = __fmaf_rn(arow[c++], __ldg(ps + d), dot);
-    }
-    if (in.Cv > 0) {
-#pragma unroll 1
-        for (int x = 0; x < 3; ++x) {
-            const float* pv = in.v + rowj * in.ldv + (long)x * in.xs;
-#pragma unroll 8
-            for (int d = 0; d < in.Cv; ++d) dot = __fmaf_rn(arow[c++], __ldg(pv + d), dot);
-        }
-    }
-    return dot;
-}
 __device__ __forceinline__ float exact_score(float dot, float xxi, float xxj)
 {
     const float inner = -2.0f * dot;
@@ -243,47 +233,14 @@ struct knn_tc_args {
     int passA3;                  // pass A with three plane products (0: six, tuning aid SVNET_KNN_PASSA=6)
     const unsigned char* pack;
     const float* xx;             // [B][NCB*256]
+    const float* xf;             // [B][NCB*256][C4] fp32 rows in chain order (zero padded)
+    int C4;
     float2* gq;                  // survivor queues [B*N rows][2 halves][CAPH] of (half-scale score, index bits)
     int* gqcnt;                  // [B*N][2]
-    int xcap;                    // finish kernel: candidate rows staged per chunk
     int stats;                   // != 0: accumulate g_knn_tc_stats (same-address atomics: profiling runs only)
     int32_t* idx32;
     int64_t* idx64;
 };
-
-// 4-byte async copy global -> shared (no register staging: many gathers in flight per lane)
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
-// brute-force exact selection of one row by one warp (queue overflow / degenerate inputs); k <= 32 R
-template <int R>
-__device__ void brute_force_row(const knn_tc_args& p, long base, int i, const float* arow, const float* xxs, int lane,
-                                kkey_t (&out)[R])
-{
-    TopK<R> L;
-#pragma unroll
-    for (int r = 0; r < R; ++r) L.k[r] = 0ull;
-    const float xi = xxs[i];
-    const int k = p.k;
-    for (int j0 = 0; j0 < p.N; j0 += 32) {
-        const int j = j0 + lane;
-        kkey_t c = 0ull;
-        if (j < p.N) c = make_key(exact_score(exact_dot(p.in, base + j, arow), xi, xxs[j]), j);
-        kkey_t worst = shfl_key(L.k[0], (k - 1) & 31);
-        if (R > 1 && k > 32) worst = shfl_key(L.k[R - 1], (k - 1) & 31);
-        unsigned m = __ballot_sync(SV_FULL, c > worst);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            topk_insert<R>(L, shfl_key(c, src), lane);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) out[r] = L.k[r];
-}
 
 __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
 {
@@ -507,14 +464,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * TNB));
 }
 
-// staged rows of the exact re-scoring: stride = multiple of 4 floats with an odd number of float4s
+// staged query rows of the exact re-scoring: stride = multiple of 4 floats with an odd number of float4s
 // (16-byte loads, lanes reading different rows fall into different bank groups)
 __host__ __device__ __forceinline__ int fin_stride(int C)
 {
     const int q = (C + 3) >> 2;
     return 4 * (q | 1);
 }
-constexpr int FIN_TAB_FLOATS = (KMAX * 8 + KMAX * 4) / 4;      // gather table: pointers + strides
 
 // bitonic sorts, descending, of 32 keys (one per lane)
 __device__ __forceinline__ void warp_sort32_desc(kkey_t& key, int lane)
@@ -574,116 +530,144 @@ __device__ __forceinline__ unsigned approx_key(float s, int lane)
     return ((hi & ~31u) | (unsigned)lane) | 32u * (hi < 64u);     // never below 32: empty slots are 0..31
 }
 
-// exact oracle-chain scores for the lanes in `flagged` (bit = lane, lane's candidate = jme, its norm = xj):
-// candidate rows are gathered with cp.async into shared memory in chunks of xcap rows, then every
-// flagged lane runs its own sequential chain (16-byte loads; zero padding is exact).  Returns the
-// order-preserving 32-bit image of the score (0 for lanes that are not flagged).
+// Exact oracle-chain score of (query row staged in shared memory, candidate row of the fp32 copy in global memory) as the
+// order-preserving 32-bit image make_key() uses.  Channel ascending; the zero padding adds fmaf(0,0,x) == x.
+__device__ __forceinline__ unsigned chain_key(const float* __restrict__ arow, const float* __restrict__ brow, int n4, float xxi,
+                                              float xxj)
+{
+    const float4* ap = reinterpret_cast<const float4*>(arow);
+    const float4* bp = reinterpret_cast<const float4*>(brow);
+    float dot = 0.0f;
+#pragma unroll 4
+    for (int c4 = 0; c4 < n4; ++c4) {
+        const float4 bv = __ldg(bp + c4);
+        const float4 av = ap[c4];
+        dot = __fmaf_rn(av.x, bv.x, dot);
+        dot = __fmaf_rn(av.y, bv.y, dot);
+        dot = __fmaf_rn(av.z, bv.z, dot);
+        dot = __fmaf_rn(av.w, bv.w, dot);
+    }
+    return (unsigned)(make_key(exact_score(dot, xxi, xxj), 0) >> 32);
+}
+__device__ __forceinline__ float key32_score(unsigned hi) { return key_score((kkey_t)hi << 32); }
+
+// brute-force exact selection of one row by one warp (queue overflow / degenerate inputs); k <= 32 R
+template <int R>
+__device__ void brute_force_row(const knn_tc_args& p, const float* __restrict__ xfc, int n4, int i, const float* arow,
+                                const float* __restrict__ xxs, int lane, kkey_t (&out)[R])
+{
+    TopK<R> L;
+#pragma unroll
+    for (int r = 0; r < R; ++r) L.k[r] = 0ull;
+    const float xi = xxs[i];
+    const int k = p.k;
+    for (int j0 = 0; j0 < p.N; j0 += 32) {
+        const int j = j0 + lane;
+        kkey_t c = 0ull;
+        if (j < p.N) c = ((kkey_t)chain_key(arow, xfc + (size_t)j * p.C4, n4, xi, xxs[j]) << 32) | (unsigned)(~j);
+        kkey_t worst = shfl_key(L.k[0], (k - 1) & 31);
+        if (R > 1 && k > 32) worst = shfl_key(L.k[R - 1], (k - 1) & 31);
+        unsigned m = __ballot_sync(SV_FULL, c > worst);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            topk_insert<R>(L, shfl_key(c, src), lane);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[r] = L.k[r];
+}
+
+
+// 16-byte async copy global -> shared (no register staging)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// per-warp state of the exact re-scoring
 struct fin_env {
-    const knn_tc_args* p;
-    const float** gtab;
-    const int* gstr;
-    float* arow;
-    float* exb;
-    long base, rg;
-    int C, Cp, lane;
+    const float* xfc;      // fp32 rows of this cloud
+    const float* xxs;
+    float* arow;           // the warp's query row in shared memory (Cp floats; doubles as the scratch of the prune)
+    int C4, n4, Cp, lane, i;
     float xxi;
     bool arow_loaded;
-    float emax;
 };
 
-__device__ __forceinline__ unsigned exact_keys(fin_env& f, unsigned flagged, int jme, float xj, float sme)
+// the query row for the paths that read candidate rows straight from global memory (brute force, heavy ties)
+__device__ __forceinline__ void ensure_query_row(fin_env& f)
 {
-    const int lane = f.lane, C = f.C, Cp = f.Cp, xcap = f.p->xcap;
-    const int T = __popc(flagged);
-    const int myo = __popc(flagged & ((1u << lane) - 1u));
-    const bool mine = (flagged >> lane) & 1u;
-    const int nu = (C + 31) >> 5;
-    unsigned sc = 0u;
-    for (int ch0 = 0; ch0 < T; ch0 += xcap) {
-        __syncwarp();
-        if (!f.arow_loaded) {
-            for (int u = 0; u < nu; ++u) {
-                const int c = lane + 32 * u;
-                if (c < C) cp_async4(f.arow + c, f.gtab[c] + f.rg * (long)f.gstr[c]);
-            }
-            if (lane < Cp - C) f.arow[C + lane] = 0.0f;            // zero padding of the float4 chains
-            f.arow_loaded = true;
-        }
-        unsigned m = flagged;
-        int o = -ch0;
-        while (m) {
-            const int srcl = __ffs(m) - 1;
-            m &= m - 1;
-            if (o >= 0 && o < xcap) {
-                const long row = f.base + __shfl_sync(SV_FULL, jme, srcl);
-                float* dstp = f.exb + o * Cp;
-                for (int u = 0; u < nu; ++u) {
-                    const int c = lane + 32 * u;
-                    if (c < C) cp_async4(dstp + c, f.gtab[c] + row * (long)f.gstr[c]);
-                }
-                if (lane < Cp - C) dstp[C + lane] = 0.0f;
-            }
-            ++o;
-        }
+    if (!f.arow_loaded) {
+        for (int c4 = f.lane; c4 < f.n4; c4 += 32) cp_async16(f.arow + 4 * c4, f.xfc + (size_t)f.i * f.C4 + 4 * c4);
         cp_async_wait_all();
-        __syncwarp();
-        const int ol = myo - ch0;
-        if (mine && ol >= 0 && ol < xcap) {
-            const float4* bp = reinterpret_cast<const float4*>(f.exb + ol * Cp);
-            const float4* ap = reinterpret_cast<const float4*>(f.arow);
-            float dot = 0.0f;      // channel ascending; the zero padding adds fmaf(0,0,x) == x
-            for (int c4 = 0; c4 < (C + 3) >> 2; ++c4) {
-                const float4 av = ap[c4], bv = bp[c4];
-                dot = __fmaf_rn(av.x, bv.x, dot);
-                dot = __fmaf_rn(av.y, bv.y, dot);
-                dot = __fmaf_rn(av.z, bv.z, dot);
-                dot = __fmaf_rn(av.w, bv.w, dot);
-            }
-            const float pe = exact_score(dot, f.xxi, xj);
-            sc = (unsigned)(make_key(pe, 0) >> 32);
-            f.emax = fmaxf(f.emax, fabsf(pe - 2.0f * sme) / (f.xxi + xj));     // 2*sme = tensor-core score
+        f.arow_loaded = true;
+    }
+    __syncwarp();
+}
+// exact oracle-chain score keys for the lanes in `flagged` (bit = lane, lane's candidate = jme, its norm = xj); 0 for the
+// others.  Every flagged lane reads its candidate row straight from the fp32 copy in global memory (L2) with 16-byte loads
+// (round 2, measured against staging the rows in shared memory by cp.async: 138 against 148 us per 32 clouds over the four
+// layers, and against pooling the pairs of a CTA's eight rows into a lane-dense pass behind a barrier: 169 us).
+__device__ __forceinline__ unsigned exact_keys(fin_env& f, unsigned flagged, int jme, float xj)
+{
+    ensure_query_row(f);
+    unsigned sc = 0u;
+    if ((flagged >> f.lane) & 1u) {
+        const float4* ap = reinterpret_cast<const float4*>(f.arow);
+        const float4* bp = reinterpret_cast<const float4*>(f.xfc + (size_t)jme * f.C4);
+        float dot = 0.0f;
+#pragma unroll 8
+        for (int c4 = 0; c4 < f.n4; ++c4) {
+            const float4 bv = __ldg(bp + c4);
+            const float4 av = ap[c4];
+            dot = __fmaf_rn(av.x, bv.x, dot);
+            dot = __fmaf_rn(av.y, bv.y, dot);
+            dot = __fmaf_rn(av.z, bv.z, dot);
+            dot = __fmaf_rn(av.w, bv.w, dot);
         }
+        sc = (unsigned)(make_key(exact_score(dot, f.xxi, xj), 0) >> 32);
     }
     return sc;
 }
 
-// ---- finish kernel: one warp = one row.  High occupancy (small register / shared-memory footprint)
-//      hides the shuffle and gather latencies that a tensor-core CTA with 8 scanner warps cannot.
-//   <= 32 survivors (the normal case): sort by approximate score; neighbours in that order which the
-//      error bound does not separate form runs; runs that touch the first k positions are re-scored
-//      with the exact chain; re-sort by (run, exact score desc, index asc).
-//   33 .. 2*CAPH survivors (heavy ties, e.g. many identical binary features): every survivor is
-//      re-scored exactly, 32 at a time, and merged into the best 32 (always correct: the survivors
-//      contain the true top k).
+// Shared memory of the finish kernels: per warp the query row, which doubles as the scratch of the pruned survivor
+// lists (32 * S float2; S = sorted positions per lane: 1 for k <= 32, 2 for 32 < k <= 48).
+__host__ __device__ inline int fin_warp_floats(int Cp, int S)
+{
+    const int a = Cp, b = 64 * S;
+    return a > b ? a : b;
+}
+// ---- finish kernel: one warp = one row; warps are independent (no CTA barriers).  High occupancy hides the shuffle
+//      and gather latencies that a tensor-core CTA with 8 scanner warps cannot.
+//   <= 32 survivors (the normal case, after the prune below if need be): sort by approximate score; neighbours in that
+//      order which the error bound does not separate form runs; runs that touch the first k positions are re-scored
+//      with the exact chain (candidate rows staged by one 16-byte cp.async per lane from the fp32 copy of the
+//      features; measured on the model: 33 - 87 % of the rows re-score 2 - 4 candidates); re-sort by
+//      (run, exact score desc, index asc).
+//   33 .. 2*CAPH survivors that the prune cannot reduce (heavy ties): every survivor is re-scored exactly by its lane,
+//      32 at a time, and merged into the best 32 (always correct: the survivors contain the true top k).
 //   queue overflow: brute force over all candidates.
-__global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_kernel(knn_tc_args p)
+template <int MINB>
+__global__ void __launch_bounds__(FIN_WARPS * 32, MINB) knn_finish_kernel(knn_tc_args p)
 {
     extern __shared__ __align__(16) float fin_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int i = blockIdx.x * FIN_WARPS + warp;
+    if (i >= p.N) return;
     const long base = (long)b * p.N;
     const long rg = base + i;
     const int k = p.k;
-    const int C = p.in.Cs + 3 * p.in.Cv, Cp = fin_stride(C);
-    const float* xxs = p.xx + (size_t)b * p.NCB * TNB;
-    const float** gtab = reinterpret_cast<const float**>(fin_smem);
-    int* gstr = reinterpret_cast<int*>(gtab + KMAX);
-    for (int c = threadIdx.x; c < C; c += FIN_WARPS * 32) {
-        const int cc2 = c - p.in.Cs;
-        const int x = (cc2 >= p.in.Cv ? 1 : 0) + (cc2 >= 2 * p.in.Cv ? 1 : 0);
-        const bool in_s = c < p.in.Cs;
-        gtab[c] = in_s ? p.in.s + c : p.in.v + (long)x * p.in.xs + (cc2 - x * p.in.Cv);
-        gstr[c] = in_s ? p.in.lds : p.in.ldv;
-    }
-    __syncthreads();
-    if (i >= p.N) return;
+    const size_t prow0 = (size_t)b * p.NCB * TNB;                 // first padded row of this cloud in xx / xf
+    const float* xxs = p.xx + prow0;
     fin_env f;
-    f.p = &p; f.gtab = gtab; f.gstr = gstr;
-    f.arow = fin_smem + FIN_TAB_FLOATS + (size_t)warp * ((1 + p.xcap) * Cp);     // query row | xcap candidate rows
-    f.exb = f.arow + Cp;
-    f.base = base; f.rg = rg; f.C = C; f.Cp = Cp; f.lane = lane;
-    f.arow_loaded = false; f.emax = 0.0f;
+    f.C4 = p.C4; f.n4 = p.C4 >> 2; f.Cp = fin_stride(p.C4); f.lane = lane; f.i = i;
+    f.xfc = p.xf + prow0 * p.C4; f.xxs = xxs;
+    f.arow = fin_smem + (size_t)warp * fin_warp_floats(f.Cp, 1);
+    f.arow_loaded = false;
+    float emax = 0.0f;
     const float2* q0 = p.gq + rg * 2 * CAPH;
     const float2 h0 = __ldg(q0 + lane), h1 = __ldg(q0 + CAPH + lane);     // may hold stale data beyond the counts
     const float xxi = __ldg(xxs + i);
@@ -692,7 +676,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
     const int c0 = cc.x, cnt = cc.x + cc.y;
     const bool brute = !(cc.x <= CAPH && cc.y <= CAPH && cnt >= k);
     bool st_exact = false;
-    int jout = 0;
+    int jout = 0, nflag = 0;
     // ---- the row's survivors as one entry per lane (the approximate-order path needs at most 32) ----
     float2 ent = make_float2(0.0f, 0.0f);
     int n = cnt;
@@ -748,7 +732,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
             kept += __popc(keep[s4]);
         }
         if (kept <= 32 && kept >= k) {
-            float2* scratch = reinterpret_cast<float2*>(f.exb);        // per-warp staging area (>= 64 floats)
+            float2* scratch = reinterpret_cast<float2*>(f.arow);        // the staging area is still unused here
             int before = 0;
 #pragma unroll
             for (int s4 = 0; s4 < 4; ++s4) {
@@ -763,10 +747,9 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
         }
     }
     if (brute) {
-        for (int c = lane; c < C; c += 32) f.arow[c] = sv_feat(p.in, rg, c);
-        __syncwarp();
+        ensure_query_row(f);
         kkey_t key[1];
-        brute_force_row<1>(p, base, i, f.arow, xxs, lane, key);
+        brute_force_row<1>(p, f.xfc, f.n4, i, f.arow, xxs, lane, key);
         jout = key_index(key[0]);
     } else if (fast) {
         const float xe = lane < n ? __ldg(xxs + __float_as_int(ent.y)) : 0.0f;      // norm of the entry's point
@@ -793,7 +776,11 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
         }
         if (rel) {
             st_exact = true;
-            const unsigned sc = exact_keys(f, rel | (rel << 1), jme, xj, sme);
+            const unsigned flagged = rel | (rel << 1);
+            nflag = __popc(flagged);
+            const unsigned sc = exact_keys(f, flagged, jme, xj);
+            if (p.stats && ((flagged >> lane) & 1u))
+                emax = fmaxf(emax, fabsf(key32_score(sc) - 2.0f * sme) / (xxi + xj));     // 2*sme = tensor-core score
             // composite key: (run start asc, exact score desc, index asc); unflagged entries are their own run
             const unsigned starts = ~(rel << 1);
             kkey_t key = 0ull;
@@ -807,16 +794,17 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
     } else {
         // ---- more than 32 survivors: exact scores for all of them, 32 at a time, keep the best 32 ----
         st_exact = true;
+        ensure_query_row(f);
         kkey_t best = 0ull;
         for (int e0 = 0; e0 < cnt; e0 += 32) {
             const int e = e0 + lane;
-            float2 ent = make_float2(0.0f, 0.0f);
-            if (e < cnt) ent = __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
-            const int jme = __float_as_int(ent.y);
-            const float xj = e < cnt ? __ldg(xxs + jme) : 0.0f;
-            const unsigned valid = __ballot_sync(SV_FULL, e < cnt);
-            const unsigned sc = exact_keys(f, valid, jme, xj, ent.x);
-            kkey_t key = e < cnt ? (((kkey_t)sc << 32) | (unsigned)(~jme)) : 0ull;     // == make_key(exact score, j)
+            kkey_t key = 0ull;
+            if (e < cnt) {
+                const float2 en = __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
+                const int je = __float_as_int(en.y);
+                const unsigned sc = chain_key(f.arow, f.xfc + (size_t)je * f.C4, f.n4, xxi, __ldg(xxs + je));
+                key = ((kkey_t)sc << 32) | (unsigned)(~je);     // == make_key(exact score, j)
+            }
             warp_sort32_desc(key, lane);
             const kkey_t rev = shfl_key(key, 31 - lane);
             best = best > rev ? best : rev;          // upper half of the bitonic merge: the 32 best of the 64
@@ -830,7 +818,6 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
         if (p.idx64) p.idx64[o] = (int64_t)jout;
     }
     if (p.stats) {
-        float emax = f.emax;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(SV_FULL, emax, o));
         if (lane == 0) {
@@ -839,57 +826,48 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_MIN_BLOCKS) knn_finish_ker
             if (brute) atomicAdd(&g_knn_tc_stats[2], 1ull);
             atomicAdd(&g_knn_tc_stats[3], (unsigned long long)cnt);
             if (cnt > 32 && !brute) atomicAdd(&g_knn_tc_stats[10], 1ull);
+            atomicAdd(&g_knn_tc_stats[11], (unsigned long long)nflag);
             if (emax > 0.0f) atomicMax(&g_knn_tc_stats[9], (unsigned long long)__float_as_uint(emax));
         }
     }
 }
 
-// ---- finish kernel for 32 < k <= 48 (part segmentation, k = 40): every survivor is re-scored with the exact
-//      chain, 32 at a time, and merged into the best 64 (two sorted registers per lane) ----
+// ---- finish kernel for 32 < k <= 48 (part segmentation, k = 40): the same path with two sorted positions per lane
+//      (64 per row); rows with more than 64 survivors after the prune re-score every survivor ----
 __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_WIDE_MIN_BLOCKS) knn_finish_wide_kernel(knn_tc_args p)
 {
     extern __shared__ __align__(16) float fin_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int i = blockIdx.x * FIN_WARPS + warp;
+    if (i >= p.N) return;
     const long base = (long)b * p.N;
     const long rg = base + i;
     const int k = p.k;
-    const int C = p.in.Cs + 3 * p.in.Cv, Cp = fin_stride(C);
-    const float* xxs = p.xx + (size_t)b * p.NCB * TNB;
-    const float** gtab = reinterpret_cast<const float**>(fin_smem);
-    int* gstr = reinterpret_cast<int*>(gtab + KMAX);
-    for (int c = threadIdx.x; c < C; c += FIN_WARPS * 32) {
-        const int cc2 = c - p.in.Cs;
-        const int x = (cc2 >= p.in.Cv ? 1 : 0) + (cc2 >= 2 * p.in.Cv ? 1 : 0);
-        const bool in_s = c < p.in.Cs;
-        gtab[c] = in_s ? p.in.s + c : p.in.v + (long)x * p.in.xs + (cc2 - x * p.in.Cv);
-        gstr[c] = in_s ? p.in.lds : p.in.ldv;
-    }
-    __syncthreads();
-    if (i >= p.N) return;
+    const size_t prow0 = (size_t)b * p.NCB * TNB;
+    const float* xxs = p.xx + prow0;
     fin_env f;
-    f.p = &p; f.gtab = gtab; f.gstr = gstr;
-    f.arow = fin_smem + FIN_TAB_FLOATS + (size_t)warp * ((1 + p.xcap) * Cp);
-    f.exb = f.arow + Cp;
-    f.base = base; f.rg = rg; f.C = C; f.Cp = Cp; f.lane = lane;
-    f.arow_loaded = false; f.emax = 0.0f;
-    f.xxi = __ldg(xxs + i);
+    f.C4 = p.C4; f.n4 = p.C4 >> 2; f.Cp = fin_stride(p.C4); f.lane = lane; f.i = i;
+    f.xfc = p.xf + prow0 * p.C4; f.xxs = xxs;
+    f.arow = fin_smem + (size_t)warp * fin_warp_floats(f.Cp, 2);
+    f.arow_loaded = false;
+    const float xxi = __ldg(xxs + i);
+    f.xxi = xxi;
     const float2* q0 = p.gq + rg * 2 * CAPH;
     const int2 cc = __ldg(reinterpret_cast<const int2*>(p.gqcnt) + rg);
     const int c0 = cc.x, cnt = cc.x + cc.y;
     const bool brute = !(cc.x <= CAPH && cc.y <= CAPH && cnt >= k);
     kkey_t best[2] = {0ull, 0ull};
+    int nflag = 0;
     if (brute) {
-        for (int c = lane; c < C; c += 32) f.arow[c] = sv_feat(p.in, rg, c);
-        __syncwarp();
-        brute_force_row<2>(p, base, i, f.arow, xxs, lane, best);
+        ensure_query_row(f);
+        brute_force_row<2>(p, f.xfc, f.n4, i, f.arow, xxs, lane, best);
     }
     // ---- 65 .. 128 survivors: prune with the survivors' own bounds first (see knn_finish_kernel): T = k-th largest
     // lower bound; entries whose upper bound is below T are out; what is left usually fits the two-entry path ----
     int n = cnt;
     bool pruned = false;
-    float2* scratch = reinterpret_cast<float2*>(f.exb);         // per-warp staging area (>= 128 floats, see the plan)
+    float2* scratch = reinterpret_cast<float2*>(f.arow);         // the staging area is still unused here (>= 128 floats)
     if (!brute && cnt > 64) {
         float2 en4[4];
         float up[4];
@@ -902,7 +880,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_WIDE_MIN_BLOCKS) knn_finis
             lk[s4] = 0u;
             if (e < cnt) {
                 en4[s4] = __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
-                const float dl = 0.5f * p.eps * (f.xxi + __ldg(xxs + __float_as_int(en4[s4].y)));
+                const float dl = 0.5f * p.eps * (xxi + __ldg(xxs + __float_as_int(en4[s4].y)));
                 const float dlt = dl + 4.76837158203125e-7f * (fabsf(en4[s4].x) + dl);
                 up[s4] = en4[s4].x + dlt;
                 const unsigned fb = __float_as_uint((en4[s4].x - dlt) + 0.0f);
@@ -986,7 +964,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_WIDE_MIN_BLOCKS) knn_finis
 #pragma unroll
             for (int s2 = 0; s2 < 2; ++s2) {
                 bool am = false;
-                if (s2 * 32 + lane + 1 < n) am = (sme[s2] - snx[s2]) <= 0.5f * p.eps * (2.0f * f.xxi + xj[s2] + xnx[s2]);
+                if (s2 * 32 + lane + 1 < n) am = (sme[s2] - snx[s2]) <= 0.5f * p.eps * (2.0f * xxi + xj[s2] + xnx[s2]);
                 amb |= (unsigned long long)__ballot_sync(SV_FULL, am) << (32 * s2);
             }
         }
@@ -999,9 +977,10 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_WIDE_MIN_BLOCKS) knn_finis
         int jout[2] = {jme[0], jme[1]};
         if (rel) {
             const unsigned long long flagged = rel | (rel << 1);
+            nflag = __popcll(flagged);
             unsigned sc[2];
-            sc[0] = exact_keys(f, (unsigned)flagged, jme[0], xj[0], sme[0]);
-            sc[1] = exact_keys(f, (unsigned)(flagged >> 32), jme[1], xj[1], sme[1]);
+            sc[0] = exact_keys(f, (unsigned)flagged, jme[0], xj[0]);
+            sc[1] = exact_keys(f, (unsigned)(flagged >> 32), jme[1], xj[1]);
             // composite key: (run start asc, exact score desc, index asc); unflagged entries are their own run
             const unsigned long long starts = ~(rel << 1);
             kkey_t key[2] = {0ull, 0ull};
@@ -1022,15 +1001,16 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_WIDE_MIN_BLOCKS) knn_finis
         best[0] = (kkey_t)(unsigned)(~jout[0]);
         best[1] = (kkey_t)(unsigned)(~jout[1]);
     } else {
+        ensure_query_row(f);
         for (int e0 = 0; e0 < cnt; e0 += 32) {
             const int e = e0 + lane;
-            float2 ent = make_float2(0.0f, 0.0f);
-            if (e < cnt) ent = __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
-            const int jme = __float_as_int(ent.y);
-            const float xj = e < cnt ? __ldg(xxs + jme) : 0.0f;
-            const unsigned valid = __ballot_sync(SV_FULL, e < cnt);
-            const unsigned sc = exact_keys(f, valid, jme, xj, ent.x);
-            kkey_t key = e < cnt ? (((kkey_t)sc << 32) | (unsigned)(~jme)) : 0ull;     // == make_key(exact score, j)
+            kkey_t key = 0ull;
+            if (e < cnt) {
+                const float2 en = __ldg(q0 + (e < c0 ? e : CAPH + e - c0));
+                const int je = __float_as_int(en.y);
+                const unsigned sc = chain_key(f.arow, f.xfc + (size_t)je * f.C4, f.n4, xxi, __ldg(xxs + je));
+                key = ((kkey_t)sc << 32) | (unsigned)(~je);     // == make_key(exact score, j)
+            }
             warp_sort32_desc(key, lane);
             // (best[0], best[1]) = the 64 best so far, sorted; merge the new 32 into the lower half, then the halves
             kkey_t rev = shfl_key(key, 31 - lane);
@@ -1056,10 +1036,11 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_WIDE_MIN_BLOCKS) knn_finis
     }
     if (p.stats && lane == 0) {
         atomicAdd(&g_knn_tc_stats[0], 1ull);
-        atomicAdd(&g_knn_tc_stats[1], 1ull);
+        if (nflag || brute || n > 64) atomicAdd(&g_knn_tc_stats[1], 1ull);
         if (brute) atomicAdd(&g_knn_tc_stats[2], 1ull);
         atomicAdd(&g_knn_tc_stats[3], (unsigned long long)cnt);
         if (cnt > 32 && !brute) atomicAdd(&g_knn_tc_stats[10], 1ull);
+        atomicAdd(&g_knn_tc_stats[11], (unsigned long long)nflag);
     }
 }
 
@@ -1090,8 +1071,9 @@ float knn_tc_eps3(int C)
 }  // namespace
 
 struct knn_tc_plan_t {
-    int NCB, NKC, stages, xcap;
-    size_t pack_bytes, xx_bytes, gq_bytes, cnt_bytes, fin_smem;
+    int NCB, NKC, stages, C4;
+    size_t pack_bytes, xx_bytes, xf_bytes, gq_bytes, cnt_bytes, fin_smem;
+    size_t total() const { return pack_bytes + xx_bytes + xf_bytes + gq_bytes + cnt_bytes; }
 };
 
 static bool knn_tc_plan(const svnet_view* in, int B, int N, int k, knn_tc_plan_t* pl)
@@ -1116,17 +1098,10 @@ static bool knn_tc_plan(const svnet_view* in, int B, int N, int k, knn_tc_plan_t
     pl->xx_bytes = ((size_t)B * pl->NCB * TNB * sizeof(float) + a256) & ~a256;
     pl->gq_bytes = ((size_t)B * N * 2 * CAPH * sizeof(float2) + a256) & ~a256;
     pl->cnt_bytes = ((size_t)B * N * 2 * sizeof(int) + a256) & ~a256;
-    const int Cp = fin_stride(C);
-    pl->xcap = Cp <= 68 ? 12 : 8;
-    {   // the staging area doubles as a scratch for the pruned entries (32 entries, k <= 32; 64 entries, k > 32)
-        const int need = k > 32 ? 128 : 64;
-        if (pl->xcap * Cp < need) pl->xcap = (need + Cp - 1) / Cp;
-    }
-    if (const char* xc = getenv("SVNET_KNN_XCAP")) {      // tuning aid
-        const int v = atoi(xc);
-        if (v >= 2 && v <= 32 && v * Cp >= (k > 32 ? 128 : 64)) pl->xcap = v;
-    }
-    pl->fin_smem = ((size_t)FIN_TAB_FLOATS + (size_t)FIN_WARPS * ((1 + pl->xcap) * Cp)) * sizeof(float);
+    pl->C4 = (C + 3) & ~3;
+    pl->xf_bytes = ((size_t)B * pl->NCB * TNB * pl->C4 * sizeof(float) + a256) & ~a256;
+    const int Cp = fin_stride(pl->C4);
+    pl->fin_smem = (size_t)FIN_WARPS * fin_warp_floats(Cp, k > 32 ? 2 : 1) * sizeof(float);
     return true;
 }
 
@@ -1135,7 +1110,7 @@ size_t svnet_knn_tc_workspace(const svnet_view* in, int B, int N, int k)
 {
     knn_tc_plan_t pl;
     if (!knn_tc_plan(in, B, N, k, &pl)) return 0;
-    return pl.pack_bytes + pl.xx_bytes + pl.gq_bytes + pl.cnt_bytes;
+    return pl.total();
 }
 
 // Returns 1 if handled, 0 if the caller should use the CUDA-core kernel, < 0 on error.
@@ -1144,11 +1119,11 @@ int svnet_knn_tc_dispatch(const svnet_view* in, int B, int N, int k, int32_t* id
 {
     knn_tc_plan_t pl;
     if (!workspace || !knn_tc_plan(in, B, N, k, &pl)) return 0;
-    if (workspace_bytes < pl.pack_bytes + pl.xx_bytes + pl.gq_bytes + pl.cnt_bytes || (reinterpret_cast<uintptr_t>(workspace) & 15))
+    if (workspace_bytes < pl.total() || (reinterpret_cast<uintptr_t>(workspace) & 15))
         return 0;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     knn_tc_args a;
-    a.in = *in; a.N = N; a.k = k; a.NCB = pl.NCB; a.NKC = pl.NKC; a.stages = pl.stages; a.xcap = pl.xcap;
+    a.in = *in; a.N = N; a.k = k; a.NCB = pl.NCB; a.NKC = pl.NKC; a.stages = pl.stages; a.C4 = pl.C4;
     a.eps = knn_tc_eps(in->Cs + 3 * in->Cv);
     a.epsA = knn_tc_eps3(in->Cs + 3 * in->Cv);
     // the three-product bound is ~6x looser: fine while neighbours are sparse relative to it, but at large N the
@@ -1165,18 +1140,23 @@ int svnet_knn_tc_dispatch(const svnet_view* in, int B, int N, int k, int32_t* id
     }
     a.pack = ws;
     a.xx = reinterpret_cast<float*>(ws + pl.pack_bytes);
-    a.gq = reinterpret_cast<float2*>(ws + pl.pack_bytes + pl.xx_bytes);
-    a.gqcnt = reinterpret_cast<int*>(ws + pl.pack_bytes + pl.xx_bytes + pl.gq_bytes);
+    a.xf = reinterpret_cast<float*>(ws + pl.pack_bytes + pl.xx_bytes);
+    a.gq = reinterpret_cast<float2*>(ws + pl.pack_bytes + pl.xx_bytes + pl.xf_bytes);
+    a.gqcnt = reinterpret_cast<int*>(ws + pl.pack_bytes + pl.xx_bytes + pl.xf_bytes + pl.gq_bytes);
     a.idx32 = idx32; a.idx64 = idx64;
-    knn_pack_kernel<<<dim3(pl.NCB * (TNB / PACK_ROWS), B), 256, (size_t)PACK_ROWS * (pl.NKC * KCH + 1) * sizeof(float), st>>>(*in, N, pl.NCB, pl.NKC, ws, const_cast<float*>(a.xx));
+    knn_pack_kernel<<<dim3(pl.NCB * (TNB / PACK_ROWS), B), 256, (size_t)PACK_ROWS * (pl.NKC * KCH + 1) * sizeof(float), st>>>(*in, N, pl.NCB, pl.NKC, ws, const_cast<float*>(a.xx), const_cast<float*>(a.xf), pl.C4);
     SV_CHECK_LAUNCH("svnet_knn(pack)");
     const size_t smem = knn_tc_smem(pl.NCB, pl.NKC, pl.stages);
     SV_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_tc_kernel<<<dim3(sv_cdiv(N, TM), B), NTHREADS, smem, st>>>(a);
     SV_CHECK_LAUNCH("svnet_knn(tcgen05)");
     if (k <= 32) {
-        SV_CUDA(cudaFuncSetAttribute(knn_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.fin_smem));
-        knn_finish_kernel<<<dim3(sv_cdiv(N, FIN_WARPS), B), FIN_WARPS * 32, pl.fin_smem, st>>>(a);
+        int mb = FIN_MIN_BLOCKS;
+        if (const char* e = getenv("SVNET_KNN_FIN_MB")) mb = atoi(e);      // tuning aid: resident CTAs per SM (register budget)
+        const dim3 grid(sv_cdiv(N, FIN_WARPS), B);
+        if (mb == 4) knn_finish_kernel<4><<<grid, FIN_WARPS * 32, pl.fin_smem, st>>>(a);
+        else if (mb == 5) knn_finish_kernel<5><<<grid, FIN_WARPS * 32, pl.fin_smem, st>>>(a);
+        else knn_finish_kernel<6><<<grid, FIN_WARPS * 32, pl.fin_smem, st>>>(a);
     } else {
         SV_CUDA(cudaFuncSetAttribute(knn_finish_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.fin_smem));
         knn_finish_wide_kernel<<<dim3(sv_cdiv(N, FIN_WARPS), B), FIN_WARPS * 32, pl.fin_smem, st>>>(a);

@@ -22,8 +22,8 @@ def knn(view, B, N, k, **kw):
     st = stats(); rows = max(st[0], 1)
     err = struct.unpack("f", struct.pack("I", st[9] & 0xffffffff))[0]
     cyc = tuple(v // max(st[4], 1) for v in st[5:9])
-    print("  knn C=%d: %.1f us | exact rows %.1f%% brute %d survivors/row %.1f max err %.2g | cycles/CTA A %d thr %d B %d fin %d" % (
-        view.Cs + 3 * view.Cv, e0.elapsed_time(e1) * 1e3, 100.0 * st[1] / rows, st[2], st[3] / rows, err, *cyc))
+    print("  knn C=%d: %.1f us | exact rows %.1f%% brute %d survivors/row %.1f flagged/exact row %.1f max err %.2g | cycles/CTA A %d thr %d B %d fin %d" % (
+        view.Cs + 3 * view.Cv, e0.elapsed_time(e1) * 1e3, 100.0 * st[1] / rows, st[2], st[3] / rows, st[11] / max(st[1], 1), err, *cyc))
     return r
 nv.knn = knn
 B = int(os.environ.get("KB", 32)); N = int(os.environ.get("KN", 1024)); SEED = int(os.environ.get("KSEED", 1002))
