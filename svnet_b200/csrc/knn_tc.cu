@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
         float R = INFINITY;
         const float hxi = row_ok ? 0.5f * xi : 0.0f;
         int qn = 0;                                   // this thread's queue fill (row, half)
+        const uint32_t stg0 = smem_u32(gm) + (uint32_t)tid * 4u;      // pass B staging: [32 slots][NSCAN threads] floats
         float2* myq = p.gq + ((base + i0 + (row_ok ? row : 0)) * 2 + half) * CAPH;
 
         for (int it = 0; it < nblk; ++it) {
@@ -429,23 +430,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
                         m[c + 3] = fmaxf(m[c + 3], fmaf(x4.w, CA, d[c + 3]));
                     }
                 } else {
-                    // thread-private survivor queue (row, half) in global memory: no atomics
+                    // survivors are rare (~2 % of the scores): the unrolled test costs six instructions per score -- the
+                    // passing accumulator goes to this thread's column of a shared staging area (the group-maxima region,
+                    // free after the threshold) and sets its bit in a mask; the few set bits are then turned into
+                    // (score, index) entries of the thread-private survivor queue (row, half) in global memory: no
+                    // atomics, ascending candidate order.  (Round 1 tested and stored every score with a predicated
+                    // 8-byte global store: 14 instructions per score.)
+                    float xr[32];
 #pragma unroll
                     for (int c = 0; c < 32; c += 4) {
                         const float4 x4 = *reinterpret_cast<const float4*>(xp + c);
-                        const float xs4[4] = {x4.x, x4.y, x4.z, x4.w};
+                        xr[c] = x4.x; xr[c + 1] = x4.y; xr[c + 2] = x4.z; xr[c + 3] = x4.w;
+                    }
+                    uint32_t sa = stg0;
+                    unsigned mask = 0u;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const bool pass = fmaf(xs4[e], CB, d[c + e]) >= R;
-                            const float val = fmaf(xs4[e], -0.5f, d[c + e]) - hxi;      // q/2: small for near neighbours
-                            const unsigned st = (pass && qn < CAPH) ? 1u : 0u;
-                            // predicated 8-byte store, no branch (a vote + uniform branch around it measured 1.8x slower)
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.v2.f32 [%1], {%2, %3};\n\t}\n" ::"r"(st),
-                                "l"(myq + qn), "f"(val), "f"(__int_as_float(j0 + part * 32 + c + e))
-                                : "memory");
-                            qn += pass ? 1 : 0;
-                        }
+                    for (int c = 0; c < 32; ++c) {
+                        const float t = fmaf(xr[c], CB, d[c]);
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %2, %3;\n\t@p st.shared.f32 [%0], %4;\n\t@p add.u32 %0, %0, %5;\n\t"
+                            "@p or.b32 %1, %1, %6;\n\t}\n"
+                            : "+r"(sa), "+r"(mask)
+                            : "f"(t), "f"(R), "f"(d[c]), "n"(NSCAN * 4), "r"(1u << c));
+                    }
+                    uint32_t ra = stg0;
+                    while (mask) {
+                        const int c = __ffs(mask) - 1;
+                        mask &= mask - 1u;
+                        float dv;
+                        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(dv) : "r"(ra));
+                        ra += NSCAN * 4;
+                        const int j = j0 + part * 32 + c;
+                        const float val = fmaf(xp[c], -0.5f, dv) - hxi;      // q/2: small for near neighbours
+                        if (qn < CAPH) myq[qn] = make_float2(val, __int_as_float(j));
+                        ++qn;
                     }
                 }
             }
