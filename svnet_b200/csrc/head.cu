@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(NT) head_kernel(svnet_head_params p)
             const int nvalid = nvalid_s;
             for (int o = tid; o < Cout; o += NT) {
                 int mism = 0;
-#pragma unroll 8
+#pragma unroll 32
                 for (int w = 0; w < Kw; ++w) mism += __popc((bits[w] ^ __ldg(L.W1b + (long)w * Cout + o)) & mask[w]);
                 float y = __fmul_rn((float)(nvalid - 2 * mism), L.scale ? L.scale[o] : 1.0f);
                 if (L.bias) y = __fadd_rn(y, L.bias[o]);
