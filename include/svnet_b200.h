@@ -216,6 +216,16 @@ size_t svnet_edge_tc_weight_bytes(int Cs, int Cv, int Cout, int Cvo, int k);
 int svnet_edge_tc_table_cols(int Cv, int Cvo);
 int svnet_edge_tc_pack_w(const float* W1, int ldw, int Cs, int Cv, int Cout, unsigned char* out, void* stream);
 
+/* The same for the full-precision edge layers (sv_layers.py:29-31,186-190; csrc/edge_fp_tc.cu): the q part of linear1
+ * (K = 6 Cv) runs on tcgen05 as six products of exact three-way bf16 splits (fp32-grade), the s part comes from the
+ * per-point table `Yab` in the epilogue.  svnet_edge_fp_tc_weight_bytes() is 0 for shapes / k the kernel does not cover
+ * (covered: the three fp edge-layer shapes of SV_DGCNN_CLS at k = 20; SVNET_EDGE_FP_TC=0 disables the path);
+ * svnet_edge_fp_tc_pack_w() turns conv.linear1.weight [Cout][2Cs + 6Cv] into the three weight planes.  A full-precision
+ * svnet_svblock_edge_fwd call takes this kernel when `W1tc` (those planes), `tab4` (float4 table, full-precision weights)
+ * and `Yab` are set; `W1q_t` and `PQ` may then be NULL. */
+size_t svnet_edge_fp_tc_weight_bytes(int Cs, int Cv, int Cout, int Cvo, int k);
+int svnet_edge_fp_tc_pack_w(const float* W1, int ldw, int Cs, int Cv, int Cout, unsigned char* out, void* stream);
+
 /* Multi-GPU: all-gather of the per-rank outputs -- `count_per_rank` floats from `local` of every rank into
  * `all` (rank-major) -- on the caller's ncclComm_t and stream; replaces nn.DataParallel's gather
  * (main_cls_dgcnn.py:125, main_partseg_dgcnn.py:116).  The library resolves ncclAllGather at the first call from the NCCL

@@ -26,6 +26,7 @@ EXPORTS = [
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
     "svnet_edge_tc_weight_bytes", "svnet_edge_tc_table_cols", "svnet_edge_tc_pack_w", "svnet_allgather_logits",
+    "svnet_edge_fp_tc_weight_bytes", "svnet_edge_fp_tc_pack_w",
 ]
 
 
@@ -83,6 +84,7 @@ def lib():
         l.svnet_binlinear_pool_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_linear_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_edge_tc_weight_bytes.restype = ctypes.c_size_t
+        l.svnet_edge_fp_tc_weight_bytes.restype = ctypes.c_size_t
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
         if l.svnet_version() != 2:
@@ -257,6 +259,20 @@ def edge_tc_pack_w(W1, Cs, Cv):
     nbytes = (2 * Cs + 8 * Cv + 31) // 32 * 32 * 128
     out = torch.empty(nbytes, dtype=torch.uint8, device=W1.device)
     _call("svnet_edge_tc_pack_w", _ptr(W1), c_int(W1.stride(0)), c_int(Cs), c_int(Cv), c_int(Cout), _ptr(out), _stream())
+    return out
+
+
+def edge_fp_tc_weight_bytes(Cs, Cv, Cout, Cvo, k):
+    """0 when the full-precision tensor-core edge kernel does not cover the layer (svnet_edge_fp_tc_weight_bytes)."""
+    return int(lib().svnet_edge_fp_tc_weight_bytes(c_int(Cs), c_int(Cv), c_int(Cout), c_int(Cvo), c_int(k)))
+
+
+def edge_fp_tc_pack_w(W1, Cs, Cv, nbytes):
+    """conv.linear1.weight (Cout, 2Cs + 6Cv), full precision -> three bf16 weight planes of csrc/edge_fp_tc.cu."""
+    W1 = _dev(W1)
+    assert W1.dim() == 2 and W1.stride(1) == 1
+    out = torch.empty(nbytes, dtype=torch.uint8, device=W1.device)
+    _call("svnet_edge_fp_tc_pack_w", _ptr(W1), c_int(W1.stride(0)), c_int(Cs), c_int(Cv), c_int(W1.shape[0]), _ptr(out), _stream())
     return out
 
 

@@ -19,6 +19,7 @@
 
 int svnet_edge_fast_dispatch(const svnet_edge_params* p, cudaStream_t st);
 int svnet_edge_tc_dispatch(const svnet_edge_params* p, cudaStream_t st);
+int svnet_edge_fp_tc_dispatch(const svnet_edge_params* p, cudaStream_t st);
 
 namespace {
 
@@ -403,7 +404,17 @@ extern "C" int svnet_svblock_edge_fwd(const svnet_edge_params* p, void* stream)
         }
         return launch_edge<true>(p, sv_stream(stream));
     }
-    SV_REQUIRE(p->Yab && p->W1q_t, "svnet_svblock_edge_fwd: fp layer needs Yab/W1q_t");
+    SV_REQUIRE(p->Yab, "svnet_svblock_edge_fwd: fp layer needs Yab");
+    {
+        const char* force = getenv("SVNET_EDGE_GENERIC");
+        if (!(force && force[0] == '1')) {
+            // tensor-core kernel when the caller supplied the packed weight planes and the float4 table (edge_fp_tc.cu)
+            int h = svnet_edge_fp_tc_dispatch(p, sv_stream(stream));
+            if (h < 0) return h;
+            if (h == 1) return SVNET_OK;
+        }
+    }
+    SV_REQUIRE(p->W1q_t && p->PQ, "svnet_svblock_edge_fwd: fp layer not covered by the tensor-core kernel needs W1q_t and PQ");
     {
         const char* force = getenv("SVNET_EDGE_GENERIC");
         if (!(force && force[0] == '1')) {

@@ -36,13 +36,13 @@
 // MACs per tile are ~0.4 us of tensor pipe against ~2 us of CUDA-core work producing the tile.
 #include "common.cuh"
 #include "edge_vector.cuh"
+#include "edge_tc_common.cuh"
 #include <stdlib.h>
 
 namespace {
 
 // tile = NW warps x 20 edge rows (UMMA N = 160 or 240); rows per k-block slab = N + 3: 4 * (N + 3) = 12 (mod 32) words
 // -> conflict-free word stores
-constexpr int EPW = 20;          // edges per warp
 constexpr int TMEM_COLS = 256;   // power of two >= rows per tile
 // Launch shape: NW warps per CTA (2 CTAs per SM) and BT = neighbour rows whose gathers are in flight together per
 // round (q-section passes, vector-branch edges, scalar-section edges).  8 warps leave 128 registers per thread
@@ -59,6 +59,7 @@ constexpr int TMEM_COLS = 256;   // power of two >= rows per tile
 
 template <int CS, int CV, int COUT, int CVO, int KE, int NW, int BT_>
 struct TC {
+    static constexpr int EPW = 20;                 // edges per warp
     static constexpr int NWARP = NW, BT = BT_;
     static constexpr int ROWS = NW * EPW, ROWS_PAD = ROWS + 3;
     static constexpr int TS = CS / 32;
@@ -81,66 +82,6 @@ struct TC {
     static_assert(KE % EPW == 0 && NWARP % WPP == 0 && NP * KE == ROWS && ROWS <= TMEM_COLS && ROWS % 16 == 0 && NW % 4 == 0, "tile shape");
     static_assert(CS % 32 == 0 && COUT % 32 == 0 && COUT <= 128 && TS <= 2, "scalar widths");
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)      // bounded: a protocol mistake traps
-{
-    uint32_t done = 0;
-    int spins = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
-            : "=r"(done)
-            : "r"(smem_u32(b)), "r"(parity)
-            : "memory");
-        if (++spins > (1 << 24)) __trap();
-    }
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* b)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
 
 // ---- K positions (shared by the weight packer, the taps and the producer lanes) -------------------------------
 // reference channel c of u = [s_j - s_i | s_i | q(3*ds + m)] -> byte position inside an operand row.
@@ -165,21 +106,6 @@ __host__ __device__ inline int tc_chan(int pos, int CS, int TS, int CV)
     return (m < 3 && ds < 2 * CV) ? 2 * CS + 3 * ds + m : -1;
 }
 
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v)
-{
-    asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(addr), "h"((unsigned short)v) : "memory");
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float4 v)
-{
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
 // two pre-scaled values -> two saturated e4m3 bytes: lo -> bits 0..7, hi -> bits 8..15
 __device__ __forceinline__ uint32_t sat2(float lo, float hi)
 {
@@ -213,7 +139,7 @@ __global__ void edge_tc_pack_w_kernel(const float* __restrict__ W1, int ldw, int
 template <typename S, int CV, int DS0, int NDS>
 struct QSection {
     static constexpr int GE = 32 / NDS;
-    static constexpr int PASSES = (EPW + GE - 1) / GE;
+    static constexpr int PASSES = (S::EPW + GE - 1) / GE;
     static constexpr bool ANY_DIFF = DS0 < CV;
     static constexpr int PB = ANY_DIFF ? (PASSES < S::BT ? PASSES : S::BT) : 1;
     int esub, dcol;
@@ -252,14 +178,14 @@ struct QSection {
 #pragma unroll
                 for (int i = 0; i < PB; ++i) {
                     const int e = (p0 + i) * GE + esub;
-                    const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, (lane_on && e < EPW) ? e : 0);
+                    const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, (lane_on && e < S::EPW) ? e : 0);
                     nb[i] = is_diff ? __ldg(vcol + (size_t)j * S::NC) : vi;
                 }
             }
 #pragma unroll
             for (int i = 0; i < PB; ++i) {
                 const int e = (p0 + i) * GE + esub;
-                const bool on = lane_on && e < EPW;
+                const bool on = lane_on && e < S::EPW;
                 const int es = on ? e : 0;
                 float ve[3];
                 if (ANY_DIFF) {
@@ -285,128 +211,12 @@ struct QSection {
     }
 };
 
-// ---- vector branch on the float4 table: w_e = P_j + (Q_i - P_i), VectorBN, gate, mean over the edges (see
-// edge_vector.cuh for the arithmetic; here every gather is one 16-byte load and VB rows are in flight per round).
-// The first round's gathers are issued by prefetch() before the tile barrier, so that their latency hides
-// behind the barrier and the MMA issue.
-template <typename S, int CVO>
-struct VBranch {
-    static constexpr int VB = S::BT;
-    static constexpr int FULL = CVO / 32, R = CVO % 32, G = R > 0 ? 32 / R : 1, NPASS = FULL + (R > 0 ? 1 : 0);
-    struct Lane {
-        bool rem, active;
-        int graw, g, c, ng, cc;
-    };
-    static __device__ __forceinline__ Lane lane_of(int pass, int lane)
-    {
-        Lane L;
-        L.rem = pass == FULL;
-        L.graw = L.rem ? lane / (R > 0 ? R : 1) : 0;
-        L.active = !L.rem || L.graw < G;
-        L.g = L.active ? L.graw : 0;            // idle lanes walk the same rounds (the index shuffles are warp-wide)
-        L.c = L.rem ? FULL * 32 + lane % (R > 0 ? R : 1) : pass * 32 + lane;
-        L.ng = L.rem ? G : 1;
-        L.cc = L.active ? L.c : 0;
-        return L;
-    }
-    float4 w0[VB], pi[NPASS], qi[NPASS];
-    float a2[NPASS], c2[NPASS], gt[NPASS];
-
-    __device__ __forceinline__ void init(const svnet_edge_params& p, int lane)
-    {
-#pragma unroll
-        for (int pass = 0; pass < NPASS; ++pass) {
-            const Lane L = lane_of(pass, lane);
-            a2[pass] = __ldg(p.bn2_a + L.cc);
-            c2[pass] = __ldg(p.bn2_c + L.cc);
-        }
-    }
-
-    __device__ __forceinline__ void load_round(float4 (&w)[VB], const float4* pcol, int my_j, int e0, int ng) const
-    {
-#pragma unroll
-        for (int i = 0; i < VB; ++i) {
-            const int e = e0 + i * ng;
-            const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, e < EPW ? e : 0);
-            w[i] = __ldg(pcol + (size_t)j * S::NC);
-        }
-    }
-    __device__ __forceinline__ void prefetch(const svnet_edge_params& p, int b, const float4* tabc, const float4* trow, int my_j, int lane)
-    {
-#pragma unroll
-        for (int pass = 0; pass < NPASS; ++pass) {
-            const Lane L = lane_of(pass, lane);
-            pi[pass] = __ldg(trow + L.cc);
-            qi[pass] = __ldg(trow + S::TQ0 + L.cc);
-            gt[pass] = __ldg(p.gate + (long)b * CVO + L.cc);
-        }
-        const Lane L = lane_of(0, lane);
-        load_round(w0, tabc + L.cc, my_j, L.g, L.ng);
-    }
-    __device__ __forceinline__ void run(const svnet_edge_params& p, long r, int b, const float4* tabc, const float4* trow, int my_j,
-                                        int ktot, int lane, float* partial) const
-    {
-        const float inv_k = 1.0f / (float)ktot;
-#pragma unroll
-        for (int pass = 0; pass < NPASS; ++pass) {
-            const Lane L = lane_of(pass, lane);
-            float sum[3] = {0.0f, 0.0f, 0.0f};
-            const float d0 = qi[pass].x - pi[pass].x, d1 = qi[pass].y - pi[pass].y, d2 = qi[pass].z - pi[pass].z;
-            const float a2p = a2[pass], c2p = c2[pass];
-            const float4* pcol = tabc + L.cc;
-            auto consume = [&](const float4 (&w)[VB], int e0) {
-#pragma unroll
-                for (int i = 0; i < VB; ++i) {
-                    if (e0 + i * L.ng < EPW) {
-                        const float w0_ = w[i].x + d0, w1 = w[i].y + d1, w2 = w[i].z + d2;
-                        const float s2 = fmaf(w2, w2, fmaf(w1, w1, w0_ * w0_));
-                        const float t = fmaf(c2p, fast_rcp(fast_sqrt(s2) + 1e-6f), a2p);      // (n a2 + c2) / n,  n = |w| + 1e-6
-                        sum[0] = fmaf(w0_, t, sum[0]);
-                        sum[1] = fmaf(w1, t, sum[1]);
-                        sum[2] = fmaf(w2, t, sum[2]);
-                    }
-                }
-            };
-            int e0 = L.g;
-            if (pass == 0) {
-                consume(w0, e0);
-                e0 += L.ng * VB;
-            }
-#pragma unroll 1
-            for (; e0 < EPW; e0 += L.ng * VB) {
-                float4 w[VB];
-                load_round(w, pcol, my_j, e0, L.ng);
-                consume(w, e0);
-            }
-            if (L.rem && G > 1) {
-#pragma unroll
-                for (int x = 0; x < 3; ++x) {
-                    float tot = sum[x];
-#pragma unroll
-                    for (int gg = 1; gg < G; ++gg) tot += __shfl_sync(SV_FULL, sum[x], (lane % (R > 0 ? R : 1)) + gg * R);
-                    sum[x] = tot;
-                }
-            }
-            if (L.active && L.graw == 0) {
-                if (partial) {
-#pragma unroll
-                    for (int x = 0; x < 3; ++x) partial[x * CVO + L.c] = sum[x];
-                } else {
-                    const float g = gt[pass] * inv_k;
-#pragma unroll
-                    for (int x = 0; x < 3; ++x) p.out.v[r * p.out.ldv + x * p.out.xs + L.c] = sum[x] * g;
-                }
-            }
-        }
-    }
-};
-
 template <int CS, int CV, int COUT, int CVO, int KE, int NW, int BT>
 __global__ void __launch_bounds__(NW * 32, 2)
 edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, const float4* __restrict__ tab4, int ntiles)
 {
     using S = TC<CS, CV, COUT, CVO, KE, NW, BT>;
-    constexpr int TS = S::TS, NWARP = NW, ROWS = S::ROWS, SB = (BT < EPW && EPW % BT == 0) ? BT : EPW / 2;
+    constexpr int TS = S::TS, NWARP = NW, ROWS = S::ROWS, SB = (BT < S::EPW && S::EPW % BT == 0) ? BT : S::EPW / 2;
     extern __shared__ __align__(1024) unsigned char smraw[];
     unsigned char* As = smraw;
     unsigned char* Bs = As + S::A_BYTES;
@@ -437,9 +247,9 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
     const uint32_t tmem_base = *tmem_slot;
 
     // ---- per-lane constants ----
-    const uint32_t zb = smem_u32(wsm + warp * S::WARP_FLOATS);     // frames [EPW][3 m][4]
-    const int pt_in_tile = warp / S::WPP, e0 = (warp % S::WPP) * EPW;
-    const uint32_t brow0 = smem_u32(Bs) + (uint32_t)(warp * EPW) * 16u;     // first operand row of this warp
+    const uint32_t zb = smem_u32(wsm + warp * S::WARP_FLOATS);     // frames [S::EPW][3 m][4]
+    const int pt_in_tile = warp / S::WPP, e0 = (warp % S::WPP) * S::EPW;
+    const uint32_t brow0 = smem_u32(Bs) + (uint32_t)(warp * S::EPW) * 16u;     // first operand row of this warp
     // scalar word of this lane: TS = 2: channels (2l, 2l+1) -> K positions 4l .. 4l+3; TS = 1: channel l -> 2l, 2l+1
     float bs[TS], bc[TS];
 #pragma unroll
@@ -470,7 +280,7 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
     int next_j = 0;
     {
         const long r = (long)blockIdx.x * S::NP + pt_in_tile;
-        if (blockIdx.x < ntiles && r < total && lane < EPW) next_j = __ldg(p.idx + r * KE + e0 + lane);
+        if (blockIdx.x < ntiles && r < total && lane < S::EPW) next_j = __ldg(p.idx + r * KE + e0 + lane);
     }
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -479,7 +289,7 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
         const int my_j = next_j;
         {
             const long rn = r + (long)gridDim.x * S::NP;
-            next_j = (tile + gridDim.x < ntiles && rn < total && lane < EPW) ? __ldg(p.idx + rn * KE + e0 + lane) : 0;
+            next_j = (tile + gridDim.x < ntiles && rn < total && lane < S::EPW) ? __ldg(p.idx + rn * KE + e0 + lane) : 0;
         }
         int b = 0;
         const float4* tabc = tab4;
@@ -495,7 +305,7 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
 #pragma unroll
             for (int rd = 0; rd < 2; ++rd) {
                 const int e = rd * 10 + e_lane;
-                const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, e < EPW ? e : 0);
+                const unsigned j = (unsigned)__shfl_sync(SV_FULL, my_j, e < S::EPW ? e : 0);
                 tj[rd] = __ldg(tabc + (size_t)j * S::NC + S::TT0 + m_lane);
             }
             const float* srow = p.in.s + r * p.in.lds;
@@ -518,7 +328,7 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
             }
             // ---- scalar section: one word per edge, SB neighbour rows in flight per round ----
 #pragma unroll 1
-            for (int eb = 0; eb < EPW; eb += SB) {
+            for (int eb = 0; eb < S::EPW; eb += SB) {
                 float sv[SB][TS];
 #pragma unroll
                 for (int i = 0; i < SB; ++i) {
@@ -557,8 +367,8 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
             if (p.dbg_bits) {
                 // parity taps: rebuild the reference-ordered sign / mask words from the operand bytes
                 __syncwarp();
-                const unsigned char* brow = Bs + (size_t)(warp * EPW) * 16;
-                for (int e = 0; e < EPW; ++e)
+                const unsigned char* brow = Bs + (size_t)(warp * S::EPW) * 16;
+                for (int e = 0; e < S::EPW; ++e)
                     for (int w = 0; w < S::KW; ++w) {
                         const int c = 32 * w + lane;
                         unsigned char byte = 0;

@@ -130,14 +130,16 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
     # wave leaves SMs idle at B = 32).  Tensor-core edge kernel (csrc/edge_tc.cu): one float4 table
     # [P | Q | T | U | v]; other kernels: the P | Q table of the vector branch.
     use_tc = blk.binary and nv.edge_tc_weight_bytes(Cs, Cv, Cout, Cvo, k) > 0
+    fp_tc_bytes = 0 if blk.binary else nv.edge_fp_tc_weight_bytes(Cs, Cv, Cout, Cvo, k)      # csrc/edge_fp_tc.cu
+    use_fp_tc = fp_tc_bytes > 0
     cur = torch.cuda.current_stream()
     side = _side_stream(dev) if (idx32 is None and SIDE_STREAM and not _STATE.in_sub_batch) else None
-    if use_tc:
+    if use_tc or use_fp_tc:
         Wt, cst = blk.edge_tc_table_weight()
         NC = Wt.shape[0]
         table = torch.empty((R, NC, 4), dtype=torch.float32, device=dev)
         args = (v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wt, NC, table, 4 * NC, 0)
-        kw = dict(sign_w=True, colscale=cst, c4=True)
+        kw = dict(sign_w=use_tc, colscale=cst, c4=True)
     else:
         Wpq, spq = blk.pq_weight()
         table = torch.empty((R, 3, 2 * Cvo), dtype=torch.float32, device=dev)
@@ -176,6 +178,14 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
             W1tc = blk.edge_tc_weight()
             p.W1tc, p.tab4 = W1tc.data_ptr(), table.data_ptr()
             keep += [W1tc]
+    elif use_fp_tc:
+        # full-precision linear1: the q part on the tensor cores (three bf16 weight planes), the s part from Ya | Yb
+        Wab = blk.yab_only_weight()
+        Yab = torch.empty((R, 2 * Cout), dtype=torch.float32, device=dev)
+        nv.linear_rows(s_in, s_in.stride(0), 0, 1, R, Cs, Wab, 2 * Cout, Yab, 2 * Cout, 0)
+        W1f = blk.edge_fp_tc_weight(fp_tc_bytes)
+        p.Yab, p.W1tc, p.tab4 = Yab.data_ptr(), W1f.data_ptr(), table.data_ptr()
+        keep += [Yab, W1f]
     else:
         Wab, Wq_t = blk.yab_weight()
         Yab = torch.empty((R, 2 * Cout), dtype=torch.float32, device=dev)
@@ -183,7 +193,7 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
         p.Yab, p.W1q_t = Yab.data_ptr(), Wq_t.data_ptr()
         keep += [Yab, Wq_t]
     p.bn1_a, p.bn1_c, p.Cout = a1.data_ptr(), c1.data_ptr(), Cout
-    p.PQ = 0 if use_tc else table.data_ptr()
+    p.PQ = 0 if (use_tc or use_fp_tc) else table.data_ptr()
     p.bn2_a, p.bn2_c, p.gate, p.Cvo = a2.data_ptr(), c2.data_ptr(), gate.data_ptr(), Cvo
     p.out = _mview(s_out, v_out)
     if taps is not None and blk.binary:

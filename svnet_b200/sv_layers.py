@@ -383,10 +383,28 @@ class SVBlock(_Cached, nn.Module):
             Wz = v2s.weight.detach()
             eye = torch.eye(cv, dtype=W.dtype, device=W.device)
             Wt = torch.cat([W[:, :cv], W[:, cv:], Wz[:, :cv], Wz[:, cv:], eye], dim=0).contiguous()
+            if not lin.bw:
+                return Wt, None                       # full-precision block: plain weights, no column scales
             sc2, zs = lin.scale.detach().reshape(-1), v2s.scale.detach().reshape(-1)
             cs = torch.cat([sc2, sc2, zs, zs, torch.ones(cv, dtype=W.dtype, device=W.device)]).contiguous()
             return Wt, cs
-        return self._packed("tc_tab", ("linear2.weight", "linear2.scale", "v2s.linear.weight", "v2s.linear.scale"), build)
+        deps = ("linear2.weight", "linear2.scale", "v2s.linear.weight", "v2s.linear.scale") if lin.bw else \
+            ("linear2.weight", "v2s.linear.weight")
+        return self._packed("tc_tab", deps, build)
+
+    def edge_fp_tc_weight(self, nbytes):
+        """The q columns of a full-precision linear1 as three bf16 planes in the operand layout of csrc/edge_fp_tc.cu."""
+        cs, cv = self.in_dims[0] // 2, self.in_dims[1] // 2
+        return self._packed("w1ftc", ("linear1.weight",),
+                            lambda: nv.edge_fp_tc_pack_w(self.linear1.weight.detach(), cs, cv, nbytes))
+
+    def yab_only_weight(self):
+        """[W1a; W1b] (2*Cout, Cs_pt) of a full-precision linear1 (the per-point table Ya | Yb)."""
+        def build():
+            W = self.linear1.weight.detach()
+            cs = self.in_dims[0] // 2
+            return torch.cat([W[:, :cs], W[:, cs:2 * cs]], dim=0).contiguous()
+        return self._packed("yab_only", ("linear1.weight",), build)
 
     def edge_tc_weight(self):
         """linear1's sign bytes (fp8 e4m3) in the operand layout of the tensor-core edge kernel."""
