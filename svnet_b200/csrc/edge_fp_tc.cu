@@ -31,10 +31,17 @@ namespace {
 
 constexpr int FTMEM_COLS = 256;
 
+// Tile shapes.  Cout <= 64 (conv2 / conv3): 8 warps x 20 edges, two CTAs per SM (as edge_tc.cu) -- the weight planes keep
+// only 64 rows per k-block (the UMMA still multiplies 128 rows: rows 64..127 alias the next k-block, their accumulator lanes
+// are never read), which is what lets two tiles fit one SM's shared memory.  Cout = 128 (conv4): the planes alone are
+// 96 KB, one CTA per SM with 16 warps x 10 edges.
 template <int CS, int CV, int COUT, int CVO, int KE>
 struct FTC {
-    static constexpr int EPW = 10;                  // edges per warp
-    static constexpr int NWARP = 16, BT = 10;
+    static constexpr bool SMALL = COUT <= 64;
+    static constexpr int EPW = SMALL ? 20 : 10;     // edges per warp
+    static constexpr int NWARP = SMALL ? 8 : 16, BT = 10;
+    static constexpr int CTAS_PER_SM = SMALL ? 2 : 1;
+    static constexpr int AROWS = SMALL ? 64 : 128;  // weight rows kept per k-block
     static constexpr int ROWS = NWARP * EPW, ROWS_PAD = ROWS + 3;
     static constexpr int WPP = KE / EPW;            // warps per point
     static constexpr int NP = NWARP / WPP;          // points per tile
@@ -42,7 +49,7 @@ struct FTC {
     static constexpr int KTOT = 2 * KH;
     static constexpr int NPH = KTOT <= 64 ? 1 : 2;  // phases through the operand buffer
     static constexpr int KPH = KTOT / NPH;          // K positions per phase
-    static constexpr int KBA = 128 * 16;            // bytes per 8-position k-block of a weight plane
+    static constexpr int KBA = AROWS * 16;          // bytes per 8-position k-block of a weight plane
     static constexpr int KBB = ROWS_PAD * 16;       // ... of an activation plane
     static constexpr int APL = (KTOT / 8) * KBA;    // bytes per weight plane
     static constexpr int BPL = (KPH / 8) * KBB;     // bytes per activation plane
@@ -53,8 +60,8 @@ struct FTC {
     static constexpr int VPART = (WPP > 1) ? NWARP * 3 * CVO : 0;
     static constexpr size_t SMEM = (size_t)A_BYTES + B_BYTES + sizeof(float) * (NWARP * WARP_FLOATS + VPART) + 16;
     static_assert(KE % EPW == 0 && NWARP % WPP == 0 && NP * KE == ROWS && ROWS <= FTMEM_COLS && ROWS % 16 == 0, "tile shape");
-    static_assert(COUT % 32 == 0 && COUT <= 128 && NP % 4 == 0 && KPH % 16 == 0, "shape");
-    static_assert(SMEM <= 227 * 1024, "shared memory");
+    static_assert(COUT % 32 == 0 && COUT <= AROWS && NP % (NWARP / 4) == 0 && KPH % 16 == 0 && EPW % 10 == 0, "shape");
+    static_assert(CTAS_PER_SM * (SMEM + 1024) <= 227 * 1024, "shared memory");
 };
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
@@ -81,13 +88,13 @@ __device__ __forceinline__ void split3(float a, uint32_t& h, uint32_t& m, uint32
 
 // ---- weights: fp32 W1 [COUT][2Cs + 6Cv] (the q columns start at 2Cs) -> three bf16 planes in the canonical K-major
 // operand layout [plane][k-block][128 rows][8], K positions by ftc_pos, zero rows / positions for padding
-__global__ void edge_fp_tc_pack_w_kernel(const float* __restrict__ W1, int ldw, int CS, int CV, int COUT, int KH,
+__global__ void edge_fp_tc_pack_w_kernel(const float* __restrict__ W1, int ldw, int CS, int CV, int COUT, int KH, int AROWS,
                                          unsigned char* __restrict__ out)
 {
     const int KTOT = 2 * KH, NKB = KTOT / 8;
-    const int APL = NKB * 128 * 16;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NKB * 128; i += gridDim.x * blockDim.x) {
-        const int row = i & 127, kb = i >> 7;
+    const int APL = NKB * AROWS * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NKB * AROWS; i += gridDim.x * blockDim.x) {
+        const int row = i % AROWS, kb = i / AROWS;
         uint32_t w[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
         for (int e = 0; e < 8; ++e) {
             const int pos = kb * 8 + e;
@@ -104,7 +111,7 @@ __global__ void edge_fp_tc_pack_w_kernel(const float* __restrict__ W1, int ldw, 
             w[2][e >> 1] |= l << (16 * (e & 1));
         }
         for (int pl = 0; pl < 3; ++pl)
-            *reinterpret_cast<uint4*>(out + (size_t)pl * APL + (size_t)kb * 2048 + (size_t)row * 16) =
+            *reinterpret_cast<uint4*>(out + (size_t)pl * APL + (size_t)kb * AROWS * 16 + (size_t)row * 16) =
                 make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
     }
 }
@@ -185,7 +192,7 @@ struct QSecF {
 };
 
 template <int CS, int CV, int COUT, int CVO, int KE>
-__global__ void __launch_bounds__(FTC<CS, CV, COUT, CVO, KE>::NWARP * 32, 1)
+__global__ void __launch_bounds__(FTC<CS, CV, COUT, CVO, KE>::NWARP * 32, FTC<CS, CV, COUT, CVO, KE>::CTAS_PER_SM)
 edge_fp_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, const float4* __restrict__ tab4, int ntiles)
 {
     using S = FTC<CS, CV, COUT, CVO, KE>;
@@ -288,13 +295,21 @@ edge_fp_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, c
             trow = tab4 + r * S::NC;
             // ---- frames z_e[x][m] = T_j + (U_i - T_i), stored [e][m][x (4)] ----
             const float4 ti = __ldg(trow + S::TT0 + m_lane), ui = __ldg(trow + S::TU0 + m_lane);
-            const unsigned jf = (unsigned)__shfl_sync(SV_FULL, my_j, e_lane < S::EPW ? e_lane : 0);
-            const float4 tj = __ldg(tabc + (size_t)jf * S::NC + S::TT0 + m_lane);
+            float4 tj[S::EPW / 10];
+#pragma unroll
+            for (int rd = 0; rd < S::EPW / 10; ++rd) {
+                const int e = rd * 10 + e_lane;
+                const unsigned jf = (unsigned)__shfl_sync(SV_FULL, my_j, e < S::EPW ? e : 0);
+                tj[rd] = __ldg(tabc + (size_t)jf * S::NC + S::TT0 + m_lane);
+            }
             qd.centre(tabc, trow);
             qc.centre(tabc, trow);
-            if (lane < 3 * S::EPW)
-                sts128(zb + (uint32_t)(e_lane * 48 + m_lane * 16),
-                       make_float4(tj.x + (ui.x - ti.x), tj.y + (ui.y - ti.y), tj.z + (ui.z - ti.z), 0.0f));
+            if (lane < 30) {
+#pragma unroll
+                for (int rd = 0; rd < S::EPW / 10; ++rd)
+                    sts128(zb + (uint32_t)((rd * 10 + e_lane) * 48 + m_lane * 16),
+                           make_float4(tj[rd].x + (ui.x - ti.x), tj[rd].y + (ui.y - ti.y), tj[rd].z + (ui.z - ti.z), 0.0f));
+            }
             __syncwarp();
             // ---- q sections of the first phase ----
             qd.run(my_j, zb);
@@ -398,7 +413,8 @@ int launch_ftc(const svnet_edge_params* p, cudaStream_t st)
     using S = FTC<CS, CV, COUT, CVO, KE>;
     const long total = (long)p->B * p->N;
     const int ntiles = sv_cdiv(total, S::NP);
-    const int grid = ntiles < ftc_sm_count() ? ntiles : ftc_sm_count();
+    const int slots = S::CTAS_PER_SM * ftc_sm_count();
+    const int grid = ntiles < slots ? ntiles : slots;
     SV_CUDA(cudaFuncSetAttribute(edge_fp_tc_kernel<CS, CV, COUT, CVO, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
     edge_fp_tc_kernel<CS, CV, COUT, CVO, KE><<<grid, S::NWARP * 32, S::SMEM, st>>>(*p, p->W1tc, reinterpret_cast<const float4*>(p->tab4), ntiles);
     SV_CHECK_LAUNCH("svnet_svblock_edge_fwd(tcgen05, fp)");
@@ -426,7 +442,7 @@ extern "C" size_t svnet_edge_fp_tc_weight_bytes(int Cs, int Cv, int Cout, int Cv
 {
     if (!ftc_covered(Cs, Cv, Cout, Cvo, k)) return 0;
     const int KH = (3 * Cv + 15) / 16 * 16;
-    return (size_t)3 * (2 * KH / 8) * 128 * 16;
+    return (size_t)3 * (2 * KH / 8) * (Cout <= 64 ? 64 : 128) * 16 + 1024;      // + the rows the last k-block's 128-row read overhangs
 }
 
 extern "C" int svnet_edge_fp_tc_pack_w(const float* W1, int ldw, int Cs, int Cv, int Cout, unsigned char* out, void* stream)
@@ -435,7 +451,9 @@ extern "C" int svnet_edge_fp_tc_pack_w(const float* W1, int ldw, int Cs, int Cv,
     SV_REQUIRE(Cs >= 1 && Cv >= 1 && Cv <= 32 && Cout >= 1 && Cout <= 128, "svnet_edge_fp_tc_pack_w: shape not covered");
     SV_REQUIRE(ldw >= 2 * Cs + 6 * Cv, "svnet_edge_fp_tc_pack_w: ldw too small");
     const int KH = (3 * Cv + 15) / 16 * 16;
-    edge_fp_tc_pack_w_kernel<<<sv_cdiv((long)(2 * KH / 8) * 128, 256), 256, 0, sv_stream(stream)>>>(W1, ldw, Cs, Cv, Cout, KH, out);
+    const int arows = Cout <= 64 ? 64 : 128;
+    SV_CUDA(cudaMemsetAsync(out + (size_t)3 * (2 * KH / 8) * arows * 16, 0, 1024, sv_stream(stream)));
+    edge_fp_tc_pack_w_kernel<<<sv_cdiv((long)(2 * KH / 8) * arows, 256), 256, 0, sv_stream(stream)>>>(W1, ldw, Cs, Cv, Cout, KH, arows, out);
     SV_CHECK_LAUNCH("svnet_edge_fp_tc_pack_w");
     return SVNET_OK;
 }

@@ -1,3 +1,4 @@
-timeout 120 python tools/fp_tc_check.py 32 > gpurun_out/fp_tc.log 2>&1; echo rc=$?; tail -3 gpurun_out/fp_tc.log
-python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; tail -3 gpurun_out/t_all.log
-python tools/profile_calls.py cls_fp 32 1024 20 2>&1 | tail -14
+python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; tail -2 gpurun_out/t_all.log
+python tools/fp_calls.py 2>&1 | tail -40
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_f.json 2> gpurun_out/bench_f.err; python -c "
+import json;d=json.load(open('gpurun_out/bench_f.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['kernel'],d['roofline']['kernel_ms'],d['roofline']['eager_ms_per_step']);print(d['extra']['cfg3']['clouds_per_s'],d['extra']['cfg4']['clouds_per_s'])"
