@@ -299,6 +299,45 @@ __global__ void svfuse_pool_reduce_kernel(const float* __restrict__ partial, int
     if (mean_out) mean_out[(size_t)b * ldo + c] = sm / (float)rows_per_cloud;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Plain sign-pack of a float matrix (Linear `ba`, Conv1d; sv_layers.py:36-39,69): one warp = one (row, 8-word chunk);
+// the eight loads of a lane are in flight together, ballots give the words, lanes 0..7 store them (32 contiguous
+// bytes per plane).  nvalid (zeroed by the caller) collects the chunks' popcounts with integer atomics.
+// Round 2: the generic three-rows-per-warp kernel took 76 us for the seg head's 16 x 1600 per-cloud matrix (one load
+// per ballot round) and 33 us for the 32768 x 256 activations of conv9 / conv10.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) signpack_kernel(const float* __restrict__ s, long lds, int K, long rows, const float* __restrict__ beta,
+                                                       uint32_t* __restrict__ bits, uint32_t* __restrict__ mask, int32_t* __restrict__ nvalid)
+{
+    const int lane = threadIdx.x & 31;
+    const int Kw = (K + 31) >> 5, nch = (Kw + 7) >> 3;
+    const long items = rows * nch;
+    for (long it = (long)blockIdx.x * 8 + (threadIdx.x >> 5); it < items; it += (long)gridDim.x * 8) {
+        const long r = it / nch;
+        const int w0 = (int)(it - r * nch) * 8;
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = (w0 + u) * 32 + lane;
+            t[u] = c < K ? __fadd_rn(__ldg(s + r * lds + c), __ldg(beta + c)) : 0.0f;
+        }
+        unsigned mypos = 0u, mynz = 0u;
+        int nval = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const unsigned pos = __ballot_sync(SV_FULL, t[u] > 0.0f);
+            const unsigned nz = __ballot_sync(SV_FULL, t[u] != 0.0f);
+            nval += __popc(nz);
+            if (lane == u) { mypos = pos; mynz = nz; }
+        }
+        if (lane < 8 && w0 + lane < Kw) {
+            bits[r * Kw + w0 + lane] = mypos;
+            mask[r * Kw + w0 + lane] = mynz;
+        }
+        if (lane == 0) atomicAdd(nvalid + r, nval);
+    }
+}
+
 }  // namespace
 
 // Returns 1 if handled, 0 if rows.cu must take the call, < 0 on error.
@@ -307,6 +346,13 @@ int svnet_rows_prep_fast_dispatch(const svnet_view* in, long rows, const float* 
 {
     const int Cs = in->Cs, Cv = in->Cv;
     const int K = Cs + 3 * Cv, Kw = (K + 31) / 32;
+    if (Cv == 0) {
+        SV_CUDA(cudaMemsetAsync(nvalid, 0, sizeof(int32_t) * (size_t)rows, st));
+        const long items = rows * ((Kw + 7) / 8);
+        signpack_kernel<<<(int)min((long)sv_cdiv(items, 8), 148L * 32), 256, 0, st>>>(in->s, in->lds, K, rows, beta, bits, mask, nvalid);
+        SV_CHECK_LAUNCH("svnet_rows_prep(sign-pack)");
+        return 1;
+    }
     if (Cv < 1 || (Cs & 31) || Cs > 512 || (Kw & 3) || rows < 1024) return 0;
     if ((reinterpret_cast<uintptr_t>(bits) | reinterpret_cast<uintptr_t>(mask)) & 15) return 0;
     const size_t smem = sizeof(float) * ((size_t)3 * rf_cvp(Cv) + (size_t)Kw * 32 + (size_t)RW * rf_warp_floats(Cv));

@@ -17,6 +17,7 @@ MIN_CLOUDS = max(1, int(os.environ.get("SVNET_MIN_CLOUDS", "8")))  # ... of at l
 _SIDE = {}
 class _State(threading.local):       # per thread: DataParallel drives one forward per device thread
     in_sub_batch = False
+    sub_index = 0
 
 
 _STATE = _State()
@@ -28,6 +29,15 @@ def _side_stream(dev, which=0):
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=dev)
     return _SIDE[key]
+
+
+def aux_stream(dev):
+    """A side stream for work that does not depend on the caller's latest kernels (e.g. the part-seg head's per-point
+    sign words next to its per-cloud branch): one per concurrent sub-batch, so that sub-batches do not meet on it.
+    None when side streams are switched off."""
+    if not SIDE_STREAM:
+        return None
+    return _side_stream(dev, 16 + _STATE.sub_index) if _STATE.in_sub_batch else _side_stream(dev, 15)
 
 
 def chunked(impl, x, extras=(), hooks=False):
@@ -72,6 +82,7 @@ def _two_streams(impl, x, extras):
         for i, (xc, ec) in enumerate(parts):
             st = _side_stream(dev, 1 + i)
             st.wait_stream(cur)
+            _STATE.sub_index = i
             with torch.cuda.stream(st):
                 y = impl(xc, *ec)
             y.record_stream(cur)

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nv
-from .fused import chunked, dgcnn_trunk
+from .fused import aux_stream, chunked, dgcnn_trunk
 from .sv_layers import Conv1d, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, dense_rows, folded_bn
 
 
@@ -99,6 +99,21 @@ class SV_DGCNN_PSEG(nn.Module):
         # svfuse1's output only feeds conv8: a binary conv8 takes its sign words straight from (s_cat, v_cat)
         lean_fine = self.binary and record is None
         x_fine = None if lean_fine else self.svfuse1.forward_rows(s_cat, v_cat)[0]          # (R, 544)
+        sv_in = sv_bits = aux = None
+        if lean_fine:
+            # conv8's per-point sign words depend on the trunk only: they run on a side stream next to the global
+            # branch below, whose per-cloud kernels (conv6, svfuse2, conv7: B rows each) leave the GPU almost idle
+            Wz1, zs1 = self.svfuse1.v2s.wz()
+            sv_in = (nv.view_of(s_cat, v_cat), R, Wz1, zs1)
+            Kc8 = self.conv8[0].in_channels - (s_cat.shape[1] + 3 * v_cat.shape[2])
+            aux = aux_stream(dev)
+            if aux is not None:
+                cur = torch.cuda.current_stream()
+                aux.wait_stream(cur)
+                with torch.cuda.stream(aux):
+                    sv_bits = self.conv8[0].sv_in_bits(sv_in, Kc8)
+                for t in sv_bits:
+                    t.record_stream(cur)
         # global branch: svpool over points -> conv6 -> svfuse2.  Per point only v5 is needed further on (with fuse3):
         # the binary conv5 pools its scalar output in the epilogue of its tensor-core linear and never writes it
         sp = torch.empty((B, C5s), dtype=torch.float32, device=dev)
@@ -128,9 +143,10 @@ class SV_DGCNN_PSEG(nn.Module):
         glob[:, C3 + x_pool.shape[1]:].copy_(lab)
         # segmentation head on rows; glob is constant per cloud
         if lean_fine:
-            Wz1, zs1 = self.svfuse1.v2s.wz()
+            if aux is not None:
+                torch.cuda.current_stream().wait_stream(aux)
             h = self.conv8[0].forward_rows(None, bn=self.conv8.bn_folded(), act=nv.ACT_LEAKY, cloud=glob, rows_per_cloud=N,
-                                           sv_in=(nv.view_of(s_cat, v_cat), R, Wz1, zs1))
+                                           sv_in=sv_in, sv_bits=sv_bits)
         else:
             h = self.conv8[0].forward_rows(x_fine, bn=self.conv8.bn_folded(), act=nv.ACT_LEAKY, cloud=glob, rows_per_cloud=N)
         h = self.conv9[0].forward_rows(h, bn=self.conv9.bn_folded(), act=nv.ACT_LEAKY)

@@ -206,7 +206,14 @@ class Conv1d(_Cached, nn.Conv1d):
     def beta_vec(self):
         return self._packed("beta", ("beta",), lambda: self.beta.detach().reshape(-1).contiguous())
 
-    def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE, cloud=None, rows_per_cloud=1, sv_in=None):
+    def sv_in_bits(self, sv_in, Kc):
+        """Sign words of SVFuse's output [s | v2s(v)] of the view ``sv_in`` = (view, rows, Wz, zscale) against this
+        layer's beta[Kc:] -- the per-point half of ``forward_rows(None, cloud=..., sv_in=...)``, callable ahead of it
+        (it does not depend on the per-cloud channels)."""
+        view, rows, Wz_in, zs_in = sv_in
+        return nv.rows_prep(view, rows, Wz=Wz_in, zscale=zs_in, beta=self.beta_vec()[Kc:], want_bits=True)
+
+    def forward_rows(self, x2d, bn=None, act=nv.ACT_NONE, cloud=None, rows_per_cloud=1, sv_in=None, sv_bits=None):
         """x2d (rows, Kp) -> (rows, Cout).  ``cloud`` (B, Kc), if given, holds per-cloud-constant
         leading input channels (the ``repeat(1, 1, num_points)`` block of sv_dgcnn_partseg.py:118):
         the layer input is [cloud[row // rows_per_cloud] | x2d[row]] and the constant part of every
@@ -228,8 +235,10 @@ class Conv1d(_Cached, nn.Conv1d):
             if cloud is not None:
                 cb, cm, cn = nv.rows_prep(nv.view_of(cloud, None), cloud.shape[0], beta=beta[:Kc], want_bits=True)
                 cdot = nv.binlinear_rows(cb, cm, cn, Kc, self.sign_bits(0, Kc), Cout, out_i32=True)
-            if sv_in is not None:
-                bits, mask, nvalid = nv.rows_prep(view, rows, Wz=Wz_in, zscale=zs_in, beta=beta[Kc:], want_bits=True)
+            if sv_bits is not None:
+                bits, mask, nvalid = sv_bits
+            elif sv_in is not None:
+                bits, mask, nvalid = self.sv_in_bits(sv_in, Kc)
             else:
                 bits, mask, nvalid = nv.rows_prep(nv.view_of(x2d, None), rows, beta=beta[Kc:], want_bits=True)
             return nv.binlinear_rows(bits, mask, nvalid, Kp, self.sign_bits(Kc, Kc + Kp), Cout, scale=self.scale_vec(),

@@ -1,4 +1,29 @@
 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; tail -2 gpurun_out/t_all.log
-python tools/fp_calls.py 2>&1 | tail -40
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_f.json 2> gpurun_out/bench_f.err; python -c "
-import json;d=json.load(open('gpurun_out/bench_f.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['kernel'],d['roofline']['kernel_ms'],d['roofline']['eager_ms_per_step']);print(d['extra']['cfg3']['clouds_per_s'],d['extra']['cfg4']['clouds_per_s'])"
+python tools/pseg_calls.py 16 2>&1 | grep -E "whole|rows_prep|sum"
+python - <<PY
+import contextlib, io, os, sys, torch
+sys.path.insert(0,'.')
+import svnet_b200 as sv
+from svnet_b200.synthetic import make_args, one_hot_labels, synthetic_clouds, synthetic_state_dict
+with contextlib.redirect_stdout(io.StringIO()):
+    net = sv.SV_DGCNN_PSEG(make_args(k=40, binary=True), 50)
+net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=1004)); net = net.cuda().eval()
+for B in (16, 128):
+    x = synthetic_clouds(B, 2048, 1004).cuda(); l = one_hot_labels(B).cuda()
+    with torch.no_grad():
+        for _ in range(3): net(x, l)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); net(x, l); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
+        print("pseg eager B=%d: %.3f ms  %.0f clouds/s" % (B, best, B / best * 1e3))
+        g = sv.GraphedForward(net, x, l)
+        for _ in range(3): g(x, l)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g(x, l); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
+        print("pseg graph B=%d: %.3f ms  %.0f clouds/s" % (B, best, B / best * 1e3))
+PY
