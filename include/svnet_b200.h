@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SVNET_ABI_VERSION 2
+#define SVNET_ABI_VERSION 3
 
 /* error codes */
 #define SVNET_OK 0
@@ -329,6 +329,32 @@ typedef struct {
     float* out; int ldo;
 } svnet_head_params;
 int svnet_head_fwd(const svnet_head_params* p, void* stream);
+
+/* Part-segmentation head as one call (sv_dgcnn_partseg.py:112-126): conv8 over [per-cloud channels | svfuse1(s_cat, v_cat)]
+ * -> conv9 -> conv10 (binarised Conv1d + BN + LeakyReLU, sv_layers.py:64-78) -> conv11 (fp Conv1d) -> logits in the
+ * reference's (B, parts, N) order.  It sequences this library's kernels on `stream` with svnet_seg_head_workspace_bytes()
+ * bytes of caller-owned scratch (16-byte aligned) and is bit-identical to the layer-by-layer calls.
+ *   sv           per-point inputs (s_cat [R][lds] (Cs used), v_cat [R][3][Cv]), R = B*N rows
+ *   Wz1/zscale1  svfuse1.v2s (sv_layers.py:206-220)
+ *   glob [B][ldg]  the Kc per-cloud-constant leading input channels of conv8 (the `repeat(1, 1, num_points)` block)
+ *   beta8 [Kc + Cs + 3Cv], W8c / W8p  sign bit-planes (svnet_pack_sign) of conv8.weight[:, :Kc] / [:, Kc:], scale8, bn8_a/_c
+ *   bits8/mask8/nvalid8  optional: conv8's per-point sign words computed by the caller ahead of time (svnet_rows_prep on
+ *                `sv` with beta8 + Kc, e.g. on another stream next to the global branch); sv/Wz1 may then be NULL
+ *   beta9 [C8], W9, ...; beta10 [C9], W10, ...; W11 [parts][C10] fp32 */
+typedef struct {
+    svnet_view sv;
+    int B; long N;
+    const float* Wz1; const float* zscale1;
+    const float* glob; int ldg; int Kc;
+    const float* beta8; const uint32_t* W8c; const uint32_t* W8p; const float* scale8; const float* bn8_a; const float* bn8_c; int C8;
+    const uint32_t* bits8; const uint32_t* mask8; const int32_t* nvalid8;
+    const float* beta9; const uint32_t* W9; const float* scale9; const float* bn9_a; const float* bn9_c; int C9;
+    const float* beta10; const uint32_t* W10; const float* scale10; const float* bn10_a; const float* bn10_c; int C10;
+    const float* W11; int parts;
+    float* logits;        /* [B][parts][N] */
+} svnet_seg_head_params;
+size_t svnet_seg_head_workspace_bytes(const svnet_seg_head_params* p);
+int svnet_seg_head_fwd(const svnet_seg_head_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
 /* VectorBN on materialised rows (module-level parity for sv_layers.VectorBN, :86-102):
  * v [rows][3][C] contiguous -> out. */

@@ -26,7 +26,7 @@ EXPORTS = [
     "svnet_edge_xyz_fwd", "svnet_svblock_edge_fwd", "svnet_rows_prep", "svnet_binlinear_rows", "svnet_linear_rows",
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
     "svnet_edge_tc_weight_bytes", "svnet_edge_tc_table_cols", "svnet_edge_tc_pack_w", "svnet_allgather_logits",
-    "svnet_edge_fp_tc_weight_bytes", "svnet_edge_fp_tc_pack_w",
+    "svnet_edge_fp_tc_weight_bytes", "svnet_edge_fp_tc_pack_w", "svnet_seg_head_fwd", "svnet_seg_head_workspace_bytes",
 ]
 
 
@@ -58,6 +58,16 @@ class GemmParams(ctypes.Structure):
                 ("ldc_x", c_int), ("c4", c_int)]
 
 
+class SegHeadParams(ctypes.Structure):
+    _fields_ = [("sv", View), ("B", c_int), ("N", c_long), ("Wz1", c_void_p), ("zscale1", c_void_p),
+                ("glob", c_void_p), ("ldg", c_int), ("Kc", c_int),
+                ("beta8", c_void_p), ("W8c", c_void_p), ("W8p", c_void_p), ("scale8", c_void_p), ("bn8_a", c_void_p),
+                ("bn8_c", c_void_p), ("C8", c_int), ("bits8", c_void_p), ("mask8", c_void_p), ("nvalid8", c_void_p),
+                ("beta9", c_void_p), ("W9", c_void_p), ("scale9", c_void_p), ("bn9_a", c_void_p), ("bn9_c", c_void_p), ("C9", c_int),
+                ("beta10", c_void_p), ("W10", c_void_p), ("scale10", c_void_p), ("bn10_a", c_void_p), ("bn10_c", c_void_p),
+                ("C10", c_int), ("W11", c_void_p), ("parts", c_int), ("logits", c_void_p)]
+
+
 class HeadLayer(ctypes.Structure):
     _fields_ = [("Cout", c_int), ("W1b", c_void_p), ("beta", c_void_p), ("W", c_void_p), ("sign_w", c_int),
                 ("scale", c_void_p), ("bias", c_void_p), ("bn_a", c_void_p), ("bn_c", c_void_p), ("act", c_int)]
@@ -85,9 +95,10 @@ def lib():
         l.svnet_linear_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_edge_tc_weight_bytes.restype = ctypes.c_size_t
         l.svnet_edge_fp_tc_weight_bytes.restype = ctypes.c_size_t
+        l.svnet_seg_head_workspace_bytes.restype = ctypes.c_size_t
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
-        if l.svnet_version() != 2:
+        if l.svnet_version() != 3:
             raise RuntimeError("svnet_b200: ABI version mismatch")
         _lib = l
     return _lib
@@ -273,6 +284,34 @@ def edge_fp_tc_pack_w(W1, Cs, Cv, nbytes):
     assert W1.dim() == 2 and W1.stride(1) == 1
     out = torch.empty(nbytes, dtype=torch.uint8, device=W1.device)
     _call("svnet_edge_fp_tc_pack_w", _ptr(W1), c_int(W1.stride(0)), c_int(Cs), c_int(Cv), c_int(W1.shape[0]), _ptr(out), _stream())
+    return out
+
+
+def seg_head_fwd(view, B, N, Wz1, zscale1, glob, layers, W11, sv_bits=None):
+    """svnet_seg_head_fwd: conv8 -> conv9 -> conv10 -> conv11 of SV_DGCNN_PSEG in one call.  ``layers`` = three dicts
+    (beta, bits (conv8: (bits of the per-cloud part, bits of the per-point part)), scale, bn (a, c), Cout);
+    ``sv_bits`` = conv8's per-point (bits, mask, nvalid) computed ahead of time, or None.  Returns (B, parts, N)."""
+    glob, W11 = _dev(glob), _dev(W11)
+    p = SegHeadParams()
+    p.sv, p.B, p.N = view, B, N
+    p.Wz1, p.zscale1 = _ptr(Wz1).value, _ptr(zscale1).value
+    p.glob, p.ldg, p.Kc = glob.data_ptr(), glob.stride(0), glob.shape[1]
+    l8, l9, l10 = layers
+    p.beta8, p.W8c, p.W8p = l8["beta"].data_ptr(), l8["bits"][0].data_ptr(), l8["bits"][1].data_ptr()
+    p.scale8, p.bn8_a, p.bn8_c, p.C8 = l8["scale"].data_ptr(), l8["bn"][0].data_ptr(), l8["bn"][1].data_ptr(), l8["Cout"]
+    if sv_bits is not None:
+        p.bits8, p.mask8, p.nvalid8 = (t.data_ptr() for t in sv_bits)
+    p.beta9, p.W9 = l9["beta"].data_ptr(), l9["bits"].data_ptr()
+    p.scale9, p.bn9_a, p.bn9_c, p.C9 = l9["scale"].data_ptr(), l9["bn"][0].data_ptr(), l9["bn"][1].data_ptr(), l9["Cout"]
+    p.beta10, p.W10 = l10["beta"].data_ptr(), l10["bits"].data_ptr()
+    p.scale10, p.bn10_a, p.bn10_c, p.C10 = l10["scale"].data_ptr(), l10["bn"][0].data_ptr(), l10["bn"][1].data_ptr(), l10["Cout"]
+    p.W11, p.parts = W11.data_ptr(), W11.shape[0]
+    out = torch.empty((B, W11.shape[0], N), dtype=torch.float32, device=glob.device)
+    p.logits = out.data_ptr()
+    nbytes = int(lib().svnet_seg_head_workspace_bytes(ctypes.byref(p)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=glob.device)
+    _call("svnet_seg_head_fwd", ctypes.byref(p), _ptr(ws), ctypes.c_size_t(nbytes), _stream())
+    LAUNCHES[0] += 11        # kernels behind the one call (sign-packs, binarised linears, GEMM, transpose)
     return out
 
 

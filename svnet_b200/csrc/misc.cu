@@ -127,9 +127,21 @@ __global__ void __launch_bounds__(256) pool_rows_kernel(const float* __restrict_
     const int rg = threadIdx.x >> 5;
     float m = -INFINITY, s = 0.0f;
     if (col < C) {
+        // eight loads in flight per thread, consumed in row order (the summation order is unchanged)
         const float* p = x + (long)b * rows * ld + col;
-        for (long r = rg; r < rows; r += 8) {
-            float t = p[r * ld];
+        long r = rg;
+        for (; r + 56 < rows; r += 64) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldg(p + (r + 8 * u) * ld);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                m = fmaxf(m, t[u]);
+                s += t[u];
+            }
+        }
+        for (; r < rows; r += 8) {
+            const float t = __ldg(p + r * ld);
             m = fmaxf(m, t);
             s += t;
         }

@@ -11,12 +11,16 @@ row-major (B*N, C) tables:
             cloud and enter the per-point popcount linear as an integer offset      (:117-121)
     conv9/10 binary conv + BN + leaky, conv11 fp                                       (:123-126)
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from . import _native as nv
 from .fused import aux_stream, chunked, dgcnn_trunk
 from .sv_layers import Conv1d, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, dense_rows, folded_bn
+
+SEG_HEAD_CALL = os.environ.get("SVNET_SEG_HEAD_CALL", "1") != "0"     # 0: the head layer by layer (parity tests compare both)
 
 
 def _get_visible_value(divisor=8):
@@ -145,6 +149,19 @@ class SV_DGCNN_PSEG(nn.Module):
         if lean_fine:
             if aux is not None:
                 torch.cuda.current_stream().wait_stream(aux)
+            if SEG_HEAD_CALL:
+                # conv8 .. conv11 and the (B, parts, N) layout as one C-ABI call (csrc/seg_head.cu)
+                c8, c9, c10 = self.conv8[0], self.conv9[0], self.conv10[0]
+                Kc = glob.shape[1]
+                W11 = self.conv11.weight.detach()[:, :, 0]
+                layers = [dict(beta=c8.beta_vec(), bits=(c8.sign_bits(0, Kc), c8.sign_bits(Kc, c8.in_channels)), scale=c8.scale_vec(),
+                               bn=self.conv8.bn_folded(), Cout=c8.out_channels),
+                          dict(beta=c9.beta_vec(), bits=c9.sign_bits(), scale=c9.scale_vec(), bn=self.conv9.bn_folded(),
+                               Cout=c9.out_channels),
+                          dict(beta=c10.beta_vec(), bits=c10.sign_bits(), scale=c10.scale_vec(), bn=self.conv10.bn_folded(),
+                               Cout=c10.out_channels)]
+                return nv.seg_head_fwd(sv_in[0], B, N, sv_in[2], sv_in[3], glob, layers, W11 if W11.is_contiguous() else W11.contiguous(),
+                                       sv_bits=sv_bits)
             h = self.conv8[0].forward_rows(None, bn=self.conv8.bn_folded(), act=nv.ACT_LEAKY, cloud=glob, rows_per_cloud=N,
                                            sv_in=sv_in, sv_bits=sv_bits)
         else:

@@ -628,6 +628,31 @@ def test_full_size_configs_run_and_are_batch_independent():
     assert torch.equal(y_full, y_chunk)
 
 
+@pytest.mark.parametrize("B,N,k", [(2, 2048, 40), (3, 200, 12)])
+def test_seg_head_call_equals_layerwise(B, N, k):
+    """svnet_seg_head_fwd (conv8 .. conv11 + the (B, parts, N) layout as one C-ABI call, csrc/seg_head.cu) against the
+    same layers called one by one (sv_dgcnn_partseg.py:112-126): bit-identical logits."""
+    import svnet_b200 as sv
+    from svnet_b200 import sv_dgcnn_partseg as ps
+    from svnet_b200.synthetic import one_hot_labels
+    net = quiet(sv.SV_DGCNN_PSEG, make_args(k=k, binary=True), 50)
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=1004))
+    net = net.to(DEV).eval()
+    x = synthetic_clouds(B, N, 1004).to(DEV)
+    l = one_hot_labels(B).to(DEV)
+    old = ps.SEG_HEAD_CALL
+    try:
+        with torch.no_grad():
+            ps.SEG_HEAD_CALL = True
+            y_call = net(x, l)
+            ps.SEG_HEAD_CALL = False
+            y_layers = net(x, l)
+    finally:
+        ps.SEG_HEAD_CALL = old
+    assert tuple(y_call.shape) == (B, 50, N) and y_call.is_contiguous()
+    assert torch.equal(y_call, y_layers)
+
+
 @pytest.mark.parametrize("cls_name,k,N", [("SV_DGCNN_PSEG", 40, 192), ("SV_DGCNN_CLS", 20, 320)])
 def test_fast_edge_kernels_teacher_forced_k_full(cls_name, k, N):
     """The shape-specialised edge kernels at the BASELINE neighbourhood sizes (k=20 cls, k=40 pseg:

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_header_symbols():
     for name in sorted(declared):
         assert hasattr(lib, name), "libsvnet_b200.so does not export %s" % name
     assert set(nv.EXPORTS) == declared
-    assert lib.svnet_version() == 2
+    assert lib.svnet_version() == 3
 
 
 def test_argument_errors_without_gpu():
