@@ -14,7 +14,7 @@ CUDA events on its launch stream; `cpu_baseline` is the oracle port (C + OpenMP)
 `--impl reference` times the UNMODIFIED reference forward (oracle/_ref, staged by oracle/make_ref.sh:
 the reference's own models/*.py, stock PyTorch on the host cores, all threads) on the same config.
 Extra keys of our line: `gpu_eager_reference` (the same reference modules on cuda: stock eager fp32),
-`extra.cfg3` / `extra.cfg4` (BASELINE.json configs[2] / configs[3], batch-sharded over the ranks: strong
+`extra.cfg3` / `extra.cfg4` / `extra.cfg5` (BASELINE.json configs[2] / configs[3] / three points of configs[4]'s sweep, batch-sharded over the ranks: strong
 scaling, cfg4 with the all-gather of the per-point logits inside the timed region).
 """
 import argparse
@@ -441,6 +441,11 @@ def main():
                                          timed, gather=False)
             extra["cfg4"] = extra_config(sv, "SV_DGCNN_PSEG", dict(k=40, binary=True), 50, 1004, 128, 2048, world, rank, dev,
                                          timed, gather=True)
+            # BASELINE.json configs[4]: three points of the B x N throughput sweep of the binary classifier, each global
+            # batch split over the ranks (the full sweep on one GPU: tools/sweep.py -> profiles/*_sweep_configs.json)
+            extra["cfg5"] = [extra_config(sv, "SV_DGCNN_CLS", dict(k=20, binary=True), 40, 1005, gb, n, world, rank, dev, timed,
+                                          gather=False, steps=3)
+                             for gb, n in ((1024, 1024), (256, 2048), (64, 4096))]
         # ---- the unmodified reference modules on the same GPU (stock PyTorch eager, fp32, TF32 off) ----
         dbg("extras done")
         eager_ref = None

@@ -1,3 +1,3 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; tail -4 gpurun_out/t_all.log
-python tools/pseg_calls.py 16 2>&1 | grep -E "whole|seg_head|pool|sum"
-python tools/profile_calls.py 2>&1 | grep -E "svfuse|sum"
+SECONDS=0
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_g.json 2> gpurun_out/bench_g.err; echo rc=$? secs=$SECONDS; tail -3 gpurun_out/bench_g.err; python -c "
+import json;d=json.load(open('gpurun_out/bench_g.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']['kernel'],d['roofline']['kernel_ms'],d['roofline']['frac']);print(json.dumps(d['extra'],indent=0)[:3000])"
