@@ -14,6 +14,7 @@ SIDE_STREAM = os.environ.get("SVNET_SIDE_STREAM", "1") != "0"
 CONCURRENT_HALVES = os.environ.get("SVNET_TWO_STREAMS", "1") != "0"
 N_SPLIT = max(2, int(os.environ.get("SVNET_STREAMS", "4")))      # sub-batches that run concurrently
 MIN_CLOUDS = max(1, int(os.environ.get("SVNET_MIN_CLOUDS", "8")))  # ... of at least this many clouds
+MIN_POINTS = max(1, int(os.environ.get("SVNET_MIN_POINTS", "16384")))  # ... and points (measured on B200: 32 x 1024 as 2 x 16 clouds)
 _SIDE = {}
 class _State(threading.local):       # per thread: DataParallel drives one forward per device thread
     in_sub_batch = False
@@ -64,9 +65,12 @@ def chunked(impl, x, extras=(), hooks=False):
     return torch.cat(outs, dim=0)
 
 
-def split_bounds(B):
-    """Contiguous sub-batch boundaries: up to N_SPLIT sub-batches of at least MIN_CLOUDS clouds."""
+def split_bounds(B, N=None):
+    """Contiguous sub-batch boundaries: up to N_SPLIT sub-batches of at least MIN_CLOUDS clouds (and, when the cloud
+    size N is given, of at least MIN_POINTS points)."""
     n = max(1, min(N_SPLIT, B // MIN_CLOUDS))
+    if N is not None:
+        n = max(1, min(n, (B * N) // MIN_POINTS))
     return [B * i // n for i in range(n + 1)]
 
 
@@ -74,7 +78,7 @@ def _two_streams(impl, x, extras):
     dev = x.device
     cur = torch.cuda.current_stream()
     B = x.shape[0]
-    bounds = split_bounds(B)
+    bounds = split_bounds(B, x.shape[-1])
     parts = [(x[lo:hi].contiguous(), [e[lo:hi].contiguous() for e in extras]) for lo, hi in zip(bounds[:-1], bounds[1:])]
     outs = []
     _STATE.in_sub_batch = True
