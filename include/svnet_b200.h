@@ -376,6 +376,25 @@ size_t svnet_svfuse_pool_workspace(int B, int Cv, long rows_per_cloud);
 int svnet_svfuse_pool(const svnet_view* in, int B, long rows_per_cloud, const float* Wz, const float* zscale,
                       float* max_out, float* mean_out, int ldo, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- whole-model entry ------------------------------------------------------------------------
+ * The binary SV-DGCNN classifier (models/sv_dgcnn_cls.py:22-82) from a checkpoint's tensors to logits.
+ * svnet_model_create() takes the state_dict as (name, device pointer, element count) triples -- the reference's key names
+ * without the 'module.' prefix (SURVEY 8(a) a-keys), fp32, contiguous -- copies what it needs and packs it once (sign
+ * bit-planes, folded BatchNorm affines, tensor-core operand bytes, per-point table weights); it synchronises `stream` before
+ * it returns, the caller's tensors may then be freed.  Covered: kind "SV_DGCNN_CLS", binary = 1, k = 20 or 40.
+ * svnet_model_forward(): x [B][3][N] -> logits [B][num_class] on `stream`, with svnet_model_workspace_bytes(m, B, N) bytes of
+ * caller-owned scratch (256-byte aligned; 0: shape not covered -- 64 <= N <= 4096).  It allocates
+ * nothing and never synchronises, so it can be captured into a CUDA graph; the logits are bit-identical to the nn.Module
+ * path (svnet_b200.SV_DGCNN_CLS), which makes the same calls through this header. */
+typedef struct { const char* name; const float* data; long numel; } svnet_tensor;
+typedef struct svnet_model svnet_model;
+int svnet_model_create(const char* kind, int k, int binary, int num_class, const svnet_tensor* tensors, int n_tensors,
+                       void* stream, svnet_model** out);
+size_t svnet_model_workspace_bytes(const svnet_model* m, int B, int N);
+int svnet_model_forward(const svnet_model* m, const float* x, int B, int N, float* logits, void* workspace,
+                        size_t workspace_bytes, void* stream);
+void svnet_model_destroy(svnet_model* m);
+
 /* Input side of the eval loop: out[b][c][n] = sum_d pts[b][n][d] * R[b][d][c]
  * (pytorch3d Rotate.transform_points, then permute(0,2,1): main_cls_dgcnn.py:229-235).
  * pts [B][N][3], R [B][3][3] or NULL (permute only) -> out [B][3][N]. */

@@ -13,3 +13,4 @@ __all__ = ["SV_DGCNN_CLS", "SV_DGCNN_PSEG", "SV_PointNet_CLS", "SV_PointNet_PSEG
            "knn", "get_graph_feature", "get_graph_feature_cross", "get_graph_feature_sv", "svpool", "svcat",
            "sv_layers", "sv_util"]
 from .graph import GraphedForward  # noqa: E402,F401
+from .native_model import NativeModel  # noqa: E402,F401

@@ -27,6 +27,7 @@ EXPORTS = [
     "svnet_vector_bn_rows", "svnet_pool_rows", "svnet_head_fwd", "svnet_rotate_permute",
     "svnet_edge_tc_weight_bytes", "svnet_edge_tc_table_cols", "svnet_edge_tc_pack_w", "svnet_allgather_logits",
     "svnet_edge_fp_tc_weight_bytes", "svnet_edge_fp_tc_pack_w", "svnet_seg_head_fwd", "svnet_seg_head_workspace_bytes",
+    "svnet_model_create", "svnet_model_workspace_bytes", "svnet_model_forward", "svnet_model_destroy",
 ]
 
 
@@ -68,6 +69,10 @@ class SegHeadParams(ctypes.Structure):
                 ("C10", c_int), ("W11", c_void_p), ("parts", c_int), ("logits", c_void_p)]
 
 
+class TensorRef(ctypes.Structure):           # svnet_tensor
+    _fields_ = [("name", ctypes.c_char_p), ("data", c_void_p), ("numel", c_long)]
+
+
 class HeadLayer(ctypes.Structure):
     _fields_ = [("Cout", c_int), ("W1b", c_void_p), ("beta", c_void_p), ("W", c_void_p), ("sign_w", c_int),
                 ("scale", c_void_p), ("bias", c_void_p), ("bn_a", c_void_p), ("bn_c", c_void_p), ("act", c_int)]
@@ -96,6 +101,10 @@ def lib():
         l.svnet_edge_tc_weight_bytes.restype = ctypes.c_size_t
         l.svnet_edge_fp_tc_weight_bytes.restype = ctypes.c_size_t
         l.svnet_seg_head_workspace_bytes.restype = ctypes.c_size_t
+        l.svnet_model_workspace_bytes.restype = ctypes.c_size_t
+        l.svnet_model_workspace_bytes.argtypes = [c_void_p, c_int, c_int]
+        l.svnet_model_destroy.restype = None
+        l.svnet_model_destroy.argtypes = [c_void_p]
         for name in EXPORTS:
             getattr(l, name)  # AttributeError if the symbol is missing
         if l.svnet_version() != 3:
@@ -313,6 +322,33 @@ def seg_head_fwd(view, B, N, Wz1, zscale1, glob, layers, W11, sv_bits=None):
     _call("svnet_seg_head_fwd", ctypes.byref(p), _ptr(ws), ctypes.c_size_t(nbytes), _stream())
     LAUNCHES[0] += 11        # kernels behind the one call (sign-packs, binarised linears, GEMM, transpose)
     return out
+
+
+def model_create(kind, k, binary, num_class, state_dict):
+    """svnet_model_create from a state_dict of CUDA fp32 tensors ('module.' prefixes are stripped); returns the handle."""
+    items = [(n[7:] if n.startswith("module.") else n, t) for n, t in state_dict.items() if t.dtype == torch.float32]
+    keep = [t.detach().contiguous() for _, t in items]
+    arr = (TensorRef * len(items))()
+    for i, ((n, _), t) in enumerate(zip(items, keep)):
+        _dev(t)
+        arr[i].name, arr[i].data, arr[i].numel = n.encode(), t.data_ptr(), t.numel()
+    h = c_void_p()
+    _call("svnet_model_create", kind.encode(), c_int(k), c_int(1 if binary else 0), c_int(num_class), arr, c_int(len(items)),
+          _stream(), ctypes.byref(h))
+    return h
+
+
+def model_workspace_bytes(h, B, N):
+    return int(lib().svnet_model_workspace_bytes(h, B, N))
+
+
+def model_forward(h, x, logits, ws):
+    B, _, N = x.shape
+    _call("svnet_model_forward", h, _ptr(_dev(x)), c_int(B), c_int(N), _ptr(logits), _ptr(ws), ctypes.c_size_t(ws.numel()), _stream())
+
+
+def model_destroy(h):
+    lib().svnet_model_destroy(h)
 
 
 def edge_tc_table_cols(Cv, Cvo):

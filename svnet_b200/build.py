@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libsvnet_b200.so")
 SOURCES = ["misc.cu", "knn.cu", "knn_tc.cu", "gate.cu", "edge_xyz.cu", "edge.cu", "edge_fast.cu", "edge_tc.cu", "edge_fp_tc.cu", "rows.cu",
-           "rows_fast.cu", "binlinear_tc.cu", "gemm.cu", "gemm_tc.cu", "gemm_tcgen05.cu", "gemm_tc3.cu", "head.cu", "seg_head.cu", "collective.cu"]
+           "rows_fast.cu", "binlinear_tc.cu", "gemm.cu", "gemm_tc.cu", "gemm_tcgen05.cu", "gemm_tc3.cu", "head.cu", "seg_head.cu", "model.cu", "collective.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -1,0 +1,415 @@
+// Whole-model C entry (svnet_model_create / _forward / _destroy): the binary SV-DGCNN classifier
+// (reference models/sv_dgcnn_cls.py:22-82) from a checkpoint's state_dict tensors to logits, without Python in the loop.
+//   create  : copies the tensors it needs, packs them once (sign bit-planes, folded BatchNorm affines, fp8 operand bytes of
+//             the tensor-core edge kernel, per-point table weights) -- the handle owns everything it uses afterwards;
+//   forward : sequences this library's own entry points on ONE stream with caller-owned scratch
+//             (svnet_model_workspace_bytes): no allocation, no synchronisation -- capturable into a CUDA graph;
+//             layer 1      svnet_knn_ws -> svnet_gate_xyz -> svnet_edge_xyz_fwd                    (sv_dgcnn_cls.py:48-53)
+//             layers 2..4  svnet_linear_rows (float4 table) -> svnet_knn_ws -> svnet_gate_edge -> svnet_svblock_edge_fwd (:55-65)
+//             conv5        svnet_gate_rows -> svnet_rows_prep -> svnet_binlinear_pool_ws -> svnet_linear_rows (vector branch) (:67-68)
+//             svfuse+pool  svnet_svfuse_pool                                                      (:69-74)
+//             head         svnet_head_fwd                                                         (:76-80)
+//   The same calls, with the same arguments, as svnet_b200/sv_dgcnn_cls.py + fused.py make through ctypes: the logits are
+//   bit-identical to the nn.Module path (tests/test_gpu_parity.py::test_model_c_entry_equals_module).
+// Covered: binary=1, k = 20 or 40 (the shapes of the tensor-core edge kernel), 64 <= N <= 4096.
+#include "common.cuh"
+#include <string.h>
+#include <string>
+#include <vector>
+
+struct svnet_model {
+    int k, ncls;
+    std::vector<void*> allocs;
+    // init_scalar + five SVBlocks
+    float* Winit;
+    struct Block {
+        int Cs, Cv, Cout, Cvo, H;      // Cs / Cv: per-point input dims (edge layers: half of the block's in_dims)
+        float *G1, *G2, *Wz, *zscale, *W1, *beta, *scale1, *bn1_a, *bn1_c, *W2, *scale2, *bn2_a, *bn2_c;
+        uint32_t* W1b;
+        unsigned char* W1tc;
+        float *Wt, *cst;
+        int NC;
+    } conv[5];
+    float *fuse_Wz, *fuse_zs;
+    // head
+    uint32_t *h1_bits, *h2_bits;
+    float *h1_beta, *h1_scale, *h1_a, *h1_c, *h2_beta, *h2_scale, *h2_a, *h2_c, *h3_W, *h3_b;
+    int Cf, C5s, C5v, h1, h2;
+};
+
+namespace {
+
+__global__ void sign_kernel(const float* __restrict__ in, long n, float* __restrict__ out)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float w = in[i]; out[i] = w > 0.0f ? 1.0f : (w < 0.0f ? -1.0f : 0.0f); }
+}
+__global__ void eye_ones_kernel(float* __restrict__ eye, int n, float* __restrict__ ones)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * n) eye[i] = (i / n == i % n) ? 1.0f : 0.0f;
+    if (i < n) ones[i] = 1.0f;
+}
+// (B, 3, N) -> (B*N, 3)
+__global__ void xyz_rows_kernel(const float* __restrict__ x, int B, int N, float* __restrict__ out)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * N) return;
+    const long b = i / N, n = i - b * N;
+    const float* p = x + b * 3 * N + n;
+    out[3 * i] = p[0]; out[3 * i + 1] = p[N]; out[3 * i + 2] = p[2L * N];
+}
+
+struct Loader {
+    const svnet_tensor* t;
+    int n;
+    svnet_model* m;
+    cudaStream_t st;
+    bool ok = true;
+    std::string err;
+    const svnet_tensor* find(const std::string& name, long numel)
+    {
+        for (int i = 0; i < n; ++i)
+            if (name == t[i].name) {
+                if (t[i].numel != numel || !t[i].data) { fail(name + ": wrong size"); return nullptr; }
+                return t + i;
+            }
+        fail(name + ": missing from the state_dict");
+        return nullptr;
+    }
+    void fail(const std::string& e) { if (ok) { ok = false; err = e; } }
+    void* alloc(size_t bytes)
+    {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) { fail("cudaMalloc failed"); return nullptr; }
+        m->allocs.push_back(p);
+        return p;
+    }
+    float* dup(const std::string& name, long numel)
+    {
+        const svnet_tensor* s = find(name, numel);
+        float* d = static_cast<float*>(alloc(sizeof(float) * numel));
+        if (s && d && cudaMemcpyAsync(d, s->data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, st) != cudaSuccess) fail("copy failed");
+        return d;
+    }
+    float* signed_copy(const std::string& name, long numel)
+    {
+        const svnet_tensor* s = find(name, numel);
+        float* d = static_cast<float*>(alloc(sizeof(float) * numel));
+        if (s && d) sign_kernel<<<sv_cdiv(numel, 256), 256, 0, st>>>(s->data, numel, d);
+        return d;
+    }
+    void fold(const std::string& bn, int C, float** a, float** c)
+    {
+        const svnet_tensor *w = find(bn + ".weight", C), *b = find(bn + ".bias", C), *mu = find(bn + ".running_mean", C),
+                           *var = find(bn + ".running_var", C);
+        *a = static_cast<float*>(alloc(sizeof(float) * C));
+        *c = static_cast<float*>(alloc(sizeof(float) * C));
+        if (w && b && mu && var && *a && *c && svnet_fold_bn(w->data, b->data, mu->data, var->data, 1e-5f, C, *a, *c, st) != SVNET_OK)
+            fail("svnet_fold_bn failed");
+    }
+    // sign bit-planes [ceil(K/32)][rows]; the zero weights of call i are counted into zc[i] (device; svnet_pack_sign
+    // resets its counter)
+    int nz = 0;
+    uint32_t* bits(const float* W, int rows, int K, int* zc)
+    {
+        uint32_t* d = static_cast<uint32_t*>(alloc(sizeof(uint32_t) * (size_t)((K + 31) / 32) * rows));
+        if (W && d && nz < 16 && svnet_pack_sign(W, rows, K, K, d, zc + nz, st) != SVNET_OK) fail("svnet_pack_sign failed");
+        ++nz;
+        return d;
+    }
+};
+
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct fwd_plan {
+    size_t xyz, idx, s_cat, v_cat, gate, table, knn, v5, g, bits, mask, nvalid, blp, fuse, s5, total;
+    size_t knn_bytes, blp_bytes, bl_bytes, fuse_bytes;
+    int Cs_cat, Cv_cat;
+};
+
+bool make_fwd_plan(const svnet_model* m, int B, int N, fwd_plan* pl)
+{
+    const long R = (long)B * N;
+    int cs = 0, cv = 0, ncmax = 0, cvomax = 0;
+    for (int l = 0; l < 4; ++l) { cs += m->conv[l].Cout; cv += m->conv[l].Cvo; }
+    for (int l = 1; l < 4; ++l) ncmax = m->conv[l].NC > ncmax ? m->conv[l].NC : ncmax;
+    for (int l = 0; l < 5; ++l) cvomax = m->conv[l].Cvo > cvomax ? m->conv[l].Cvo : cvomax;
+    pl->Cs_cat = cs; pl->Cv_cat = cv;
+    size_t o = 0;
+    pl->xyz = o; o += up256(sizeof(float) * 3 * R);
+    pl->idx = o; o += up256(sizeof(int32_t) * R * m->k);
+    pl->s_cat = o; o += up256(sizeof(float) * R * cs);
+    pl->v_cat = o; o += up256(sizeof(float) * R * 3 * cv);
+    pl->gate = o; o += up256(sizeof(float) * B * cvomax);
+    pl->table = o; o += up256(sizeof(float) * R * ncmax * 4);
+    // kNN scratch: the largest of the four layers
+    size_t kb = 0;
+    {
+        svnet_view v = {};
+        v.Cs = 3;
+        kb = svnet_knn_workspace_bytes(&v, B, N, m->k);
+        for (int l = 1; l < 4; ++l) {
+            v.Cs = m->conv[l - 1].Cout; v.Cv = m->conv[l - 1].Cvo;
+            const size_t b = svnet_knn_workspace_bytes(&v, B, N, m->k);
+            kb = b > kb ? b : kb;
+        }
+    }
+    pl->knn_bytes = kb;
+    pl->knn = o; o += up256(kb);
+    pl->v5 = o; o += up256(sizeof(float) * R * 3 * m->C5v);
+    pl->g = o; o += up256(sizeof(float) * B * 2 * m->Cf);
+    const int K5 = cs + 3 * cv, Kw = (K5 + 31) / 32;
+    pl->bits = o; o += up256(sizeof(uint32_t) * R * Kw);
+    pl->mask = o; o += up256(sizeof(uint32_t) * R * Kw);
+    pl->nvalid = o; o += up256(sizeof(int32_t) * R);
+    pl->blp_bytes = svnet_binlinear_pool_workspace_bytes(R, K5, m->C5s, N);
+    pl->bl_bytes = pl->blp_bytes ? 0 : svnet_binlinear_workspace_bytes(R, K5, m->C5s);
+    pl->blp = o; o += up256(pl->blp_bytes + pl->bl_bytes);
+    // few rows: conv5's scalar output is materialised and pooled (svnet_binlinear_rows_ws + svnet_pool_rows)
+    pl->s5 = o; o += pl->blp_bytes ? 0 : up256(sizeof(float) * R * m->C5s);
+    pl->fuse_bytes = svnet_svfuse_pool_workspace(B, m->C5v, N);
+    pl->fuse = o; o += up256(pl->fuse_bytes);
+    pl->total = o;
+    return kb > 0;
+}
+
+}  // namespace
+
+extern "C" void svnet_model_destroy(svnet_model* m)
+{
+    if (!m) return;
+    for (void* p : m->allocs) cudaFree(p);
+    delete m;
+}
+
+extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_class, const svnet_tensor* tensors, int n_tensors,
+                                  void* stream, svnet_model** out)
+{
+    SV_REQUIRE(kind && tensors && out && n_tensors > 0, "svnet_model_create: null pointer");
+    SV_REQUIRE(strcmp(kind, "SV_DGCNN_CLS") == 0, "svnet_model_create: kind '%s' not covered (SV_DGCNN_CLS; the other models go through the nn.Module API)", kind);
+    SV_REQUIRE(binary == 1, "svnet_model_create: only the binary model is covered (the fp model goes through the nn.Module API)");
+    SV_REQUIRE(k == 20 || k == 40, "svnet_model_create: k = %d not covered (20 or 40: the tensor-core edge kernel's shapes)", k);
+    SV_REQUIRE(num_class >= 1, "svnet_model_create: bad num_class");
+    svnet_model* m = new svnet_model();
+    m->k = k; m->ncls = num_class;
+    Loader L{tensors, n_tensors, m, sv_stream(stream)};
+    int* zc = static_cast<int*>(L.alloc(16 * sizeof(int)));
+    if (zc) cudaMemsetAsync(zc, 0, 16 * sizeof(int), L.st);
+    m->Winit = L.dup("init_scalar.linear.weight", 3 * 2);
+    // per-point dims entering each block / leaving it (sv_dgcnn_cls.py:29-34)
+    const int cs_in[5] = {3, 32, 32, 64, 256}, cv_in[5] = {1, 10, 10, 21, 83};
+    const int cs_out[5] = {32, 32, 64, 128, 512}, cv_out[5] = {10, 10, 21, 42, 170};
+    for (int l = 0; l < 5 && L.ok; ++l) {
+        svnet_model::Block& b = m->conv[l];
+        const std::string p = "conv" + std::to_string(l + 1) + ".";
+        b = svnet_model::Block();
+        b.Cs = cs_in[l]; b.Cv = cv_in[l]; b.Cout = cs_out[l]; b.Cvo = cv_out[l]; b.H = b.Cvo / 2;
+        // the block's own input dims: layer 1 (6, 2) full precision; edge layers (2Cs, 2Cv); conv5 (Cs, Cv)
+        const int bcs = l == 0 ? 6 : (l < 4 ? 2 * b.Cs : b.Cs), bcv = l == 0 ? 2 : (l < 4 ? 2 * b.Cv : b.Cv);
+        const int K1 = bcs + 3 * bcv;
+        b.G1 = L.dup(p + "gate.0.weight", (long)b.H * bcs);
+        b.G2 = L.dup(p + "gate.2.weight", (long)b.Cvo * b.H);
+        L.fold(p + "bn1", b.Cout, &b.bn1_a, &b.bn1_c);
+        L.fold(p + "bn2.bn", b.Cvo, &b.bn2_a, &b.bn2_c);
+        b.W1 = L.dup(p + "linear1.weight", (long)b.Cout * K1);
+        b.W2 = L.dup(p + "linear2.weight", (long)b.Cvo * bcv);
+        if (l == 0) {
+            b.Wz = L.dup(p + "v2s.linear.weight", 3 * bcv);
+            continue;
+        }
+        b.Wz = L.signed_copy(p + "v2s.linear.weight", 3 * bcv);
+        b.zscale = L.dup(p + "v2s.linear.scale", 3);
+        b.beta = L.dup(p + "linear1.beta", K1);
+        b.scale1 = L.dup(p + "linear1.scale", b.Cout);
+        b.scale2 = L.dup(p + "linear2.scale", b.Cvo);
+        b.W1b = L.bits(b.W1, b.Cout, K1, zc);
+        if (l < 4) {
+            const size_t wb = svnet_edge_tc_weight_bytes(b.Cs, b.Cv, b.Cout, b.Cvo, k);
+            if (wb == 0) { L.fail(p + ": shape not covered by the tensor-core edge kernel"); break; }
+            b.W1tc = static_cast<unsigned char*>(L.alloc(wb));
+            if (b.W1tc && svnet_edge_tc_pack_w(b.W1, K1, b.Cs, b.Cv, b.Cout, b.W1tc, stream) != SVNET_OK) L.fail("svnet_edge_tc_pack_w failed");
+            // table weights [W2a | W2b | Wz_a | Wz_b | I] (rows) over the Cv input channels, and their column scales
+            const int cv = b.Cv;
+            b.NC = 2 * b.Cvo + 6 + cv;
+            b.Wt = static_cast<float*>(L.alloc(sizeof(float) * (size_t)b.NC * cv));
+            b.cst = static_cast<float*>(L.alloc(sizeof(float) * b.NC));
+            const svnet_tensor* wz = L.find(p + "v2s.linear.weight", 3 * bcv);
+            if (b.Wt && b.cst && wz && L.ok) {
+                const size_t w = sizeof(float) * cv;
+                cudaMemcpy2DAsync(b.Wt, w, b.W2, sizeof(float) * bcv, w, b.Cvo, cudaMemcpyDeviceToDevice, L.st);
+                cudaMemcpy2DAsync(b.Wt + (size_t)b.Cvo * cv, w, b.W2 + cv, sizeof(float) * bcv, w, b.Cvo, cudaMemcpyDeviceToDevice, L.st);
+                cudaMemcpy2DAsync(b.Wt + (size_t)2 * b.Cvo * cv, w, wz->data, sizeof(float) * bcv, w, 3, cudaMemcpyDeviceToDevice, L.st);
+                cudaMemcpy2DAsync(b.Wt + (size_t)(2 * b.Cvo + 3) * cv, w, wz->data + cv, sizeof(float) * bcv, w, 3, cudaMemcpyDeviceToDevice, L.st);
+                eye_ones_kernel<<<sv_cdiv(cv * cv, 256), 256, 0, L.st>>>(b.Wt + (size_t)(2 * b.Cvo + 6) * cv, cv, b.cst + 2 * b.Cvo + 6);
+                cudaMemcpyAsync(b.cst, b.scale2, sizeof(float) * b.Cvo, cudaMemcpyDeviceToDevice, L.st);
+                cudaMemcpyAsync(b.cst + b.Cvo, b.scale2, sizeof(float) * b.Cvo, cudaMemcpyDeviceToDevice, L.st);
+                cudaMemcpyAsync(b.cst + 2 * b.Cvo, b.zscale, sizeof(float) * 3, cudaMemcpyDeviceToDevice, L.st);
+                cudaMemcpyAsync(b.cst + 2 * b.Cvo + 3, b.zscale, sizeof(float) * 3, cudaMemcpyDeviceToDevice, L.st);
+            }
+        }
+    }
+    m->C5s = cs_out[4]; m->C5v = cv_out[4]; m->Cf = m->C5s + 3 * m->C5v;
+    m->h1 = 512; m->h2 = 256;
+    if (L.ok) {
+        m->fuse_Wz = L.signed_copy("svfuse.v2s.linear.weight", 3 * m->C5v);
+        m->fuse_zs = L.dup("svfuse.v2s.linear.scale", 3);
+        const svnet_tensor* w1 = L.find("linear1.weight", (long)m->h1 * 2 * m->Cf);
+        const svnet_tensor* w2 = L.find("linear2.weight", (long)m->h2 * m->h1);
+        m->h1_bits = L.bits(w1 ? w1->data : nullptr, m->h1, 2 * m->Cf, zc);
+        m->h2_bits = L.bits(w2 ? w2->data : nullptr, m->h2, m->h1, zc);
+        m->h1_beta = L.dup("linear1.beta", 2 * m->Cf);
+        m->h1_scale = L.dup("linear1.scale", m->h1);
+        m->h2_beta = L.dup("linear2.beta", m->h1);
+        m->h2_scale = L.dup("linear2.scale", m->h2);
+        L.fold("bn1", m->h1, &m->h1_a, &m->h1_c);
+        L.fold("bn2", m->h2, &m->h2_a, &m->h2_c);
+        m->h3_W = L.dup("linear3.weight", (long)num_class * m->h2);
+        m->h3_b = L.dup("linear3.bias", num_class);
+    }
+    if (L.ok) {
+        int zh[16] = {0};
+        int zeros = 0;
+        if (cudaMemcpyAsync(zh, zc, sizeof(zh), cudaMemcpyDeviceToHost, L.st) != cudaSuccess || cudaStreamSynchronize(L.st) != cudaSuccess)
+            L.fail("CUDA error while packing");
+        for (int i = 0; i < 16; ++i) zeros += zh[i];
+        if (L.ok && zeros != 0)
+            L.fail("a binarised weight contains exact zeros (sign(0) = 0 plane not supported by the popcount kernels)");
+    }
+    if (!L.ok) {
+        svnet_set_error("svnet_model_create: %s", L.err.c_str());
+        svnet_model_destroy(m);
+        return SVNET_ERR_ARG;
+    }
+    *out = m;
+    return SVNET_OK;
+}
+
+extern "C" size_t svnet_model_workspace_bytes(const svnet_model* m, int B, int N)
+{
+    if (!m || B < 1 || N < 64 || N > 4096) return 0;
+    fwd_plan pl;
+    if (!make_fwd_plan(m, B, N, &pl)) return 0;
+    return pl.total;
+}
+
+extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, int N, float* logits, void* workspace,
+                                   size_t workspace_bytes, void* stream)
+{
+    SV_REQUIRE(m && x && logits, "svnet_model_forward: null pointer");
+    SV_REQUIRE(B >= 0 && N >= 64 && N <= 4096, "svnet_model_forward: N = %d not covered (64..4096)", N);
+    if (B == 0) return SVNET_OK;
+    fwd_plan pl;
+    SV_REQUIRE(make_fwd_plan(m, B, N, &pl), "svnet_model_forward: shape not covered by the tensor-core paths");
+    SV_REQUIRE(workspace && workspace_bytes >= pl.total && !(reinterpret_cast<uintptr_t>(workspace) & 255),
+               "svnet_model_forward: workspace too small (svnet_model_workspace_bytes) or not 256-byte aligned");
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    cudaStream_t st = sv_stream(stream);
+    const long R = (long)B * N;
+    const int k = m->k;
+    float* xyz = reinterpret_cast<float*>(ws + pl.xyz);
+    int32_t* idx = reinterpret_cast<int32_t*>(ws + pl.idx);
+    float* s_cat = reinterpret_cast<float*>(ws + pl.s_cat);
+    float* v_cat = reinterpret_cast<float*>(ws + pl.v_cat);
+    float* gate = reinterpret_cast<float*>(ws + pl.gate);
+    float* table = reinterpret_cast<float*>(ws + pl.table);
+    void* knn_ws = ws + pl.knn;
+    const int lds = pl.Cs_cat, xs = pl.Cv_cat, ldv = 3 * pl.Cv_cat;
+    int rc;
+    xyz_rows_kernel<<<sv_cdiv(R, 256), 256, 0, st>>>(x, B, N, xyz);
+    SV_CHECK_LAUNCH("svnet_model_forward(xyz)");
+    int so = 0, vo = 0;
+    svnet_view prev = {};
+    for (int l = 0; l < 4; ++l) {
+        const svnet_model::Block& b = m->conv[l];
+        svnet_mview out = {};
+        out.s = s_cat + so; out.lds = lds; out.Cs = b.Cout;
+        out.v = v_cat + vo; out.ldv = ldv; out.xs = xs; out.Cv = b.Cvo;
+        if (l == 0) {
+            svnet_view xv = {};
+            xv.s = xyz; xv.lds = 3; xv.Cs = 3;
+            rc = svnet_knn_ws(&xv, B, N, k, idx, nullptr, knn_ws, pl.knn_bytes, stream);
+            if (rc != SVNET_OK) return rc;
+            rc = svnet_gate_xyz(xyz, idx, B, N, k, 2, m->Winit, b.G1, b.G2, b.H, b.Cvo, gate, stream);
+            if (rc != SVNET_OK) return rc;
+            svnet_edge_xyz_params p = {};
+            p.xyz = xyz; p.idx = idx; p.B = B; p.N = N; p.k = k; p.nv = 2;
+            p.Winit = m->Winit; p.Wz = b.Wz; p.W1 = b.W1; p.bn1_a = b.bn1_a; p.bn1_c = b.bn1_c;
+            p.W2 = b.W2; p.bn2_a = b.bn2_a; p.bn2_c = b.bn2_c; p.gate = gate; p.Cout = b.Cout; p.Cvo = b.Cvo; p.out = out;
+            rc = svnet_edge_xyz_fwd(&p, stream);
+            if (rc != SVNET_OK) return rc;
+        } else {
+            // per-point float4 table [P | Q | T | U | v] of the tensor-core edge kernel
+            svnet_gemm_params g = {};
+            g.A = prev.v; g.lda_g = prev.ldv; g.lda_x = prev.xs; g.G = 3;
+            g.W = b.Wt; g.ldw = b.Cv; g.M = 3 * R; g.N = b.NC; g.K = b.Cv;
+            g.sign_w = 1; g.colscale = b.cst; g.C = table; g.ldc_g = 4 * b.NC; g.ldc_x = 0; g.c4 = 1; g.groups_per_cloud = 1;
+            rc = svnet_linear_rows_ws(&g, nullptr, 0, stream);
+            if (rc != SVNET_OK) return rc;
+            rc = svnet_knn_ws(&prev, B, N, k, idx, nullptr, knn_ws, pl.knn_bytes, stream);
+            if (rc != SVNET_OK) return rc;
+            rc = svnet_gate_edge(&prev, idx, B, N, k, b.G1, b.G2, b.H, b.Cvo, gate, stream);
+            if (rc != SVNET_OK) return rc;
+            svnet_edge_params p = {};
+            p.in = prev; p.idx = idx; p.B = B; p.N = N; p.k = k; p.binary = 1;
+            p.Wz = b.Wz; p.zscale = b.zscale; p.beta = b.beta; p.W1b = b.W1b; p.scale1 = b.scale1;
+            p.bn1_a = b.bn1_a; p.bn1_c = b.bn1_c; p.Cout = b.Cout;
+            p.bn2_a = b.bn2_a; p.bn2_c = b.bn2_c; p.gate = gate; p.Cvo = b.Cvo; p.out = out;
+            p.W1tc = b.W1tc; p.tab4 = table;
+            rc = svnet_svblock_edge_fwd(&p, stream);
+            if (rc != SVNET_OK) return rc;
+        }
+        prev.s = out.s; prev.lds = out.lds; prev.Cs = out.Cs;
+        prev.v = out.v; prev.ldv = out.ldv; prev.xs = out.xs; prev.Cv = out.Cv;
+        so += b.Cout; vo += b.Cvo;
+    }
+    // ---- conv5 (per point) -> svfuse -> max | mean over the points ----
+    const svnet_model::Block& c5 = m->conv[4];
+    float* v5 = reinterpret_cast<float*>(ws + pl.v5);
+    float* g = reinterpret_cast<float*>(ws + pl.g);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(ws + pl.bits);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(ws + pl.mask);
+    int32_t* nvalid = reinterpret_cast<int32_t*>(ws + pl.nvalid);
+    const int Cf = m->Cf, K5 = pl.Cs_cat + 3 * pl.Cv_cat;
+    rc = svnet_gate_rows(s_cat, lds, pl.Cs_cat, B, N, c5.G1, c5.G2, c5.H, c5.Cvo, gate, stream);
+    if (rc != SVNET_OK) return rc;
+    svnet_view cat = {};
+    cat.s = s_cat; cat.lds = lds; cat.Cs = pl.Cs_cat; cat.v = v_cat; cat.ldv = ldv; cat.xs = xs; cat.Cv = pl.Cv_cat;
+    rc = svnet_rows_prep(&cat, R, c5.Wz, c5.zscale, nullptr, c5.beta, nullptr, 0, nullptr, bits, mask, nvalid, stream);
+    if (rc != SVNET_OK) return rc;
+    if (pl.blp_bytes) {
+        rc = svnet_binlinear_pool_ws(bits, mask, R, K5, c5.W1b, c5.Cout, c5.scale1, c5.bn1_a, c5.bn1_c, N, g, g + Cf, 2 * Cf,
+                                     ws + pl.blp, pl.blp_bytes, stream);
+        if (rc != SVNET_OK) return rc;
+    } else {
+        float* s5 = reinterpret_cast<float*>(ws + pl.s5);
+        rc = svnet_binlinear_rows_ws(bits, mask, nvalid, R, K5, c5.W1b, c5.Cout, c5.scale1, nullptr, c5.bn1_a, c5.bn1_c, SVNET_ACT_LEAKY,
+                                     nullptr, 1, s5, c5.Cout, nullptr, pl.bl_bytes ? ws + pl.blp : nullptr, pl.bl_bytes, stream);
+        if (rc != SVNET_OK) return rc;
+        rc = svnet_pool_rows(s5, c5.Cout, c5.Cout, B, N, g, g + Cf, 2 * Cf, stream);
+        if (rc != SVNET_OK) return rc;
+    }
+    {
+        svnet_gemm_params q = {};
+        q.A = v_cat; q.lda_g = ldv; q.lda_x = xs; q.G = 3;
+        q.W = c5.W2; q.ldw = c5.Cv; q.M = 3 * R; q.N = c5.Cvo; q.K = c5.Cv;
+        q.sign_w = 1; q.colscale = c5.scale2; q.bn_a = c5.bn2_a; q.bn_c = c5.bn2_c; q.vbn = 1; q.gate = gate; q.groups_per_cloud = N;
+        q.C = v5; q.ldc_g = 3 * c5.Cvo; q.ldc_x = c5.Cvo;
+        rc = svnet_linear_rows_ws(&q, nullptr, 0, stream);
+        if (rc != SVNET_OK) return rc;
+    }
+    svnet_view v5v = {};
+    v5v.v = v5; v5v.ldv = 3 * c5.Cvo; v5v.xs = c5.Cvo; v5v.Cv = c5.Cvo;
+    rc = svnet_svfuse_pool(&v5v, B, N, m->fuse_Wz, m->fuse_zs, g + m->C5s, g + Cf + m->C5s, 2 * Cf, ws + pl.fuse, pl.fuse_bytes, stream);
+    if (rc != SVNET_OK) return rc;
+    // ---- head ----
+    svnet_head_params h = {};
+    h.x = g; h.ldx = 2 * Cf; h.K0 = 2 * Cf; h.B = B; h.nlayers = 3;
+    h.layer[0].Cout = m->h1; h.layer[0].W1b = m->h1_bits; h.layer[0].beta = m->h1_beta; h.layer[0].scale = m->h1_scale;
+    h.layer[0].bn_a = m->h1_a; h.layer[0].bn_c = m->h1_c; h.layer[0].act = SVNET_ACT_LEAKY;
+    h.layer[1].Cout = m->h2; h.layer[1].W1b = m->h2_bits; h.layer[1].beta = m->h2_beta; h.layer[1].scale = m->h2_scale;
+    h.layer[1].bn_a = m->h2_a; h.layer[1].bn_c = m->h2_c; h.layer[1].act = SVNET_ACT_LEAKY;
+    h.layer[2].Cout = m->ncls; h.layer[2].W = m->h3_W; h.layer[2].bias = m->h3_b; h.layer[2].act = SVNET_ACT_NONE;
+    h.out = logits; h.ldo = m->ncls;
+    return svnet_head_fwd(&h, stream);
+}

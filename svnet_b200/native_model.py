@@ -1,0 +1,50 @@
+"""The whole-model C entry (include/svnet_b200.h: svnet_model_create / _forward / _destroy) behind a Python callable --
+what a C or C++ host would do with the library, spelled out: build the handle from a checkpoint's tensors once, then
+`forward` with caller-owned scratch.  Covered: the binary SV_DGCNN_CLS at k = 20 / 40, 64 <= N <= 4096.
+
+    native = svnet_b200.NativeModel("SV_DGCNN_CLS", checkpoint["state_dict"], k=20, binary=True, num_class=40)
+    logits = native(batch)                     # (B, 3, N) float32 CUDA -> (B, num_class); bit-identical to the nn.Module
+
+The nn.Module classes remain the drop-in for the reference's Python code; this class exists for hosts without Python
+model code and as the executable documentation of the C entry.
+"""
+import torch
+
+from . import _native as nv
+
+
+class NativeModel:
+    def __init__(self, kind, state_dict, k, binary, num_class, device=None):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(dev):
+            sd = {n: t.to(dev) for n, t in state_dict.items() if torch.is_tensor(t) and t.dtype == torch.float32}
+            self._h = nv.model_create(kind, k, binary, num_class, sd)
+        self.device, self.num_class = dev, num_class
+        self._ws = {}
+
+    def __call__(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("NativeModel needs a CUDA tensor (there is no CPU path)")
+        B, _, N = x.shape
+        with torch.cuda.device(x.device):
+            key = (B, N)
+            if key not in self._ws:
+                nbytes = nv.model_workspace_bytes(self._h, B, N)
+                if nbytes == 0:
+                    raise ValueError("shape (B=%d, N=%d) is not covered by svnet_model_forward (64 <= N <= 4096)" % (B, N))
+                self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            logits = torch.empty((B, self.num_class), dtype=torch.float32, device=x.device)
+            nv.model_forward(self._h, x.contiguous(), logits, self._ws[key])
+            nv.LAUNCHES[0] += 32
+        return logits
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            nv.model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

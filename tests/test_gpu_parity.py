@@ -628,6 +628,40 @@ def test_full_size_configs_run_and_are_batch_independent():
     assert torch.equal(y_full, y_chunk)
 
 
+@pytest.mark.parametrize("B,N,k", [(4, 1024, 20), (3, 200, 20), (2, 512, 40)])
+def test_model_c_entry_equals_module(B, N, k):
+    """svnet_model_create / _forward / _destroy (the whole binary SV-DGCNN classifier behind one C call,
+    csrc/model.cu) against the nn.Module path on the same checkpoint tensors: bit-identical logits, also when the
+    C forward is captured into a CUDA graph; uncovered shapes and kinds fail loudly."""
+    import svnet_b200 as sv
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=k, binary=True), 40)
+    sd = synthetic_state_dict(net.state_dict(), seed=1002)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    x = synthetic_clouds(B, N, 1002).to(DEV)
+    native = sv.NativeModel("SV_DGCNN_CLS", {"module." + n: t for n, t in sd.items()}, k=k, binary=True, num_class=40, device=DEV)
+    with torch.no_grad():
+        y_mod = net(x)
+        y_c = native(x)
+    assert tuple(y_c.shape) == (B, 40)
+    assert torch.equal(y_c, y_mod)
+    # graph capture of the C forward (no allocation / synchronisation inside)
+    g = torch.cuda.CUDAGraph()
+    xs = x.clone()
+    native(xs)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        y_g = native(xs)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y_g, y_mod)
+    with pytest.raises(ValueError):
+        native(synthetic_clouds(1, 48, 1).to(DEV))           # N < 64: not covered
+    with pytest.raises(RuntimeError):
+        sv.NativeModel("SV_DGCNN_PSEG", sd, k=k, binary=True, num_class=40, device=DEV)
+    native.close()
+
+
 @pytest.mark.parametrize("B,N,k", [(2, 2048, 40), (3, 200, 12)])
 def test_seg_head_call_equals_layerwise(B, N, k):
     """svnet_seg_head_fwd (conv8 .. conv11 + the (B, parts, N) layout as one C-ABI call, csrc/seg_head.cu) against the
