@@ -377,11 +377,11 @@ int svnet_svfuse_pool(const svnet_view* in, int B, long rows_per_cloud, const fl
                       float* max_out, float* mean_out, int ldo, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- whole-model entry ------------------------------------------------------------------------
- * The binary SV-DGCNN classifier (models/sv_dgcnn_cls.py:22-82) from a checkpoint's tensors to logits.
+ * The SV-DGCNN classifier, binary or full precision (models/sv_dgcnn_cls.py:22-82), from a checkpoint's tensors to logits.
  * svnet_model_create() takes the state_dict as (name, device pointer, element count) triples -- the reference's key names
  * without the 'module.' prefix (SURVEY 8(a) a-keys), fp32, contiguous -- copies what it needs and packs it once (sign
  * bit-planes, folded BatchNorm affines, tensor-core operand bytes, per-point table weights); it synchronises `stream` before
- * it returns, the caller's tensors may then be freed.  Covered: kind "SV_DGCNN_CLS", binary = 1, k = 20 or 40.
+ * it returns, the caller's tensors may then be freed.  Covered: kind "SV_DGCNN_CLS", k = 20 (binary = 1 also k = 40).
  * svnet_model_forward(): x [B][3][N] -> logits [B][num_class] on `stream`, with svnet_model_workspace_bytes(m, B, N) bytes of
  * caller-owned scratch (256-byte aligned; 0: shape not covered -- 64 <= N <= 4096).  It allocates
  * nothing and never synchronises, so it can be captured into a CUDA graph; the logits are bit-identical to the nn.Module

@@ -1,4 +1,4 @@
-// Whole-model C entry (svnet_model_create / _forward / _destroy): the binary SV-DGCNN classifier
+// Whole-model C entry (svnet_model_create / _forward / _destroy): the SV-DGCNN classifier, binary or full precision,
 // (reference models/sv_dgcnn_cls.py:22-82) from a checkpoint's state_dict tensors to logits, without Python in the loop.
 //   create  : copies the tensors it needs, packs them once (sign bit-planes, folded BatchNorm affines, fp8 operand bytes of
 //             the tensor-core edge kernel, per-point table weights) -- the handle owns everything it uses afterwards;
@@ -11,14 +11,16 @@
 //             head         svnet_head_fwd                                                         (:76-80)
 //   The same calls, with the same arguments, as svnet_b200/sv_dgcnn_cls.py + fused.py make through ctypes: the logits are
 //   bit-identical to the nn.Module path (tests/test_gpu_parity.py::test_model_c_entry_equals_module).
-// Covered: binary=1, k = 20 or 40 (the shapes of the tensor-core edge kernel), 64 <= N <= 4096.
+// Covered: k = 20 (binary also 40: the shapes of the tensor-core edge kernels), 64 <= N <= 4096.  The list of calls above is
+// the binary model's; the full-precision model takes svnet_linear_rows_ws where the binary one takes the sign-word kernels
+// (sv_dgcnn_cls.py in this package shows both).
 #include "common.cuh"
 #include <string.h>
 #include <string>
 #include <vector>
 
 struct svnet_model {
-    int k, ncls;
+    int k, ncls, binary;
     std::vector<void*> allocs;
     // init_scalar + five SVBlocks
     float* Winit;
@@ -27,13 +29,14 @@ struct svnet_model {
         float *G1, *G2, *Wz, *zscale, *W1, *beta, *scale1, *bn1_a, *bn1_c, *W2, *scale2, *bn2_a, *bn2_c;
         uint32_t* W1b;
         unsigned char* W1tc;
-        float *Wt, *cst;
+        float *Wt, *cst, *Wab;        // Wab: [W1a; W1b] (2 Cout x Cs) of a full-precision linear1 (the Ya | Yb table)
         int NC;
     } conv[5];
     float *fuse_Wz, *fuse_zs;
     // head
     uint32_t *h1_bits, *h2_bits;
     float *h1_beta, *h1_scale, *h1_a, *h1_c, *h2_beta, *h2_scale, *h2_a, *h2_c, *h3_W, *h3_b;
+    float *h1_W, *h2_W;              // full-precision head
     int Cf, C5s, C5v, h1, h2;
 };
 
@@ -123,8 +126,8 @@ struct Loader {
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct fwd_plan {
-    size_t xyz, idx, s_cat, v_cat, gate, table, knn, v5, g, bits, mask, nvalid, blp, fuse, s5, total;
-    size_t knn_bytes, blp_bytes, bl_bytes, fuse_bytes;
+    size_t xyz, idx, s_cat, v_cat, gate, table, knn, v5, g, bits, mask, nvalid, blp, fuse, s5, yab, u5, lin, h1, total;
+    size_t knn_bytes, blp_bytes, bl_bytes, fuse_bytes, lin_bytes;
     int Cs_cat, Cv_cat;
 };
 
@@ -163,6 +166,37 @@ bool make_fwd_plan(const svnet_model* m, int B, int N, fwd_plan* pl)
     pl->bits = o; o += up256(sizeof(uint32_t) * R * Kw);
     pl->mask = o; o += up256(sizeof(uint32_t) * R * Kw);
     pl->nvalid = o; o += up256(sizeof(int32_t) * R);
+    if (!m->binary) {
+        // full precision: Ya | Yb table of the edge layers, conv5's u = [s | v2s(v)] rows and scalar output, head layer 1
+        pl->bits = pl->mask = pl->nvalid = pl->blp = 0;
+        pl->blp_bytes = pl->bl_bytes = 0;
+        pl->yab = o; o += up256(sizeof(float) * R * 2 * m->conv[3].Cout);
+        pl->u5 = o; o += up256(sizeof(float) * R * K5);
+        pl->s5 = o; o += up256(sizeof(float) * R * m->C5s);
+        pl->h1 = o; o += up256(sizeof(float) * B * m->h1);
+        svnet_gemm_params q = {};
+        q.G = 1; q.M = R; q.N = m->C5s; q.K = K5; q.bn_a = reinterpret_cast<const float*>(1); q.act = SVNET_ACT_LEAKY;
+        size_t lb = svnet_linear_workspace_bytes(&q);
+        for (int l = 1; l < 4; ++l) {
+            svnet_gemm_params y = {};
+            y.G = 1; y.M = R; y.N = 2 * m->conv[l].Cout; y.K = m->conv[l].Cs;
+            const size_t b2 = svnet_linear_workspace_bytes(&y);
+            lb = b2 > lb ? b2 : lb;
+        }
+        {
+            svnet_gemm_params y = {};
+            y.G = 1; y.M = B; y.N = m->h1; y.K = 2 * m->Cf; y.bn_a = reinterpret_cast<const float*>(1); y.act = SVNET_ACT_LEAKY;
+            const size_t b2 = svnet_linear_workspace_bytes(&y);
+            lb = b2 > lb ? b2 : lb;
+        }
+        pl->lin_bytes = lb;
+        pl->lin = o; o += up256(lb);
+        pl->fuse_bytes = svnet_svfuse_pool_workspace(B, m->C5v, N);
+        pl->fuse = o; o += up256(pl->fuse_bytes);
+        pl->total = o;
+        return kb > 0;
+    }
+    pl->lin_bytes = 0;
     pl->blp_bytes = svnet_binlinear_pool_workspace_bytes(R, K5, m->C5s, N);
     pl->bl_bytes = pl->blp_bytes ? 0 : svnet_binlinear_workspace_bytes(R, K5, m->C5s);
     pl->blp = o; o += up256(pl->blp_bytes + pl->bl_bytes);
@@ -188,11 +222,11 @@ extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_c
 {
     SV_REQUIRE(kind && tensors && out && n_tensors > 0, "svnet_model_create: null pointer");
     SV_REQUIRE(strcmp(kind, "SV_DGCNN_CLS") == 0, "svnet_model_create: kind '%s' not covered (SV_DGCNN_CLS; the other models go through the nn.Module API)", kind);
-    SV_REQUIRE(binary == 1, "svnet_model_create: only the binary model is covered (the fp model goes through the nn.Module API)");
-    SV_REQUIRE(k == 20 || k == 40, "svnet_model_create: k = %d not covered (20 or 40: the tensor-core edge kernel's shapes)", k);
+    SV_REQUIRE(binary == 0 || binary == 1, "svnet_model_create: binary must be 0 or 1");
+    SV_REQUIRE(k == 20 || (binary && k == 40), "svnet_model_create: k = %d not covered (the tensor-core edge kernels' shapes: 20, binary also 40)", k);
     SV_REQUIRE(num_class >= 1, "svnet_model_create: bad num_class");
     svnet_model* m = new svnet_model();
-    m->k = k; m->ncls = num_class;
+    m->k = k; m->ncls = num_class; m->binary = binary;
     Loader L{tensors, n_tensors, m, sv_stream(stream)};
     int* zc = static_cast<int*>(L.alloc(16 * sizeof(int)));
     if (zc) cudaMemsetAsync(zc, 0, 16 * sizeof(int), L.st);
@@ -216,6 +250,34 @@ extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_c
         b.W2 = L.dup(p + "linear2.weight", (long)b.Cvo * bcv);
         if (l == 0) {
             b.Wz = L.dup(p + "v2s.linear.weight", 3 * bcv);
+            continue;
+        }
+        if (!binary) {
+            // full precision: raw weights; edge layers: three bf16 planes of linear1's q columns, [W1a; W1b] for the Ya | Yb
+            // table, table weights without column scales
+            b.Wz = L.dup(p + "v2s.linear.weight", 3 * bcv);
+            if (l < 4) {
+                const size_t wb = svnet_edge_fp_tc_weight_bytes(b.Cs, b.Cv, b.Cout, b.Cvo, k);
+                if (wb == 0) { L.fail(p + ": shape not covered by the full-precision tensor-core edge kernel"); break; }
+                b.W1tc = static_cast<unsigned char*>(L.alloc(wb));
+                if (b.W1tc && svnet_edge_fp_tc_pack_w(b.W1, K1, b.Cs, b.Cv, b.Cout, b.W1tc, stream) != SVNET_OK) L.fail("svnet_edge_fp_tc_pack_w failed");
+                const int cs = b.Cs, cv = b.Cv;
+                b.Wab = static_cast<float*>(L.alloc(sizeof(float) * (size_t)2 * b.Cout * cs));
+                b.NC = 2 * b.Cvo + 6 + cv;
+                b.Wt = static_cast<float*>(L.alloc(sizeof(float) * (size_t)b.NC * cv));
+                float* scratch_ones = static_cast<float*>(L.alloc(sizeof(float) * cv));
+                if (b.Wab && b.Wt && scratch_ones && L.ok) {
+                    cudaMemcpy2DAsync(b.Wab, sizeof(float) * cs, b.W1, sizeof(float) * K1, sizeof(float) * cs, b.Cout, cudaMemcpyDeviceToDevice, L.st);
+                    cudaMemcpy2DAsync(b.Wab + (size_t)b.Cout * cs, sizeof(float) * cs, b.W1 + cs, sizeof(float) * K1, sizeof(float) * cs, b.Cout,
+                                      cudaMemcpyDeviceToDevice, L.st);
+                    const size_t w = sizeof(float) * cv;
+                    cudaMemcpy2DAsync(b.Wt, w, b.W2, sizeof(float) * bcv, w, b.Cvo, cudaMemcpyDeviceToDevice, L.st);
+                    cudaMemcpy2DAsync(b.Wt + (size_t)b.Cvo * cv, w, b.W2 + cv, sizeof(float) * bcv, w, b.Cvo, cudaMemcpyDeviceToDevice, L.st);
+                    cudaMemcpy2DAsync(b.Wt + (size_t)2 * b.Cvo * cv, w, b.Wz, sizeof(float) * bcv, w, 3, cudaMemcpyDeviceToDevice, L.st);
+                    cudaMemcpy2DAsync(b.Wt + (size_t)(2 * b.Cvo + 3) * cv, w, b.Wz + cv, sizeof(float) * bcv, w, 3, cudaMemcpyDeviceToDevice, L.st);
+                    eye_ones_kernel<<<sv_cdiv(cv * cv, 256), 256, 0, L.st>>>(b.Wt + (size_t)(2 * b.Cvo + 6) * cv, cv, scratch_ones);
+                }
+            }
             continue;
         }
         b.Wz = L.signed_copy(p + "v2s.linear.weight", 3 * bcv);
@@ -251,7 +313,16 @@ extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_c
     }
     m->C5s = cs_out[4]; m->C5v = cv_out[4]; m->Cf = m->C5s + 3 * m->C5v;
     m->h1 = 512; m->h2 = 256;
-    if (L.ok) {
+    if (L.ok && !binary) {
+        m->fuse_Wz = L.dup("svfuse.v2s.linear.weight", 3 * m->C5v);
+        m->h1_W = L.dup("linear1.weight", (long)m->h1 * 2 * m->Cf);
+        m->h2_W = L.dup("linear2.weight", (long)m->h2 * m->h1);
+        L.fold("bn1", m->h1, &m->h1_a, &m->h1_c);
+        L.fold("bn2", m->h2, &m->h2_a, &m->h2_c);
+        m->h3_W = L.dup("linear3.weight", (long)num_class * m->h2);
+        m->h3_b = L.dup("linear3.bias", num_class);
+    }
+    if (L.ok && binary) {
         m->fuse_Wz = L.signed_copy("svfuse.v2s.linear.weight", 3 * m->C5v);
         m->fuse_zs = L.dup("svfuse.v2s.linear.scale", 3);
         const svnet_tensor* w1 = L.find("linear1.weight", (long)m->h1 * 2 * m->Cf);
@@ -343,7 +414,8 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
             svnet_gemm_params g = {};
             g.A = prev.v; g.lda_g = prev.ldv; g.lda_x = prev.xs; g.G = 3;
             g.W = b.Wt; g.ldw = b.Cv; g.M = 3 * R; g.N = b.NC; g.K = b.Cv;
-            g.sign_w = 1; g.colscale = b.cst; g.C = table; g.ldc_g = 4 * b.NC; g.ldc_x = 0; g.c4 = 1; g.groups_per_cloud = 1;
+            g.sign_w = m->binary; g.colscale = m->binary ? b.cst : nullptr; g.C = table; g.ldc_g = 4 * b.NC; g.ldc_x = 0; g.c4 = 1;
+            g.groups_per_cloud = 1;
             rc = svnet_linear_rows_ws(&g, nullptr, 0, stream);
             if (rc != SVNET_OK) return rc;
             rc = svnet_knn_ws(&prev, B, N, k, idx, nullptr, knn_ws, pl.knn_bytes, stream);
@@ -351,7 +423,19 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
             rc = svnet_gate_edge(&prev, idx, B, N, k, b.G1, b.G2, b.H, b.Cvo, gate, stream);
             if (rc != SVNET_OK) return rc;
             svnet_edge_params p = {};
-            p.in = prev; p.idx = idx; p.B = B; p.N = N; p.k = k; p.binary = 1;
+            p.in = prev; p.idx = idx; p.B = B; p.N = N; p.k = k; p.binary = m->binary;
+            if (!m->binary) {
+                // Ya | Yb = s [W1a; W1b]^T per point (the s part of linear1)
+                float* yab = reinterpret_cast<float*>(ws + pl.yab);
+                svnet_gemm_params y = {};
+                y.A = prev.s; y.lda_g = prev.lds; y.lda_x = 0; y.G = 1;
+                y.W = b.Wab; y.ldw = b.Cs; y.M = R; y.N = 2 * b.Cout; y.K = b.Cs;
+                y.C = yab; y.ldc_g = 2 * b.Cout; y.ldc_x = 0; y.groups_per_cloud = 1;
+                const size_t yb = svnet_linear_workspace_bytes(&y);
+                rc = svnet_linear_rows_ws(&y, yb ? ws + pl.lin : nullptr, yb, stream);
+                if (rc != SVNET_OK) return rc;
+                p.Yab = yab;
+            }
             p.Wz = b.Wz; p.zscale = b.zscale; p.beta = b.beta; p.W1b = b.W1b; p.scale1 = b.scale1;
             p.bn1_a = b.bn1_a; p.bn1_c = b.bn1_c; p.Cout = b.Cout;
             p.bn2_a = b.bn2_a; p.bn2_c = b.bn2_c; p.gate = gate; p.Cvo = b.Cvo; p.out = out;
@@ -375,9 +459,24 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
     if (rc != SVNET_OK) return rc;
     svnet_view cat = {};
     cat.s = s_cat; cat.lds = lds; cat.Cs = pl.Cs_cat; cat.v = v_cat; cat.ldv = ldv; cat.xs = xs; cat.Cv = pl.Cv_cat;
+    if (!m->binary) {
+        // u = [s | v2s(v)] rows -> dense linear1 + BN + LeakyReLU -> max | mean over the points
+        float* u5 = reinterpret_cast<float*>(ws + pl.u5);
+        float* s5 = reinterpret_cast<float*>(ws + pl.s5);
+        rc = svnet_rows_prep(&cat, R, c5.Wz, nullptr, nullptr, nullptr, u5, K5, nullptr, nullptr, nullptr, nullptr, stream);
+        if (rc != SVNET_OK) return rc;
+        svnet_gemm_params q = {};
+        q.A = u5; q.lda_g = K5; q.lda_x = 0; q.G = 1; q.W = c5.W1; q.ldw = K5; q.M = R; q.N = c5.Cout; q.K = K5;
+        q.bn_a = c5.bn1_a; q.bn_c = c5.bn1_c; q.act = SVNET_ACT_LEAKY; q.C = s5; q.ldc_g = c5.Cout; q.ldc_x = 0; q.groups_per_cloud = 1;
+        const size_t qb = svnet_linear_workspace_bytes(&q);
+        rc = svnet_linear_rows_ws(&q, qb ? ws + pl.lin : nullptr, qb, stream);
+        if (rc != SVNET_OK) return rc;
+    } else {
     rc = svnet_rows_prep(&cat, R, c5.Wz, c5.zscale, nullptr, c5.beta, nullptr, 0, nullptr, bits, mask, nvalid, stream);
     if (rc != SVNET_OK) return rc;
-    if (pl.blp_bytes) {
+    }
+    if (!m->binary) {
+    } else if (pl.blp_bytes) {
         rc = svnet_binlinear_pool_ws(bits, mask, R, K5, c5.W1b, c5.Cout, c5.scale1, c5.bn1_a, c5.bn1_c, N, g, g + Cf, 2 * Cf,
                                      ws + pl.blp, pl.blp_bytes, stream);
         if (rc != SVNET_OK) return rc;
@@ -393,16 +492,37 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
         svnet_gemm_params q = {};
         q.A = v_cat; q.lda_g = ldv; q.lda_x = xs; q.G = 3;
         q.W = c5.W2; q.ldw = c5.Cv; q.M = 3 * R; q.N = c5.Cvo; q.K = c5.Cv;
-        q.sign_w = 1; q.colscale = c5.scale2; q.bn_a = c5.bn2_a; q.bn_c = c5.bn2_c; q.vbn = 1; q.gate = gate; q.groups_per_cloud = N;
+        q.sign_w = m->binary; q.colscale = m->binary ? c5.scale2 : nullptr; q.bn_a = c5.bn2_a; q.bn_c = c5.bn2_c; q.vbn = 1; q.gate = gate;
+        q.groups_per_cloud = N;
         q.C = v5; q.ldc_g = 3 * c5.Cvo; q.ldc_x = c5.Cvo;
         rc = svnet_linear_rows_ws(&q, nullptr, 0, stream);
         if (rc != SVNET_OK) return rc;
     }
+    if (!m->binary) {
+        rc = svnet_pool_rows(reinterpret_cast<float*>(ws + pl.s5), c5.Cout, c5.Cout, B, N, g, g + Cf, 2 * Cf, stream);
+        if (rc != SVNET_OK) return rc;
+    }
     svnet_view v5v = {};
     v5v.v = v5; v5v.ldv = 3 * c5.Cvo; v5v.xs = c5.Cvo; v5v.Cv = c5.Cvo;
-    rc = svnet_svfuse_pool(&v5v, B, N, m->fuse_Wz, m->fuse_zs, g + m->C5s, g + Cf + m->C5s, 2 * Cf, ws + pl.fuse, pl.fuse_bytes, stream);
+    rc = svnet_svfuse_pool(&v5v, B, N, m->fuse_Wz, m->binary ? m->fuse_zs : nullptr, g + m->C5s, g + Cf + m->C5s, 2 * Cf, ws + pl.fuse, pl.fuse_bytes, stream);
     if (rc != SVNET_OK) return rc;
     // ---- head ----
+    if (!m->binary) {
+        // the full-precision first layer (2044 x 512 weights) as one GEMM over the batch, then the fused two-layer head
+        float* h1 = reinterpret_cast<float*>(ws + pl.h1);
+        svnet_gemm_params q = {};
+        q.A = g; q.lda_g = 2 * Cf; q.lda_x = 0; q.G = 1; q.W = m->h1_W; q.ldw = 2 * Cf; q.M = B; q.N = m->h1; q.K = 2 * Cf;
+        q.bn_a = m->h1_a; q.bn_c = m->h1_c; q.act = SVNET_ACT_LEAKY; q.C = h1; q.ldc_g = m->h1; q.ldc_x = 0; q.groups_per_cloud = 1;
+        const size_t qb = svnet_linear_workspace_bytes(&q);
+        rc = svnet_linear_rows_ws(&q, qb ? ws + pl.lin : nullptr, qb, stream);
+        if (rc != SVNET_OK) return rc;
+        svnet_head_params hf = {};
+        hf.x = h1; hf.ldx = m->h1; hf.K0 = m->h1; hf.B = B; hf.nlayers = 2;
+        hf.layer[0].Cout = m->h2; hf.layer[0].W = m->h2_W; hf.layer[0].bn_a = m->h2_a; hf.layer[0].bn_c = m->h2_c; hf.layer[0].act = SVNET_ACT_LEAKY;
+        hf.layer[1].Cout = m->ncls; hf.layer[1].W = m->h3_W; hf.layer[1].bias = m->h3_b; hf.layer[1].act = SVNET_ACT_NONE;
+        hf.out = logits; hf.ldo = m->ncls;
+        return svnet_head_fwd(&hf, stream);
+    }
     svnet_head_params h = {};
     h.x = g; h.ldx = 2 * Cf; h.K0 = 2 * Cf; h.B = B; h.nlayers = 3;
     h.layer[0].Cout = m->h1; h.layer[0].W1b = m->h1_bits; h.layer[0].beta = m->h1_beta; h.layer[0].scale = m->h1_scale;

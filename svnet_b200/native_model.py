@@ -1,6 +1,6 @@
 """The whole-model C entry (include/svnet_b200.h: svnet_model_create / _forward / _destroy) behind a Python callable --
 what a C or C++ host would do with the library, spelled out: build the handle from a checkpoint's tensors once, then
-`forward` with caller-owned scratch.  Covered: the binary SV_DGCNN_CLS at k = 20 / 40, 64 <= N <= 4096.
+`forward` with caller-owned scratch.  Covered: SV_DGCNN_CLS, binary (k = 20 / 40) or full precision (k = 20), 64 <= N <= 4096.
 
     native = svnet_b200.NativeModel("SV_DGCNN_CLS", checkpoint["state_dict"], k=20, binary=True, num_class=40)
     logits = native(batch)                     # (B, 3, N) float32 CUDA -> (B, num_class); bit-identical to the nn.Module

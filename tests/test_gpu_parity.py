@@ -628,18 +628,18 @@ def test_full_size_configs_run_and_are_batch_independent():
     assert torch.equal(y_full, y_chunk)
 
 
-@pytest.mark.parametrize("B,N,k", [(4, 1024, 20), (3, 200, 20), (2, 512, 40)])
-def test_model_c_entry_equals_module(B, N, k):
-    """svnet_model_create / _forward / _destroy (the whole binary SV-DGCNN classifier behind one C call,
+@pytest.mark.parametrize("B,N,k,binary", [(4, 1024, 20, True), (3, 200, 20, True), (2, 512, 40, True), (4, 1024, 20, False), (3, 200, 20, False)])
+def test_model_c_entry_equals_module(B, N, k, binary):
+    """svnet_model_create / _forward / _destroy (the whole SV-DGCNN classifier, binary or fp, behind one C call,
     csrc/model.cu) against the nn.Module path on the same checkpoint tensors: bit-identical logits, also when the
     C forward is captured into a CUDA graph; uncovered shapes and kinds fail loudly."""
     import svnet_b200 as sv
-    net = quiet(sv.SV_DGCNN_CLS, make_args(k=k, binary=True), 40)
+    net = quiet(sv.SV_DGCNN_CLS, make_args(k=k, binary=binary), 40)
     sd = synthetic_state_dict(net.state_dict(), seed=1002)
     net.load_state_dict(sd)
     net = net.to(DEV).eval()
     x = synthetic_clouds(B, N, 1002).to(DEV)
-    native = sv.NativeModel("SV_DGCNN_CLS", {"module." + n: t for n, t in sd.items()}, k=k, binary=True, num_class=40, device=DEV)
+    native = sv.NativeModel("SV_DGCNN_CLS", {"module." + n: t for n, t in sd.items()}, k=k, binary=binary, num_class=40, device=DEV)
     with torch.no_grad():
         y_mod = net(x)
         y_c = native(x)
@@ -658,7 +658,7 @@ def test_model_c_entry_equals_module(B, N, k):
     with pytest.raises(ValueError):
         native(synthetic_clouds(1, 48, 1).to(DEV))           # N < 64: not covered
     with pytest.raises(RuntimeError):
-        sv.NativeModel("SV_DGCNN_PSEG", sd, k=k, binary=True, num_class=40, device=DEV)
+        sv.NativeModel("SV_DGCNN_PSEG", sd, k=k, binary=binary, num_class=40, device=DEV)
     native.close()
 
 
