@@ -13,6 +13,7 @@ MAX_POINTS_PER_PASS = int(os.environ.get("SVNET_MAX_POINTS", 1 << 19))
 SIDE_STREAM = os.environ.get("SVNET_SIDE_STREAM", "1") != "0"
 CONCURRENT_HALVES = os.environ.get("SVNET_TWO_STREAMS", "1") != "0"
 N_SPLIT = max(2, int(os.environ.get("SVNET_STREAMS", "4")))      # sub-batches that run concurrently
+TABLE_AUX = os.environ.get("SVNET_TABLE_AUX", "1") != "0"          # per-point tables next to the kNN kernels also inside sub-batches
 MIN_CLOUDS = max(1, int(os.environ.get("SVNET_MIN_CLOUDS", "8")))  # ... of at least this many clouds
 MIN_POINTS = max(1, int(os.environ.get("SVNET_MIN_POINTS", "16384")))  # ... and points (measured on B200: 32 x 1024 as 2 x 16 clouds)
 _SIDE = {}
@@ -148,7 +149,7 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
     fp_tc_bytes = 0 if blk.binary else nv.edge_fp_tc_weight_bytes(Cs, Cv, Cout, Cvo, k)      # csrc/edge_fp_tc.cu
     use_fp_tc = fp_tc_bytes > 0
     cur = torch.cuda.current_stream()
-    side = _side_stream(dev) if (idx32 is None and SIDE_STREAM and not _STATE.in_sub_batch) else None
+    side = (aux_stream(dev) if TABLE_AUX else (_side_stream(dev) if not _STATE.in_sub_batch else None)) if (idx32 is None and SIDE_STREAM) else None
     if use_tc or use_fp_tc:
         Wt, cst = blk.edge_tc_table_weight()
         NC = Wt.shape[0]

@@ -443,7 +443,6 @@ class SVBlock(_Cached, nn.Module):
         Cso, Cvo = self.out_dims
         dev = s2d.device
         G1, G2 = self.gate_weights()
-        gate = nv.gate_rows(s2d, s2d.stride(0), Cs, B, rows_per_cloud, G1, G2)
         Wz, zs = self.v2s.wz()
         view = nv.view_of(s2d, v3, Cs=Cs, Cv=Cv)
         bn1 = self.bn1_folded()
@@ -453,7 +452,20 @@ class SVBlock(_Cached, nn.Module):
         if s_out is None and not fused_pool:
             s_out = torch.empty((R, Cso), dtype=torch.float32, device=dev)
             lds_out = Cso
-        if self.binary:
+        aux = None
+        if self.binary and fused_pool:
+            # the scalar branch (sign words -> tensor-core linear + pooling) does not need the gate: it runs on a side
+            # stream next to gate -> vector linear (two independent chains of ~100 us each at conv5's shape)
+            from .fused import aux_stream
+            aux = aux_stream(dev)
+        if self.binary and aux is not None:
+            cur = torch.cuda.current_stream()
+            beta1, sbits, sc1 = self.linear1.beta_vec(), self.linear1.sign_bits(), self.linear1.scale_vec()
+            aux.wait_stream(cur)
+            with torch.cuda.stream(aux):
+                bits, mask, nvalid = nv.rows_prep(view, R, Wz=Wz, zscale=zs, beta=beta1, want_bits=True)
+                nv.binlinear_pool(bits, mask, K, sbits, Cso, sc1, bn1, rows_per_cloud, s_pool[0], s_pool[1], s_pool[2])
+        elif self.binary:
             bits, mask, nvalid = nv.rows_prep(view, R, Wz=Wz, zscale=zs, beta=self.linear1.beta_vec(), want_bits=True)
             if fused_pool:
                 nv.binlinear_pool(bits, mask, K, self.linear1.sign_bits(), Cso, self.linear1.scale_vec(), bn1,
@@ -469,10 +481,13 @@ class SVBlock(_Cached, nn.Module):
         if v_out is None:
             v_out = torch.empty((R, 3, Cvo), dtype=torch.float32, device=dev)
         lin2 = self.linear2
+        gate = nv.gate_rows(s2d, s2d.stride(0), Cs, B, rows_per_cloud, G1, G2)
         nv.linear_rows(v3, v3.stride(0), v3.stride(1), 3, 3 * R, Cv, lin2.weight.detach(), Cvo, v_out,
                        v_out.stride(0), v_out.stride(1), sign_w=lin2.bw,
                        colscale=lin2.scale_vec() if lin2.bw else None, bn=self.bn2.folded(), vbn=True, gate=gate,
                        groups_per_cloud=rows_per_cloud)
+        if aux is not None:
+            torch.cuda.current_stream().wait_stream(aux)
         if s_pool is not None and not fused_pool:
             nv.pool_rows(s_out, lds_out, Cso, B, rows_per_cloud, want_max=s_pool[0] is not None,
                          want_mean=s_pool[1] is not None, max_out=s_pool[0], mean_out=s_pool[1], ldo=s_pool[2])
