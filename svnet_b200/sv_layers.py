@@ -452,32 +452,29 @@ class SVBlock(_Cached, nn.Module):
         if s_out is None and not fused_pool:
             s_out = torch.empty((R, Cso), dtype=torch.float32, device=dev)
             lds_out = Cso
+        # the scalar branch (v2s + linear1 [+ pooling]) does not need the gate: with enough rows it runs on a side stream next
+        # to gate -> vector linear (two independent chains of ~100 us each at conv5's shape)
         aux = None
-        if self.binary and fused_pool:
-            # the scalar branch (sign words -> tensor-core linear + pooling) does not need the gate: it runs on a side
-            # stream next to gate -> vector linear (two independent chains of ~100 us each at conv5's shape)
+        if R >= 1024:
             from .fused import aux_stream
             aux = aux_stream(dev)
-        if self.binary and aux is not None:
-            cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream()
+        if self.binary:
             beta1, sbits, sc1 = self.linear1.beta_vec(), self.linear1.sign_bits(), self.linear1.scale_vec()
+        if aux is not None:
             aux.wait_stream(cur)
-            with torch.cuda.stream(aux):
+        with torch.cuda.stream(aux if aux is not None else cur):
+            if self.binary:
                 bits, mask, nvalid = nv.rows_prep(view, R, Wz=Wz, zscale=zs, beta=beta1, want_bits=True)
-                nv.binlinear_pool(bits, mask, K, sbits, Cso, sc1, bn1, rows_per_cloud, s_pool[0], s_pool[1], s_pool[2])
-        elif self.binary:
-            bits, mask, nvalid = nv.rows_prep(view, R, Wz=Wz, zscale=zs, beta=self.linear1.beta_vec(), want_bits=True)
-            if fused_pool:
-                nv.binlinear_pool(bits, mask, K, self.linear1.sign_bits(), Cso, self.linear1.scale_vec(), bn1,
-                                  rows_per_cloud, s_pool[0], s_pool[1], s_pool[2])
+                if fused_pool:
+                    nv.binlinear_pool(bits, mask, K, sbits, Cso, sc1, bn1, rows_per_cloud, s_pool[0], s_pool[1], s_pool[2])
+                else:
+                    nv.binlinear_rows(bits, mask, nvalid, K, sbits, Cso, scale=sc1, bn=bn1, act=nv.ACT_LEAKY, out=s_out, ldo=lds_out)
             else:
-                nv.binlinear_rows(bits, mask, nvalid, K, self.linear1.sign_bits(), Cso, scale=self.linear1.scale_vec(),
-                                  bn=bn1, act=nv.ACT_LEAKY, out=s_out, ldo=lds_out)
-        else:
-            u = torch.empty((R, K), dtype=torch.float32, device=dev)
-            nv.rows_prep(view, R, Wz=Wz, zscale=zs, u_out=u, ldu=K)
-            nv.linear_rows(u, K, 0, 1, R, K, self.linear1.weight.detach(), Cso, s_out, lds_out, 0, bn=bn1,
-                           act=nv.ACT_LEAKY)
+                u = torch.empty((R, K), dtype=torch.float32, device=dev)
+                nv.rows_prep(view, R, Wz=Wz, zscale=zs, u_out=u, ldu=K)
+                nv.linear_rows(u, K, 0, 1, R, K, self.linear1.weight.detach(), Cso, s_out, lds_out, 0, bn=bn1,
+                               act=nv.ACT_LEAKY)
         if v_out is None:
             v_out = torch.empty((R, 3, Cvo), dtype=torch.float32, device=dev)
         lin2 = self.linear2
