@@ -134,7 +134,7 @@ struct QSecF {
     {
         esub = lane / NDS;
         const int ds = DS0 + lane % NDS;
-        lane_on = lane < GE * NDS && ds < 2 * CV;
+        lane_on = lane < GE * NDS && ds < (DIFF ? CV : 2 * CV);
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
             const int pos = ftc_pos(lane_on ? ds : DS0, m, CV, S::KH) - PH0;
@@ -231,11 +231,17 @@ edge_fp_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, c
     const int pt_in_tile = warp / S::WPP, e0 = (warp % S::WPP) * S::EPW;
     const uint32_t brow0 = smem_u32(Bs) + (uint32_t)(warp * S::EPW) * 16u;     // first operand row of this warp
     // q sections: the diff half and the centre half; halves wider than 32 channels never occur (Cv <= 24)
-    static_assert(CV <= 32, "one section per half");
-    QSecF<S, CV, 0, CV, 0> qd;
-    QSecF<S, CV, CV, CV, (S::NPH == 1 ? 0 : S::KH)> qc;
+    static_assert(CV <= 32, "two sections per half");
+    // a half wider than 16 channels is walked as 16 + rest channels (32 / 30 of 32 lanes busy instead of Cv of 32)
+    constexpr int NA = CV > 16 ? 16 : CV, NB2 = CV - NA;
+    constexpr int PHC = S::NPH == 1 ? 0 : S::KH;
+    QSecF<S, CV, 0, NA, 0> qd;
+    QSecF<S, CV, NA, (NB2 > 0 ? NB2 : 1), 0> qd2;
+    QSecF<S, CV, CV, NA, PHC> qc;
+    QSecF<S, CV, CV + NA, (NB2 > 0 ? NB2 : 1), PHC> qc2;
     qd.init(lane, brow0);
     qc.init(lane, brow0);
+    if (NB2 > 0) { qd2.init(lane, brow0); qc2.init(lane, brow0); }
     // epilogue role: TMEM lane quarter = output channels, column group = points
     const int q4 = warp & 3, grp = warp >> 2;
     const int oc = q4 * 32 + lane;
@@ -304,6 +310,7 @@ edge_fp_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, c
             }
             qd.centre(tabc, trow);
             qc.centre(tabc, trow);
+            if (NB2 > 0) { qd2.centre(tabc, trow); qc2.centre(tabc, trow); }
             if (lane < 30) {
 #pragma unroll
                 for (int rd = 0; rd < S::EPW / 10; ++rd)
@@ -313,7 +320,8 @@ edge_fp_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, c
             __syncwarp();
             // ---- q sections of the first phase ----
             qd.run(my_j, zb);
-            if (S::NPH == 1) qc.run(my_j, zb);
+            if (NB2 > 0) qd2.run(my_j, zb);
+            if (S::NPH == 1) { qc.run(my_j, zb); if (NB2 > 0) qc2.run(my_j, zb); }
         }
         // first vector-branch gathers go out before the barrier
         if (valid) vb.prefetch(p, b, tabc, trow, my_j, lane);
@@ -333,7 +341,7 @@ edge_fp_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, c
             mbar_wait(bar, phase);
             phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            if (valid) qc.run(my_j, zb);
+            if (valid) { qc.run(my_j, zb); if (NB2 > 0) qc2.run(my_j, zb); }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncthreads();
