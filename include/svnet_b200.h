@@ -381,7 +381,8 @@ int svnet_svfuse_pool(const svnet_view* in, int B, long rows_per_cloud, const fl
  * svnet_model_create() takes the state_dict as (name, device pointer, element count) triples -- the reference's key names
  * without the 'module.' prefix (SURVEY 8(a) a-keys), fp32, contiguous -- copies what it needs and packs it once (sign
  * bit-planes, folded BatchNorm affines, tensor-core operand bytes, per-point table weights); it synchronises `stream` before
- * it returns, the caller's tensors may then be freed.  Covered: kind "SV_DGCNN_CLS", k = 20 (binary = 1 also k = 40).
+ * it returns, the caller's tensors may then be freed.  Covered: kind "SV_DGCNN_CLS", k = 20 (binary = 1 also k = 40); kind
+ * "SV_DGCNN_PSEG" below.
  * svnet_model_forward(): x [B][3][N] -> logits [B][num_class] on `stream`, with svnet_model_workspace_bytes(m, B, N) bytes of
  * caller-owned scratch (256-byte aligned; 0: shape not covered -- 64 <= N <= 4096).  It allocates
  * nothing and never synchronises, so it can be captured into a CUDA graph; the logits are bit-identical to the nn.Module
@@ -394,6 +395,11 @@ size_t svnet_model_workspace_bytes(const svnet_model* m, int B, int N);
 int svnet_model_forward(const svnet_model* m, const float* x, int B, int N, float* logits, void* workspace,
                         size_t workspace_bytes, void* stream);
 void svnet_model_destroy(svnet_model* m);
+/* kind "SV_DGCNN_PSEG" (models/sv_dgcnn_partseg.py:40-128; binary = 1, k = 20 or 40, num_class = number of parts):
+ * x [B][3][N], label_onehot [B][16] -> logits [B][parts][N], with svnet_model_seg_workspace_bytes() bytes of scratch. */
+size_t svnet_model_seg_workspace_bytes(const svnet_model* m, int B, int N);
+int svnet_model_forward_seg(const svnet_model* m, const float* x, const float* label_onehot, int B, int N, float* logits,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* Input side of the eval loop: out[b][c][n] = sum_d pts[b][n][d] * R[b][d][c]
  * (pytorch3d Rotate.transform_points, then permute(0,2,1): main_cls_dgcnn.py:229-235).

@@ -28,6 +28,7 @@ EXPORTS = [
     "svnet_edge_tc_weight_bytes", "svnet_edge_tc_table_cols", "svnet_edge_tc_pack_w", "svnet_allgather_logits",
     "svnet_edge_fp_tc_weight_bytes", "svnet_edge_fp_tc_pack_w", "svnet_seg_head_fwd", "svnet_seg_head_workspace_bytes",
     "svnet_model_create", "svnet_model_workspace_bytes", "svnet_model_forward", "svnet_model_destroy",
+    "svnet_model_seg_workspace_bytes", "svnet_model_forward_seg",
 ]
 
 
@@ -103,6 +104,8 @@ def lib():
         l.svnet_seg_head_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_model_workspace_bytes.restype = ctypes.c_size_t
         l.svnet_model_workspace_bytes.argtypes = [c_void_p, c_int, c_int]
+        l.svnet_model_seg_workspace_bytes.restype = ctypes.c_size_t
+        l.svnet_model_seg_workspace_bytes.argtypes = [c_void_p, c_int, c_int]
         l.svnet_model_destroy.restype = None
         l.svnet_model_destroy.argtypes = [c_void_p]
         for name in EXPORTS:
@@ -345,6 +348,16 @@ def model_workspace_bytes(h, B, N):
 def model_forward(h, x, logits, ws):
     B, _, N = x.shape
     _call("svnet_model_forward", h, _ptr(_dev(x)), c_int(B), c_int(N), _ptr(logits), _ptr(ws), ctypes.c_size_t(ws.numel()), _stream())
+
+
+def model_seg_workspace_bytes(h, B, N):
+    return int(lib().svnet_model_seg_workspace_bytes(h, B, N))
+
+
+def model_forward_seg(h, x, label, logits, ws):
+    B, _, N = x.shape
+    _call("svnet_model_forward_seg", h, _ptr(_dev(x)), _ptr(_dev(label)), c_int(B), c_int(N), _ptr(logits), _ptr(ws),
+          ctypes.c_size_t(ws.numel()), _stream())
 
 
 def model_destroy(h):

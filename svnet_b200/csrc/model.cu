@@ -21,6 +21,7 @@
 
 struct svnet_model {
     int k, ncls, binary;
+    int pseg;                        // 0: SV_DGCNN_CLS, 1: SV_DGCNN_PSEG (ncls = parts)
     std::vector<void*> allocs;
     // init_scalar + five SVBlocks
     float* Winit;
@@ -31,12 +32,17 @@ struct svnet_model {
         unsigned char* W1tc;
         float *Wt, *cst, *Wab;        // Wab: [W1a; W1b] (2 Cout x Cs) of a full-precision linear1 (the Ya | Yb table)
         int NC;
-    } conv[5];
+    } conv[6];
     float *fuse_Wz, *fuse_zs;
     // head
     uint32_t *h1_bits, *h2_bits;
     float *h1_beta, *h1_scale, *h1_a, *h1_c, *h2_beta, *h2_scale, *h2_a, *h2_c, *h3_W, *h3_b;
     float *h1_W, *h2_W;              // full-precision head
+    // part segmentation: svfuse1 / 2 / 3, conv7 (labels), conv8 .. conv11
+    float *f1_Wz, *f1_zs, *f2_Wz, *f2_zs, *f3_Wz, *f3_zs, *c7_W, *c7_a, *c7_c;
+    struct SegConv { float *beta, *scale, *bn_a, *bn_c; uint32_t *bits, *bits_c; int Cin, Cout; } c8, c9, c10;
+    float* c11_W;
+    int C6s, C6v, Kc;
     int Cf, C5s, C5v, h1, h2;
 };
 
@@ -131,13 +137,14 @@ struct fwd_plan {
     int Cs_cat, Cv_cat;
 };
 
-bool make_fwd_plan(const svnet_model* m, int B, int N, fwd_plan* pl)
+// scratch of the four edge layers; returns the running offset
+size_t plan_trunk(const svnet_model* m, int B, int N, fwd_plan* pl)
 {
     const long R = (long)B * N;
     int cs = 0, cv = 0, ncmax = 0, cvomax = 0;
     for (int l = 0; l < 4; ++l) { cs += m->conv[l].Cout; cv += m->conv[l].Cvo; }
     for (int l = 1; l < 4; ++l) ncmax = m->conv[l].NC > ncmax ? m->conv[l].NC : ncmax;
-    for (int l = 0; l < 5; ++l) cvomax = m->conv[l].Cvo > cvomax ? m->conv[l].Cvo : cvomax;
+    for (int l = 0; l < 6; ++l) cvomax = m->conv[l].Cvo > cvomax ? m->conv[l].Cvo : cvomax;
     pl->Cs_cat = cs; pl->Cv_cat = cv;
     size_t o = 0;
     pl->xyz = o; o += up256(sizeof(float) * 3 * R);
@@ -160,6 +167,15 @@ bool make_fwd_plan(const svnet_model* m, int B, int N, fwd_plan* pl)
     }
     pl->knn_bytes = kb;
     pl->knn = o; o += up256(kb);
+    return o;
+}
+
+bool make_fwd_plan(const svnet_model* m, int B, int N, fwd_plan* pl)
+{
+    const long R = (long)B * N;
+    size_t o = plan_trunk(m, B, N, pl);
+    const int cs = pl->Cs_cat, cv = pl->Cv_cat;
+    const size_t kb = pl->knn_bytes;
     pl->v5 = o; o += up256(sizeof(float) * R * 3 * m->C5v);
     pl->g = o; o += up256(sizeof(float) * B * 2 * m->Cf);
     const int K5 = cs + 3 * cv, Kw = (K5 + 31) / 32;
@@ -221,26 +237,37 @@ extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_c
                                   void* stream, svnet_model** out)
 {
     SV_REQUIRE(kind && tensors && out && n_tensors > 0, "svnet_model_create: null pointer");
-    SV_REQUIRE(strcmp(kind, "SV_DGCNN_CLS") == 0, "svnet_model_create: kind '%s' not covered (SV_DGCNN_CLS; the other models go through the nn.Module API)", kind);
+    const bool pseg = strcmp(kind, "SV_DGCNN_PSEG") == 0;
+    SV_REQUIRE(pseg || strcmp(kind, "SV_DGCNN_CLS") == 0,
+               "svnet_model_create: kind '%s' not covered (SV_DGCNN_CLS, SV_DGCNN_PSEG; the PointNet models go through the nn.Module API)", kind);
     SV_REQUIRE(binary == 0 || binary == 1, "svnet_model_create: binary must be 0 or 1");
+    SV_REQUIRE(!pseg || binary, "svnet_model_create: the full-precision part-segmentation model goes through the nn.Module API");
     SV_REQUIRE(k == 20 || (binary && k == 40), "svnet_model_create: k = %d not covered (the tensor-core edge kernels' shapes: 20, binary also 40)", k);
     SV_REQUIRE(num_class >= 1, "svnet_model_create: bad num_class");
     svnet_model* m = new svnet_model();
-    m->k = k; m->ncls = num_class; m->binary = binary;
+    m->k = k; m->ncls = num_class; m->binary = binary; m->pseg = pseg ? 1 : 0;
     Loader L{tensors, n_tensors, m, sv_stream(stream)};
     int* zc = static_cast<int*>(L.alloc(16 * sizeof(int)));
     if (zc) cudaMemsetAsync(zc, 0, 16 * sizeof(int), L.st);
     m->Winit = L.dup("init_scalar.linear.weight", 3 * 2);
     // per-point dims entering each block / leaving it (sv_dgcnn_cls.py:29-34)
-    const int cs_in[5] = {3, 32, 32, 64, 256}, cv_in[5] = {1, 10, 10, 21, 83};
-    const int cs_out[5] = {32, 32, 64, 128, 512}, cv_out[5] = {10, 10, 21, 42, 170};
-    for (int l = 0; l < 5 && L.ok; ++l) {
+    // (sv_dgcnn_partseg.py:52-64: channel counts rounded to multiples of 8; conv6 takes conv5's pooled output, one row per cloud)
+    const int cls_cs_in[6] = {3, 32, 32, 64, 256, 0}, cls_cv_in[6] = {1, 10, 10, 21, 83, 0};
+    const int cls_cs_out[6] = {32, 32, 64, 128, 512, 0}, cls_cv_out[6] = {10, 10, 21, 42, 170, 0};
+    const int seg_cs_in[6] = {3, 32, 32, 64, 256, 512}, seg_cv_in[6] = {1, 16, 16, 24, 96, 168};
+    const int seg_cs_out[6] = {32, 32, 64, 128, 512, 256}, seg_cv_out[6] = {16, 16, 24, 40, 168, 88};
+    const int* cs_in = pseg ? seg_cs_in : cls_cs_in;
+    const int* cv_in = pseg ? seg_cv_in : cls_cv_in;
+    const int* cs_out = pseg ? seg_cs_out : cls_cs_out;
+    const int* cv_out = pseg ? seg_cv_out : cls_cv_out;
+    const int nblocks = pseg ? 6 : 5;
+    for (int l = 0; l < nblocks && L.ok; ++l) {
         svnet_model::Block& b = m->conv[l];
         const std::string p = "conv" + std::to_string(l + 1) + ".";
         b = svnet_model::Block();
         b.Cs = cs_in[l]; b.Cv = cv_in[l]; b.Cout = cs_out[l]; b.Cvo = cv_out[l]; b.H = b.Cvo / 2;
         // the block's own input dims: layer 1 (6, 2) full precision; edge layers (2Cs, 2Cv); conv5 (Cs, Cv)
-        const int bcs = l == 0 ? 6 : (l < 4 ? 2 * b.Cs : b.Cs), bcv = l == 0 ? 2 : (l < 4 ? 2 * b.Cv : b.Cv);
+        const int bcs = l == 0 ? 6 : (l < 4 ? 2 * b.Cs : b.Cs), bcv = l == 0 ? 2 : (l < 4 ? 2 * b.Cv : b.Cv);      // l >= 4: row blocks
         const int K1 = bcs + 3 * bcv;
         b.G1 = L.dup(p + "gate.0.weight", (long)b.H * bcs);
         b.G2 = L.dup(p + "gate.2.weight", (long)b.Cvo * b.H);
@@ -313,7 +340,48 @@ extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_c
     }
     m->C5s = cs_out[4]; m->C5v = cv_out[4]; m->Cf = m->C5s + 3 * m->C5v;
     m->h1 = 512; m->h2 = 256;
-    if (L.ok && !binary) {
+    if (L.ok && pseg) {
+        m->C6s = cs_out[5]; m->C6v = cv_out[5];
+        const int cs_cat = 256, cv_cat = 96;
+        m->f1_Wz = L.signed_copy("svfuse1.v2s.linear.weight", 3 * cv_cat);
+        m->f1_zs = L.dup("svfuse1.v2s.linear.scale", 3);
+        m->f2_Wz = L.signed_copy("svfuse2.v2s.linear.weight", 3 * m->C6v);
+        m->f2_zs = L.dup("svfuse2.v2s.linear.scale", 3);
+        m->f3_Wz = L.signed_copy("svfuse3.v2s.linear.weight", 3 * m->C5v);
+        m->f3_zs = L.dup("svfuse3.v2s.linear.scale", 3);
+        m->c7_W = L.dup("conv7.0.weight", 64 * 16);
+        L.fold("conv7.1", 64, &m->c7_a, &m->c7_c);
+        // conv8 input = [glob (per cloud): s5 max | v2s(v5) max | svfuse2(conv6) | conv7(label)] ++ [svfuse1(s_cat, v_cat) per point]
+        m->Kc = m->C5s + 3 * m->C5v + (m->C6s + 3 * m->C6v) + 64;
+        const int Kp = cs_cat + 3 * cv_cat;
+        auto seg_conv = [&](const char* name, int Cin, int Cout, svnet_model::SegConv* c, int split) {
+            const std::string p = std::string(name) + ".";
+            c->Cin = Cin; c->Cout = Cout;
+            const svnet_tensor* w = L.find(p + "0.weight", (long)Cout * Cin);
+            c->beta = L.dup(p + "0.beta", Cin);
+            c->scale = L.dup(p + "0.scale", Cout);
+            L.fold(p + "1", Cout, &c->bn_a, &c->bn_c);
+            c->bits = c->bits_c = nullptr;
+            if (!w) return;
+            if (split > 0) {
+                // sign planes of the per-cloud columns [:, :split] and of the per-point columns [:, split:]
+                c->bits_c = static_cast<uint32_t*>(L.alloc(sizeof(uint32_t) * (size_t)((split + 31) / 32) * Cout));
+                c->bits = static_cast<uint32_t*>(L.alloc(sizeof(uint32_t) * (size_t)((Cin - split + 31) / 32) * Cout));
+                if (c->bits_c && c->bits && L.nz + 2 <= 16) {
+                    if (svnet_pack_sign(w->data, Cout, split, Cin, c->bits_c, zc + L.nz, L.st) != SVNET_OK) L.fail("svnet_pack_sign failed");
+                    if (svnet_pack_sign(w->data + split, Cout, Cin - split, Cin, c->bits, zc + L.nz + 1, L.st) != SVNET_OK) L.fail("svnet_pack_sign failed");
+                }
+                L.nz += 2;
+            } else {
+                c->bits = L.bits(w->data, Cout, Cin, zc);
+            }
+        };
+        seg_conv("conv8", m->Kc + Kp, 256, &m->c8, m->Kc);
+        seg_conv("conv9", 256, 256, &m->c9, 0);
+        seg_conv("conv10", 256, 128, &m->c10, 0);
+        m->c11_W = L.dup("conv11.weight", (long)num_class * 128);
+    }
+    if (L.ok && !pseg && !binary) {
         m->fuse_Wz = L.dup("svfuse.v2s.linear.weight", 3 * m->C5v);
         m->h1_W = L.dup("linear1.weight", (long)m->h1 * 2 * m->Cf);
         m->h2_W = L.dup("linear2.weight", (long)m->h2 * m->h1);
@@ -322,7 +390,7 @@ extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_c
         m->h3_W = L.dup("linear3.weight", (long)num_class * m->h2);
         m->h3_b = L.dup("linear3.bias", num_class);
     }
-    if (L.ok && binary) {
+    if (L.ok && !pseg && binary) {
         m->fuse_Wz = L.signed_copy("svfuse.v2s.linear.weight", 3 * m->C5v);
         m->fuse_zs = L.dup("svfuse.v2s.linear.scale", 3);
         const svnet_tensor* w1 = L.find("linear1.weight", (long)m->h1 * 2 * m->Cf);
@@ -358,23 +426,17 @@ extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_c
 
 extern "C" size_t svnet_model_workspace_bytes(const svnet_model* m, int B, int N)
 {
-    if (!m || B < 1 || N < 64 || N > 4096) return 0;
+    if (!m || m->pseg || B < 1 || N < 64 || N > 4096) return 0;
     fwd_plan pl;
     if (!make_fwd_plan(m, B, N, &pl)) return 0;
     return pl.total;
 }
 
-extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, int N, float* logits, void* workspace,
-                                   size_t workspace_bytes, void* stream)
+namespace {
+
+// the four edge layers (sv_dgcnn_cls.py:47-65, sv_dgcnn_partseg.py:81-103): fills the svcat table (s_cat, v_cat) in `ws`
+int run_trunk(const svnet_model* m, const float* x, int B, int N, unsigned char* ws, const fwd_plan& pl, void* stream)
 {
-    SV_REQUIRE(m && x && logits, "svnet_model_forward: null pointer");
-    SV_REQUIRE(B >= 0 && N >= 64 && N <= 4096, "svnet_model_forward: N = %d not covered (64..4096)", N);
-    if (B == 0) return SVNET_OK;
-    fwd_plan pl;
-    SV_REQUIRE(make_fwd_plan(m, B, N, &pl), "svnet_model_forward: shape not covered by the tensor-core paths");
-    SV_REQUIRE(workspace && workspace_bytes >= pl.total && !(reinterpret_cast<uintptr_t>(workspace) & 255),
-               "svnet_model_forward: workspace too small (svnet_model_workspace_bytes) or not 256-byte aligned");
-    unsigned char* ws = static_cast<unsigned char*>(workspace);
     cudaStream_t st = sv_stream(stream);
     const long R = (long)B * N;
     const int k = m->k;
@@ -447,6 +509,30 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
         prev.v = out.v; prev.ldv = out.ldv; prev.xs = out.xs; prev.Cv = out.Cv;
         so += b.Cout; vo += b.Cvo;
     }
+    return SVNET_OK;
+}
+
+}  // namespace
+
+extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, int N, float* logits, void* workspace,
+                                   size_t workspace_bytes, void* stream)
+{
+    SV_REQUIRE(m && x && logits, "svnet_model_forward: null pointer");
+    SV_REQUIRE(!m->pseg, "svnet_model_forward: the handle is a part-segmentation model (svnet_model_forward_seg)");
+    SV_REQUIRE(B >= 0 && N >= 64 && N <= 4096, "svnet_model_forward: N = %d not covered (64..4096)", N);
+    if (B == 0) return SVNET_OK;
+    fwd_plan pl;
+    SV_REQUIRE(make_fwd_plan(m, B, N, &pl), "svnet_model_forward: shape not covered by the tensor-core paths");
+    SV_REQUIRE(workspace && workspace_bytes >= pl.total && !(reinterpret_cast<uintptr_t>(workspace) & 255),
+               "svnet_model_forward: workspace too small (svnet_model_workspace_bytes) or not 256-byte aligned");
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    const long R = (long)B * N;
+    float* s_cat = reinterpret_cast<float*>(ws + pl.s_cat);
+    float* v_cat = reinterpret_cast<float*>(ws + pl.v_cat);
+    float* gate = reinterpret_cast<float*>(ws + pl.gate);
+    const int lds = pl.Cs_cat, xs = pl.Cv_cat, ldv = 3 * pl.Cv_cat;
+    int rc = run_trunk(m, x, B, N, ws, pl, stream);
+    if (rc != SVNET_OK) return rc;
     // ---- conv5 (per point) -> svfuse -> max | mean over the points ----
     const svnet_model::Block& c5 = m->conv[4];
     float* v5 = reinterpret_cast<float*>(ws + pl.v5);
@@ -532,4 +618,176 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
     h.layer[2].Cout = m->ncls; h.layer[2].W = m->h3_W; h.layer[2].bias = m->h3_b; h.layer[2].act = SVNET_ACT_NONE;
     h.out = logits; h.ldo = m->ncls;
     return svnet_head_fwd(&h, stream);
+}
+
+// ---- part segmentation (sv_dgcnn_partseg.py:80-128) -------------------------------------------------------------------
+namespace {
+
+struct seg_plan2 {
+    fwd_plan t;
+    size_t bits8, mask8, nvalid8, bits5, mask5, nvalid5, blp, s5, v5, glob, vp, v6, bits6, mask6, nvalid6, fuse, head, total;
+    size_t blp_bytes, bl_bytes, fuse_bytes, head_bytes;
+};
+
+svnet_seg_head_params seg_head_params(const svnet_model* m, int B, int N)
+{
+    svnet_seg_head_params h = {};
+    h.sv.Cs = 256; h.sv.Cv = 96; h.sv.lds = 256; h.sv.ldv = 3 * 96; h.sv.xs = 96;
+    h.B = B; h.N = N; h.Wz1 = m->f1_Wz; h.zscale1 = m->f1_zs; h.ldg = m->Kc; h.Kc = m->Kc;
+    h.beta8 = m->c8.beta; h.W8c = m->c8.bits_c; h.W8p = m->c8.bits; h.scale8 = m->c8.scale; h.bn8_a = m->c8.bn_a; h.bn8_c = m->c8.bn_c; h.C8 = m->c8.Cout;
+    h.beta9 = m->c9.beta; h.W9 = m->c9.bits; h.scale9 = m->c9.scale; h.bn9_a = m->c9.bn_a; h.bn9_c = m->c9.bn_c; h.C9 = m->c9.Cout;
+    h.beta10 = m->c10.beta; h.W10 = m->c10.bits; h.scale10 = m->c10.scale; h.bn10_a = m->c10.bn_a; h.bn10_c = m->c10.bn_c; h.C10 = m->c10.Cout;
+    h.W11 = m->c11_W; h.parts = m->ncls;
+    return h;
+}
+
+bool make_seg_plan(const svnet_model* m, int B, int N, seg_plan2* pl)
+{
+    const long R = (long)B * N;
+    size_t o = plan_trunk(m, B, N, &pl->t);
+    const int cs = pl->t.Cs_cat, cv = pl->t.Cv_cat;
+    const int Kp = cs + 3 * cv, Kpw = (Kp + 31) / 32;
+    const int K6 = m->C5s + 3 * m->C5v, K6w = (K6 + 31) / 32;
+    pl->bits8 = o; o += up256(sizeof(uint32_t) * R * Kpw);
+    pl->mask8 = o; o += up256(sizeof(uint32_t) * R * Kpw);
+    pl->nvalid8 = o; o += up256(sizeof(int32_t) * R);
+    pl->bits5 = o; o += up256(sizeof(uint32_t) * R * Kpw);
+    pl->mask5 = o; o += up256(sizeof(uint32_t) * R * Kpw);
+    pl->nvalid5 = o; o += up256(sizeof(int32_t) * R);
+    pl->blp_bytes = svnet_binlinear_pool_workspace_bytes(R, Kp, m->C5s, N);
+    pl->bl_bytes = pl->blp_bytes ? 0 : svnet_binlinear_workspace_bytes(R, Kp, m->C5s);
+    pl->blp = o; o += up256(pl->blp_bytes + pl->bl_bytes);
+    pl->s5 = o; o += pl->blp_bytes ? 0 : up256(sizeof(float) * R * m->C5s);
+    pl->v5 = o; o += up256(sizeof(float) * R * 3 * m->C5v);
+    pl->glob = o; o += up256(sizeof(float) * B * m->Kc);
+    pl->vp = o; o += up256(sizeof(float) * B * 3 * m->C5v);
+    pl->v6 = o; o += up256(sizeof(float) * B * 3 * m->C6v);
+    pl->bits6 = o; o += up256(sizeof(uint32_t) * B * K6w);
+    pl->mask6 = o; o += up256(sizeof(uint32_t) * B * K6w);
+    pl->nvalid6 = o; o += up256(sizeof(int32_t) * B);
+    pl->fuse_bytes = svnet_svfuse_pool_workspace(B, m->C5v, N);
+    pl->fuse = o; o += up256(pl->fuse_bytes);
+    const svnet_seg_head_params h = seg_head_params(m, B, N);
+    pl->head_bytes = svnet_seg_head_workspace_bytes(&h);
+    pl->head = o; o += up256(pl->head_bytes);
+    pl->total = o;
+    return pl->t.knn_bytes > 0 && pl->head_bytes > 0;
+}
+
+}  // namespace
+
+extern "C" size_t svnet_model_seg_workspace_bytes(const svnet_model* m, int B, int N)
+{
+    if (!m || !m->pseg || B < 1 || N < 64 || N > 4096) return 0;
+    seg_plan2 pl;
+    if (!make_seg_plan(m, B, N, &pl)) return 0;
+    return pl.total;
+}
+
+extern "C" int svnet_model_forward_seg(const svnet_model* m, const float* x, const float* label_onehot, int B, int N, float* logits,
+                                       void* workspace, size_t workspace_bytes, void* stream)
+{
+    SV_REQUIRE(m && x && label_onehot && logits, "svnet_model_forward_seg: null pointer");
+    SV_REQUIRE(m->pseg, "svnet_model_forward_seg: the handle is not a part-segmentation model (svnet_model_forward)");
+    SV_REQUIRE(B >= 0 && N >= 64 && N <= 4096, "svnet_model_forward_seg: N = %d not covered (64..4096)", N);
+    if (B == 0) return SVNET_OK;
+    seg_plan2 pl;
+    SV_REQUIRE(make_seg_plan(m, B, N, &pl), "svnet_model_forward_seg: shape not covered by the tensor-core paths");
+    SV_REQUIRE(workspace && workspace_bytes >= pl.total && !(reinterpret_cast<uintptr_t>(workspace) & 255),
+               "svnet_model_forward_seg: workspace too small (svnet_model_seg_workspace_bytes) or not 256-byte aligned");
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    const long R = (long)B * N;
+    int rc = run_trunk(m, x, B, N, ws, pl.t, stream);
+    if (rc != SVNET_OK) return rc;
+    float* s_cat = reinterpret_cast<float*>(ws + pl.t.s_cat);
+    float* v_cat = reinterpret_cast<float*>(ws + pl.t.v_cat);
+    float* gate = reinterpret_cast<float*>(ws + pl.t.gate);
+    const int lds = pl.t.Cs_cat, xs = pl.t.Cv_cat, ldv = 3 * pl.t.Cv_cat, Kp = lds + 3 * xs, Kc = m->Kc;
+    const int C5s = m->C5s, C5v = m->C5v, C6s = m->C6s, C6v = m->C6v, C3 = C5s + 3 * C5v;
+    svnet_view cat = {};
+    cat.s = s_cat; cat.lds = lds; cat.Cs = lds; cat.v = v_cat; cat.ldv = ldv; cat.xs = xs; cat.Cv = xs;
+    // conv8's per-point sign words: svfuse1(s_cat, v_cat) against beta8[Kc:] (the float table is never written)
+    uint32_t* bits8 = reinterpret_cast<uint32_t*>(ws + pl.bits8);
+    uint32_t* mask8 = reinterpret_cast<uint32_t*>(ws + pl.mask8);
+    int32_t* nvalid8 = reinterpret_cast<int32_t*>(ws + pl.nvalid8);
+    rc = svnet_rows_prep(&cat, R, m->f1_Wz, m->f1_zs, nullptr, m->c8.beta + Kc, nullptr, 0, nullptr, bits8, mask8, nvalid8, stream);
+    if (rc != SVNET_OK) return rc;
+    // conv5 per point: scalar output only pooled (max) -> glob[:, :C5s]; vector output v5
+    const svnet_model::Block& c5 = m->conv[4];
+    float* glob = reinterpret_cast<float*>(ws + pl.glob);
+    float* v5 = reinterpret_cast<float*>(ws + pl.v5);
+    uint32_t* bits5 = reinterpret_cast<uint32_t*>(ws + pl.bits5);
+    uint32_t* mask5 = reinterpret_cast<uint32_t*>(ws + pl.mask5);
+    int32_t* nvalid5 = reinterpret_cast<int32_t*>(ws + pl.nvalid5);
+    rc = svnet_rows_prep(&cat, R, c5.Wz, c5.zscale, nullptr, c5.beta, nullptr, 0, nullptr, bits5, mask5, nvalid5, stream);
+    if (rc != SVNET_OK) return rc;
+    if (pl.blp_bytes) {
+        rc = svnet_binlinear_pool_ws(bits5, mask5, R, Kp, c5.W1b, C5s, c5.scale1, c5.bn1_a, c5.bn1_c, N, glob, nullptr, Kc, ws + pl.blp,
+                                     pl.blp_bytes, stream);
+        if (rc != SVNET_OK) return rc;
+    } else {
+        float* s5 = reinterpret_cast<float*>(ws + pl.s5);
+        rc = svnet_binlinear_rows_ws(bits5, mask5, nvalid5, R, Kp, c5.W1b, C5s, c5.scale1, nullptr, c5.bn1_a, c5.bn1_c, SVNET_ACT_LEAKY, nullptr,
+                                     1, s5, C5s, nullptr, pl.bl_bytes ? ws + pl.blp : nullptr, pl.bl_bytes, stream);
+        if (rc != SVNET_OK) return rc;
+        rc = svnet_pool_rows(s5, C5s, C5s, B, N, glob, nullptr, Kc, stream);
+        if (rc != SVNET_OK) return rc;
+    }
+    rc = svnet_gate_rows(s_cat, lds, lds, B, N, c5.G1, c5.G2, c5.H, c5.Cvo, gate, stream);
+    if (rc != SVNET_OK) return rc;
+    {
+        svnet_gemm_params q = {};
+        q.A = v_cat; q.lda_g = ldv; q.lda_x = xs; q.G = 3; q.W = c5.W2; q.ldw = c5.Cv; q.M = 3 * R; q.N = C5v; q.K = c5.Cv;
+        q.sign_w = 1; q.colscale = c5.scale2; q.bn_a = c5.bn2_a; q.bn_c = c5.bn2_c; q.vbn = 1; q.gate = gate; q.groups_per_cloud = N;
+        q.C = v5; q.ldc_g = 3 * C5v; q.ldc_x = C5v;
+        rc = svnet_linear_rows_ws(&q, nullptr, 0, stream);
+        if (rc != SVNET_OK) return rc;
+    }
+    // global branch: svpool over the points -> conv6 (one row per cloud) -> svfuse2
+    float* vp = reinterpret_cast<float*>(ws + pl.vp);
+    float* v6 = reinterpret_cast<float*>(ws + pl.v6);
+    rc = svnet_pool_rows(v5, 3 * C5v, 3 * C5v, B, N, nullptr, vp, 3 * C5v, stream);
+    if (rc != SVNET_OK) return rc;
+    const svnet_model::Block& c6 = m->conv[5];
+    svnet_view pv = {};
+    pv.s = glob; pv.lds = Kc; pv.Cs = C5s; pv.v = vp; pv.ldv = 3 * C5v; pv.xs = C5v; pv.Cv = C5v;
+    uint32_t* bits6 = reinterpret_cast<uint32_t*>(ws + pl.bits6);
+    uint32_t* mask6 = reinterpret_cast<uint32_t*>(ws + pl.mask6);
+    int32_t* nvalid6 = reinterpret_cast<int32_t*>(ws + pl.nvalid6);
+    rc = svnet_rows_prep(&pv, B, c6.Wz, c6.zscale, nullptr, c6.beta, nullptr, 0, nullptr, bits6, mask6, nvalid6, stream);
+    if (rc != SVNET_OK) return rc;
+    rc = svnet_binlinear_rows_ws(bits6, mask6, nvalid6, B, C5s + 3 * C5v, c6.W1b, C6s, c6.scale1, nullptr, c6.bn1_a, c6.bn1_c, SVNET_ACT_LEAKY,
+                                 nullptr, 1, glob + C3, Kc, nullptr, nullptr, 0, stream);
+    if (rc != SVNET_OK) return rc;
+    rc = svnet_gate_rows(glob, Kc, C5s, B, 1, c6.G1, c6.G2, c6.H, c6.Cvo, gate, stream);
+    if (rc != SVNET_OK) return rc;
+    {
+        svnet_gemm_params q = {};
+        q.A = vp; q.lda_g = 3 * C5v; q.lda_x = C5v; q.G = 3; q.W = c6.W2; q.ldw = C5v; q.M = 3L * B; q.N = C6v; q.K = C5v;
+        q.sign_w = 1; q.colscale = c6.scale2; q.bn_a = c6.bn2_a; q.bn_c = c6.bn2_c; q.vbn = 1; q.gate = gate; q.groups_per_cloud = 1;
+        q.C = v6; q.ldc_g = 3 * C6v; q.ldc_x = C6v;
+        rc = svnet_linear_rows_ws(&q, nullptr, 0, stream);
+        if (rc != SVNET_OK) return rc;
+    }
+    svnet_view v6v = {};
+    v6v.v = v6; v6v.ldv = 3 * C6v; v6v.xs = C6v; v6v.Cv = C6v;
+    rc = svnet_rows_prep(&v6v, B, m->f2_Wz, m->f2_zs, nullptr, nullptr, glob + C3 + C6s, Kc, nullptr, nullptr, nullptr, nullptr, stream);
+    if (rc != SVNET_OK) return rc;
+    // svfuse3 + max over the points: v2s(v5) reduced on the fly -> glob[:, C5s:C3]
+    svnet_view v5v = {};
+    v5v.v = v5; v5v.ldv = 3 * C5v; v5v.xs = C5v; v5v.Cv = C5v;
+    rc = svnet_svfuse_pool(&v5v, B, N, m->f3_Wz, m->f3_zs, glob + C5s, nullptr, Kc, ws + pl.fuse, pl.fuse_bytes, stream);
+    if (rc != SVNET_OK) return rc;
+    // conv7: the one-hot object label -> 64 channels (fp Conv1d + BN + LeakyReLU)
+    {
+        svnet_gemm_params q = {};
+        q.A = label_onehot; q.lda_g = 16; q.lda_x = 0; q.G = 1; q.W = m->c7_W; q.ldw = 16; q.M = B; q.N = 64; q.K = 16;
+        q.bn_a = m->c7_a; q.bn_c = m->c7_c; q.act = SVNET_ACT_LEAKY; q.C = glob + C3 + C6s + 3 * C6v; q.ldc_g = Kc; q.ldc_x = 0; q.groups_per_cloud = 1;
+        rc = svnet_linear_rows_ws(&q, nullptr, 0, stream);
+        if (rc != SVNET_OK) return rc;
+    }
+    // segmentation head
+    svnet_seg_head_params h = seg_head_params(m, B, N);
+    h.glob = glob; h.bits8 = bits8; h.mask8 = mask8; h.nvalid8 = nvalid8; h.logits = logits;
+    return svnet_seg_head_fwd(&h, ws + pl.head, pl.head_bytes, stream);
 }

@@ -1,6 +1,7 @@
 """The whole-model C entry (include/svnet_b200.h: svnet_model_create / _forward / _destroy) behind a Python callable --
 what a C or C++ host would do with the library, spelled out: build the handle from a checkpoint's tensors once, then
-`forward` with caller-owned scratch.  Covered: SV_DGCNN_CLS, binary (k = 20 / 40) or full precision (k = 20), 64 <= N <= 4096.
+`forward` with caller-owned scratch.  Covered: SV_DGCNN_CLS, binary (k = 20 / 40) or full precision (k = 20), and the binary
+SV_DGCNN_PSEG (`native(batch, label_one_hot)` -> (B, parts, N)); 64 <= N <= 4096.
 
     native = svnet_b200.NativeModel("SV_DGCNN_CLS", checkpoint["state_dict"], k=20, binary=True, num_class=40)
     logits = native(batch)                     # (B, 3, N) float32 CUDA -> (B, num_class); bit-identical to the nn.Module
@@ -19,13 +20,27 @@ class NativeModel:
         with torch.cuda.device(dev):
             sd = {n: t.to(dev) for n, t in state_dict.items() if torch.is_tensor(t) and t.dtype == torch.float32}
             self._h = nv.model_create(kind, k, binary, num_class, sd)
-        self.device, self.num_class = dev, num_class
+        self.device, self.num_class, self.kind = dev, num_class, kind
         self._ws = {}
 
-    def __call__(self, x):
+    def __call__(self, x, label=None):
         if not x.is_cuda:
             raise RuntimeError("NativeModel needs a CUDA tensor (there is no CPU path)")
         B, _, N = x.shape
+        if self.kind == "SV_DGCNN_PSEG":
+            if label is None:
+                raise TypeError("SV_DGCNN_PSEG needs the one-hot object label (B, 16)")
+            with torch.cuda.device(x.device):
+                key = (B, N)
+                if key not in self._ws:
+                    nbytes = nv.model_seg_workspace_bytes(self._h, B, N)
+                    if nbytes == 0:
+                        raise ValueError("shape (B=%d, N=%d) is not covered by svnet_model_forward_seg (64 <= N <= 4096)" % (B, N))
+                    self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                logits = torch.empty((B, self.num_class, N), dtype=torch.float32, device=x.device)
+                nv.model_forward_seg(self._h, x.contiguous(), label.reshape(B, -1).contiguous().float(), logits, self._ws[key])
+                nv.LAUNCHES[0] += 60
+            return logits
         with torch.cuda.device(x.device):
             key = (B, N)
             if key not in self._ws:

@@ -662,6 +662,30 @@ def test_model_c_entry_equals_module(B, N, k, binary):
     native.close()
 
 
+@pytest.mark.parametrize("B,N,k", [(2, 2048, 40), (3, 320, 20)])
+def test_model_c_entry_partseg_equals_module(B, N, k):
+    """svnet_model_forward_seg: the whole binary SV-DGCNN part-segmentation model behind one C call (csrc/model.cu) against
+    the nn.Module path on the same checkpoint tensors: bit-identical per-point logits (B, parts, N)."""
+    import svnet_b200 as sv
+    from svnet_b200.synthetic import one_hot_labels
+    net = quiet(sv.SV_DGCNN_PSEG, make_args(k=k, binary=True), 50)
+    sd = synthetic_state_dict(net.state_dict(), seed=1004)
+    net.load_state_dict(sd)
+    net = net.to(DEV).eval()
+    x = synthetic_clouds(B, N, 1004).to(DEV)
+    l = one_hot_labels(B).to(DEV)
+    native = sv.NativeModel("SV_DGCNN_PSEG", sd, k=k, binary=True, num_class=50, device=DEV)
+    with torch.no_grad():
+        y_mod = net(x, l)
+        y_c = native(x, l)
+    assert tuple(y_c.shape) == (B, 50, N)
+    assert torch.equal(y_c, y_mod)
+    with pytest.raises(RuntimeError):
+        nv_native = sv.NativeModel("SV_DGCNN_CLS", {n: t for n, t in sd.items()}, k=k, binary=True, num_class=50, device=DEV)   # wrong kind for these tensors
+        del nv_native
+    native.close()
+
+
 @pytest.mark.parametrize("B,N,k", [(2, 2048, 40), (3, 200, 12)])
 def test_seg_head_call_equals_layerwise(B, N, k):
     """svnet_seg_head_fwd (conv8 .. conv11 + the (B, parts, N) layout as one C-ABI call, csrc/seg_head.cu) against the

@@ -1,3 +1,1 @@
-python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/t_multi.log 2>&1; tail -1 gpurun_out/t_multi.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2i_bench_n2.json 2> gpurun_out/bench_n2.err; echo rc=$?; python -c "
-import json;d=json.loads(open('gpurun_out/r2i_bench_n2.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value'],d['n_gpus']);e=d['extra'];print(e['cfg3']['clouds_per_s'],e['cfg4']['clouds_per_s'],e['cfg4']['allgather_ms'],[c['clouds_per_s'] for c in e['cfg5']])"
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "model_c_entry" > gpurun_out/t_model.log 2>&1; tail -25 gpurun_out/t_model.log
