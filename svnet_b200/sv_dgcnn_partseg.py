@@ -127,24 +127,35 @@ class SV_DGCNN_PSEG(nn.Module):
         else:
             s5, v5 = self.conv5.forward_rows(s_cat, v_cat, B, N)                  # (R,512), (R,3,168)
             nv.pool_rows(s5, C5s, C5s, B, N, want_max=True, want_mean=False, max_out=sp)
+        C3 = C5s + 3 * C5v
+        xw = self.conv6.out_dims[0] + 3 * self.conv6.out_dims[1]                 # width of svfuse2's output (520)
+        glob = torch.empty((B, C3 + xw + 64), dtype=torch.float32, device=dev)
+        # svfuse3 + max over points (sv_dgcnn_partseg.py:110-111) without the (R, 1016) table: the scalar half is the
+        # max of s5 that conv6's input already needed (sp), v2s(v5) is reduced on the fly (svnet_svfuse_pool).  It and
+        # conv7 (the label branch) run on the side stream next to pool -> conv6 -> svfuse2, whose one-row-per-cloud
+        # kernels leave the GPU almost idle; the two sides write disjoint columns of glob.
+        aux2 = aux_stream(dev) if (fuse3 and record is None) else None
+        cur = torch.cuda.current_stream()
+        if aux2 is not None:
+            aux2.wait_stream(cur)
+        with torch.cuda.stream(aux2 if aux2 is not None else cur):
+            if fuse3:
+                Wz3, zs3 = self.svfuse3.v2s.wz()
+                nv.svfuse_pool(v5, B, N, Wz3, zs3, glob[:, C5s:], None, glob.shape[1])
+            lab = dense_rows(self.conv7[0].weight, l.reshape(B, -1).contiguous().float(), bn=self.conv7.bn_folded(),
+                             act=nv.ACT_LEAKY)
+            glob[:, C3 + xw:].copy_(lab)
         nv.pool_rows(v5, 3 * C5v, 3 * C5v, B, N, want_max=False, want_mean=True, mean_out=vp)
         s6, v6 = self.conv6.forward_rows(sp, vp, B, 1)
         x_pool, _ = self.svfuse2.forward_rows(s6, v6)                             # (B, 520)
-        # svfuse3 + max over points (sv_dgcnn_partseg.py:110-111) without the (R, 1016) table: the scalar half is the
-        # max of s5 that conv6's input already needed (sp), v2s(v5) is reduced on the fly (svnet_svfuse_pool)
-        C3 = C5s + 3 * C5v
-        glob = torch.empty((B, C3 + x_pool.shape[1] + 64), dtype=torch.float32, device=dev)
         if fuse3:
             glob[:, :C5s].copy_(sp)
-            Wz3, zs3 = self.svfuse3.v2s.wz()
-            nv.svfuse_pool(v5, B, N, Wz3, zs3, glob[:, C5s:], None, glob.shape[1])
         else:
             f3, _ = self.svfuse3.forward_rows(s5, v5)                             # (R, 1016)
             nv.pool_rows(f3, C3, C3, B, N, want_max=True, max_out=glob, ldo=glob.shape[1])
-        glob[:, C3:C3 + x_pool.shape[1]].copy_(x_pool)
-        lab = dense_rows(self.conv7[0].weight, l.reshape(B, -1).contiguous().float(), bn=self.conv7.bn_folded(),
-                         act=nv.ACT_LEAKY)
-        glob[:, C3 + x_pool.shape[1]:].copy_(lab)
+        glob[:, C3:C3 + xw].copy_(x_pool)
+        if aux2 is not None:
+            cur.wait_stream(aux2)
         # segmentation head on rows; glob is constant per cloud
         if lean_fine:
             if aux is not None:
