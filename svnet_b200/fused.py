@@ -161,12 +161,17 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
         table = torch.empty((R, 3, 2 * Cvo), dtype=torch.float32, device=dev)
         args = (v_in, v_in.stride(0), v_in.stride(1), 3, 3 * R, Cv, Wpq, 2 * Cvo, table, 6 * Cvo, 2 * Cvo)
         kw = dict(sign_w=blk.linear2.bw, colscale=spq)
+    # full-precision layers: the Ya | Yb table (the s part of linear1) does not depend on the graph either
+    Yab = Wab = None
+    if not blk.binary:
+        Wab = blk.yab_only_weight() if use_fp_tc else blk.yab_weight()[0]
+        Yab = torch.empty((R, 2 * Cout), dtype=torch.float32, device=dev)
     if side is not None:
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            nv.linear_rows(*args, **kw)
-    else:
+    with torch.cuda.stream(side if side is not None else cur):
         nv.linear_rows(*args, **kw)
+        if Yab is not None:
+            nv.linear_rows(s_in, s_in.stride(0), 0, 1, R, Cs, Wab, 2 * Cout, Yab, 2 * Cout, 0)
     if idx32 is None:
         idx32, _ = nv.knn(view, B, N, k)
     G1, G2 = blk.gate_weights()
@@ -196,16 +201,11 @@ def sv_edge_layer(s_in, v_in, B, N, k, blk, s_out, v_out, idx32=None, taps=None)
             keep += [W1tc]
     elif use_fp_tc:
         # full-precision linear1: the q part on the tensor cores (three bf16 weight planes), the s part from Ya | Yb
-        Wab = blk.yab_only_weight()
-        Yab = torch.empty((R, 2 * Cout), dtype=torch.float32, device=dev)
-        nv.linear_rows(s_in, s_in.stride(0), 0, 1, R, Cs, Wab, 2 * Cout, Yab, 2 * Cout, 0)
         W1f = blk.edge_fp_tc_weight(fp_tc_bytes)
         p.Yab, p.W1tc, p.tab4 = Yab.data_ptr(), W1f.data_ptr(), table.data_ptr()
         keep += [Yab, W1f]
     else:
-        Wab, Wq_t = blk.yab_weight()
-        Yab = torch.empty((R, 2 * Cout), dtype=torch.float32, device=dev)
-        nv.linear_rows(s_in, s_in.stride(0), 0, 1, R, Cs, Wab, 2 * Cout, Yab, 2 * Cout, 0)
+        Wq_t = blk.yab_weight()[1]
         p.Yab, p.W1q_t = Yab.data_ptr(), Wq_t.data_ptr()
         keep += [Yab, Wq_t]
     p.bn1_a, p.bn1_c, p.Cout = a1.data_ptr(), c1.data_ptr(), Cout
