@@ -872,6 +872,39 @@ def test_two_stream_halves_equal_single_stream(model):
     assert y2.shape == y1.shape and torch.equal(y2, y1)
 
 
+@pytest.mark.parametrize("model,binary", [("cls", True), ("cls", False), ("pseg", True)])
+def test_auxiliary_streams_do_not_change_bits(model, binary):
+    """Round 2 runs independent chains of a forward on auxiliary streams (per-point tables / Ya|Yb next to the kNN kernels,
+    conv5's scalar branch next to gate -> vector linear, the part-seg head's early sign words and label branch): with the
+    side streams switched off -- everything on one stream, the seg head's sign words computed inside svnet_seg_head_fwd --
+    the outputs must be the same bits, repeatedly."""
+    import svnet_b200 as sv
+    from svnet_b200 import fused
+    from svnet_b200.synthetic import one_hot_labels
+    B, N, k = (4, 1024, 20) if model == "cls" else (2, 2048, 40)
+    x = synthetic_clouds(B, N, 33).to(DEV)
+    if model == "pseg":
+        net = quiet(sv.SV_DGCNN_PSEG, make_args(k=k, binary=True), 50)
+        extra = (one_hot_labels(B).to(DEV),)
+    else:
+        net = quiet(sv.SV_DGCNN_CLS, make_args(k=k, binary=binary), 40)
+        extra = ()
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=9))
+    net = net.to(DEV).eval()
+    keep = fused.SIDE_STREAM
+    try:
+        with torch.no_grad():
+            fused.SIDE_STREAM = True
+            ys = [net(x, *extra).clone() for _ in range(3)]
+            fused.SIDE_STREAM = False
+            y1 = net(x, *extra)
+    finally:
+        fused.SIDE_STREAM = keep
+    torch.cuda.synchronize()
+    for y in ys:
+        assert torch.equal(y, y1)
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor-core edge kernel (csrc/edge_tc.cu) against the XNOR/popcount kernel and against itself
 # ------------------------------------------------------------------------------------------------
