@@ -11,6 +11,22 @@ namespace {
 
 constexpr int NT = 512;
 
+// bulk copy global -> shared behind an mbarrier (the binary layers' sign planes are prefetched at kernel start)
+__device__ __forceinline__ uint32_t hsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hbar_wait(uint64_t* b, uint32_t parity)      // bounded: a protocol mistake traps
+{
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+            : "=r"(done)
+            : "r"(hsmem_u32(b)), "r"(parity)
+            : "memory");
+        if (++spins > (1 << 24)) __trap();
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll
@@ -18,7 +34,10 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-__global__ void __launch_bounds__(NT) head_kernel(svnet_head_params p)
+// prefetch != 0: the sign planes W1b of all binary layers (up to ~150 KB) are fetched into shared memory by cp.async.bulk
+// while the input row is loaded and sign-packed (round 2: the popcount loop's dependent-latency weight loads were 40 % of
+// the kernel's 31 us, the other threads' barrier waits another 30 %)
+__global__ void __launch_bounds__(NT) head_kernel(svnet_head_params p, int prefetch)
 {
     extern __shared__ __align__(16) float sm[];
     // two ping-pong activation buffers + sign words
@@ -31,10 +50,48 @@ __global__ void __launch_bounds__(NT) head_kernel(svnet_head_params p)
     uint32_t* mask = bits + maxw;
     float* wst = reinterpret_cast<float*>(mask + maxw);      // staged weights of a small fp layer, row stride K + 1
     __shared__ int nvalid_s;
+    __shared__ __align__(8) uint64_t wbar;
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // prefetched sign planes live behind the staging area of the fp layer
+    size_t wst_floats = 0;
+    {
+        int Kl = p.K0;
+        for (int l = 0; l < p.nlayers; ++l) {
+            const svnet_head_layer& L = p.layer[l];
+            if (!L.W1b && (long)Kl * L.Cout <= 32768) wst_floats = max(wst_floats, (size_t)L.Cout * (Kl + 1));
+            Kl = L.Cout;
+        }
+    }
+    uint32_t* wpre = reinterpret_cast<uint32_t*>(wst + ((wst_floats + 3) & ~(size_t)3));
+    if (prefetch && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(hsmem_u32(&wbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        uint32_t total = 0;
+        int Kl = p.K0;
+        for (int l = 0; l < p.nlayers; ++l) {
+            if (p.layer[l].W1b) total += (uint32_t)((Kl + 31) / 32) * p.layer[l].Cout * 4u;
+            Kl = p.layer[l].Cout;
+        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(hsmem_u32(&wbar)), "r"(total) : "memory");
+        uint32_t off = 0;
+        Kl = p.K0;
+        for (int l = 0; l < p.nlayers; ++l) {
+            if (p.layer[l].W1b) {
+                const uint32_t bytes = (uint32_t)((Kl + 31) / 32) * p.layer[l].Cout * 4u;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                                 hsmem_u32(wpre) + off),
+                             "l"(p.layer[l].W1b), "r"(bytes), "r"(hsmem_u32(&wbar))
+                             : "memory");
+                off += bytes;
+            }
+            Kl = p.layer[l].Cout;
+        }
+    }
     for (int c = tid; c < p.K0; c += NT) act0[c] = p.x[(long)b * p.ldx + c];
     __syncthreads();
+    uint32_t pre_off = 0;         // words of the prefetch area consumed by earlier binary layers
+    bool pre_ready = false;
     float* cur = act0;
     float* nxt = act1;
     int K = p.K0;
@@ -55,10 +112,21 @@ __global__ void __launch_bounds__(NT) head_kernel(svnet_head_params p)
             }
             __syncthreads();
             const int nvalid = nvalid_s;
+            if (prefetch && !pre_ready) {
+                hbar_wait(&wbar, 0);
+                pre_ready = true;
+            }
+            const uint32_t* wsm = wpre + pre_off;
+            pre_off += (uint32_t)Kw * Cout;
             for (int o = tid; o < Cout; o += NT) {
                 int mism = 0;
+                if (prefetch) {
+#pragma unroll 8
+                    for (int w = 0; w < Kw; ++w) mism += __popc((bits[w] ^ wsm[(size_t)w * Cout + o]) & mask[w]);
+                } else {
 #pragma unroll 32
-                for (int w = 0; w < Kw; ++w) mism += __popc((bits[w] ^ __ldg(L.W1b + (long)w * Cout + o)) & mask[w]);
+                    for (int w = 0; w < Kw; ++w) mism += __popc((bits[w] ^ __ldg(L.W1b + (long)w * Cout + o)) & mask[w]);
+                }
                 float y = __fmul_rn((float)(nvalid - 2 * mism), L.scale ? L.scale[o] : 1.0f);
                 if (L.bias) y = __fadd_rn(y, L.bias[o]);
                 if (L.bn_a) y = __fadd_rn(__fmul_rn(y, L.bn_a[o]), L.bn_c[o]);
@@ -130,10 +198,27 @@ extern "C" int svnet_head_fwd(const svnet_head_params* p, void* stream)
     }
     SV_REQUIRE(p->ldx >= p->K0 && p->ldo >= K, "svnet_head_fwd: ldx/ldo too small");
     if (p->B == 0) return SVNET_OK;
-    const size_t smem = sizeof(float) * ((size_t)2 * maxc + 2 * ((maxc + 31) / 32) + wstage);
+    size_t smem = sizeof(float) * ((size_t)2 * maxc + 2 * ((maxc + 31) / 32) + ((wstage + 3) & ~(size_t)3));
     SV_REQUIRE(smem <= 200 * 1024, "svnet_head_fwd: layer too wide");
+    // sign planes of the binary layers prefetched into shared memory when they fit and are 16-byte granular
+    size_t pre = 0;
+    bool pre_ok = true;
+    {
+        int Kl = p->K0;
+        for (int l = 0; l < p->nlayers; ++l) {
+            const svnet_head_layer& L = p->layer[l];
+            if (L.W1b) {
+                const size_t bytes = (size_t)((Kl + 31) / 32) * L.Cout * 4;
+                pre += bytes;
+                if ((bytes & 15) || (reinterpret_cast<uintptr_t>(L.W1b) & 15)) pre_ok = false;
+            }
+            Kl = L.Cout;
+        }
+    }
+    const int prefetch = (pre > 0 && pre_ok && (smem & 15) == 0 && smem + pre <= 220 * 1024) ? 1 : 0;
+    if (prefetch) smem += pre;
     if (smem > 48 * 1024) SV_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_kernel<<<p->B, NT, smem, sv_stream(stream)>>>(*p);
+    head_kernel<<<p->B, NT, smem, sv_stream(stream)>>>(*p, prefetch);
     SV_CHECK_LAUNCH("svnet_head_fwd");
     return SVNET_OK;
 }
