@@ -446,6 +446,23 @@ def main():
             extra["cfg5"] = [extra_config(sv, "SV_DGCNN_CLS", dict(k=20, binary=True), 40, 1005, gb, n, world, rank, dev, timed,
                                           gather=False, steps=3)
                              for gb, n in ((1024, 1024), (256, 2048), (64, 4096))]
+            # the whole-model C entry (svnet_model_create / _forward, csrc/model.cu) on the headline workload: what a host
+            # without Python model code gets -- one stream, eager, and replayed from a CUDA graph (same bits as `value`'s path)
+            native = sv.NativeModel("SV_DGCNN_CLS", net.state_dict(), k=K_NN, binary=True, num_class=N_CLASS, device=dev)
+            for _ in range(3):
+                native(x_dev)
+            ms_c = timed(lambda: native(x_dev), 10)
+            gc_ = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gc_):
+                y_c = native(x_dev)
+            ms_cg = timed(gc_.replay, 10)
+            same = bool(torch.equal(y_c, net(x_dev)))
+            extra["c_entry"] = {"call": "svnet_model_forward (one stream), B=%d/GPU" % x_dev.shape[0],
+                                "eager_ms_per_step": ms_c, "eager_clouds_per_s": world * x_dev.shape[0] / (ms_c * 1e-3),
+                                "graph_ms_per_step": ms_cg, "graph_clouds_per_s": world * x_dev.shape[0] / (ms_cg * 1e-3),
+                                "logits_identical_to_module": same}
+            del gc_, native
         # ---- the unmodified reference modules on the same GPU (stock PyTorch eager, fp32, TF32 off) ----
         dbg("extras done")
         eager_ref = None
