@@ -447,7 +447,8 @@ def main():
                                           gather=False, steps=3)
                              for gb, n in ((1024, 1024), (256, 2048), (64, 4096))]
             # the whole-model C entry (svnet_model_create / _forward, csrc/model.cu) on the headline workload: what a host
-            # without Python model code gets -- one stream, eager, and replayed from a CUDA graph (same bits as `value`'s path)
+            # without Python model code gets -- eager (the call forks onto the handle's own streams and joins) and replayed from a
+            # CUDA graph (same bits as `value`'s path)
             native = sv.NativeModel("SV_DGCNN_CLS", net.state_dict(), k=K_NN, binary=True, num_class=N_CLASS, device=dev)
             for _ in range(3):
                 native(x_dev)
@@ -458,7 +459,7 @@ def main():
                 y_c = native(x_dev)
             ms_cg = timed(gc_.replay, 10)
             same = bool(torch.equal(y_c, net(x_dev)))
-            extra["c_entry"] = {"call": "svnet_model_forward (one stream), B=%d/GPU" % x_dev.shape[0],
+            extra["c_entry"] = {"call": "svnet_model_forward (two sub-batch streams + auxiliary streams inside the call), B=%d/GPU" % x_dev.shape[0],
                                 "eager_ms_per_step": ms_c, "eager_clouds_per_s": world * x_dev.shape[0] / (ms_c * 1e-3),
                                 "graph_ms_per_step": ms_cg, "graph_clouds_per_s": world * x_dev.shape[0] / (ms_cg * 1e-3),
                                 "logits_identical_to_module": same}

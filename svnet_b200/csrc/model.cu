@@ -2,8 +2,11 @@
 // (reference models/sv_dgcnn_cls.py:22-82) from a checkpoint's state_dict tensors to logits, without Python in the loop.
 //   create  : copies the tensors it needs, packs them once (sign bit-planes, folded BatchNorm affines, fp8 operand bytes of
 //             the tensor-core edge kernel, per-point table weights) -- the handle owns everything it uses afterwards;
-//   forward : sequences this library's own entry points on ONE stream with caller-owned scratch
-//             (svnet_model_workspace_bytes): no allocation, no synchronisation -- capturable into a CUDA graph;
+//   forward : sequences this library's own entry points with caller-owned scratch (svnet_model_workspace_bytes): no
+//             allocation, no host synchronisation -- capturable into a CUDA graph.  Launch structure as the Python path's: a
+//             batch of >= 32 768 points runs as two sub-batches on the handle's two streams, and inside each the chains that
+//             do not depend on the kNN graph or the gate (per-point tables, conv5's scalar branch) run on an auxiliary
+//             stream; everything forks from and joins the caller's stream through events (SVNET_MODEL_ONE_STREAM=1: no split);
 //             layer 1      svnet_knn_ws -> svnet_gate_xyz -> svnet_edge_xyz_fwd                    (sv_dgcnn_cls.py:48-53)
 //             layers 2..4  svnet_linear_rows (float4 table) -> svnet_knn_ws -> svnet_gate_edge -> svnet_svblock_edge_fwd (:55-65)
 //             conv5        svnet_gate_rows -> svnet_rows_prep -> svnet_binlinear_pool_ws -> svnet_linear_rows (vector branch) (:67-68)
@@ -15,6 +18,7 @@
 // the binary model's; the full-precision model takes svnet_linear_rows_ws where the binary one takes the sign-word kernels
 // (sv_dgcnn_cls.py in this package shows both).
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -43,6 +47,11 @@ struct svnet_model {
     struct SegConv { float *beta, *scale, *bn_a, *bn_c; uint32_t *bits, *bits_c; int Cin, Cout; } c8, c9, c10;
     float* c11_W;
     int C6s, C6v, Kc;
+    // launch structure of svnet_model_forward: two sub-batch streams, each with an auxiliary stream for the chains that do
+    // not depend on the kNN graph (per-point tables, conv5's scalar branch); events for the forks / joins
+    cudaStream_t sub[2], aux[2];
+    cudaEvent_t ev[10];
+    bool streams_ok;
     int Cf, C5s, C5v, h1, h2;
 };
 
@@ -229,6 +238,10 @@ bool make_fwd_plan(const svnet_model* m, int B, int N, fwd_plan* pl)
 extern "C" void svnet_model_destroy(svnet_model* m)
 {
     if (!m) return;
+    if (m->streams_ok) {
+        for (int i = 0; i < 2; ++i) { cudaStreamDestroy(m->sub[i]); cudaStreamDestroy(m->aux[i]); }
+        for (int i = 0; i < 10; ++i) cudaEventDestroy(m->ev[i]);
+    }
     for (void* p : m->allocs) cudaFree(p);
     delete m;
 }
@@ -420,13 +433,36 @@ extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_c
         svnet_model_destroy(m);
         return SVNET_ERR_ARG;
     }
+    m->streams_ok = true;
+    for (int i = 0; i < 2; ++i) {
+        if (cudaStreamCreateWithFlags(&m->sub[i], cudaStreamNonBlocking) != cudaSuccess) m->streams_ok = false;
+        if (cudaStreamCreateWithFlags(&m->aux[i], cudaStreamNonBlocking) != cudaSuccess) m->streams_ok = false;
+    }
+    for (int i = 0; i < 10; ++i)
+        if (cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming) != cudaSuccess) m->streams_ok = false;
     *out = m;
     return SVNET_OK;
 }
 
+namespace {
+// the two sub-batches of a large enough batch run on the handle's two streams (clouds are independent in eval mode, so the
+// bits do not depend on the split); SVNET_MODEL_ONE_STREAM=1 keeps everything on the caller's stream
+bool split_batch(const svnet_model* m, int B, int N)
+{
+    static const bool off = [] { const char* e = getenv("SVNET_MODEL_ONE_STREAM"); return e && e[0] == '1'; }();
+    return !off && m->streams_ok && B >= 2 && (long)B * N >= 2L * 16384;
+}
+
+}  // namespace
+
 extern "C" size_t svnet_model_workspace_bytes(const svnet_model* m, int B, int N)
 {
     if (!m || m->pseg || B < 1 || N < 64 || N > 4096) return 0;
+    if (split_batch(m, B, N)) {
+        fwd_plan p0, p1;
+        if (!make_fwd_plan(m, B / 2, N, &p0) || !make_fwd_plan(m, B - B / 2, N, &p1)) return 0;
+        return p0.total + p1.total;
+    }
     fwd_plan pl;
     if (!make_fwd_plan(m, B, N, &pl)) return 0;
     return pl.total;
@@ -435,7 +471,8 @@ extern "C" size_t svnet_model_workspace_bytes(const svnet_model* m, int B, int N
 namespace {
 
 // the four edge layers (sv_dgcnn_cls.py:47-65, sv_dgcnn_partseg.py:81-103): fills the svcat table (s_cat, v_cat) in `ws`
-int run_trunk(const svnet_model* m, const float* x, int B, int N, unsigned char* ws, const fwd_plan& pl, void* stream)
+int run_trunk(const svnet_model* m, const float* x, int B, int N, unsigned char* ws, const fwd_plan& pl, void* stream,
+              cudaStream_t aux = nullptr, cudaEvent_t eF = nullptr, cudaEvent_t eJ = nullptr)
 {
     cudaStream_t st = sv_stream(stream);
     const long R = (long)B * N;
@@ -478,26 +515,36 @@ int run_trunk(const svnet_model* m, const float* x, int B, int N, unsigned char*
             g.W = b.Wt; g.ldw = b.Cv; g.M = 3 * R; g.N = b.NC; g.K = b.Cv;
             g.sign_w = m->binary; g.colscale = m->binary ? b.cst : nullptr; g.C = table; g.ldc_g = 4 * b.NC; g.ldc_x = 0; g.c4 = 1;
             g.groups_per_cloud = 1;
-            rc = svnet_linear_rows_ws(&g, nullptr, 0, stream);
+            // the tables do not depend on the graph: with an auxiliary stream they run next to the kNN kernels
+            void* tst = stream;
+            if (aux) {
+                SV_CUDA(cudaEventRecord(eF, st));
+                SV_CUDA(cudaStreamWaitEvent(aux, eF, 0));
+                tst = aux;
+            }
+            rc = svnet_linear_rows_ws(&g, nullptr, 0, tst);
             if (rc != SVNET_OK) return rc;
+            float* yab = nullptr;
+            if (!m->binary) {
+                // Ya | Yb = s [W1a; W1b]^T per point (the s part of linear1)
+                yab = reinterpret_cast<float*>(ws + pl.yab);
+                svnet_gemm_params y = {};
+                y.A = prev.s; y.lda_g = prev.lds; y.lda_x = 0; y.G = 1;
+                y.W = b.Wab; y.ldw = b.Cs; y.M = R; y.N = 2 * b.Cout; y.K = b.Cs;
+                y.C = yab; y.ldc_g = 2 * b.Cout; y.ldc_x = 0; y.groups_per_cloud = 1;
+                const size_t yb = svnet_linear_workspace_bytes(&y);
+                rc = svnet_linear_rows_ws(&y, yb ? ws + pl.lin : nullptr, yb, tst);
+                if (rc != SVNET_OK) return rc;
+            }
+            if (aux) SV_CUDA(cudaEventRecord(eJ, aux));
             rc = svnet_knn_ws(&prev, B, N, k, idx, nullptr, knn_ws, pl.knn_bytes, stream);
             if (rc != SVNET_OK) return rc;
             rc = svnet_gate_edge(&prev, idx, B, N, k, b.G1, b.G2, b.H, b.Cvo, gate, stream);
             if (rc != SVNET_OK) return rc;
             svnet_edge_params p = {};
             p.in = prev; p.idx = idx; p.B = B; p.N = N; p.k = k; p.binary = m->binary;
-            if (!m->binary) {
-                // Ya | Yb = s [W1a; W1b]^T per point (the s part of linear1)
-                float* yab = reinterpret_cast<float*>(ws + pl.yab);
-                svnet_gemm_params y = {};
-                y.A = prev.s; y.lda_g = prev.lds; y.lda_x = 0; y.G = 1;
-                y.W = b.Wab; y.ldw = b.Cs; y.M = R; y.N = 2 * b.Cout; y.K = b.Cs;
-                y.C = yab; y.ldc_g = 2 * b.Cout; y.ldc_x = 0; y.groups_per_cloud = 1;
-                const size_t yb = svnet_linear_workspace_bytes(&y);
-                rc = svnet_linear_rows_ws(&y, yb ? ws + pl.lin : nullptr, yb, stream);
-                if (rc != SVNET_OK) return rc;
-                p.Yab = yab;
-            }
+            p.Yab = yab;
+            if (aux) SV_CUDA(cudaStreamWaitEvent(st, eJ, 0));
             p.Wz = b.Wz; p.zscale = b.zscale; p.beta = b.beta; p.W1b = b.W1b; p.scale1 = b.scale1;
             p.bn1_a = b.bn1_a; p.bn1_c = b.bn1_c; p.Cout = b.Cout;
             p.bn2_a = b.bn2_a; p.bn2_c = b.bn2_c; p.gate = gate; p.Cvo = b.Cvo; p.out = out;
@@ -514,26 +561,28 @@ int run_trunk(const svnet_model* m, const float* x, int B, int N, unsigned char*
 
 }  // namespace
 
-extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, int N, float* logits, void* workspace,
-                                   size_t workspace_bytes, void* stream)
+namespace {
+
+// one (sub-)batch on stream `stream`; `aux` (optional) takes the chains that do not depend on the kNN graphs / the gate
+int forward_cls_one(const svnet_model* m, const float* x, int B, int N, float* logits, unsigned char* ws, const fwd_plan& pl,
+                    void* stream, cudaStream_t aux, cudaEvent_t eF, cudaEvent_t eJ)
 {
-    SV_REQUIRE(m && x && logits, "svnet_model_forward: null pointer");
-    SV_REQUIRE(!m->pseg, "svnet_model_forward: the handle is a part-segmentation model (svnet_model_forward_seg)");
-    SV_REQUIRE(B >= 0 && N >= 64 && N <= 4096, "svnet_model_forward: N = %d not covered (64..4096)", N);
-    if (B == 0) return SVNET_OK;
-    fwd_plan pl;
-    SV_REQUIRE(make_fwd_plan(m, B, N, &pl), "svnet_model_forward: shape not covered by the tensor-core paths");
-    SV_REQUIRE(workspace && workspace_bytes >= pl.total && !(reinterpret_cast<uintptr_t>(workspace) & 255),
-               "svnet_model_forward: workspace too small (svnet_model_workspace_bytes) or not 256-byte aligned");
-    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    cudaStream_t st = sv_stream(stream);
     const long R = (long)B * N;
     float* s_cat = reinterpret_cast<float*>(ws + pl.s_cat);
     float* v_cat = reinterpret_cast<float*>(ws + pl.v_cat);
     float* gate = reinterpret_cast<float*>(ws + pl.gate);
     const int lds = pl.Cs_cat, xs = pl.Cv_cat, ldv = 3 * pl.Cv_cat;
-    int rc = run_trunk(m, x, B, N, ws, pl, stream);
+    int rc = run_trunk(m, x, B, N, ws, pl, stream, aux, eF, eJ);
     if (rc != SVNET_OK) return rc;
     // ---- conv5 (per point) -> svfuse -> max | mean over the points ----
+    // scalar branch (v2s + linear1 + pooling) on `sst` next to gate -> vector linear on the main stream
+    void* sst = stream;
+    if (aux) {
+        SV_CUDA(cudaEventRecord(eF, st));
+        SV_CUDA(cudaStreamWaitEvent(aux, eF, 0));
+        sst = aux;
+    }
     const svnet_model::Block& c5 = m->conv[4];
     float* v5 = reinterpret_cast<float*>(ws + pl.v5);
     float* g = reinterpret_cast<float*>(ws + pl.g);
@@ -541,39 +590,40 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
     uint32_t* mask = reinterpret_cast<uint32_t*>(ws + pl.mask);
     int32_t* nvalid = reinterpret_cast<int32_t*>(ws + pl.nvalid);
     const int Cf = m->Cf, K5 = pl.Cs_cat + 3 * pl.Cv_cat;
-    rc = svnet_gate_rows(s_cat, lds, pl.Cs_cat, B, N, c5.G1, c5.G2, c5.H, c5.Cvo, gate, stream);
-    if (rc != SVNET_OK) return rc;
     svnet_view cat = {};
     cat.s = s_cat; cat.lds = lds; cat.Cs = pl.Cs_cat; cat.v = v_cat; cat.ldv = ldv; cat.xs = xs; cat.Cv = pl.Cv_cat;
     if (!m->binary) {
         // u = [s | v2s(v)] rows -> dense linear1 + BN + LeakyReLU -> max | mean over the points
         float* u5 = reinterpret_cast<float*>(ws + pl.u5);
         float* s5 = reinterpret_cast<float*>(ws + pl.s5);
-        rc = svnet_rows_prep(&cat, R, c5.Wz, nullptr, nullptr, nullptr, u5, K5, nullptr, nullptr, nullptr, nullptr, stream);
+        rc = svnet_rows_prep(&cat, R, c5.Wz, nullptr, nullptr, nullptr, u5, K5, nullptr, nullptr, nullptr, nullptr, sst);
         if (rc != SVNET_OK) return rc;
         svnet_gemm_params q = {};
         q.A = u5; q.lda_g = K5; q.lda_x = 0; q.G = 1; q.W = c5.W1; q.ldw = K5; q.M = R; q.N = c5.Cout; q.K = K5;
         q.bn_a = c5.bn1_a; q.bn_c = c5.bn1_c; q.act = SVNET_ACT_LEAKY; q.C = s5; q.ldc_g = c5.Cout; q.ldc_x = 0; q.groups_per_cloud = 1;
         const size_t qb = svnet_linear_workspace_bytes(&q);
-        rc = svnet_linear_rows_ws(&q, qb ? ws + pl.lin : nullptr, qb, stream);
+        rc = svnet_linear_rows_ws(&q, qb ? ws + pl.lin : nullptr, qb, sst);
         if (rc != SVNET_OK) return rc;
     } else {
-    rc = svnet_rows_prep(&cat, R, c5.Wz, c5.zscale, nullptr, c5.beta, nullptr, 0, nullptr, bits, mask, nvalid, stream);
+    rc = svnet_rows_prep(&cat, R, c5.Wz, c5.zscale, nullptr, c5.beta, nullptr, 0, nullptr, bits, mask, nvalid, sst);
     if (rc != SVNET_OK) return rc;
     }
     if (!m->binary) {
     } else if (pl.blp_bytes) {
         rc = svnet_binlinear_pool_ws(bits, mask, R, K5, c5.W1b, c5.Cout, c5.scale1, c5.bn1_a, c5.bn1_c, N, g, g + Cf, 2 * Cf,
-                                     ws + pl.blp, pl.blp_bytes, stream);
+                                     ws + pl.blp, pl.blp_bytes, sst);
         if (rc != SVNET_OK) return rc;
     } else {
         float* s5 = reinterpret_cast<float*>(ws + pl.s5);
         rc = svnet_binlinear_rows_ws(bits, mask, nvalid, R, K5, c5.W1b, c5.Cout, c5.scale1, nullptr, c5.bn1_a, c5.bn1_c, SVNET_ACT_LEAKY,
-                                     nullptr, 1, s5, c5.Cout, nullptr, pl.bl_bytes ? ws + pl.blp : nullptr, pl.bl_bytes, stream);
+                                     nullptr, 1, s5, c5.Cout, nullptr, pl.bl_bytes ? ws + pl.blp : nullptr, pl.bl_bytes, sst);
         if (rc != SVNET_OK) return rc;
-        rc = svnet_pool_rows(s5, c5.Cout, c5.Cout, B, N, g, g + Cf, 2 * Cf, stream);
+        rc = svnet_pool_rows(s5, c5.Cout, c5.Cout, B, N, g, g + Cf, 2 * Cf, sst);
         if (rc != SVNET_OK) return rc;
     }
+    if (aux) SV_CUDA(cudaEventRecord(eJ, aux));
+    rc = svnet_gate_rows(s_cat, lds, pl.Cs_cat, B, N, c5.G1, c5.G2, c5.H, c5.Cvo, gate, stream);
+    if (rc != SVNET_OK) return rc;
     {
         svnet_gemm_params q = {};
         q.A = v_cat; q.lda_g = ldv; q.lda_x = xs; q.G = 3;
@@ -584,6 +634,7 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
         rc = svnet_linear_rows_ws(&q, nullptr, 0, stream);
         if (rc != SVNET_OK) return rc;
     }
+    if (aux) SV_CUDA(cudaStreamWaitEvent(st, eJ, 0));
     if (!m->binary) {
         rc = svnet_pool_rows(reinterpret_cast<float*>(ws + pl.s5), c5.Cout, c5.Cout, B, N, g, g + Cf, 2 * Cf, stream);
         if (rc != SVNET_OK) return rc;
@@ -618,6 +669,43 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
     h.layer[2].Cout = m->ncls; h.layer[2].W = m->h3_W; h.layer[2].bias = m->h3_b; h.layer[2].act = SVNET_ACT_NONE;
     h.out = logits; h.ldo = m->ncls;
     return svnet_head_fwd(&h, stream);
+}
+
+}  // namespace
+
+extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, int N, float* logits, void* workspace,
+                                   size_t workspace_bytes, void* stream)
+{
+    SV_REQUIRE(m && x && logits, "svnet_model_forward: null pointer");
+    SV_REQUIRE(!m->pseg, "svnet_model_forward: the handle is a part-segmentation model (svnet_model_forward_seg)");
+    SV_REQUIRE(B >= 0 && N >= 64 && N <= 4096, "svnet_model_forward: N = %d not covered (64..4096)", N);
+    if (B == 0) return SVNET_OK;
+    SV_REQUIRE(workspace && !(reinterpret_cast<uintptr_t>(workspace) & 255), "svnet_model_forward: workspace null or not 256-byte aligned");
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    cudaStream_t st = sv_stream(stream);
+    if (!split_batch(m, B, N)) {
+        fwd_plan pl;
+        SV_REQUIRE(make_fwd_plan(m, B, N, &pl), "svnet_model_forward: shape not covered by the tensor-core paths");
+        SV_REQUIRE(workspace_bytes >= pl.total, "svnet_model_forward: workspace too small (svnet_model_workspace_bytes)");
+        const bool ax = m->streams_ok;
+        return forward_cls_one(m, x, B, N, logits, ws, pl, stream, ax ? m->aux[0] : nullptr, ax ? m->ev[0] : nullptr, ax ? m->ev[1] : nullptr);
+    }
+    const int B0 = B / 2, B1 = B - B0;
+    fwd_plan p0, p1;
+    SV_REQUIRE(make_fwd_plan(m, B0, N, &p0) && make_fwd_plan(m, B1, N, &p1), "svnet_model_forward: shape not covered by the tensor-core paths");
+    SV_REQUIRE(workspace_bytes >= p0.total + p1.total, "svnet_model_forward: workspace too small (svnet_model_workspace_bytes)");
+    SV_CUDA(cudaEventRecord(m->ev[8], st));
+    SV_CUDA(cudaStreamWaitEvent(m->sub[0], m->ev[8], 0));
+    SV_CUDA(cudaStreamWaitEvent(m->sub[1], m->ev[8], 0));
+    int rc = forward_cls_one(m, x, B0, N, logits, ws, p0, m->sub[0], m->aux[0], m->ev[0], m->ev[1]);
+    if (rc != SVNET_OK) return rc;
+    rc = forward_cls_one(m, x + (size_t)B0 * 3 * N, B1, N, logits + (size_t)B0 * m->ncls, ws + p0.total, p1, m->sub[1], m->aux[1], m->ev[2], m->ev[3]);
+    if (rc != SVNET_OK) return rc;
+    SV_CUDA(cudaEventRecord(m->ev[4], m->sub[0]));
+    SV_CUDA(cudaEventRecord(m->ev[5], m->sub[1]));
+    SV_CUDA(cudaStreamWaitEvent(st, m->ev[4], 0));
+    SV_CUDA(cudaStreamWaitEvent(st, m->ev[5], 0));
+    return SVNET_OK;
 }
 
 // ---- part segmentation (sv_dgcnn_partseg.py:80-128) -------------------------------------------------------------------
