@@ -767,25 +767,32 @@ bool make_seg_plan(const svnet_model* m, int B, int N, seg_plan2* pl)
 extern "C" size_t svnet_model_seg_workspace_bytes(const svnet_model* m, int B, int N)
 {
     if (!m || !m->pseg || B < 1 || N < 64 || N > 4096) return 0;
+    if (split_batch(m, B, N)) {
+        seg_plan2 p0, p1;
+        if (!make_seg_plan(m, B / 2, N, &p0) || !make_seg_plan(m, B - B / 2, N, &p1)) return 0;
+        return p0.total + p1.total;
+    }
     seg_plan2 pl;
     if (!make_seg_plan(m, B, N, &pl)) return 0;
     return pl.total;
 }
 
-extern "C" int svnet_model_forward_seg(const svnet_model* m, const float* x, const float* label_onehot, int B, int N, float* logits,
-                                       void* workspace, size_t workspace_bytes, void* stream)
+namespace {
+
+// one (sub-)batch of the part-segmentation model on `stream`; `aux` (optional) takes the chains that do not depend on the
+// gate / the per-cloud branch: conv8's per-point sign words and conv5's scalar branch, then svfuse3's pooling and the label branch
+int forward_seg_one(const svnet_model* m, const float* x, const float* label_onehot, int B, int N, float* logits, unsigned char* ws,
+                    const seg_plan2& pl, void* stream, cudaStream_t aux, cudaEvent_t eF, cudaEvent_t eJ)
 {
-    SV_REQUIRE(m && x && label_onehot && logits, "svnet_model_forward_seg: null pointer");
-    SV_REQUIRE(m->pseg, "svnet_model_forward_seg: the handle is not a part-segmentation model (svnet_model_forward)");
-    SV_REQUIRE(B >= 0 && N >= 64 && N <= 4096, "svnet_model_forward_seg: N = %d not covered (64..4096)", N);
-    if (B == 0) return SVNET_OK;
-    seg_plan2 pl;
-    SV_REQUIRE(make_seg_plan(m, B, N, &pl), "svnet_model_forward_seg: shape not covered by the tensor-core paths");
-    SV_REQUIRE(workspace && workspace_bytes >= pl.total && !(reinterpret_cast<uintptr_t>(workspace) & 255),
-               "svnet_model_forward_seg: workspace too small (svnet_model_seg_workspace_bytes) or not 256-byte aligned");
-    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    cudaStream_t st = sv_stream(stream);
     const long R = (long)B * N;
-    int rc = run_trunk(m, x, B, N, ws, pl.t, stream);
+    int rc = run_trunk(m, x, B, N, ws, pl.t, stream, aux, eF, eJ);
+    void* sst = stream;
+    if (aux) {
+        SV_CUDA(cudaEventRecord(eF, st));
+        SV_CUDA(cudaStreamWaitEvent(aux, eF, 0));
+        sst = aux;
+    }
     if (rc != SVNET_OK) return rc;
     float* s_cat = reinterpret_cast<float*>(ws + pl.t.s_cat);
     float* v_cat = reinterpret_cast<float*>(ws + pl.t.v_cat);
@@ -798,7 +805,7 @@ extern "C" int svnet_model_forward_seg(const svnet_model* m, const float* x, con
     uint32_t* bits8 = reinterpret_cast<uint32_t*>(ws + pl.bits8);
     uint32_t* mask8 = reinterpret_cast<uint32_t*>(ws + pl.mask8);
     int32_t* nvalid8 = reinterpret_cast<int32_t*>(ws + pl.nvalid8);
-    rc = svnet_rows_prep(&cat, R, m->f1_Wz, m->f1_zs, nullptr, m->c8.beta + Kc, nullptr, 0, nullptr, bits8, mask8, nvalid8, stream);
+    rc = svnet_rows_prep(&cat, R, m->f1_Wz, m->f1_zs, nullptr, m->c8.beta + Kc, nullptr, 0, nullptr, bits8, mask8, nvalid8, sst);
     if (rc != SVNET_OK) return rc;
     // conv5 per point: scalar output only pooled (max) -> glob[:, :C5s]; vector output v5
     const svnet_model::Block& c5 = m->conv[4];
@@ -807,20 +814,21 @@ extern "C" int svnet_model_forward_seg(const svnet_model* m, const float* x, con
     uint32_t* bits5 = reinterpret_cast<uint32_t*>(ws + pl.bits5);
     uint32_t* mask5 = reinterpret_cast<uint32_t*>(ws + pl.mask5);
     int32_t* nvalid5 = reinterpret_cast<int32_t*>(ws + pl.nvalid5);
-    rc = svnet_rows_prep(&cat, R, c5.Wz, c5.zscale, nullptr, c5.beta, nullptr, 0, nullptr, bits5, mask5, nvalid5, stream);
+    rc = svnet_rows_prep(&cat, R, c5.Wz, c5.zscale, nullptr, c5.beta, nullptr, 0, nullptr, bits5, mask5, nvalid5, sst);
     if (rc != SVNET_OK) return rc;
     if (pl.blp_bytes) {
         rc = svnet_binlinear_pool_ws(bits5, mask5, R, Kp, c5.W1b, C5s, c5.scale1, c5.bn1_a, c5.bn1_c, N, glob, nullptr, Kc, ws + pl.blp,
-                                     pl.blp_bytes, stream);
+                                     pl.blp_bytes, sst);
         if (rc != SVNET_OK) return rc;
     } else {
         float* s5 = reinterpret_cast<float*>(ws + pl.s5);
         rc = svnet_binlinear_rows_ws(bits5, mask5, nvalid5, R, Kp, c5.W1b, C5s, c5.scale1, nullptr, c5.bn1_a, c5.bn1_c, SVNET_ACT_LEAKY, nullptr,
-                                     1, s5, C5s, nullptr, pl.bl_bytes ? ws + pl.blp : nullptr, pl.bl_bytes, stream);
+                                     1, s5, C5s, nullptr, pl.bl_bytes ? ws + pl.blp : nullptr, pl.bl_bytes, sst);
         if (rc != SVNET_OK) return rc;
-        rc = svnet_pool_rows(s5, C5s, C5s, B, N, glob, nullptr, Kc, stream);
+        rc = svnet_pool_rows(s5, C5s, C5s, B, N, glob, nullptr, Kc, sst);
         if (rc != SVNET_OK) return rc;
     }
+    if (aux) SV_CUDA(cudaEventRecord(eJ, aux));
     rc = svnet_gate_rows(s_cat, lds, lds, B, N, c5.G1, c5.G2, c5.H, c5.Cvo, gate, stream);
     if (rc != SVNET_OK) return rc;
     {
@@ -830,6 +838,13 @@ extern "C" int svnet_model_forward_seg(const svnet_model* m, const float* x, con
         q.C = v5; q.ldc_g = 3 * C5v; q.ldc_x = C5v;
         rc = svnet_linear_rows_ws(&q, nullptr, 0, stream);
         if (rc != SVNET_OK) return rc;
+    }
+    if (aux) {
+        // join (conv5's pooled scalars are conv6's input), then fork again: svfuse3's pooling of v5 and the label branch next
+        // to pool -> conv6 -> svfuse2, whose one-row-per-cloud kernels leave the GPU almost idle
+        SV_CUDA(cudaStreamWaitEvent(st, eJ, 0));
+        SV_CUDA(cudaEventRecord(eF, st));
+        SV_CUDA(cudaStreamWaitEvent(aux, eF, 0));
     }
     // global branch: svpool over the points -> conv6 (one row per cloud) -> svfuse2
     float* vp = reinterpret_cast<float*>(ws + pl.vp);
@@ -864,18 +879,61 @@ extern "C" int svnet_model_forward_seg(const svnet_model* m, const float* x, con
     // svfuse3 + max over the points: v2s(v5) reduced on the fly -> glob[:, C5s:C3]
     svnet_view v5v = {};
     v5v.v = v5; v5v.ldv = 3 * C5v; v5v.xs = C5v; v5v.Cv = C5v;
-    rc = svnet_svfuse_pool(&v5v, B, N, m->f3_Wz, m->f3_zs, glob + C5s, nullptr, Kc, ws + pl.fuse, pl.fuse_bytes, stream);
+    rc = svnet_svfuse_pool(&v5v, B, N, m->f3_Wz, m->f3_zs, glob + C5s, nullptr, Kc, ws + pl.fuse, pl.fuse_bytes, sst);
     if (rc != SVNET_OK) return rc;
     // conv7: the one-hot object label -> 64 channels (fp Conv1d + BN + LeakyReLU)
     {
         svnet_gemm_params q = {};
         q.A = label_onehot; q.lda_g = 16; q.lda_x = 0; q.G = 1; q.W = m->c7_W; q.ldw = 16; q.M = B; q.N = 64; q.K = 16;
         q.bn_a = m->c7_a; q.bn_c = m->c7_c; q.act = SVNET_ACT_LEAKY; q.C = glob + C3 + C6s + 3 * C6v; q.ldc_g = Kc; q.ldc_x = 0; q.groups_per_cloud = 1;
-        rc = svnet_linear_rows_ws(&q, nullptr, 0, stream);
+        rc = svnet_linear_rows_ws(&q, nullptr, 0, sst);
         if (rc != SVNET_OK) return rc;
+    }
+    if (aux) {
+        SV_CUDA(cudaEventRecord(eJ, aux));
+        SV_CUDA(cudaStreamWaitEvent(st, eJ, 0));
     }
     // segmentation head
     svnet_seg_head_params h = seg_head_params(m, B, N);
     h.glob = glob; h.bits8 = bits8; h.mask8 = mask8; h.nvalid8 = nvalid8; h.logits = logits;
     return svnet_seg_head_fwd(&h, ws + pl.head, pl.head_bytes, stream);
+}
+
+}  // namespace
+
+extern "C" int svnet_model_forward_seg(const svnet_model* m, const float* x, const float* label_onehot, int B, int N, float* logits,
+                                       void* workspace, size_t workspace_bytes, void* stream)
+{
+    SV_REQUIRE(m && x && label_onehot && logits, "svnet_model_forward_seg: null pointer");
+    SV_REQUIRE(m->pseg, "svnet_model_forward_seg: the handle is not a part-segmentation model (svnet_model_forward)");
+    SV_REQUIRE(B >= 0 && N >= 64 && N <= 4096, "svnet_model_forward_seg: N = %d not covered (64..4096)", N);
+    if (B == 0) return SVNET_OK;
+    SV_REQUIRE(workspace && !(reinterpret_cast<uintptr_t>(workspace) & 255), "svnet_model_forward_seg: workspace null or not 256-byte aligned");
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    cudaStream_t st = sv_stream(stream);
+    const bool ax = m->streams_ok;
+    if (!split_batch(m, B, N)) {
+        seg_plan2 pl;
+        SV_REQUIRE(make_seg_plan(m, B, N, &pl), "svnet_model_forward_seg: shape not covered by the tensor-core paths");
+        SV_REQUIRE(workspace_bytes >= pl.total, "svnet_model_forward_seg: workspace too small (svnet_model_seg_workspace_bytes)");
+        return forward_seg_one(m, x, label_onehot, B, N, logits, ws, pl, stream, ax ? m->aux[0] : nullptr, ax ? m->ev[0] : nullptr,
+                               ax ? m->ev[1] : nullptr);
+    }
+    const int B0 = B / 2, B1 = B - B0;
+    seg_plan2 p0, p1;
+    SV_REQUIRE(make_seg_plan(m, B0, N, &p0) && make_seg_plan(m, B1, N, &p1), "svnet_model_forward_seg: shape not covered by the tensor-core paths");
+    SV_REQUIRE(workspace_bytes >= p0.total + p1.total, "svnet_model_forward_seg: workspace too small (svnet_model_seg_workspace_bytes)");
+    SV_CUDA(cudaEventRecord(m->ev[8], st));
+    SV_CUDA(cudaStreamWaitEvent(m->sub[0], m->ev[8], 0));
+    SV_CUDA(cudaStreamWaitEvent(m->sub[1], m->ev[8], 0));
+    int rc = forward_seg_one(m, x, label_onehot, B0, N, logits, ws, p0, m->sub[0], m->aux[0], m->ev[0], m->ev[1]);
+    if (rc != SVNET_OK) return rc;
+    rc = forward_seg_one(m, x + (size_t)B0 * 3 * N, label_onehot + (size_t)B0 * 16, B1, N, logits + (size_t)B0 * m->ncls * N, ws + p0.total, p1,
+                         m->sub[1], m->aux[1], m->ev[2], m->ev[3]);
+    if (rc != SVNET_OK) return rc;
+    SV_CUDA(cudaEventRecord(m->ev[4], m->sub[0]));
+    SV_CUDA(cudaEventRecord(m->ev[5], m->sub[1]));
+    SV_CUDA(cudaStreamWaitEvent(st, m->ev[4], 0));
+    SV_CUDA(cudaStreamWaitEvent(st, m->ev[5], 0));
+    return SVNET_OK;
 }
