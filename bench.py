@@ -342,7 +342,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # The step is the public inference call: svnet_b200.GraphedForward(net, example) captures the forward
-    # once (CUDA graph with the batch split into four sub-batches on four streams) and replays it per batch.
+    # once (CUDA graph; model(batch) runs through the whole-model C entry: two sub-batches on two streams plus auxiliary
+    # streams for the chains that do not depend on the kNN graphs) and replays it per batch.
     in_graph = world > 1 and GRAPH_ALLGATHER
     dbg("model ready, capturing (all-gather in graph: %s)" % in_graph)
     fast = sv.GraphedForward(net, x_dev, epilogue=(lambda y: dist.all_gather_into_tensor(gathered, y)) if in_graph else None)
@@ -406,8 +407,10 @@ def main():
         nv.TIMED.clear()
         nv.ORDER.clear()
         l0 = nv.LAUNCHES[0]
-        two_streams = sv_fused.CONCURRENT_HALVES
+        two_streams, native_fwd, side = sv_fused.CONCURRENT_HALVES, sv_fused.NATIVE_FORWARD, sv_fused.SIDE_STREAM
         sv_fused.CONCURRENT_HALVES = False       # one stream, 32 clouds per launch: un-overlapped kernel times
+        sv_fused.NATIVE_FORWARD = False          # the stages as separate C-ABI calls from Python, so that events can bracket them
+        sv_fused.SIDE_STREAM = False             # (model(x) otherwise makes the same calls inside svnet_model_forward)
         try:
             for _ in range(max(3, args.warmup)):          # the eager path has its own allocations to warm up
                 step_eager(x_dev)
@@ -416,7 +419,7 @@ def main():
             l0 = nv.LAUNCHES[0]
             ms_eager = timed(lambda: step_eager(x_dev), args.steps)
         finally:
-            sv_fused.CONCURRENT_HALVES = two_streams
+            sv_fused.CONCURRENT_HALVES, sv_fused.NATIVE_FORWARD, sv_fused.SIDE_STREAM = two_streams, native_fwd, side
         launches = (nv.LAUNCHES[0] - l0) // args.steps
         nv.PROFILE[0] = None
         clocks = sampler.stop() if rank == 0 else None
@@ -564,7 +567,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (+u32 XNOR/popcount for the binarised linears; exact bf16x3 tcgen05 filter in front of the fp32 kNN)", "data": "synthetic",
         "config": bench_config(world),
-        "call": "svnet_b200.GraphedForward(net, batch): CUDA-graph replay, four sub-batches of 8 clouds on four streams"
+        "call": "svnet_b200.GraphedForward(net, batch): CUDA-graph replay of model(batch); the forward is sequenced by svnet_model_forward (two sub-batches of 16 clouds on two streams, graph-independent chains on auxiliary streams)"
                 + ("; the logits all-gather is captured in the same graph" if (world > 1 and GRAPH_ALLGATHER) else ""),
         "clocks": clocks,
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clouds/s", "ms_per_step": ms_e2e,

@@ -20,7 +20,7 @@ class NativeModel:
         with torch.cuda.device(dev):
             sd = {n: t.to(dev) for n, t in state_dict.items() if torch.is_tensor(t) and t.dtype == torch.float32}
             self._h = nv.model_create(kind, k, binary, num_class, sd)
-        self.device, self.num_class, self.kind = dev, num_class, kind
+        self.device, self.num_class, self.kind, self.binary = dev, num_class, kind, bool(binary)
         self._ws = {}
 
     def __call__(self, x, label=None):
@@ -39,7 +39,7 @@ class NativeModel:
                     self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
                 logits = torch.empty((B, self.num_class, N), dtype=torch.float32, device=x.device)
                 nv.model_forward_seg(self._h, x.contiguous(), label.reshape(B, -1).contiguous().float(), logits, self._ws[key])
-                nv.LAUNCHES[0] += 60
+                nv.LAUNCHES[0] += 60 * self._sub_batches(B, N) - 1     # kernels behind the one call (per sub-batch: trunk 24, conv5 / conv6 branch 18, head 11, ...)
             return logits
         with torch.cuda.device(x.device):
             key = (B, N)
@@ -50,8 +50,13 @@ class NativeModel:
                 self._ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             logits = torch.empty((B, self.num_class), dtype=torch.float32, device=x.device)
             nv.model_forward(self._h, x.contiguous(), logits, self._ws[key])
-            nv.LAUNCHES[0] += 32
+            nv.LAUNCHES[0] += (33 if self.binary else 38) * self._sub_batches(B, N) - 1     # kernels behind the one call
         return logits
+
+    @staticmethod
+    def _sub_batches(B, N):
+        """svnet_model_forward runs a batch of >= 32 768 points as two sub-batches (csrc/model.cu: split_batch)."""
+        return 2 if (B >= 2 and B * N >= 2 * 16384) else 1
 
     def close(self):
         if getattr(self, "_h", None) is not None:

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nv
-from .fused import chunked, dgcnn_trunk
+from .fused import chunked, dgcnn_trunk, native_forward
 from .sv_layers import Linear, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, folded_bn, head_layer
 
 
@@ -44,6 +44,11 @@ class SV_DGCNN_CLS(_Cached, nn.Module):
 
     def forward(self, x, forced_idx=None, record=None):
         hooks = forced_idx is not None or record is not None
+        if not hooks:
+            _inference_only(self)
+            y = native_forward(self, "SV_DGCNN_CLS", x)      # the same calls sequenced in C (csrc/model.cu); None: not covered
+            if y is not None:
+                return y
         return chunked(lambda xc: self._forward(xc, forced_idx, record), x, hooks=hooks)
 
     def _forward(self, x, forced_idx=None, record=None):

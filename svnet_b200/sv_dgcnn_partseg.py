@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nv
-from .fused import aux_stream, chunked, dgcnn_trunk
+from .fused import aux_stream, chunked, dgcnn_trunk, native_forward
 from .sv_layers import Conv1d, SVBlock, SVFuse, Vector2Scalar, _Cached, _inference_only, dense_rows, folded_bn
 
 SEG_HEAD_CALL = os.environ.get("SVNET_SEG_HEAD_CALL", "1") != "0"     # 0: the head layer by layer (parity tests compare both)
@@ -45,7 +45,7 @@ class _Seq(_Cached, nn.Sequential):
         return self._packed("fold", ("1.weight", "1.bias", "1.running_mean", "1.running_var"), lambda: nv.fold_bn(bn))
 
 
-class SV_DGCNN_PSEG(nn.Module):
+class SV_DGCNN_PSEG(_Cached, nn.Module):
     def __init__(self, args, num_part):
         super(SV_DGCNN_PSEG, self).__init__()
         self.args = args
@@ -89,6 +89,11 @@ class SV_DGCNN_PSEG(nn.Module):
 
     def forward(self, x, l, forced_idx=None, record=None):
         hooks = forced_idx is not None or record is not None
+        if not hooks and SEG_HEAD_CALL:
+            _inference_only(self)
+            y = native_forward(self, "SV_DGCNN_PSEG", x, l)   # the same calls sequenced in C (csrc/model.cu); None: not covered
+            if y is not None:
+                return y
         return chunked(lambda xc, lc: self._forward(xc, lc, forced_idx, record), x, (l,), hooks=hooks)
 
     def _forward(self, x, l, forced_idx=None, record=None):

@@ -640,9 +640,18 @@ def test_model_c_entry_equals_module(B, N, k, binary):
     net = net.to(DEV).eval()
     x = synthetic_clouds(B, N, 1002).to(DEV)
     native = sv.NativeModel("SV_DGCNN_CLS", {"module." + n: t for n, t in sd.items()}, k=k, binary=binary, num_class=40, device=DEV)
-    with torch.no_grad():
-        y_mod = net(x)
-        y_c = native(x)
+    from svnet_b200 import fused
+    keep = fused.NATIVE_FORWARD
+    try:
+        with torch.no_grad():
+            fused.NATIVE_FORWARD = False            # the nn.Module path sequenced in Python
+            y_mod = net(x)
+            fused.NATIVE_FORWARD = True             # model(x) delegating to the C entry (the default)
+            y_del = net(x)
+            y_c = native(x)
+    finally:
+        fused.NATIVE_FORWARD = keep
+    assert torch.equal(y_del, y_mod)
     assert tuple(y_c.shape) == (B, 40)
     assert torch.equal(y_c, y_mod)
     # graph capture of the C forward (no allocation / synchronisation inside)
@@ -675,9 +684,18 @@ def test_model_c_entry_partseg_equals_module(B, N, k):
     x = synthetic_clouds(B, N, 1004).to(DEV)
     l = one_hot_labels(B).to(DEV)
     native = sv.NativeModel("SV_DGCNN_PSEG", sd, k=k, binary=True, num_class=50, device=DEV)
-    with torch.no_grad():
-        y_mod = net(x, l)
-        y_c = native(x, l)
+    from svnet_b200 import fused
+    keep = fused.NATIVE_FORWARD
+    try:
+        with torch.no_grad():
+            fused.NATIVE_FORWARD = False
+            y_mod = net(x, l)
+            fused.NATIVE_FORWARD = True
+            y_del = net(x, l)
+            y_c = native(x, l)
+    finally:
+        fused.NATIVE_FORWARD = keep
+    assert torch.equal(y_del, y_mod)
     assert tuple(y_c.shape) == (B, 50, N)
     assert torch.equal(y_c, y_mod)
     with pytest.raises(RuntimeError):
@@ -698,15 +716,17 @@ def test_seg_head_call_equals_layerwise(B, N, k):
     net = net.to(DEV).eval()
     x = synthetic_clouds(B, N, 1004).to(DEV)
     l = one_hot_labels(B).to(DEV)
-    old = ps.SEG_HEAD_CALL
+    from svnet_b200 import fused
+    old, old_n = ps.SEG_HEAD_CALL, fused.NATIVE_FORWARD
     try:
         with torch.no_grad():
+            fused.NATIVE_FORWARD = False            # Python-sequenced forward: the head as one call / layer by layer
             ps.SEG_HEAD_CALL = True
             y_call = net(x, l)
             ps.SEG_HEAD_CALL = False
             y_layers = net(x, l)
     finally:
-        ps.SEG_HEAD_CALL = old
+        ps.SEG_HEAD_CALL, fused.NATIVE_FORWARD = old, old_n
     assert tuple(y_call.shape) == (B, 50, N) and y_call.is_contiguous()
     assert torch.equal(y_call, y_layers)
 
@@ -891,15 +911,16 @@ def test_auxiliary_streams_do_not_change_bits(model, binary):
         extra = ()
     net.load_state_dict(synthetic_state_dict(net.state_dict(), seed=9))
     net = net.to(DEV).eval()
-    keep = fused.SIDE_STREAM
+    keep, keep_n = fused.SIDE_STREAM, fused.NATIVE_FORWARD
     try:
         with torch.no_grad():
+            fused.NATIVE_FORWARD = False            # the Python-sequenced path is the one under test
             fused.SIDE_STREAM = True
             ys = [net(x, *extra).clone() for _ in range(3)]
             fused.SIDE_STREAM = False
             y1 = net(x, *extra)
     finally:
-        fused.SIDE_STREAM = keep
+        fused.SIDE_STREAM, fused.NATIVE_FORWARD = keep, keep_n
     torch.cuda.synchronize()
     for y in ys:
         assert torch.equal(y, y1)
