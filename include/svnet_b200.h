@@ -386,7 +386,7 @@ int svnet_svfuse_pool(const svnet_view* in, int B, long rows_per_cloud, const fl
  * svnet_model_forward(): x [B][3][N] -> logits [B][num_class] on `stream`, with svnet_model_workspace_bytes(m, B, N) bytes of
  * caller-owned scratch (256-byte aligned; 0: shape not covered -- 64 <= N <= 4096).  It allocates
  * nothing and never synchronises the host, so it can be captured into a CUDA graph; inside, the work forks from `stream` onto
- * streams owned by the handle (two sub-batches, auxiliary chains) and joins it again -- one handle must not run two forwards
+ * streams owned by the handle (up to four sub-batches, auxiliary chains) and joins it again -- one handle must not run two forwards
  * concurrently.  The logits are bit-identical to the nn.Module path (svnet_b200.SV_DGCNN_CLS), which makes the same calls
  * through this header. */
 typedef struct { const char* name; const float* data; long numel; } svnet_tensor;

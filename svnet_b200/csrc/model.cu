@@ -4,7 +4,7 @@
 //             the tensor-core edge kernel, per-point table weights) -- the handle owns everything it uses afterwards;
 //   forward : sequences this library's own entry points with caller-owned scratch (svnet_model_workspace_bytes): no
 //             allocation, no host synchronisation -- capturable into a CUDA graph.  Launch structure as the Python path's: a
-//             batch of >= 32 768 points runs as two sub-batches on the handle's two streams, and inside each the chains that
+//             batch of >= 32 768 points runs as two to four sub-batches (>= 16 384 points each) on the handle's streams, and inside each the chains that
 //             do not depend on the kNN graph or the gate (per-point tables, conv5's scalar branch) run on an auxiliary
 //             stream; everything forks from and joins the caller's stream through events (SVNET_MODEL_ONE_STREAM=1: no split);
 //             layer 1      svnet_knn_ws -> svnet_gate_xyz -> svnet_edge_xyz_fwd                    (sv_dgcnn_cls.py:48-53)
@@ -49,8 +49,8 @@ struct svnet_model {
     int C6s, C6v, Kc;
     // launch structure of svnet_model_forward: two sub-batch streams, each with an auxiliary stream for the chains that do
     // not depend on the kNN graph (per-point tables, conv5's scalar branch); events for the forks / joins
-    cudaStream_t sub[2], aux[2];
-    cudaEvent_t ev[10];
+    cudaStream_t sub[4], aux[4];
+    cudaEvent_t ev[13];
     bool streams_ok;
     int Cf, C5s, C5v, h1, h2;
 };
@@ -239,8 +239,8 @@ extern "C" void svnet_model_destroy(svnet_model* m)
 {
     if (!m) return;
     if (m->streams_ok) {
-        for (int i = 0; i < 2; ++i) { cudaStreamDestroy(m->sub[i]); cudaStreamDestroy(m->aux[i]); }
-        for (int i = 0; i < 10; ++i) cudaEventDestroy(m->ev[i]);
+        for (int i = 0; i < 4; ++i) { cudaStreamDestroy(m->sub[i]); cudaStreamDestroy(m->aux[i]); }
+        for (int i = 0; i < 13; ++i) cudaEventDestroy(m->ev[i]);
     }
     for (void* p : m->allocs) cudaFree(p);
     delete m;
@@ -434,34 +434,43 @@ extern "C" int svnet_model_create(const char* kind, int k, int binary, int num_c
         return SVNET_ERR_ARG;
     }
     m->streams_ok = true;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
         if (cudaStreamCreateWithFlags(&m->sub[i], cudaStreamNonBlocking) != cudaSuccess) m->streams_ok = false;
         if (cudaStreamCreateWithFlags(&m->aux[i], cudaStreamNonBlocking) != cudaSuccess) m->streams_ok = false;
     }
-    for (int i = 0; i < 10; ++i)
+    for (int i = 0; i < 13; ++i)
         if (cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming) != cudaSuccess) m->streams_ok = false;
     *out = m;
     return SVNET_OK;
 }
 
 namespace {
-// the two sub-batches of a large enough batch run on the handle's two streams (clouds are independent in eval mode, so the
-// bits do not depend on the split); SVNET_MODEL_ONE_STREAM=1 keeps everything on the caller's stream
-bool split_batch(const svnet_model* m, int B, int N)
+// a large enough batch runs as up to four sub-batches of >= 16 384 points on the handle's streams (clouds are independent in
+// eval mode, so the bits do not depend on the split); SVNET_MODEL_ONE_STREAM=1 keeps everything on the caller's stream
+int split_count(const svnet_model* m, int B, int N)
 {
     static const bool off = [] { const char* e = getenv("SVNET_MODEL_ONE_STREAM"); return e && e[0] == '1'; }();
-    return !off && m->streams_ok && B >= 2 && (long)B * N >= 2L * 16384;
+    if (off || !m->streams_ok) return 1;
+    long n = ((long)B * N) / 16384;
+    n = n < 1 ? 1 : (n > 4 ? 4 : n);
+    return (int)(n > B ? B : n);
 }
+inline int sub_lo(int B, int n, int i) { return (int)((long)B * i / n); }
 
 }  // namespace
 
 extern "C" size_t svnet_model_workspace_bytes(const svnet_model* m, int B, int N)
 {
     if (!m || m->pseg || B < 1 || N < 64 || N > 4096) return 0;
-    if (split_batch(m, B, N)) {
-        fwd_plan p0, p1;
-        if (!make_fwd_plan(m, B / 2, N, &p0) || !make_fwd_plan(m, B - B / 2, N, &p1)) return 0;
-        return p0.total + p1.total;
+    const int ns = split_count(m, B, N);
+    if (ns > 1) {
+        size_t tot = 0;
+        for (int i = 0; i < ns; ++i) {
+            fwd_plan pi;
+            if (!make_fwd_plan(m, sub_lo(B, ns, i + 1) - sub_lo(B, ns, i), N, &pi)) return 0;
+            tot += pi.total;
+        }
+        return tot;
     }
     fwd_plan pl;
     if (!make_fwd_plan(m, B, N, &pl)) return 0;
@@ -683,28 +692,29 @@ extern "C" int svnet_model_forward(const svnet_model* m, const float* x, int B, 
     SV_REQUIRE(workspace && !(reinterpret_cast<uintptr_t>(workspace) & 255), "svnet_model_forward: workspace null or not 256-byte aligned");
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     cudaStream_t st = sv_stream(stream);
-    if (!split_batch(m, B, N)) {
+    const int ns = split_count(m, B, N);
+    if (ns == 1) {
         fwd_plan pl;
         SV_REQUIRE(make_fwd_plan(m, B, N, &pl), "svnet_model_forward: shape not covered by the tensor-core paths");
         SV_REQUIRE(workspace_bytes >= pl.total, "svnet_model_forward: workspace too small (svnet_model_workspace_bytes)");
         const bool ax = m->streams_ok;
         return forward_cls_one(m, x, B, N, logits, ws, pl, stream, ax ? m->aux[0] : nullptr, ax ? m->ev[0] : nullptr, ax ? m->ev[1] : nullptr);
     }
-    const int B0 = B / 2, B1 = B - B0;
-    fwd_plan p0, p1;
-    SV_REQUIRE(make_fwd_plan(m, B0, N, &p0) && make_fwd_plan(m, B1, N, &p1), "svnet_model_forward: shape not covered by the tensor-core paths");
-    SV_REQUIRE(workspace_bytes >= p0.total + p1.total, "svnet_model_forward: workspace too small (svnet_model_workspace_bytes)");
+    SV_REQUIRE(workspace_bytes >= svnet_model_workspace_bytes(m, B, N), "svnet_model_forward: workspace too small (svnet_model_workspace_bytes)");
     SV_CUDA(cudaEventRecord(m->ev[8], st));
-    SV_CUDA(cudaStreamWaitEvent(m->sub[0], m->ev[8], 0));
-    SV_CUDA(cudaStreamWaitEvent(m->sub[1], m->ev[8], 0));
-    int rc = forward_cls_one(m, x, B0, N, logits, ws, p0, m->sub[0], m->aux[0], m->ev[0], m->ev[1]);
-    if (rc != SVNET_OK) return rc;
-    rc = forward_cls_one(m, x + (size_t)B0 * 3 * N, B1, N, logits + (size_t)B0 * m->ncls, ws + p0.total, p1, m->sub[1], m->aux[1], m->ev[2], m->ev[3]);
-    if (rc != SVNET_OK) return rc;
-    SV_CUDA(cudaEventRecord(m->ev[4], m->sub[0]));
-    SV_CUDA(cudaEventRecord(m->ev[5], m->sub[1]));
-    SV_CUDA(cudaStreamWaitEvent(st, m->ev[4], 0));
-    SV_CUDA(cudaStreamWaitEvent(st, m->ev[5], 0));
+    size_t off = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int lo = sub_lo(B, ns, i), Bi = sub_lo(B, ns, i + 1) - lo;
+        fwd_plan pi;
+        SV_REQUIRE(make_fwd_plan(m, Bi, N, &pi), "svnet_model_forward: shape not covered by the tensor-core paths");
+        SV_CUDA(cudaStreamWaitEvent(m->sub[i], m->ev[8], 0));
+        const int rc = forward_cls_one(m, x + (size_t)lo * 3 * N, Bi, N, logits + (size_t)lo * m->ncls, ws + off, pi, m->sub[i], m->aux[i],
+                                       m->ev[2 * i], m->ev[2 * i + 1]);
+        if (rc != SVNET_OK) return rc;
+        off += pi.total;
+        SV_CUDA(cudaEventRecord(m->ev[9 + i], m->sub[i]));
+        SV_CUDA(cudaStreamWaitEvent(st, m->ev[9 + i], 0));
+    }
     return SVNET_OK;
 }
 
@@ -767,10 +777,15 @@ bool make_seg_plan(const svnet_model* m, int B, int N, seg_plan2* pl)
 extern "C" size_t svnet_model_seg_workspace_bytes(const svnet_model* m, int B, int N)
 {
     if (!m || !m->pseg || B < 1 || N < 64 || N > 4096) return 0;
-    if (split_batch(m, B, N)) {
-        seg_plan2 p0, p1;
-        if (!make_seg_plan(m, B / 2, N, &p0) || !make_seg_plan(m, B - B / 2, N, &p1)) return 0;
-        return p0.total + p1.total;
+    const int ns = split_count(m, B, N);
+    if (ns > 1) {
+        size_t tot = 0;
+        for (int i = 0; i < ns; ++i) {
+            seg_plan2 pi;
+            if (!make_seg_plan(m, sub_lo(B, ns, i + 1) - sub_lo(B, ns, i), N, &pi)) return 0;
+            tot += pi.total;
+        }
+        return tot;
     }
     seg_plan2 pl;
     if (!make_seg_plan(m, B, N, &pl)) return 0;
@@ -912,28 +927,28 @@ extern "C" int svnet_model_forward_seg(const svnet_model* m, const float* x, con
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     cudaStream_t st = sv_stream(stream);
     const bool ax = m->streams_ok;
-    if (!split_batch(m, B, N)) {
+    const int ns = split_count(m, B, N);
+    if (ns == 1) {
         seg_plan2 pl;
         SV_REQUIRE(make_seg_plan(m, B, N, &pl), "svnet_model_forward_seg: shape not covered by the tensor-core paths");
         SV_REQUIRE(workspace_bytes >= pl.total, "svnet_model_forward_seg: workspace too small (svnet_model_seg_workspace_bytes)");
         return forward_seg_one(m, x, label_onehot, B, N, logits, ws, pl, stream, ax ? m->aux[0] : nullptr, ax ? m->ev[0] : nullptr,
                                ax ? m->ev[1] : nullptr);
     }
-    const int B0 = B / 2, B1 = B - B0;
-    seg_plan2 p0, p1;
-    SV_REQUIRE(make_seg_plan(m, B0, N, &p0) && make_seg_plan(m, B1, N, &p1), "svnet_model_forward_seg: shape not covered by the tensor-core paths");
-    SV_REQUIRE(workspace_bytes >= p0.total + p1.total, "svnet_model_forward_seg: workspace too small (svnet_model_seg_workspace_bytes)");
+    SV_REQUIRE(workspace_bytes >= svnet_model_seg_workspace_bytes(m, B, N), "svnet_model_forward_seg: workspace too small (svnet_model_seg_workspace_bytes)");
     SV_CUDA(cudaEventRecord(m->ev[8], st));
-    SV_CUDA(cudaStreamWaitEvent(m->sub[0], m->ev[8], 0));
-    SV_CUDA(cudaStreamWaitEvent(m->sub[1], m->ev[8], 0));
-    int rc = forward_seg_one(m, x, label_onehot, B0, N, logits, ws, p0, m->sub[0], m->aux[0], m->ev[0], m->ev[1]);
-    if (rc != SVNET_OK) return rc;
-    rc = forward_seg_one(m, x + (size_t)B0 * 3 * N, label_onehot + (size_t)B0 * 16, B1, N, logits + (size_t)B0 * m->ncls * N, ws + p0.total, p1,
-                         m->sub[1], m->aux[1], m->ev[2], m->ev[3]);
-    if (rc != SVNET_OK) return rc;
-    SV_CUDA(cudaEventRecord(m->ev[4], m->sub[0]));
-    SV_CUDA(cudaEventRecord(m->ev[5], m->sub[1]));
-    SV_CUDA(cudaStreamWaitEvent(st, m->ev[4], 0));
-    SV_CUDA(cudaStreamWaitEvent(st, m->ev[5], 0));
+    size_t off = 0;
+    for (int i = 0; i < ns; ++i) {
+        const int lo = sub_lo(B, ns, i), Bi = sub_lo(B, ns, i + 1) - lo;
+        seg_plan2 pi;
+        SV_REQUIRE(make_seg_plan(m, Bi, N, &pi), "svnet_model_forward_seg: shape not covered by the tensor-core paths");
+        SV_CUDA(cudaStreamWaitEvent(m->sub[i], m->ev[8], 0));
+        const int rc = forward_seg_one(m, x + (size_t)lo * 3 * N, label_onehot + (size_t)lo * 16, Bi, N, logits + (size_t)lo * m->ncls * N, ws + off, pi,
+                                       m->sub[i], m->aux[i], m->ev[2 * i], m->ev[2 * i + 1]);
+        if (rc != SVNET_OK) return rc;
+        off += pi.total;
+        SV_CUDA(cudaEventRecord(m->ev[9 + i], m->sub[i]));
+        SV_CUDA(cudaStreamWaitEvent(st, m->ev[9 + i], 0));
+    }
     return SVNET_OK;
 }

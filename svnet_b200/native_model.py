@@ -55,8 +55,8 @@ class NativeModel:
 
     @staticmethod
     def _sub_batches(B, N):
-        """svnet_model_forward runs a batch of >= 32 768 points as two sub-batches (csrc/model.cu: split_batch)."""
-        return 2 if (B >= 2 and B * N >= 2 * 16384) else 1
+        """svnet_model_forward runs a batch as up to four sub-batches of >= 16 384 points (csrc/model.cu: split_count)."""
+        return max(1, min(4, (B * N) // 16384, B))
 
     def close(self):
         if getattr(self, "_h", None) is not None:
