@@ -21,7 +21,7 @@ class NativeModel:
             sd = {n: t.to(dev) for n, t in state_dict.items() if torch.is_tensor(t) and t.dtype == torch.float32}
             self._h = nv.model_create(kind, k, binary, num_class, sd)
         self.device, self.num_class, self.kind, self.binary = dev, num_class, kind, bool(binary)
-        self._ws = {}
+        self._ws = {}          # scratch per batch shape, kept for the handle's lifetime (a captured CUDA graph may hold its address)
 
     def __call__(self, x, label=None):
         if not x.is_cuda:
