@@ -628,7 +628,8 @@ def test_full_size_configs_run_and_are_batch_independent():
     assert torch.equal(y_full, y_chunk)
 
 
-@pytest.mark.parametrize("B,N,k,binary", [(4, 1024, 20, True), (3, 200, 20, True), (2, 512, 40, True), (4, 1024, 20, False), (3, 200, 20, False)])
+@pytest.mark.parametrize("B,N,k,binary", [(4, 1024, 20, True), (3, 200, 20, True), (2, 512, 40, True), (4, 1024, 20, False), (3, 200, 20, False),
+                                               (1, 64, 20, True), (2, 4096, 20, True), (5, 1000, 20, False), (33, 1024, 20, True)])
 def test_model_c_entry_equals_module(B, N, k, binary):
     """svnet_model_create / _forward / _destroy (the whole SV-DGCNN classifier, binary or fp, behind one C call,
     csrc/model.cu) against the nn.Module path on the same checkpoint tensors: bit-identical logits, also when the
