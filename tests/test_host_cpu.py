@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import golden, quiet
+from tests.util import GOLDEN, golden, quiet
 from svnet_b200.synthetic import (make_args, state_dict_digest, strip_module_prefix, synthetic_clouds,
                                   synthetic_state_dict, wrap_checkpoint)
 
@@ -220,6 +220,36 @@ def test_dataset_readers_without_h5py(tmp_path):
         D.ModelNet40(num_points=1024, data_dir=str(tmp_path / "nowhere"), partition="test")
     unit = D.pc_normalize(shards[0][0][0])
     assert abs(np.linalg.norm(unit, axis=1).max() - 1.0) < 1e-12 and np.abs(unit.mean(0)).max() < 1e-12
+
+
+def test_dataset_readers_equal_reference_readers(tmp_path):
+    """SURVEY 8(f) f4, pinned: tests/golden/data_readers.npz holds what the UNMODIFIED reference readers
+    (data.py:186-201, 260-340, run over a stand-in h5py by tests/golden/make_golden_data.py) returned for seeded
+    items of every partition; the npz readers must return the same arrays, dtypes and draw order."""
+    import importlib.util
+    from svnet_b200 import data as D
+    spec = importlib.util.spec_from_file_location("make_golden_data", os.path.join(GOLDEN, "make_golden_data.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(GOLDEN, "data_readers.npz"))
+    shards = {}
+    for key in gold.files:
+        if key.startswith("shard|"):
+            _, rel, name = key.split("|")
+            shards.setdefault(rel, {})[name] = gold[key]
+    assert len(shards) == 9
+    gen.write_shards(str(tmp_path), shards)
+    got = gen.run_cases(D, str(tmp_path))
+    assert len(got) > 40
+    for key, val in got.items():
+        want = gold[key]
+        if key.endswith("_dtype"):
+            assert str(val) == str(want), key
+        else:
+            assert np.asarray(val).shape == want.shape and np.array_equal(val, want), key
+    assert np.array_equal(D.pc_normalize(gold["pc_normalize_in"]), gold["pc_normalize_out"])
+    np.random.seed(5)
+    assert np.array_equal(D.translate_pointcloud(shards["modelnet40_ply_hdf5_2048/ply_data_test0"]["data"][0]), gold["translate_out"])
 
 
 def test_sub_batch_bounds_cover_the_batch():
