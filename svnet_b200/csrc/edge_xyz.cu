@@ -24,6 +24,41 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): two IEEE-rounded operations per issue slot, the same bits
+// per element as the scalar instructions
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int NV>
 __global__ void __launch_bounds__(WARPS * 32) edge_xyz_kernel(svnet_edge_xyz_params p)
 {
@@ -135,12 +170,22 @@ __global__ void __launch_bounds__(WARPS * 32) edge_xyz_kernel(svnet_edge_xyz_par
 // the point's edges sequentially and keeps the running max / sum of all outputs in registers; only
 // two shuffle steps per output at the very end.  All 32 lanes stay busy (the generic kernel above
 // uses one lane per edge: 20 of 32 at k=20) and there is no per-edge cross-lane reduction.
+// Scalar branch: the sequential chains of outputs (o, o + 1) advance together as packed fp32 pairs (FFMA2: the same
+// IEEE fma per element, half the issue slots); weights sit in shared memory as [o / 2][t][o & 1] so that one 16-byte
+// load feeds two chain steps of a pair; LeakyReLU(y) = max(y, 0.2 y) (slope < 1: identical bits, signed zeros included).
+// Vector branch: tolerance-level arithmetic as in edge_vector.cuh (approximate sqrt / reciprocal).
 template <int NV, int COUT, int CVO>
 __global__ void __launch_bounds__(WARPS * 32, 2) edge_xyz_fast_kernel(svnet_edge_xyz_params p)
 {
     constexpr int KU = 6 * NV;
-    __shared__ float W1[COUT * KU], a1[COUT], c1[COUT], W2[CVO * NV], a2[CVO], c2[CVO], Wi[3 * NV], Wz[3 * NV];
-    for (int i = threadIdx.x; i < COUT * KU; i += blockDim.x) W1[i] = p.W1[i];
+    static_assert(COUT % 2 == 0 && KU % 2 == 0, "packed pairs");
+    __shared__ __align__(16) float W1[COUT * KU];                 // [o / 2][t][o & 1]
+    __shared__ __align__(8) float a1[COUT], c1[COUT];
+    __shared__ float W2[CVO * NV], a2[CVO], c2[CVO], Wi[3 * NV], Wz[3 * NV];
+    for (int i = threadIdx.x; i < COUT * KU; i += blockDim.x) {
+        const int o = i / KU, t = i - o * KU;
+        W1[((o >> 1) * KU + t) * 2 + (o & 1)] = p.W1[i];
+    }
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) { a1[i] = p.bn1_a[i]; c1[i] = p.bn1_c[i]; }
     for (int i = threadIdx.x; i < CVO * NV; i += blockDim.x) W2[i] = p.W2[i];
     for (int i = threadIdx.x; i < CVO; i += blockDim.x) { a2[i] = p.bn2_a[i]; c2[i] = p.bn2_c[i]; }
@@ -196,14 +241,28 @@ __global__ void __launch_bounds__(WARPS * 32, 2) edge_xyz_fast_kernel(svnet_edge
                     u[pass * 3 * NV + d * 3 + m] = q;
                 }
         }
+        f32x2 up[KU];
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-            float y = 0.0f;
+        for (int t = 0; t < KU; ++t) up[t] = pk2(u[t], u[t]);
+        const f32x2 slope = pk2(0.2f, 0.2f);
 #pragma unroll
-            for (int t = 0; t < KU; ++t) y = __fmaf_rn(u[t], W1[o * KU + t], y);
-            y = __fadd_rn(__fmul_rn(y, a1[o]), c1[o]);
-            y = y > 0.0f ? y : __fmul_rn(0.2f, y);
-            smax[o] = fmaxf(smax[o], y);
+        for (int o2 = 0; o2 < COUT / 2; ++o2) {
+            f32x2 y = pk2(0.0f, 0.0f);
+#pragma unroll
+            for (int t = 0; t < KU; t += 2) {
+                const float4 w = *reinterpret_cast<const float4*>(W1 + (o2 * KU + t) * 2);
+                y = fma2(up[t], pk2(w.x, w.y), y);
+                y = fma2(up[t + 1], pk2(w.z, w.w), y);
+            }
+            const float2 a = *reinterpret_cast<const float2*>(a1 + 2 * o2), c = *reinterpret_cast<const float2*>(c1 + 2 * o2);
+            // BN as separately rounded multiply and add (scalar intrinsics: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2)
+            float y0, y1, l0, l1;
+            upk2(y, y0, y1);
+            y0 = __fadd_rn(__fmul_rn(y0, a.x), c.x);
+            y1 = __fadd_rn(__fmul_rn(y1, a.y), c.y);
+            upk2(mul2(slope, pk2(y0, y1)), l0, l1);
+            smax[2 * o2] = fmaxf(smax[2 * o2], fmaxf(y0, l0));
+            smax[2 * o2 + 1] = fmaxf(smax[2 * o2 + 1], fmaxf(y1, l1));
         }
 #pragma unroll
         for (int c = 0; c < CVO; ++c) {
@@ -215,12 +274,11 @@ __global__ void __launch_bounds__(WARPS * 32, 2) edge_xyz_fast_kernel(svnet_edge
                 for (int d = 0; d < NV; ++d) t = __fmaf_rn(ve[a][d], W2[c * NV + d], t);
                 w[a] = t;
             }
-            const float n = __fadd_rn(
-                __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(w[0], w[0]), __fmul_rn(w[1], w[1])), __fmul_rn(w[2], w[2]))),
-                1e-6f);
-            const float nb = __fadd_rn(__fmul_rn(n, a2[c]), c2[c]);
+            // (n a2 + c2) / n with n = |w| + 1e-6
+            const float s2 = fmaf(w[2], w[2], fmaf(w[1], w[1], w[0] * w[0]));
+            const float t = fmaf(c2[c], fast_rcp(fast_sqrt(s2) + 1e-6f), a2[c]);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) vsum[a][c] += __fmul_rn(__fdiv_rn(w[a], n), nb);
+            for (int a = 0; a < 3; ++a) vsum[a][c] = fmaf(w[a], t, vsum[a][c]);
         }
     }
     // combine the four lanes of a point; lane `sub` stores outputs o = sub, sub+4, ...
