@@ -205,10 +205,20 @@ __global__ void __launch_bounds__(WARPS * 32, 2) edge_xyz_fast_kernel(svnet_edge
 #pragma unroll
     for (int c = 0; c < CVO; ++c) { vsum[0][c] = 0.0f; vsum[1][c] = 0.0f; vsum[2][c] = 0.0f; }
 
+    // neighbour coordinates arrive one edge ahead, indices two edges ahead (the gathers are L2 latency)
+    const int* irow = p.idx + rr * p.k;
+    const float* xc = p.xyz + (long)b * p.N * 3;
+    int j1 = sub + 4 < p.k ? __ldg(irow + sub + 4) : 0;
+    float xn[3];
+    {
+        const int j0 = sub < p.k ? __ldg(irow + sub) : 0;
+        xn[0] = __ldg(xc + j0 * 3); xn[1] = __ldg(xc + j0 * 3 + 1); xn[2] = __ldg(xc + j0 * 3 + 2);
+    }
     for (int e = sub; e < p.k; e += 4) {
         asm volatile("" ::: "memory");   // keep the (loop-invariant) weight loads inside the loop: no register blow-up
-        const long j = (long)b * p.N + p.idx[rr * p.k + e];
-        const float xj[3] = {p.xyz[j * 3], p.xyz[j * 3 + 1], p.xyz[j * 3 + 2]};
+        const float xj[3] = {xn[0], xn[1], xn[2]};
+        xn[0] = __ldg(xc + j1 * 3); xn[1] = __ldg(xc + j1 * 3 + 1); xn[2] = __ldg(xc + j1 * 3 + 2);
+        j1 = e + 8 < p.k ? __ldg(irow + e + 8) : 0;
         float ve[3][NV];
 #pragma unroll
         for (int a = 0; a < 3; ++a) { ve[a][0] = __fsub_rn(xj[a], xi[a]); ve[a][1] = xi[a]; }

@@ -451,6 +451,8 @@ int split_count(const svnet_model* m, int B, int N)
 {
     static const bool off = [] { const char* e = getenv("SVNET_MODEL_ONE_STREAM"); return e && e[0] == '1'; }();
     if (off || !m->streams_ok) return 1;
+    static const int forced = [] { const char* e = getenv("SVNET_MODEL_SPLIT"); return e ? atoi(e) : 0; }();   // tuning aid
+    if (forced >= 1 && forced <= 4) return forced > B ? B : forced;
     long n = ((long)B * N) / 16384;
     n = n < 1 ? 1 : (n > 4 ? 4 : n);
     return (int)(n > B ? B : n);

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "svnet_b200", "libsvnet_b200.so")
-WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "UBLKCP", "SYNCS", "F2FP", "POPC", "HMMA", "IMMA", "LDGSTS", "MUFU", "FFMA", "LDG", "STG"]
+WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "UBLKCP", "SYNCS", "F2FP", "POPC", "HMMA", "IMMA", "LDGSTS", "MUFU", "FFMA", "FFMA2", "LDG", "STG"]
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 kern, hist = None, collections.OrderedDict()
 for line in out.splitlines():
