@@ -41,6 +41,13 @@ static inline int sv_cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 // ---- device helpers -------------------------------------------------------------------------------
 #define SV_FULL 0xffffffffu
 
+// Warp index / a warp-invariant value in a form the compiler's divergence analysis recognises as warp-uniform (a
+// broadcast from lane 0).  Branches and loops on `threadIdx.x >> 5` or on a value every lane loaded from the same
+// address are convergent, but ptxas cannot know that and wraps every *_sync collective inside them as
+// WARPSYNC + op + ENDCOLLECTIVE on sm_100a; on a broadcast value the collectives compile to one instruction.
+__device__ __forceinline__ int sv_warp_id() { return __shfl_sync(SV_FULL, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ int sv_uniform(int v) { return __shfl_sync(SV_FULL, v, 0); }
+
 // k-th channel of the kNN feature vector [s | v(x=0) | v(x=1) | v(x=2)] of row r (sv_util.py:100)
 __device__ __forceinline__ float sv_feat(const svnet_view& in, long r, int c)
 {

@@ -225,7 +225,7 @@ edge_bin_tc_kernel(svnet_edge_params p, const unsigned char* __restrict__ W1tc, 
     uint64_t* bar = reinterpret_cast<uint64_t*>(vpart + S::VPART);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = sv_warp_id();
     const long total = (long)p.B * p.N;
 
     // ---- one-time setup: weights resident, operand tile zeroed (pads and the K tail stay zero), barrier, TMEM ----

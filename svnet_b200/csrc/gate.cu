@@ -29,7 +29,7 @@ __device__ __forceinline__ float warp_sum(float v)
 template <int OB, typename F>
 __device__ __forceinline__ void gate_linear(const float* x, int Cin, const float* __restrict__ W, int Cout, F&& store)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = sv_warp_id();
     for (int j0 = warp * OB; j0 < Cout; j0 += (NT / 32) * OB) {
         float acc[OB];
 #pragma unroll
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(NT) gate_rows_kernel(const float* __restrict__
     float* h = mean + Cs;
     float* part = h + H;
     const int b = blockIdx.x;
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, rg = sv_warp_id();
     const float* p = s + (long)b * rows * lds;
     for (int c0 = 0; c0 < Cs; c0 += 32) {
         const int c = c0 + lane;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NT) gate_rows_cluster_kernel(const float* __re
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     const int b = blockIdx.x / CL;
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, rg = sv_warp_id();
     const long r_lo = rows * rank / CL, r_hi = rows * (rank + 1) / CL;
     const float* p = s + (long)b * rows * lds;
     // one pass over this CTA's rows per 256-column super block: 8 independent accumulators per thread keep
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NT) gate_edge_kernel(svnet_view in, const int3
     float* part = h + H;
     int* indeg = reinterpret_cast<int*>(part + 2 * 8 * 32);
     const int b = blockIdx.x;
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, rg = sv_warp_id();
     for (int i = threadIdx.x; i < N; i += NT) indeg[i] = 0;
     __syncthreads();
     const int32_t* ib = idx + (long)b * N * k;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(NT) gate_edge_cluster_kernel(svnet_view in, co
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     const int b = blockIdx.x / CL;
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, rg = sv_warp_id();
     for (int i = threadIdx.x; i < N; i += NT) hist[i] = 0;
     __syncthreads();
     const long E = (long)N * k;

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(NT) head_kernel(svnet_head_params p, int prefe
     __shared__ int nvalid_s;
     __shared__ __align__(8) uint64_t wbar;
 
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = sv_warp_id();
     // prefetched sign planes live behind the staging area of the fp layer
     size_t wst_floats = 0;
     {

@@ -671,7 +671,7 @@ template <int MINB>
 __global__ void __launch_bounds__(FIN_WARPS * 32, MINB) knn_finish_kernel(knn_tc_args p)
 {
     extern __shared__ __align__(16) float fin_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = sv_warp_id();
     const int b = blockIdx.y;
     const int i = blockIdx.x * FIN_WARPS + warp;
     if (i >= p.N) return;
@@ -690,7 +690,8 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, MINB) knn_finish_kernel(knn_tc
     const float2 h0 = __ldg(q0 + lane), h1 = __ldg(q0 + CAPH + lane);     // may hold stale data beyond the counts
     const float xxi = __ldg(xxs + i);
     f.xxi = xxi;
-    const int2 cc = __ldg(reinterpret_cast<const int2*>(p.gqcnt) + rg);
+    int2 cc = __ldg(reinterpret_cast<const int2*>(p.gqcnt) + rg);
+    cc.x = sv_uniform(cc.x); cc.y = sv_uniform(cc.y);             // the same for every lane: keep the branches on them convergent
     const int c0 = cc.x, cnt = cc.x + cc.y;
     const bool brute = !(cc.x <= CAPH && cc.y <= CAPH && cnt >= k);
     bool st_exact = false;
@@ -855,7 +856,7 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, MINB) knn_finish_kernel(knn_tc
 __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_WIDE_MIN_BLOCKS) knn_finish_wide_kernel(knn_tc_args p)
 {
     extern __shared__ __align__(16) float fin_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = sv_warp_id();
     const int b = blockIdx.y;
     const int i = blockIdx.x * FIN_WARPS + warp;
     if (i >= p.N) return;
@@ -872,7 +873,8 @@ __global__ void __launch_bounds__(FIN_WARPS * 32, FIN_WIDE_MIN_BLOCKS) knn_finis
     const float xxi = __ldg(xxs + i);
     f.xxi = xxi;
     const float2* q0 = p.gq + rg * 2 * CAPH;
-    const int2 cc = __ldg(reinterpret_cast<const int2*>(p.gqcnt) + rg);
+    int2 cc = __ldg(reinterpret_cast<const int2*>(p.gqcnt) + rg);
+    cc.x = sv_uniform(cc.x); cc.y = sv_uniform(cc.y);             // the same for every lane: keep the branches on them convergent
     const int c0 = cc.x, cnt = cc.x + cc.y;
     const bool brute = !(cc.x <= CAPH && cc.y <= CAPH && cnt >= k);
     kkey_t best[2] = {0ull, 0ull};

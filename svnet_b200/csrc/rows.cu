@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(PW * 32) rows_prep_kernel(svnet_view in, long 
                                                             int32_t* __restrict__ nvalid)
 {
     __shared__ float zb_all[PW][28];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = sv_warp_id();
     float* zb = zb_all[warp];
     const int Cs = in.Cs, Cv = in.Cv;
     const int K = Cs + 3 * Cv, Kw = (K + 31) / 32;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(PW * 32) rows_prep_staged_kernel(svnet_view in
                                                                    int32_t* __restrict__ nvalid)
 {
     extern __shared__ float rp_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = sv_warp_id();
     const int Cs = in.Cs, Cv = in.Cv;
     const int K = Cs + 3 * Cv, Kw = (K + 31) / 32;
     const int V3 = 3 * Cv;                       // vector floats per row

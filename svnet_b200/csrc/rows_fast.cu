@@ -86,14 +86,18 @@ __device__ __forceinline__ void frames(const float* vsm, const float* wzs, float
 // ---------------------------------------------------------------------------------------------
 // sign / mask words of [s | q] + beta.  Requires Cs % 32 == 0, Cs <= 512, Kw % 4 == 0.
 // ---------------------------------------------------------------------------------------------
+// CS_T / CV_T > 0: the widths as compile-time constants (conv5 of the classifier: 256 / 83) -- the word loops unroll, the
+// running word index and its slot become constants (no selects), the predicates on ws / nq disappear; 0: runtime widths.
+template <int CS_T, int CV_T>
 __global__ void __launch_bounds__(RW * 32) rows_prep_bits_kernel(svnet_view in, long rows, const float* __restrict__ Wz,
                                                                  const float* __restrict__ zscale, const float* __restrict__ beta,
                                                                  uint32_t* __restrict__ bits, uint32_t* __restrict__ mask,
                                                                  int32_t* __restrict__ nvalid)
 {
     extern __shared__ __align__(16) float rf_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int Cs = in.Cs, Cv = in.Cv, CvP = rf_cvp(Cv);
+    constexpr bool STATIC = CS_T > 0 && CV_T > 0;
+    const int lane = threadIdx.x & 31, warp = sv_warp_id();
+    const int Cs = STATIC ? CS_T : in.Cs, Cv = STATIC ? CV_T : in.Cv, CvP = rf_cvp(Cv);
     const int K = Cs + 3 * Cv, Kw = (K + 31) / 32, KQ = 3 * Cv;
     const int ws = Cs >> 5, nq = Kw - ws;
     float* wzs = rf_smem;                                   // [3][CvP], zero padded
@@ -132,8 +136,10 @@ __global__ void __launch_bounds__(RW * 32) rows_prep_bits_kernel(svnet_view in, 
         __syncwarp();
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-            if (g >= ng) break;
-            const long r = r0 + g;
+            // rows beyond the end (last group only) are computed on stale staging data and not stored: no divergent exit
+            // in front of the ballots
+            const bool gon = g < ng;
+            const long r = r0 + (gon ? g : 0);
             uint4* bout = reinterpret_cast<uint4*>(bits + r * Kw);
             uint4* mout = reinterpret_cast<uint4*>(mask + r * Kw);
             int nval = 0;
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(RW * 32) rows_prep_bits_kernel(svnet_view in, 
                     pw[w & 3] = __ballot_sync(SV_FULL, t > 0.0f);
                     nw[w & 3] = __ballot_sync(SV_FULL, t != 0.0f);
                     nval += __popc(nw[w & 3]);
-                    if ((w & 3) == 3 && lane == 0) {
+                    if ((w & 3) == 3 && lane == 0 && gon) {
                         bout[w >> 2] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                         mout[w >> 2] = make_uint4(nw[0], nw[1], nw[2], nw[3]);
                     }
@@ -162,6 +168,7 @@ __global__ void __launch_bounds__(RW * 32) rows_prep_bits_kernel(svnet_view in, 
                 for (int x = 0; x < 3; ++x) zs[j][x] = z[3 * x + mj[j]];
             // the running word index continues after the ws scalar words; ws % 4 may be non-zero
             int wd = ws;
+#pragma unroll(STATIC ? 8 : 1)
             for (int wq = 0; wq < nq; wq += 3) {
                 const int ddo = (wq / 3) * 32;
 #pragma unroll
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(RW * 32) rows_prep_bits_kernel(svnet_view in, 
                         pw[1] = slot == 1 ? pos : pw[1]; nw[1] = slot == 1 ? nz : nw[1];
                         pw[2] = slot == 2 ? pos : pw[2]; nw[2] = slot == 2 ? nz : nw[2];
                         pw[3] = slot == 3 ? pos : pw[3]; nw[3] = slot == 3 ? nz : nw[3];
-                        if (slot == 3 && lane == 0) {
+                        if (slot == 3 && lane == 0 && gon) {
                             bout[wd >> 2] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                             mout[wd >> 2] = make_uint4(nw[0], nw[1], nw[2], nw[3]);
                         }
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(RW * 32) rows_prep_bits_kernel(svnet_view in, 
                     }
                 }
             }
-            if (lane == 0) nvalid[r] = nval;
+            if (lane == 0 && gon) nvalid[r] = nval;
         }
         __syncwarp();
     }
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(RW * 32) svfuse_pool_kernel(svnet_view in, int
                                                               const float* __restrict__ zscale, float* __restrict__ partial)
 {
     extern __shared__ __align__(16) float rf_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = sv_warp_id();
     const int Cv = in.Cv, CvP = rf_cvp(Cv), KQ = 3 * Cv, nq = (KQ + 31) / 32;
     float* wzs = rf_smem;
     float* red = wzs + 3 * CvP;                              // [RW][2][PQW * 32]
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(256) signpack_kernel(const float* __restrict__
     const int lane = threadIdx.x & 31;
     const int Kw = (K + 31) >> 5, nch = (Kw + 7) >> 3;
     const long items = rows * nch;
-    for (long it = (long)blockIdx.x * 8 + (threadIdx.x >> 5); it < items; it += (long)gridDim.x * 8) {
+    for (long it = (long)blockIdx.x * 8 + sv_warp_id(); it < items; it += (long)gridDim.x * 8) {
         const long r = it / nch;
         const int w0 = (int)(it - r * nch) * 8;
         float t[8];
@@ -357,10 +364,15 @@ int svnet_rows_prep_fast_dispatch(const svnet_view* in, long rows, const float* 
     if ((reinterpret_cast<uintptr_t>(bits) | reinterpret_cast<uintptr_t>(mask)) & 15) return 0;
     const size_t smem = sizeof(float) * ((size_t)3 * rf_cvp(Cv) + (size_t)Kw * 32 + (size_t)RW * rf_warp_floats(Cv));
     if (smem > 64 * 1024) return 0;
-    SV_CUDA(cudaFuncSetAttribute(rows_prep_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long ngroups = (rows + 2) / 3;
     const int grid = (int)min((long)sv_cdiv(ngroups, RW), 148L * 32);
-    rows_prep_bits_kernel<<<grid, RW * 32, smem, st>>>(*in, rows, Wz, zscale, beta, bits, mask, nvalid);
+    if (Cs == 256 && Cv == 83) {
+        SV_CUDA(cudaFuncSetAttribute(rows_prep_bits_kernel<256, 83>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rows_prep_bits_kernel<256, 83><<<grid, RW * 32, smem, st>>>(*in, rows, Wz, zscale, beta, bits, mask, nvalid);
+    } else {
+        SV_CUDA(cudaFuncSetAttribute(rows_prep_bits_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rows_prep_bits_kernel<0, 0><<<grid, RW * 32, smem, st>>>(*in, rows, Wz, zscale, beta, bits, mask, nvalid);
+    }
     SV_CHECK_LAUNCH("svnet_rows_prep(fast)");
     return 1;
 }
