@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(NTH, 1) binlinear_tc_kernel(bl_args p)
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = sv_warp_id();
     const long r0 = (long)blockIdx.x * TR;
 
     if (tid == 0) {

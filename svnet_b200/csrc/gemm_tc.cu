@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(NTH) signlinear_tc_kernel(svnet_gemm_params p,
     const int KS = Kpad + 8;
     unsigned short* Ws = reinterpret_cast<unsigned short*>(smraw);
     unsigned short* As = Ws + (size_t)Npad * KS;   // plane pl, row r: As[(pl*PT*48 + r)*KS + k]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = sv_warp_id();
     const int g = lane >> 2, q = lane & 3;
 
     // ---- weights: sign -> bf16 +-1 (0 for exact zeros), zero padded ----

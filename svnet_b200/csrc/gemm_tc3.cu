@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(NTH, 1) gemm_tc3_kernel(tc3_args p)
     uint64_t* done = bempty + 2;            // all accumulators complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = sv_warp_id();
     const long r0 = (long)blockIdx.x * TR;
     const int mt0 = blockIdx.y * MT;         // first channel tile of this CTA
 

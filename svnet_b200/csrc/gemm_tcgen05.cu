@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(NTH, WP == 1 ? 2 : 1) vlinear_tcgen05_kernel(s
     uint64_t* mbar = reinterpret_cast<uint64_t*>(Bs + 3 * plane_bytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = sv_warp_id();
 
     // ---- one-time: weights -> bf16 (+-1, or three exact planes) in the canonical layout; barrier; tensor memory ----
     for (int i = tid; i < WROWS * KB; i += NTH) {

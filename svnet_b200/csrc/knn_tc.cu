@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) knn_pack_kernel(svnet_view in, int N, int
     const int r0 = blockIdx.x * PACK_ROWS;          // first (padded) row of this CTA within the cloud
     const int C = in.Cs + 3 * in.Cv;
     const int Kpad = NKC * KCH, ld = Kpad + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = sv_warp_id();
     // channel -> address pieces of this lane's channels
     for (int c = lane; c < Kpad; c += 32) {
         const float* src = nullptr;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) knn_tc_kernel(knn_tc_args p)
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = sv_warp_id();
     const int rb = blockIdx.x, b = blockIdx.y;
     const int i0 = rb * TM;
     const long base = (long)b * p.N;

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) pool_rows_kernel(const float* __restrict_
     __shared__ float smax[8][32], ssum[8][32];
     const int b = blockIdx.y;
     const int col = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int rg = threadIdx.x >> 5;
+    const int rg = sv_warp_id();
     float m = -INFINITY, s = 0.0f;
     if (col < C) {
         // eight loads in flight per thread, consumed in row order (the summation order is unchanged)

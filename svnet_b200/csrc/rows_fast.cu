@@ -210,12 +210,14 @@ __global__ void __launch_bounds__(RW * 32) rows_prep_bits_kernel(svnet_view in, 
 // ---------------------------------------------------------------------------------------------
 constexpr int PQW = 16;   // q words per lane held in registers
 
+// CV_T > 0: the width as a compile-time constant (svfuse of the classifier: 170); 0: runtime width
+template <int CV_T>
 __global__ void __launch_bounds__(RW * 32) svfuse_pool_kernel(svnet_view in, int rows_per_cloud, int rpp, const float* __restrict__ Wz,
                                                               const float* __restrict__ zscale, float* __restrict__ partial)
 {
     extern __shared__ __align__(16) float rf_smem[];
     const int lane = threadIdx.x & 31, warp = sv_warp_id();
-    const int Cv = in.Cv, CvP = rf_cvp(Cv), KQ = 3 * Cv, nq = (KQ + 31) / 32;
+    const int Cv = CV_T > 0 ? CV_T : in.Cv, CvP = rf_cvp(Cv), KQ = 3 * Cv, nq = (KQ + 31) / 32;
     float* wzs = rf_smem;
     float* red = wzs + 3 * CvP;                              // [RW][2][PQW * 32]
     float* vsm = red + RW * 2 * PQW * 32 + (size_t)warp * rf_warp_floats(Cv);
@@ -401,9 +403,15 @@ extern "C" int svnet_svfuse_pool(const svnet_view* in, int B, long rows_per_clou
     const size_t smem = sizeof(float) * ((size_t)3 * rf_cvp(Cv) + (size_t)RW * 2 * PQW * 32 + (size_t)RW * rf_warp_floats(Cv));
     SV_REQUIRE(smem <= 96 * 1024, "svnet_svfuse_pool: Cv = %d too large", Cv);
     cudaStream_t st = sv_stream(stream);
-    SV_CUDA(cudaFuncSetAttribute(svfuse_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    svfuse_pool_kernel<<<dim3(parts, B), RW * 32, smem, st>>>(*in, (int)rows_per_cloud, rpp, Wz, zscale,
-                                                              static_cast<float*>(workspace));
+    if (Cv == 170) {
+        SV_CUDA(cudaFuncSetAttribute(svfuse_pool_kernel<170>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        svfuse_pool_kernel<170><<<dim3(parts, B), RW * 32, smem, st>>>(*in, (int)rows_per_cloud, rpp, Wz, zscale,
+                                                                       static_cast<float*>(workspace));
+    } else {
+        SV_CUDA(cudaFuncSetAttribute(svfuse_pool_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        svfuse_pool_kernel<0><<<dim3(parts, B), RW * 32, smem, st>>>(*in, (int)rows_per_cloud, rpp, Wz, zscale,
+                                                                     static_cast<float*>(workspace));
+    }
     SV_CHECK_LAUNCH("svnet_svfuse_pool");
     svfuse_pool_reduce_kernel<<<dim3(sv_cdiv(KQ, 128), B), 128, 0, st>>>(static_cast<const float*>(workspace), parts, KQ,
                                                                           (int)rows_per_cloud, max_out, mean_out, ldo);
