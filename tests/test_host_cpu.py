@@ -294,3 +294,34 @@ def test_packed_cache_keys_replicas_on_their_source_and_invalidates():
     assert blk.pq_weight()[0] is not w1
     seq = quiet(sv.SV_DGCNN_PSEG, make_args(k=4, binary=True), 50)     # '1.weight' paths of the nn.Sequential blocks
     assert seq.conv8._packed("probe", ("1.weight",), lambda: 1) == 1
+
+
+def test_committed_bench_line_keeps_the_contract():
+    """The newest bench line under profiles/ (written by `python bench.py` on the GPU box) carries every key of the
+    bench contract and is internally consistent: value = clouds per step / time, roofline.frac = achieved / peak,
+    achieved = algorithmic bytes per launch / kernel time, e2e measured with real copies, launches counted."""
+    prof = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
+    names = sorted(n for n in os.listdir(prof) if re.fullmatch(r"r2[a-z]_bench\.json", n))
+    assert names, "no bench line committed"
+    d = json.loads(open(os.path.join(prof, names[-1])).read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["unit"] == "clouds/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["data"] == "synthetic" and "workload" in d["config"] and "model" not in d["config"]
+    per_step = d["config"]["global_batch"]
+    assert abs(d["value"] - per_step * 1000.0 / d["ms_per_step"]) <= 1e-6 * d["value"]
+    assert d["warmup"] >= 3 and d["gpu_launches"] >= d["steps"]
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and 0 < e["value"] < d["value"]
+    assert e["h2d_bytes_per_step"] == per_step * 3 * d["config"]["n_points"] * 4 and e["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["kernel_ms"] * 1e-3) / 1e9) <= 1e-6 * r["achieved"]
+    assert r["kernel_ms"] < d["ms_per_step"] and r["traffic"] >= r["algorithmic_bytes_per_launch"]
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["unit"] == d["unit"] and c["sample"]
+    k = d["clocks"]
+    assert not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert k["sm_mhz"] >= 0.9 * k["sm_max_mhz"]
