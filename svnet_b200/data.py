@@ -3,7 +3,8 @@
 The reference reads ModelNet40 / ShapeNetPart / ScanObjectNN from HDF5 (data.py:71-115, 186-201,
 260-340); h5py is not installable here, so the same arrays are read from ``.npz`` files that sit where
 the ``.h5`` files sit and hold the same keys (``data``, ``label``, ``pid``): ``convert_h5_to_npz`` makes
-them once on a machine that has h5py.  Class names, constructor arguments, item tuples and partition
+them once on a machine that has h5py.  Where h5py is installed and no ``.npz`` shard matches, the ``.h5``
+files themselves are read.  Class names, constructor arguments, item tuples and partition
 behaviour follow the reference, so ``DataLoader(ModelNet40(partition='test', num_points=1024,
 data_dir=...))`` feeds ``model(data.permute(0, 2, 1))`` exactly as main_cls_dgcnn.py:218-238 does.
 """
@@ -39,20 +40,46 @@ def convert_h5_to_npz(h5_path, npz_path=None):
     return npz_path
 
 
+def _h5py():
+    try:
+        import h5py
+        return h5py
+    except ImportError:
+        return None
+
+
+def _shards(pattern):
+    """Shards matching ``pattern`` (written with a ``.npz`` suffix): the npz files if there are any, else -- where
+    h5py is installed -- the reference's own ``.h5`` files under the same names (data.py:78, 99-102, 318)."""
+    files = glob.glob(pattern)
+    if not files and _h5py() is not None:
+        files = glob.glob(pattern[:-4] + ".h5")
+    return files
+
+
 def _load(files, keys):
     if not files:
-        raise FileNotFoundError("no .npz shards found (convert the .h5 files with svnet_b200.data.convert_h5_to_npz)")
+        raise FileNotFoundError("no .npz shards found (convert the .h5 files with svnet_b200.data.convert_h5_to_npz, "
+                                "or install h5py to read them directly)")
     cols = [[] for _ in keys]
     for name in sorted(files):
-        with np.load(name) as z:
-            for c, (k, dt) in zip(cols, keys):
-                c.append(z[k].astype(dt))
+        if name.endswith(".h5"):
+            f = _h5py().File(name, "r")
+            try:
+                for c, (k, dt) in zip(cols, keys):
+                    c.append(np.asarray(f[k]).astype(dt))
+            finally:
+                f.close()
+        else:
+            with np.load(name) as z:
+                for c, (k, dt) in zip(cols, keys):
+                    c.append(z[k].astype(dt))
     return tuple(np.concatenate(c, axis=0) for c in cols)
 
 
 def load_data_cls(data_dir, partition):
     """data.py:71-88: every ``modelnet40*hdf5_2048/*<partition>*`` shard, concatenated."""
-    return _load(glob.glob(os.path.join(data_dir, 'modelnet40*hdf5_2048', '*%s*.npz' % partition)),
+    return _load(_shards(os.path.join(data_dir, 'modelnet40*hdf5_2048', '*%s*.npz' % partition)),
                  [("data", "float32"), ("label", "int64")])
 
 
@@ -60,9 +87,9 @@ def load_data_partseg(data_dir, partition):
     """data.py:91-115: 'trainval' joins the train and val shards."""
     root = os.path.join(data_dir, 'shapenet*hdf5*')
     if partition == 'trainval':
-        files = glob.glob(os.path.join(root, '*train*.npz')) + glob.glob(os.path.join(root, '*val*.npz'))
+        files = _shards(os.path.join(root, '*train*.npz')) + _shards(os.path.join(root, '*val*.npz'))
     else:
-        files = glob.glob(os.path.join(root, '*%s*.npz' % partition))
+        files = _shards(os.path.join(root, '*%s*.npz' % partition))
     return _load(files, [("data", "float32"), ("label", "int64"), ("pid", "int64")])
 
 
@@ -130,8 +157,8 @@ class ScanObjectNNCls(Dataset):
         if partition not in ('train', 'test'):
             raise ValueError('not recognized partition {}'.format(partition))
         name = self._files[(partition, 'easy' if subset == 'easy' else 'hard')]
-        path = os.path.join(data_dir, 'h5_files', 'main_split', name + '.npz')
-        self.points, self.labels = _load([path] if os.path.exists(path) else [], [("data", "float32"), ("label", "int64")])
+        self.points, self.labels = _load(_shards(os.path.join(data_dir, 'h5_files', 'main_split', name + '.npz')),
+                                         [("data", "float32"), ("label", "int64")])
         self.num_points = num_points
         self.partition = partition
 
